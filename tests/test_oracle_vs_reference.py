@@ -47,4 +47,4 @@ def test_param_spec_is_the_reference_named_parameters():
         mine = [(p.name, p.shape) for p in param_spec(ModelConfig(cfg_path))]
         assert ref == mine
         dead = {p.name for p in param_spec(ModelConfig(cfg_path)) if not p.live}
-        assert len(dead) == 36
+        assert len(dead) == (36 if f == 'vilbert.json' else 20)
