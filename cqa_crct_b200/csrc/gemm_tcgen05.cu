@@ -1,0 +1,413 @@
+// K1 — persistent, warp-specialised tcgen05/TMEM GEMM fed by TMA (sm_100a).
+//
+//   D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ),  bf16 operands, fp32 accumulation in tensor memory.
+//
+// Replaces the cuBLAS calls behind every nn.Linear of the reference transformer and their autograd
+// backward (reference: CRCT/backbone/vilbert.py:373-375,388-390,420,446,463,502-504,551,577,594,
+// 637-646,732,739,1453).  One CTA per SM, 12 warps:
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers)
+//   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
+//   warps 4-11  epilogue       (tcgen05.ld -> registers -> fused bias/GELU/dropout/residual -> global)
+// Tile 128 x BN x 64 (BN = 128 or 256), 4-6 smem stages, double-buffered accumulators so the epilogue
+// of tile i overlaps the MMAs of tile i+1.  K-major and MN-major operands are both native (UMMA
+// descriptor major bits + transposed TMA boxes), so dgrad / wgrad need no transposed copies.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;           // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_WARPS = 8;
+
+template <int BN>
+struct Cfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BN * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+};
+
+struct KParams {
+    int M, N, K;
+    int num_n_tiles, num_tiles, split_k, kb_total, kb_per_split;
+    void* D;
+    void* D2;
+    const float* bias;
+    const bf16* aux;
+    int ldd, ldaux;
+    int accumulate;
+    uint32_t drop_thr;
+    float drop_scale;
+    uint64_t seed;
+    uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;   // bytes
+};
+
+// UMMA shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// UMMA instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+template <int BN, bool A_MN, bool B_MN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_row32(const KParams& p, int row, int col0, const uint32_t (&v)[32]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int col = col0 + g * 8;
+        if (col >= p.N) break;                       // N % 8 == 0: a group is entirely in or out
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+        const size_t off = (size_t)row * p.ldd + col;
+        if constexpr (EPI == CRCT_EPI_F32) {
+            float* d = reinterpret_cast<float*>(p.D) + off;
+            if (p.accumulate) {
+                ptx::red_add_f32x4(d, f[0], f[1], f[2], f[3]);
+                ptx::red_add_f32x4(d + 4, f[4], f[5], f[6], f[7]);
+            } else {
+                *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            }
+        } else {
+            if constexpr (EPI != CRCT_EPI_DGELU) {
+                if (p.bias != nullptr) {
+                    float b[8];
+                    load8_f32(p.bias + col, b);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += b[j];
+                }
+            }
+            if constexpr (EPI == CRCT_EPI_BIAS_GELU) {
+                if (p.D2 != nullptr) store8_bf16(reinterpret_cast<bf16*>(p.D2) + off, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = gelu_f(f[j]);
+            }
+            if constexpr (EPI == CRCT_EPI_BIAS_RES) {
+                if (p.drop_thr != 0u) {
+                    const uint64_t e0 = (uint64_t)row * (uint64_t)p.N + (uint64_t)col;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = crct_keep(p.seed, e0 + j, p.drop_thr) ? f[j] * p.drop_scale : 0.f;
+                }
+                if (p.aux != nullptr) {
+                    float a[8];
+                    load8_bf16(p.aux + (size_t)row * p.ldaux + col, a);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += a[j];
+                }
+            }
+            if constexpr (EPI == CRCT_EPI_DGELU) {
+                float a[8];
+                load8_bf16(p.aux + (size_t)row * p.ldaux + col, a);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] *= gelu_grad_f(a[j]);
+            }
+            store8_bf16(reinterpret_cast<bf16*>(p.D) + off, f);
+        }
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* gbase = smem_raw + (base - raw_addr);
+    const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
+    auto smem_a = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
+    auto smem_b = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES + C::A_BYTES; };
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * C::STAGES + i); };
+    auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * C::STAGES + 2 + i); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::tma_prefetch_desc(&tmA);
+        ptx::tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(tfull_bar(i), 1);
+            ptx::mbar_init(tempty_bar(i), NUM_EPI_WARPS);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int ks = tile % p.split_k;
+                const int mn = tile / p.split_k;
+                const int m0 = (mn / p.num_n_tiles) * BLOCK_M;
+                const int n0 = (mn % p.num_n_tiles) * BN;
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    const int k0 = kb * BLOCK_K;
+                    if constexpr (!A_MN) {
+                        ptx::tma_load_2d(smem_a(stage), &tmA, full_bar(stage), k0, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_M / 64; ++j)
+                            ptx::tma_load_2d(smem_a(stage) + j * (BLOCK_K * 128), &tmA, full_bar(stage), m0 + j * 64, k0);
+                    }
+                    if constexpr (!B_MN) {
+                        ptx::tma_load_2d(smem_b(stage), &tmB, full_bar(stage), k0, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            ptx::tma_load_2d(smem_b(stage) + j * (BLOCK_K * 128), &tmB, full_bar(stage), n0 + j * 64, k0);
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int ks = tile % p.split_k;
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t adesc = make_smem_desc(smem_a(stage) + k * p.a_kstep, p.a_lbo, p.a_sbo);
+                        const uint64_t bdesc = make_smem_desc(smem_b(stage) + k * p.b_kstep, p.b_lbo, p.b_sbo);
+                        ptx::tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    ptx::tc_commit(empty_bar(stage));          // smem slot reusable once these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+                ptx::tc_commit(tfull_bar(acc));                 // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue =====================
+        const int lane_grp = warp & 3;                          // TMEM lanes [32*lane_grp, +32) are this warp's
+        const int col_half = (warp - EPI_WARP0) >> 2;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int mn = tile / p.split_k;
+            const int m0 = (mn / p.num_n_tiles) * BLOCK_M;
+            const int n0 = (mn % p.num_n_tiles) * BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const int row = m0 + lane_grp * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < BN / 64; ++c) {
+                const int cc = col_half * (BN / 2) + c * 32;
+                const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN + cc);
+                uint32_t v[32];
+                ptx::tc_ld_32x32(taddr, v);
+                ptx::tc_wait_ld();
+                if (row < p.M && n0 + cc < p.N) epilogue_row32<EPI>(p, row, n0 + cc, v);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+        if (q != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// 2-D bf16 tensor, `inner` contiguous elements per row, `outer` rows of stride ld elements
+int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) CRCT_FAIL(CRCT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) CRCT_FAIL(CRCT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u",
+                                     (int)r, ptr, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+    return CRCT_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int grid, cudaStream_t st) {
+    auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>;
+    static bool configured = false;       // per instantiation
+    if (!configured) {
+        CRCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+        configured = true;
+    }
+    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+template <int BN>
+int dispatch(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int grid, cudaStream_t st) {
+    if (!a_mn && !b_mn) {
+        if (epi == CRCT_EPI_BIAS) return launch<BN, false, false, CRCT_EPI_BIAS>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_BIAS_GELU) return launch<BN, false, false, CRCT_EPI_BIAS_GELU>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_BIAS_RES) return launch<BN, false, false, CRCT_EPI_BIAS_RES>(tmA, tmB, p, grid, st);
+    } else if (!a_mn && b_mn) {
+        if (epi == CRCT_EPI_BIAS) return launch<BN, false, true, CRCT_EPI_BIAS>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_BIAS_RES) return launch<BN, false, true, CRCT_EPI_BIAS_RES>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_DGELU) return launch<BN, false, true, CRCT_EPI_DGELU>(tmA, tmB, p, grid, st);
+    } else if (a_mn && b_mn) {
+        if (epi == CRCT_EPI_F32) return launch<BN, true, true, CRCT_EPI_F32>(tmA, tmB, p, grid, st);
+    }
+    CRCT_FAIL(CRCT_ERR_ARG, "unsupported GEMM variant a_major=%d b_major=%d epilogue=%d", a_mn, b_mn, epi);
+}
+
+}  // namespace
+
+extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t stream) {
+    if (!a || !a->A || !a->B || !a->D) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: null pointer");
+    if (a->M <= 0 || a->N <= 0 || a->K <= 0) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_gemm_bf16: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
+    if (a->N % 8) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_gemm_bf16: N=%d must be a multiple of 8", a->N);
+    if ((a->lda % 8) || (a->ldb % 8) || (a->ldd % 8) || (a->aux && (a->ldaux % 8)))
+        CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: leading dimensions must be multiples of 8 elements");
+    if (((uintptr_t)a->A | (uintptr_t)a->B | (uintptr_t)a->D | (uintptr_t)a->D2 | (uintptr_t)a->aux | (uintptr_t)a->bias) & 15)
+        CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: pointers must be 16-byte aligned");
+    if ((a->epilogue == CRCT_EPI_DGELU) && !a->aux) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: DGELU epilogue needs aux");
+    const bool f32 = a->epilogue == CRCT_EPI_F32;
+    int split_k = a->split_k;
+    const int kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
+    const int sms = a->max_ctas > 0 ? a->max_ctas : crct_num_sms();
+    if (sms <= 0) return CRCT_ERR_CUDA;
+
+    int bn = a->block_n;
+    if (bn == 0) {
+        auto cost = [&](int b) {
+            long tiles = (long)((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + b - 1) / b);
+            return ((tiles + sms - 1) / sms) * (long)b;
+        };
+        bn = (cost(128) < cost(256)) ? 128 : 256;
+        if (f32) bn = 128;             // wgrad: more, smaller tiles + split-K fill the SMs better
+    }
+    if (bn != 128 && bn != 256) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: block_n must be 0, 128 or 256");
+    const int num_m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+    const int num_n_tiles = (a->N + bn - 1) / bn;
+    if (split_k <= 0) {
+        split_k = 1;
+        if (f32 && a->accumulate) {
+            const int mn = num_m_tiles * num_n_tiles;
+            split_k = sms / mn;
+            if (split_k > kb_total / 4) split_k = kb_total / 4;
+            if (split_k < 1) split_k = 1;
+        }
+    }
+    if (split_k > 1 && !(f32 && a->accumulate)) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: split_k > 1 needs CRCT_EPI_F32 with accumulate");
+    if (split_k > kb_total) split_k = kb_total;
+    const int kb_per_split = (kb_total + split_k - 1) / split_k;
+    split_k = (kb_total + kb_per_split - 1) / kb_per_split;      // no empty split
+
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.num_n_tiles = num_n_tiles;
+    p.split_k = split_k;
+    p.num_tiles = num_m_tiles * num_n_tiles * split_k;
+    p.kb_total = kb_total;
+    p.kb_per_split = kb_per_split;
+    p.D = a->D; p.D2 = a->D2; p.bias = a->bias; p.aux = reinterpret_cast<const bf16*>(a->aux);
+    p.ldd = a->ldd; p.ldaux = a->ldaux;
+    p.accumulate = a->accumulate;
+    p.drop_thr = crct_drop_threshold(a->dropout_p);
+    p.drop_scale = a->dropout_p > 0.f ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
+    p.seed = a->seed;
+    // K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO); LBO unused; +32 B per UMMA_K step.
+    // MN-major, SWIZZLE_128B: one TMA box = 64 (MN) x BLOCK_K (K) -> K-groups of 8 rows 1024 B apart (SBO),
+    //                         64-wide MN atoms BLOCK_K*128 B apart (LBO); +16 rows * 128 B per UMMA_K step.
+    p.a_lbo = a->a_major ? BLOCK_K * 128 : 16;  p.a_sbo = 1024;  p.a_kstep = a->a_major ? UMMA_K * 128 : UMMA_K * 2;
+    p.b_lbo = a->b_major ? BLOCK_K * 128 : 16;  p.b_sbo = 1024;  p.b_kstep = a->b_major ? UMMA_K * 128 : UMMA_K * 2;
+    if (a->dbg[0]) {   // bring-up overrides: {enable, a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep}
+        p.a_lbo = a->dbg[1]; p.a_sbo = a->dbg[2]; p.a_kstep = a->dbg[3];
+        p.b_lbo = a->dbg[4]; p.b_sbo = a->dbg[5]; p.b_kstep = a->dbg[6];
+    }
+
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (!a->a_major) rc = make_tmap(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BLOCK_K, BLOCK_M);
+    else             rc = make_tmap(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BLOCK_K);
+    if (rc) return rc;
+    if (!a->b_major) rc = make_tmap(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)bn);
+    else             rc = make_tmap(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K);
+    if (rc) return rc;
+
+    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    cudaStream_t st = as_stream(stream);
+    if (bn == 256) return dispatch<256>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
+    return dispatch<128>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
+}

@@ -1,0 +1,638 @@
+// K4/K5/K6 — fused, vectorised (128-bit), warp-shuffle row kernels: LayerNorm forward/backward,
+// text / visual embedding assembly, RoI-feature softmax, column sums, casts, masks.
+// All are HBM-bound: one warp owns one row, the row lives in registers, statistics are fp32.
+//
+// reference: CRCT/backbone/vilbert.py:281-294 (BertLayerNorm, eps inside the sqrt),
+//            :320-358 (BertEmbeddingLocation), :1474-1496 (BertImageEmbeddings), :1380-1396 (masks).
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXC = 4;                 // 16-byte chunks per lane: rows up to 32*4*8 = 1024 columns
+constexpr int ROW_THREADS = 256;        // 8 warps = 8 rows per CTA
+constexpr float LN_EPS = 1e-12f;
+
+// a row of H (= 8*nchunks) values distributed over a warp: lane l holds chunks l, l+32, ...
+struct Row {
+    float v[MAXC][8];
+};
+
+__device__ __forceinline__ void row_stats(const Row& r, int nchunks, int lane, int H, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+        if (lane + 32 * c < nchunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += r.v[c][j];
+        }
+    mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+        if (lane + 32 * c < nchunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = r.v[c][j] - mean; q += d * d; }
+        }
+    rstd = rsqrtf(warp_sum(q) / (float)H + LN_EPS);
+}
+
+// y = (z - mean) * rstd * gamma + beta, optional dropout on y; writes y (bf16)
+__device__ __forceinline__ void ln_write(const Row& z, int nchunks, int lane, float mean, float rstd, const float* gamma,
+                                         const float* beta, bf16* y_row, uint64_t row_idx0, uint32_t thr, float scale, uint64_t seed) {
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunks) {
+            float g[8], b[8], o[8];
+            load8_f32(gamma + ch * 8, g);
+            load8_f32(beta + ch * 8, b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                o[j] = (z.v[c][j] - mean) * rstd * g[j] + b[j];
+                if (thr != 0u) o[j] = crct_keep(seed, row_idx0 + ch * 8 + j, thr) ? o[j] * scale : 0.f;
+            }
+            store8_bf16(y_row + ch * 8, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n8) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float f[8];
+        load8_f32(src + i * 8, f);
+        store8_bf16(dst + i * 8, f);
+    }
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) additive_mask_kernel(const void* __restrict__ mask, int kind, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m;
+    if (kind == 0) m = reinterpret_cast<const uint8_t*>(mask)[i] ? 1.f : 0.f;            // torch.bool
+    else if (kind == 1) m = (float)reinterpret_cast<const long long*>(mask)[i];            // int64
+    else m = reinterpret_cast<const float*>(mask)[i];                                      // fp32
+    out[i] = (1.0f - m) * -10000.0f;                                                       // vilbert.py:1391,1396
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+layernorm_fwd_kernel(const bf16* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
+    if (row >= rows) return;
+    const int nchunks = H >> 3;
+    Row r;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+        if (lane + 32 * c < nchunks) load8_bf16(z + (size_t)row * H + (lane + 32 * c) * 8, r.v[c]);
+    float mean, rstd;
+    row_stats(r, nchunks, lane, H, mean, rstd);
+    ln_write(r, nchunks, lane, mean, rstd, gamma, beta, y + (size_t)row * H, 0, 0u, 1.f, 0);
+    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// dz = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)), dxh = dy * gamma
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dbias += sum_rows dzm (optional)
+// dy may carry an input dropout mask (seed_in), dzm = dz * keep(seed_out) * scale (optional second output)
+__global__ void __launch_bounds__(ROW_THREADS)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ mean_in,
+                     const float* __restrict__ rstd_in, const float* __restrict__ gamma, bf16* __restrict__ dz,
+                     bf16* __restrict__ dzm, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                     int rows, int H, uint32_t thr_in, float scale_in, uint64_t seed_in, uint32_t thr_out, float scale_out,
+                     uint64_t seed_out) {
+    extern __shared__ float red[];                       // [8 warps][H]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = H >> 3;
+    Row ag, ab, abias;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ag.v[c][j] = 0.f; ab.v[c][j] = 0.f; abias.v[c][j] = 0.f; }
+
+    for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < rows; row += gridDim.x * (ROW_THREADS / 32)) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        Row g, x;                                         // g: dy then dxh ; x: xhat
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int ch = lane + 32 * c;
+            if (ch < nchunks) {
+                float gm[8];
+                load8_bf16(dy + (size_t)row * H + ch * 8, g.v[c]);
+                load8_bf16(z + (size_t)row * H + ch * 8, x.v[c]);
+                load8_f32(gamma + ch * 8, gm);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float d = g.v[c][j];
+                    if (thr_in != 0u) d = crct_keep(seed_in, (uint64_t)row * H + ch * 8 + j, thr_in) ? d * scale_in : 0.f;
+                    const float xh = (x.v[c][j] - mean) * rstd;
+                    ag.v[c][j] += d * xh;
+                    ab.v[c][j] += d;
+                    const float dxh = d * gm[j];
+                    s1 += dxh;
+                    s2 += dxh * xh;
+                    g.v[c][j] = dxh;
+                    x.v[c][j] = xh;
+                }
+            }
+        }
+        const float m1 = warp_sum(s1) / (float)H, m2 = warp_sum(s2) / (float)H;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int ch = lane + 32 * c;
+            if (ch < nchunks) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rstd * (g.v[c][j] - m1 - x.v[c][j] * m2);
+                store8_bf16(dz + (size_t)row * H + ch * 8, o);
+                if (dzm != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        o[j] = crct_keep(seed_out, (uint64_t)row * H + ch * 8 + j, thr_out) ? o[j] * scale_out : 0.f;
+                    store8_bf16(dzm + (size_t)row * H + ch * 8, o);
+                }
+                if (dbias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) abias.v[c][j] += o[j];
+                }
+            }
+        }
+    }
+    // cross-warp reduction of the three column sums, one array at a time through smem
+    for (int which = 0; which < 3; ++which) {
+        float* out = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+        if (out == nullptr) continue;                      // uniform across the CTA
+        const Row& a = which == 0 ? ag : (which == 1 ? ab : abias);
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int ch = lane + 32 * c;
+            if (ch < nchunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) red[warp * H + ch * 8 + j] = a.v[c][j];
+            }
+        }
+        __syncthreads();
+        for (int col = threadIdx.x; col < H; col += ROW_THREADS) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < ROW_THREADS / 32; ++w) s += red[w * H + col];
+            atomicAdd(out + col, s);
+        }
+    }
+}
+
+// out[n] += sum_rows x[row, n]
+__global__ void __launch_bounds__(ROW_THREADS)
+colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows, int N, int ld) {
+    __shared__ float red[ROW_THREADS / 32][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 256 + lane * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (col < N) {
+        for (int row = blockIdx.y * (ROW_THREADS / 32) + warp; row < rows; row += gridDim.y * (ROW_THREADS / 32)) {
+            float f[8];
+            load8_bf16(x + (size_t)row * ld + col, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+    __syncthreads();
+    const int c = threadIdx.x;
+    if (blockIdx.x * 256 + c < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < ROW_THREADS / 32; ++w) s += red[w][c];
+        atomicAdd(out + blockIdx.x * 256 + c, s);
+    }
+}
+
+// softmax over the F RoI features of one region, fp32 in -> bf16 GEMM operand (vilbert.py:1476)
+__global__ void __launch_bounds__(ROW_THREADS)
+softmax_rows_kernel(const float* __restrict__ x, bf16* __restrict__ out, int rows, int F) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
+    if (row >= rows) return;
+    const int nchunks = F >> 3;
+    Row r;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+        if (lane + 32 * c < nchunks) {
+            load8_f32(x + (size_t)row * F + (lane + 32 * c) * 8, r.v[c]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mx = fmaxf(mx, r.v[c][j]);
+        }
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+        if (lane + 32 * c < nchunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { r.v[c][j] = __expf(r.v[c][j] - mx); s += r.v[c][j]; }
+        }
+    const float inv = 1.0f / warp_sum(s);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+        if (lane + 32 * c < nchunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r.v[c][j] *= inv;
+            store8_bf16(out + (size_t)row * F + (lane + 32 * c) * 8, r.v[c]);
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// text embedding (vilbert.py:320-358): word + position(QA tokens only, counted from the first QA token)
+// + plotqa type (-1 -> 0, zero for type 0) + Linear(4->H)(box) (zero incl. bias for all-zero boxes) -> LN -> dropout
+struct TextEmbArgs {
+    const long long* ids; const long long* types; const float* loc;
+    const float* word; const float* pos; const float* type; const float* w_loc; const float* b_loc;
+    const float* gamma; const float* beta;
+    bf16* y; bf16* z; float* mean; float* rstd;
+    int B, T, H;
+    uint32_t thr; float scale; uint64_t seed;
+};
+
+__device__ __forceinline__ int first_qa_index(const long long* types_row, int T, int lane) {
+    int first = T;
+    for (int t = lane; t < T; t += 32) {
+        const long long ty = types_row[t];
+        if ((ty == -1 || ty == 1) && t < first) first = t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    return first;
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) embed_text_fwd_kernel(const TextEmbArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
+    if (row >= a.B * a.T) return;
+    const int b = row / a.T, t = row % a.T;
+    const int H = a.H, nchunks = H >> 3;
+    const int first = first_qa_index(a.types + (size_t)b * a.T, a.T, lane);
+    const long long ty = a.types[row];
+    const bool qa = (ty == -1 || ty == 1);
+    const long long id = a.ids[row];
+    const float4 bx = *reinterpret_cast<const float4*>(a.loc + (size_t)row * 4);
+    const bool loc_on = (fabsf(bx.x) + fabsf(bx.y) + fabsf(bx.z) + fabsf(bx.w)) != 0.f;
+    const long long ty_idx = ty == -1 ? 0 : ty;
+    Row r;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunks) {
+            load8_f32(a.word + (size_t)id * H + ch * 8, r.v[c]);
+            float tmp[8];
+            if (qa) {
+                load8_f32(a.pos + (size_t)(t - first) * H + ch * 8, tmp);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r.v[c][j] += tmp[j];
+            }
+            if (ty != 0) {
+                load8_f32(a.type + (size_t)ty_idx * H + ch * 8, tmp);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r.v[c][j] += tmp[j];
+            }
+            if (loc_on) {
+                load8_f32(a.b_loc + ch * 8, tmp);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 w = *reinterpret_cast<const float4*>(a.w_loc + (size_t)(ch * 8 + j) * 4);
+                    r.v[c][j] += tmp[j] + w.x * bx.x + w.y * bx.y + w.z * bx.z + w.w * bx.w;
+                }
+            }
+            if (a.z) store8_bf16(a.z + (size_t)row * H + ch * 8, r.v[c]);
+        }
+    }
+    // LayerNorm statistics are taken on the bf16-rounded z when z is materialised, so that the backward
+    // (which re-reads z) sees exactly the normalised values of the forward
+    if (a.z) {
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+            if (lane + 32 * c < nchunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r.v[c][j] = __bfloat162float(__float2bfloat16(r.v[c][j]));
+            }
+    }
+    float mean, rstd;
+    row_stats(r, nchunks, lane, H, mean, rstd);
+    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)row * H, a.thr, a.scale, a.seed);
+    if (lane == 0 && a.mean) { a.mean[row] = mean; a.rstd[row] = rstd; }
+}
+
+// backward scatter of dz (bf16, already through the LayerNorm backward) into the embedding tables
+struct TextEmbBwdArgs {
+    const long long* ids; const long long* types; const float* loc; const bf16* dz;
+    float* g_word; float* g_pos; float* g_type; float* g_wloc; float* g_bloc;
+    int B, T, H;
+};
+
+__global__ void __launch_bounds__(ROW_THREADS) embed_text_bwd_kernel(const TextEmbBwdArgs a) {
+    extern __shared__ float red[];                        // [8 warps][H] reused 5x
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = a.H, nchunks = H >> 3;
+    Row acc[5];                                           // d b_loc, d w_loc[:,0..3]
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[k].v[c][j] = 0.f;
+    const int rows = a.B * a.T;
+    for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < rows; row += gridDim.x * (ROW_THREADS / 32)) {
+        const int b = row / a.T, t = row % a.T;
+        const int first = first_qa_index(a.types + (size_t)b * a.T, a.T, lane);
+        const long long ty = a.types[row];
+        const bool qa = (ty == -1 || ty == 1);
+        const long long id = a.ids[row];
+        const float4 bx = *reinterpret_cast<const float4*>(a.loc + (size_t)row * 4);
+        const bool loc_on = (fabsf(bx.x) + fabsf(bx.y) + fabsf(bx.z) + fabsf(bx.w)) != 0.f;
+        const long long ty_idx = ty == -1 ? 0 : ty;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int ch = lane + 32 * c;
+            if (ch < nchunks) {
+                float d[8];
+                load8_bf16(a.dz + (size_t)row * H + ch * 8, d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    atomicAdd(a.g_word + (size_t)id * H + ch * 8 + j, d[j]);
+                    if (qa) atomicAdd(a.g_pos + (size_t)(t - first) * H + ch * 8 + j, d[j]);
+                    if (ty != 0) atomicAdd(a.g_type + (size_t)ty_idx * H + ch * 8 + j, d[j]);
+                    if (loc_on) {
+                        acc[0].v[c][j] += d[j];
+                        acc[1].v[c][j] += d[j] * bx.x; acc[2].v[c][j] += d[j] * bx.y;
+                        acc[3].v[c][j] += d[j] * bx.z; acc[4].v[c][j] += d[j] * bx.w;
+                    }
+                }
+            }
+        }
+    }
+    for (int k = 0; k < 5; ++k) {
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int ch = lane + 32 * c;
+            if (ch < nchunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) red[warp * H + ch * 8 + j] = acc[k].v[c][j];
+            }
+        }
+        __syncthreads();
+        for (int col = threadIdx.x; col < H; col += ROW_THREADS) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < ROW_THREADS / 32; ++w) s += red[w * H + col];
+            if (k == 0) atomicAdd(a.g_bloc + col, s);
+            else atomicAdd(a.g_wloc + (size_t)col * 4 + (k - 1), s);
+        }
+    }
+}
+
+// visual embedding tail (vilbert.py:1478-1496): z = G + Linear(4->Hv)(box) + color_emb[class] ; LN ; dropout
+struct VisEmbArgs {
+    const bf16* g; const float* box; const long long* cls;
+    const float* w_loc; const float* b_loc; const float* color; const float* gamma; const float* beta;
+    bf16* y; bf16* z; float* mean; float* rstd;
+    int rows, H;
+    uint32_t thr; float scale; uint64_t seed;
+};
+
+__global__ void __launch_bounds__(ROW_THREADS) embed_vis_fwd_kernel(const VisEmbArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
+    if (row >= a.rows) return;
+    const int H = a.H, nchunks = H >> 3;
+    const float4 bx = *reinterpret_cast<const float4*>(a.box + (size_t)row * 4);
+    const long long cls = a.cls[row];
+    Row r;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunks) {
+            float tmp[8], bl[8];
+            load8_bf16(a.g + (size_t)row * H + ch * 8, r.v[c]);
+            load8_f32(a.color + (size_t)cls * H + ch * 8, tmp);
+            load8_f32(a.b_loc + ch * 8, bl);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 w = *reinterpret_cast<const float4*>(a.w_loc + (size_t)(ch * 8 + j) * 4);
+                r.v[c][j] += tmp[j] + bl[j] + w.x * bx.x + w.y * bx.y + w.z * bx.z + w.w * bx.w;
+            }
+            if (a.z) {
+                store8_bf16(a.z + (size_t)row * H + ch * 8, r.v[c]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r.v[c][j] = __bfloat162float(__float2bfloat16(r.v[c][j]));
+            }
+        }
+    }
+    float mean, rstd;
+    row_stats(r, nchunks, lane, H, mean, rstd);
+    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)row * H, a.thr, a.scale, a.seed);
+    if (lane == 0 && a.mean) { a.mean[row] = mean; a.rstd[row] = rstd; }
+}
+
+struct VisEmbBwdArgs {
+    const bf16* dz; const float* box; const long long* cls;
+    float* g_color; float* g_wloc;
+    int rows, H;
+};
+
+__global__ void __launch_bounds__(ROW_THREADS) embed_vis_bwd_kernel(const VisEmbBwdArgs a) {
+    extern __shared__ float red[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = a.H, nchunks = H >> 3;
+    Row acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[k].v[c][j] = 0.f;
+    for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < a.rows; row += gridDim.x * (ROW_THREADS / 32)) {
+        const float4 bx = *reinterpret_cast<const float4*>(a.box + (size_t)row * 4);
+        const long long cls = a.cls[row];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int ch = lane + 32 * c;
+            if (ch < nchunks) {
+                float d[8];
+                load8_bf16(a.dz + (size_t)row * H + ch * 8, d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    atomicAdd(a.g_color + (size_t)cls * H + ch * 8 + j, d[j]);
+                    acc[0].v[c][j] += d[j] * bx.x; acc[1].v[c][j] += d[j] * bx.y;
+                    acc[2].v[c][j] += d[j] * bx.z; acc[3].v[c][j] += d[j] * bx.w;
+                }
+            }
+        }
+    }
+    for (int k = 0; k < 4; ++k) {
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int ch = lane + 32 * c;
+            if (ch < nchunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) red[warp * H + ch * 8 + j] = acc[k].v[c][j];
+            }
+        }
+        __syncthreads();
+        for (int col = threadIdx.x; col < H; col += ROW_THREADS) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < ROW_THREADS / 32; ++w) s += red[w * H + col];
+            atomicAdd(a.g_wloc + (size_t)col * 4 + k, s);
+        }
+    }
+}
+
+inline int check_row_width(int H, const char* what) {
+    if (H <= 0 || (H % 8) || H > MAXC * 256) CRCT_FAIL(CRCT_ERR_SHAPE, "%s: row width %d must be a multiple of 8 and <= %d", what, H, MAXC * 256);
+    return CRCT_OK;
+}
+inline int row_grid(int rows) { return (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32); }
+
+}  // namespace
+
+extern "C" CRCT_API int crct_cast_f32_to_bf16(const float* src, void* dst, size_t n, crct_stream_t s) {
+    if (!src || !dst) CRCT_FAIL(CRCT_ERR_ARG, "crct_cast_f32_to_bf16: null pointer");
+    if (n % 8) CRCT_FAIL(CRCT_ERR_ARG, "crct_cast_f32_to_bf16: n must be a multiple of 8");
+    if (n == 0) return CRCT_OK;
+    const size_t n8 = n / 8;
+    size_t blocks = (n8 + ROW_THREADS - 1) / ROW_THREADS;
+    const size_t cap = (size_t)crct_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    cast_kernel<<<(unsigned)blocks, ROW_THREADS, 0, as_stream(s)>>>(src, reinterpret_cast<bf16*>(dst), n8);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_additive_mask(const void* mask, int kind, float* out, int n, crct_stream_t s) {
+    if (!mask || !out || n <= 0 || kind < 0 || kind > 2) CRCT_FAIL(CRCT_ERR_ARG, "crct_additive_mask: bad argument");
+    additive_mask_kernel<<<(n + ROW_THREADS - 1) / ROW_THREADS, ROW_THREADS, 0, as_stream(s)>>>(mask, kind, out, n);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_layernorm_fwd(const void* z, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                  int rows, int H, crct_stream_t s) {
+    if (!z || !gamma || !beta || !y || (mean == nullptr) != (rstd == nullptr)) CRCT_FAIL(CRCT_ERR_ARG, "crct_layernorm_fwd: bad pointer");
+    if (int rc = check_row_width(H, "crct_layernorm_fwd")) return rc;
+    if (rows <= 0) return CRCT_OK;
+    layernorm_fwd_kernel<<<row_grid(rows), ROW_THREADS, 0, as_stream(s)>>>(reinterpret_cast<const bf16*>(z), gamma, beta,
+                                                                          reinterpret_cast<bf16*>(y), mean, rstd, rows, H);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_layernorm_bwd(const crct_ln_bwd_t* a, crct_stream_t s) {
+    if (!a || !a->dy || !a->z || !a->mean || !a->rstd || !a->gamma || !a->dz) CRCT_FAIL(CRCT_ERR_ARG, "crct_layernorm_bwd: null pointer");
+    if (int rc = check_row_width(a->H, "crct_layernorm_bwd")) return rc;
+    if (a->rows <= 0) return CRCT_OK;
+    int grid = crct_num_sms();
+    if (grid > row_grid(a->rows)) grid = row_grid(a->rows);
+    const size_t smem = (size_t)(ROW_THREADS / 32) * a->H * sizeof(float);
+    const bool dzm = a->dzm != nullptr && a->p_out > 0.f;
+    layernorm_bwd_kernel<<<grid, ROW_THREADS, smem, as_stream(s)>>>(
+        reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), a->mean, a->rstd, a->gamma,
+        reinterpret_cast<bf16*>(a->dz), dzm ? reinterpret_cast<bf16*>(a->dzm) : nullptr, a->dgamma, a->dbeta, a->dbias,
+        a->rows, a->H, crct_drop_threshold(a->p_in), a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, a->seed_in,
+        crct_drop_threshold(a->p_out), a->p_out > 0.f ? 1.f / (1.f - a->p_out) : 1.f, a->seed_out);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_colsum_bf16(const void* x, float* out, int rows, int N, int ld, crct_stream_t s) {
+    if (!x || !out) CRCT_FAIL(CRCT_ERR_ARG, "crct_colsum_bf16: null pointer");
+    if ((N % 8) || (ld % 8)) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_colsum_bf16: N and ld must be multiples of 8");
+    if (rows <= 0 || N <= 0) return CRCT_OK;
+    const int gx = (N + 255) / 256;
+    int gy = (2 * crct_num_sms() + gx - 1) / gx;
+    const int max_gy = (rows + 63) / 64;
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    colsum_kernel<<<dim3(gx, gy), ROW_THREADS, 0, as_stream(s)>>>(reinterpret_cast<const bf16*>(x), out, rows, N, ld);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_softmax_rows(const float* x, void* out, int rows, int F, crct_stream_t s) {
+    if (!x || !out) CRCT_FAIL(CRCT_ERR_ARG, "crct_softmax_rows: null pointer");
+    if (int rc = check_row_width(F, "crct_softmax_rows")) return rc;
+    if (rows <= 0) return CRCT_OK;
+    softmax_rows_kernel<<<row_grid(rows), ROW_THREADS, 0, as_stream(s)>>>(x, reinterpret_cast<bf16*>(out), rows, F);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_embed_text_fwd(const crct_embed_text_t* a, crct_stream_t s) {
+    if (!a || !a->ids || !a->types || !a->loc || !a->word || !a->pos || !a->type || !a->w_loc || !a->b_loc || !a->gamma ||
+        !a->beta || !a->y)
+        CRCT_FAIL(CRCT_ERR_ARG, "crct_embed_text_fwd: null pointer");
+    if (int rc = check_row_width(a->H, "crct_embed_text_fwd")) return rc;
+    if (a->T > a->max_pos) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_embed_text_fwd: T=%d exceeds the position table (%d)", a->T, a->max_pos);
+    TextEmbArgs k;
+    k.ids = reinterpret_cast<const long long*>(a->ids); k.types = reinterpret_cast<const long long*>(a->types); k.loc = a->loc;
+    k.word = a->word; k.pos = a->pos; k.type = a->type; k.w_loc = a->w_loc; k.b_loc = a->b_loc; k.gamma = a->gamma; k.beta = a->beta;
+    k.y = reinterpret_cast<bf16*>(a->y); k.z = reinterpret_cast<bf16*>(a->z); k.mean = a->mean; k.rstd = a->rstd;
+    k.B = a->B; k.T = a->T; k.H = a->H;
+    k.thr = crct_drop_threshold(a->dropout_p); k.scale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; k.seed = a->seed;
+    if (a->B * a->T <= 0) return CRCT_OK;
+    embed_text_fwd_kernel<<<row_grid(a->B * a->T), ROW_THREADS, 0, as_stream(s)>>>(k);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_embed_text_bwd(const crct_embed_text_bwd_t* a, crct_stream_t s) {
+    if (!a || !a->ids || !a->types || !a->loc || !a->dz || !a->g_word || !a->g_pos || !a->g_type || !a->g_wloc || !a->g_bloc)
+        CRCT_FAIL(CRCT_ERR_ARG, "crct_embed_text_bwd: null pointer");
+    if (int rc = check_row_width(a->H, "crct_embed_text_bwd")) return rc;
+    TextEmbBwdArgs k;
+    k.ids = reinterpret_cast<const long long*>(a->ids); k.types = reinterpret_cast<const long long*>(a->types); k.loc = a->loc;
+    k.dz = reinterpret_cast<const bf16*>(a->dz);
+    k.g_word = a->g_word; k.g_pos = a->g_pos; k.g_type = a->g_type; k.g_wloc = a->g_wloc; k.g_bloc = a->g_bloc;
+    k.B = a->B; k.T = a->T; k.H = a->H;
+    const int rows = a->B * a->T;
+    if (rows <= 0) return CRCT_OK;
+    int grid = crct_num_sms();
+    if (grid > row_grid(rows)) grid = row_grid(rows);
+    embed_text_bwd_kernel<<<grid, ROW_THREADS, (size_t)(ROW_THREADS / 32) * a->H * sizeof(float), as_stream(s)>>>(k);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_embed_vis_fwd(const crct_embed_vis_t* a, crct_stream_t s) {
+    if (!a || !a->g || !a->box || !a->cls || !a->w_loc || !a->b_loc || !a->color || !a->gamma || !a->beta || !a->y)
+        CRCT_FAIL(CRCT_ERR_ARG, "crct_embed_vis_fwd: null pointer");
+    if (int rc = check_row_width(a->H, "crct_embed_vis_fwd")) return rc;
+    VisEmbArgs k;
+    k.g = reinterpret_cast<const bf16*>(a->g); k.box = a->box; k.cls = reinterpret_cast<const long long*>(a->cls);
+    k.w_loc = a->w_loc; k.b_loc = a->b_loc; k.color = a->color; k.gamma = a->gamma; k.beta = a->beta;
+    k.y = reinterpret_cast<bf16*>(a->y); k.z = reinterpret_cast<bf16*>(a->z); k.mean = a->mean; k.rstd = a->rstd;
+    k.rows = a->rows; k.H = a->H;
+    k.thr = crct_drop_threshold(a->dropout_p); k.scale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; k.seed = a->seed;
+    if (a->rows <= 0) return CRCT_OK;
+    embed_vis_fwd_kernel<<<row_grid(a->rows), ROW_THREADS, 0, as_stream(s)>>>(k);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_embed_vis_bwd(const crct_embed_vis_bwd_t* a, crct_stream_t s) {
+    if (!a || !a->dz || !a->box || !a->cls || !a->g_color || !a->g_wloc) CRCT_FAIL(CRCT_ERR_ARG, "crct_embed_vis_bwd: null pointer");
+    if (int rc = check_row_width(a->H, "crct_embed_vis_bwd")) return rc;
+    VisEmbBwdArgs k;
+    k.dz = reinterpret_cast<const bf16*>(a->dz); k.box = a->box; k.cls = reinterpret_cast<const long long*>(a->cls);
+    k.g_color = a->g_color; k.g_wloc = a->g_wloc; k.rows = a->rows; k.H = a->H;
+    if (a->rows <= 0) return CRCT_OK;
+    int grid = crct_num_sms();
+    if (grid > row_grid(a->rows)) grid = row_grid(a->rows);
+    embed_vis_bwd_kernel<<<grid, ROW_THREADS, (size_t)(ROW_THREADS / 32) * a->H * sizeof(float), as_stream(s)>>>(k);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
