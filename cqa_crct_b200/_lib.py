@@ -1,5 +1,8 @@
 """ctypes binding of libcrct_b200.so (include/crct_b200.h).  No fallback: if the library is missing or
-the device is not a B200-class GPU, every call raises."""
+the device is not a B200-class GPU, every call raises.
+
+Every wrapper takes torch CUDA tensors (memory owners) and passes raw device pointers + sizes, enqueuing on
+torch's current stream."""
 from __future__ import annotations
 
 import ctypes as C
@@ -11,6 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcrct_b200.so')
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_F32 = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
+
+vp, i32, i64, f32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
 
 
 class CrctError(RuntimeError):
@@ -18,17 +24,79 @@ class CrctError(RuntimeError):
 
 
 class GemmArgs(C.Structure):
-    _fields_ = [('A', C.c_void_p), ('B', C.c_void_p), ('D', C.c_void_p), ('D2', C.c_void_p),
-                ('bias', C.c_void_p), ('aux', C.c_void_p),
-                ('M', C.c_int32), ('N', C.c_int32), ('K', C.c_int32),
-                ('lda', C.c_int32), ('ldb', C.c_int32), ('ldd', C.c_int32), ('ldaux', C.c_int32),
-                ('a_major', C.c_int32), ('b_major', C.c_int32), ('epilogue', C.c_int32),
-                ('accumulate', C.c_int32), ('split_k', C.c_int32), ('block_n', C.c_int32),
-                ('dropout_p', C.c_float), ('seed', C.c_uint64), ('max_ctas', C.c_int32),
-                ('dbg', C.c_int32 * 7)]
+    _fields_ = [('A', vp), ('B', vp), ('D', vp), ('D2', vp), ('bias', vp), ('aux', vp),
+                ('M', i32), ('N', i32), ('K', i32), ('lda', i32), ('ldb', i32), ('ldd', i32), ('ldaux', i32),
+                ('a_major', i32), ('b_major', i32), ('epilogue', i32), ('accumulate', i32), ('split_k', i32),
+                ('block_n', i32), ('dropout_p', f32), ('seed', u64), ('max_ctas', i32), ('dbg', i32 * 7)]
 
+
+class LnBwdArgs(C.Structure):
+    _fields_ = [('dy', vp), ('z', vp), ('mean', vp), ('rstd', vp), ('gamma', vp), ('dz', vp), ('dzm', vp),
+                ('dgamma', vp), ('dbeta', vp), ('dbias', vp), ('rows', i32), ('H', i32),
+                ('p_in', f32), ('seed_in', u64), ('p_out', f32), ('seed_out', u64)]
+
+
+class EmbedTextArgs(C.Structure):
+    _fields_ = [('ids', vp), ('types', vp), ('loc', vp), ('word', vp), ('pos', vp), ('type', vp), ('w_loc', vp),
+                ('b_loc', vp), ('gamma', vp), ('beta', vp), ('y', vp), ('z', vp), ('mean', vp), ('rstd', vp),
+                ('B', i32), ('T', i32), ('H', i32), ('max_pos', i32), ('dropout_p', f32), ('seed', u64)]
+
+
+class EmbedTextBwdArgs(C.Structure):
+    _fields_ = [('ids', vp), ('types', vp), ('loc', vp), ('dz', vp), ('g_word', vp), ('g_pos', vp), ('g_type', vp),
+                ('g_wloc', vp), ('g_bloc', vp), ('B', i32), ('T', i32), ('H', i32)]
+
+
+class EmbedVisArgs(C.Structure):
+    _fields_ = [('g', vp), ('box', vp), ('cls', vp), ('w_loc', vp), ('b_loc', vp), ('color', vp), ('gamma', vp),
+                ('beta', vp), ('y', vp), ('z', vp), ('mean', vp), ('rstd', vp), ('rows', i32), ('H', i32),
+                ('dropout_p', f32), ('seed', u64)]
+
+
+class EmbedVisBwdArgs(C.Structure):
+    _fields_ = [('dz', vp), ('box', vp), ('cls', vp), ('g_color', vp), ('g_wloc', vp), ('rows', i32), ('H', i32)]
+
+
+class AttnFwdArgs(C.Structure):
+    _fields_ = [('q', vp), ('k', vp), ('v', vp), ('ldq', i32), ('ldk', i32), ('ldv', i32), ('mask_add', vp),
+                ('out', vp), ('ldo', i32), ('lse', vp), ('B', i32), ('nh', i32), ('dh', i32), ('Lq', i32), ('Lk', i32),
+                ('dropout_p', f32), ('seed', u64)]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [('q', vp), ('k', vp), ('v', vp), ('ldq', i32), ('ldk', i32), ('ldv', i32), ('mask_add', vp),
+                ('out', vp), ('ldo', i32), ('dout', vp), ('lddo', i32), ('lse', vp), ('dq', vp), ('dk', vp), ('dv', vp),
+                ('lddq', i32), ('lddk', i32), ('lddv', i32), ('B', i32), ('nh', i32), ('dh', i32), ('Lq', i32),
+                ('Lk', i32), ('dropout_p', f32), ('seed', u64)]
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [('A', vp), ('sa_m', i64), ('sa_k', i64), ('B', vp), ('sb_k', i64), ('sb_n', i64), ('C', vp), ('ldc', i64),
+                ('bias', vp), ('dmask', vp), ('ldm', i64), ('M', i32), ('N', i32), ('K', i32), ('act', i32),
+                ('slope', f32), ('accumulate', i32)]
+
+
+class LossArgs(C.Structure):
+    _fields_ = [('logits', vp), ('reg', vp), ('labels', vp), ('R', vp), ('reg_pred', vp), ('reg_loss', vp), ('reg_l1', vp),
+                ('reg_dist', vp), ('scalars', vp), ('dlogits', vp), ('dpre', vp), ('B', i32), ('l1', i32),
+                ('zero_impossible', i32), ('unit_grads', i32), ('tol_margin', f32), ('nsp_coeff', f32), ('reg_coeff', f32)]
+
+
+class AdamWArgs(C.Structure):
+    _fields_ = [('w', vp), ('g', vp), ('m', vp), ('v', vp), ('w_bf16', vp), ('group_of_block64', vp), ('n', C.c_size_t),
+                ('lr', f32 * 4), ('weight_decay', f32 * 4), ('beta1', f32), ('beta2', f32), ('eps', f32), ('step', i32),
+                ('grad_scale', f32)]
+
+
+# every symbol include/crct_b200.h declares (tests check the .so exports exactly these)
+EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf16', 'crct_cast_f32_to_bf16',
+           'crct_additive_mask', 'crct_layernorm_fwd', 'crct_layernorm_bwd', 'crct_colsum_bf16', 'crct_softmax_rows',
+           'crct_embed_text_fwd', 'crct_embed_text_bwd', 'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd',
+           'crct_attn_bwd', 'crct_linear_f32', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
+           'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw']
 
 _lib = None
+LAUNCHES = 0          # kernels enqueued through this binding (bench.py reports it as gpu_launches)
 
 
 def lib():
@@ -41,30 +109,64 @@ def lib():
         _lib.crct_last_error.restype = C.c_char_p
         for name in EXPORTS:
             getattr(_lib, name)          # fail loudly on a stale library
+        _lib.crct_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]
+        _lib.crct_additive_mask.argtypes = [vp, C.c_int, vp, C.c_int, vp]
+        _lib.crct_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        _lib.crct_colsum_bf16.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        _lib.crct_softmax_rows.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        _lib.crct_gather_first.argtypes = [vp, C.c_longlong, vp, C.c_int, C.c_int, vp]
+        _lib.crct_scatter_first.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, vp]
+        _lib.crct_colsum_f32.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, vp]
+        _lib.crct_scale_rows.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp]
+        _lib.crct_pool_mul_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp]
+        _lib.crct_pool_mul_bwd.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp]
+        for name in ('crct_gemm_bf16', 'crct_layernorm_bwd', 'crct_embed_text_fwd', 'crct_embed_text_bwd',
+                     'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd', 'crct_attn_bwd', 'crct_linear_f32',
+                     'crct_hybrid_loss', 'crct_adamw'):
+            getattr(_lib, name).argtypes = [vp, vp]
     return _lib
 
 
-# every symbol include/crct_b200.h declares (tests check the .so exports exactly these)
-EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf16']
-
-
 def check(rc: int):
+    global LAUNCHES
+    if rc != 0:
+        raise CrctError(f'libcrct_b200 error {rc}: {lib().crct_last_error().decode()}')
+    LAUNCHES += 1
+
+
+def device_check():
+    rc = lib().crct_device_check()
     if rc != 0:
         raise CrctError(f'libcrct_b200 error {rc}: {lib().crct_last_error().decode()}')
 
 
-def stream_ptr() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
 
 
 def ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    return None if t is None else t.data_ptr()
+
+
+def _bf16(t, what):
+    if t is not None and t.dtype != torch.bfloat16:
+        raise CrctError(f'{what} must be bfloat16, got {t.dtype}')
+
+
+def _f32(t, what):
+    if t is not None and t.dtype != torch.float32:
+        raise CrctError(f'{what} must be float32, got {t.dtype}')
 
 
 def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None, aux=None, D2=None,
          lda=None, ldb=None, ldd=None, ldaux=None, accumulate=0, split_k=0, block_n=0, dropout_p=0.0, seed=0,
          max_ctas=0, dbg=None):
     """D[M,N] = epilogue(A·Bᵀ) — see include/crct_b200.h for operand majors."""
+    _bf16(A, 'A'); _bf16(B, 'B'); _bf16(aux, 'aux'); _bf16(D2, 'D2'); _f32(bias, 'bias')
+    if epilogue == EPI_F32:
+        _f32(D, 'D')
+    else:
+        _bf16(D, 'D')
     a = GemmArgs()
     a.A, a.B, a.D, a.D2, a.bias, a.aux = ptr(A), ptr(B), ptr(D), ptr(D2), ptr(bias), ptr(aux)
     a.M, a.N, a.K = M, N, K
@@ -79,3 +181,160 @@ def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None
         for i, v in enumerate(dbg):
             a.dbg[i] = v
     check(lib().crct_gemm_bf16(C.byref(a), stream_ptr()))
+
+
+def cast_f32_to_bf16(src, dst):
+    _f32(src, 'src'); _bf16(dst, 'dst')
+    check(lib().crct_cast_f32_to_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()))
+
+
+def additive_mask(mask, out):
+    kind = {torch.bool: 0, torch.uint8: 0, torch.int64: 1, torch.float32: 2}.get(mask.dtype)
+    if kind is None:
+        raise CrctError(f'unsupported mask dtype {mask.dtype}')
+    check(lib().crct_additive_mask(ptr(mask), kind, ptr(out), mask.numel(), stream_ptr()))
+
+
+def layernorm_fwd(z, gamma, beta, y, mean=None, rstd=None):
+    _bf16(z, 'z'); _bf16(y, 'y'); _f32(gamma, 'gamma')
+    rows, H = z.shape
+    check(lib().crct_layernorm_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, H, stream_ptr()))
+
+
+def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0,
+                  seed_out=0):
+    _bf16(dy, 'dy'); _bf16(z, 'z'); _bf16(dz, 'dz'); _bf16(dzm, 'dzm')
+    a = LnBwdArgs()
+    a.dy, a.z, a.mean, a.rstd, a.gamma, a.dz, a.dzm = ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma), ptr(dz), ptr(dzm)
+    a.dgamma, a.dbeta, a.dbias = ptr(dgamma), ptr(dbeta), ptr(dbias)
+    a.rows, a.H = z.shape
+    a.p_in, a.seed_in, a.p_out, a.seed_out = p_in, seed_in, p_out, seed_out
+    check(lib().crct_layernorm_bwd(C.byref(a), stream_ptr()))
+
+
+def colsum_bf16(x, out, rows=None, N=None, ld=None):
+    _bf16(x, 'x'); _f32(out, 'out')
+    rows = x.shape[0] if rows is None else rows
+    N = x.shape[1] if N is None else N
+    check(lib().crct_colsum_bf16(ptr(x), ptr(out), rows, N, x.stride(0) if ld is None else ld, stream_ptr()))
+
+
+def softmax_rows(x, out):
+    _f32(x, 'x'); _bf16(out, 'out')
+    rows, F = x.shape
+    check(lib().crct_softmax_rows(ptr(x), ptr(out), rows, F, stream_ptr()))
+
+
+def embed_text_fwd(ids, types, loc, word, pos, type_, w_loc, b_loc, gamma, beta, y, z=None, mean=None, rstd=None,
+                   dropout_p=0.0, seed=0):
+    a = EmbedTextArgs()
+    a.ids, a.types, a.loc = ptr(ids), ptr(types), ptr(loc)
+    a.word, a.pos, a.type, a.w_loc, a.b_loc, a.gamma, a.beta = (ptr(word), ptr(pos), ptr(type_), ptr(w_loc), ptr(b_loc),
+                                                                ptr(gamma), ptr(beta))
+    a.y, a.z, a.mean, a.rstd = ptr(y), ptr(z), ptr(mean), ptr(rstd)
+    a.B, a.T = ids.shape
+    a.H, a.max_pos = word.shape[1], pos.shape[0]
+    a.dropout_p, a.seed = dropout_p, seed
+    check(lib().crct_embed_text_fwd(C.byref(a), stream_ptr()))
+
+
+def embed_text_bwd(ids, types, loc, dz, g_word, g_pos, g_type, g_wloc, g_bloc):
+    a = EmbedTextBwdArgs()
+    a.ids, a.types, a.loc, a.dz = ptr(ids), ptr(types), ptr(loc), ptr(dz)
+    a.g_word, a.g_pos, a.g_type, a.g_wloc, a.g_bloc = ptr(g_word), ptr(g_pos), ptr(g_type), ptr(g_wloc), ptr(g_bloc)
+    a.B, a.T = ids.shape
+    a.H = dz.shape[-1]
+    check(lib().crct_embed_text_bwd(C.byref(a), stream_ptr()))
+
+
+def embed_vis_fwd(g, box, cls, w_loc, b_loc, color, gamma, beta, y, z=None, mean=None, rstd=None, dropout_p=0.0, seed=0):
+    a = EmbedVisArgs()
+    a.g, a.box, a.cls, a.w_loc, a.b_loc, a.color, a.gamma, a.beta = (ptr(g), ptr(box), ptr(cls), ptr(w_loc), ptr(b_loc),
+                                                                     ptr(color), ptr(gamma), ptr(beta))
+    a.y, a.z, a.mean, a.rstd = ptr(y), ptr(z), ptr(mean), ptr(rstd)
+    a.rows, a.H = g.shape
+    a.dropout_p, a.seed = dropout_p, seed
+    check(lib().crct_embed_vis_fwd(C.byref(a), stream_ptr()))
+
+
+def embed_vis_bwd(dz, box, cls, g_color, g_wloc):
+    a = EmbedVisBwdArgs()
+    a.dz, a.box, a.cls, a.g_color, a.g_wloc = ptr(dz), ptr(box), ptr(cls), ptr(g_color), ptr(g_wloc)
+    a.rows, a.H = dz.shape
+    check(lib().crct_embed_vis_bwd(C.byref(a), stream_ptr()))
+
+
+def attn_fwd(q, k, v, mask_add, out, lse, *, B, nh, dh, Lq, Lk, ldq, ldk, ldv, ldo, dropout_p=0.0, seed=0):
+    a = AttnFwdArgs()
+    a.q, a.k, a.v, a.mask_add, a.out, a.lse = ptr(q), ptr(k), ptr(v), ptr(mask_add), ptr(out), ptr(lse)
+    a.ldq, a.ldk, a.ldv, a.ldo = ldq, ldk, ldv, ldo
+    a.B, a.nh, a.dh, a.Lq, a.Lk = B, nh, dh, Lq, Lk
+    a.dropout_p, a.seed = dropout_p, seed
+    check(lib().crct_attn_fwd(C.byref(a), stream_ptr()))
+
+
+def attn_bwd(q, k, v, mask_add, out, dout, lse, dq, dk, dv, *, B, nh, dh, Lq, Lk, ldq, ldk, ldv, ldo, lddo, lddq, lddk,
+             lddv, dropout_p=0.0, seed=0):
+    a = AttnBwdArgs()
+    a.q, a.k, a.v, a.mask_add, a.out, a.dout, a.lse = ptr(q), ptr(k), ptr(v), ptr(mask_add), ptr(out), ptr(dout), ptr(lse)
+    a.dq, a.dk, a.dv = ptr(dq), ptr(dk), ptr(dv)
+    a.ldq, a.ldk, a.ldv, a.ldo, a.lddo, a.lddq, a.lddk, a.lddv = ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv
+    a.B, a.nh, a.dh, a.Lq, a.Lk = B, nh, dh, Lq, Lk
+    a.dropout_p, a.seed = dropout_p, seed
+    check(lib().crct_attn_bwd(C.byref(a), stream_ptr()))
+
+
+def linear_f32(A, sa_m, sa_k, B, sb_k, sb_n, Cout, ldc, M, N, K, bias=None, act=ACT_NONE, dmask=None, ldm=0, slope=0.0,
+               accumulate=0):
+    a = LinearArgs()
+    a.A, a.sa_m, a.sa_k, a.B, a.sb_k, a.sb_n, a.C, a.ldc = ptr(A), sa_m, sa_k, ptr(B), sb_k, sb_n, ptr(Cout), ldc
+    a.bias, a.dmask, a.ldm = ptr(bias), ptr(dmask), ldm
+    a.M, a.N, a.K, a.act, a.slope, a.accumulate = M, N, K, act, slope, accumulate
+    check(lib().crct_linear_f32(C.byref(a), stream_ptr()))
+
+
+def gather_first(src, row_stride, out):
+    B, H = out.shape
+    check(lib().crct_gather_first(ptr(src), row_stride, ptr(out), B, H, stream_ptr()))
+
+
+def scatter_first(g, dst, row_stride):
+    B, H = g.shape
+    check(lib().crct_scatter_first(ptr(g), ptr(dst), row_stride, B, H, stream_ptr()))
+
+
+def colsum_f32(x, out, M, N, ld):
+    check(lib().crct_colsum_f32(ptr(x), ptr(out), M, N, ld, stream_ptr()))
+
+
+def pool_mul_fwd(pt, pv, out, p=0.0, seed=0):
+    check(lib().crct_pool_mul_fwd(ptr(pt), ptr(pv), ptr(out), pt.numel(), p, seed, stream_ptr()))
+
+
+def pool_mul_bwd(dpooled, pt, pv, dut, duv, p=0.0, seed=0):
+    check(lib().crct_pool_mul_bwd(ptr(dpooled), ptr(pt), ptr(pv), ptr(dut), ptr(duv), pt.numel(), p, seed, stream_ptr()))
+
+
+def hybrid_loss(logits, reg, labels, R, reg_pred, reg_loss, reg_l1, reg_dist, scalars, dlogits=None, dpre=None, *, l1,
+                zero_impossible, tol_margin, nsp_coeff=1.0, reg_coeff=1.0, unit_grads=0):
+    a = LossArgs()
+    a.logits, a.reg, a.labels, a.R = ptr(logits), ptr(reg), ptr(labels), ptr(R)
+    a.reg_pred, a.reg_loss, a.reg_l1, a.reg_dist, a.scalars = ptr(reg_pred), ptr(reg_loss), ptr(reg_l1), ptr(reg_dist), ptr(scalars)
+    a.dlogits, a.dpre = ptr(dlogits), ptr(dpre)
+    a.B, a.l1, a.zero_impossible, a.unit_grads = logits.shape[0], int(l1), int(zero_impossible), int(unit_grads)
+    a.tol_margin, a.nsp_coeff, a.reg_coeff = tol_margin, nsp_coeff, reg_coeff
+    check(lib().crct_hybrid_loss(C.byref(a), stream_ptr()))
+
+
+def scale_rows(x, s, out):
+    B, n = x.shape
+    check(lib().crct_scale_rows(ptr(x), ptr(s), 1 if s.numel() == B else 0, ptr(out), B, n, stream_ptr()))
+
+
+def adamw(w, g, m, v, w_bf16, group, n, lr4, wd4, beta1, beta2, eps, step, grad_scale=1.0):
+    a = AdamWArgs()
+    a.w, a.g, a.m, a.v, a.w_bf16, a.group_of_block64, a.n = ptr(w), ptr(g), ptr(m), ptr(v), ptr(w_bf16), ptr(group), n
+    for i in range(4):
+        a.lr[i], a.weight_decay[i] = lr4[i], wd4[i]
+    a.beta1, a.beta2, a.eps, a.step, a.grad_scale = beta1, beta2, eps, step, grad_scale
+    check(lib().crct_adamw(C.byref(a), stream_ptr()))

@@ -1,0 +1,335 @@
+// K7/K8 — the small-M tail of the model in fp32 on CUDA cores: poolers, classifier, regressor MLPs,
+// the hybrid loss (cross-entropy + L1 / SmoothL1) and their backward.  M = batch size (80 / 512), N <= 1024,
+// and two outputs are 1 and 2 columns wide, so none of this maps to UMMA tiles; it is 0.03 % of the FLOPs
+// and is launch/latency bound.  Weights are read in fp32 straight from the master parameters, so the
+// class logits and the regression value do not see bf16 weight rounding.
+//
+// reference: CRCT/backbone/vilbert.py:955-976 (poolers), :1052-1060 (classifier), CRCT/backbone/regressor.py:36-42,
+//            vilbert.py:1586-1657 (losses, metrics), CRCT/backbone/encoder_decorator.py:144-153 (loss combine).
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, LIN_THREADS = 256;
+
+struct LinParams {
+    const float* A; long long sa_m, sa_k;     // A(m,k) = A[m*sa_m + k*sa_k]
+    const float* B; long long sb_k, sb_n;     // B(k,n) = B[k*sb_k + n*sb_n]
+    float* C; long long ldc;                  // C[m*ldc + n]
+    const float* bias;                        // [N] or null
+    const float* dmask; long long ldm;        // multiply result by (dmask[m*ldm+n] > 0 ? 1 : slope), or null
+    int M, N, K;
+    int act;                                  // 0 none, 1 relu, 2 leaky(0.01), 3 tanh
+    float slope;
+    int accumulate;
+};
+
+__global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinParams p) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const bool a_kfast = p.sa_k == 1, b_nfast = p.sb_n == 1;
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < (BM * BK) / LIN_THREADS; ++i) {
+            const int e = tid + i * LIN_THREADS;
+            const int kk = a_kfast ? (e % BK) : (e / BM), m = a_kfast ? (e / BK) : (e % BM);
+            float v = 0.f;
+            if (m0 + m < p.M && k0 + kk < p.K) v = p.A[(long long)(m0 + m) * p.sa_m + (long long)(k0 + kk) * p.sa_k];
+            As[kk][m] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < (BN * BK) / LIN_THREADS; ++i) {
+            const int e = tid + i * LIN_THREADS;
+            const int kk = b_nfast ? (e / BN) : (e % BK), n = b_nfast ? (e % BN) : (e / BK);
+            float v = 0.f;
+            if (n0 + n < p.N && k0 + kk < p.K) v = p.B[(long long)(k0 + kk) * p.sb_k + (long long)(n0 + n) * p.sb_n];
+            Bs[kk][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= p.N) continue;
+            float v = acc[i][j];
+            if (p.bias) v += p.bias[n];
+            if (p.act == 1) v = fmaxf(v, 0.f);
+            else if (p.act == 2) v = v > 0.f ? v : 0.01f * v;
+            else if (p.act == 3) v = tanhf(v);
+            if (p.dmask) v *= (p.dmask[(long long)m * p.ldm + n] > 0.f ? 1.f : p.slope);
+            float* c = p.C + (long long)m * p.ldc + n;
+            if (p.accumulate) *c += v; else *c = v;
+        }
+    }
+}
+
+// out[b, :] = float(src[b * row_stride + :])  (first token / region of every sample)
+__global__ void gather_first_kernel(const bf16* __restrict__ src, long long row_stride, float* __restrict__ out, int B, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H) return;
+    const int b = i / H, c = i % H;
+    out[i] = __bfloat162float(src[(long long)b * row_stride + c]);
+}
+// dst[b * row_stride + :] = bf16(g[b, :]); every other row of dst must already be zero
+__global__ void scatter_first_kernel(const float* __restrict__ g, bf16* __restrict__ dst, long long row_stride, int B, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H) return;
+    const int b = i / H, c = i % H;
+    dst[(long long)b * row_stride + c] = __float2bfloat16(g[i]);
+}
+__global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, long long ld) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += x[(long long)m * ld + n];
+    out[n] += s;
+}
+// pooled = dropout(pt * pv)   (vilbert.py:1055)
+__global__ void pool_mul_fwd_kernel(const float* __restrict__ pt, const float* __restrict__ pv, float* __restrict__ out, int n,
+                                    uint32_t thr, float scale, uint64_t seed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = pt[i] * pv[i];
+    if (thr != 0u) v = crct_keep(seed, (uint64_t)i, thr) ? v * scale : 0.f;
+    out[i] = v;
+}
+// dut = dpooled * keep * pv * [pt > 0] ; duv = dpooled * keep * pt * [pv > 0]   (ReLU poolers, vilbert.py:959-960,974-975)
+__global__ void pool_mul_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ pt, const float* __restrict__ pv,
+                                    float* __restrict__ dut, float* __restrict__ duv, int n, uint32_t thr, float scale, uint64_t seed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d = dpooled[i];
+    if (thr != 0u) d = crct_keep(seed, (uint64_t)i, thr) ? d * scale : 0.f;
+    const float a = pt[i], b = pv[i];
+    dut[i] = a > 0.f ? d * b : 0.f;
+    duv[i] = b > 0.f ? d * a : 0.f;
+}
+
+struct LossParams {
+    const float* logits; const float* reg; const long long* labels; const float* R;
+    float* reg_pred; float* reg_loss; float* reg_l1; float* reg_dist;
+    float* scalars;                    // [0] total loss, [1] nsp loss, [2] mean reg loss, [3] #within 5 %, [4] #within tol
+    float* dlogits; float* dpre;       // gradients (training) or null
+    int B;
+    int l1; int smooth_kind; int unit_grads; float tol_margin; float nsp_coeff, reg_coeff;
+};
+
+// one CTA; vilbert.py:1586-1657 evaluated densely over all B rows (rows with R[:,1] != 1 are masked)
+__global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
+    __shared__ float red[5][256];
+    float s_nsp = 0.f, s_valid = 0.f, s_reg = 0.f, s_r5 = 0.f, s_rt = 0.f;
+    for (int b = threadIdx.x; b < p.B; b += 256) {
+        const float val = p.R[b * 4 + 0], needs = p.R[b * 4 + 1], scale = p.R[b * 4 + 3];
+        const bool need = needs == 1.0f;
+        const float pred = p.reg[b];
+        float out_pred = 0.f, out_loss = 0.f, out_l1 = 0.f, out_dist = 0.f, dl = 0.f;
+        if (need) {
+            const float tgt = val / scale;                       // vilbert.py:1617
+            const float diff = pred - tgt;
+            const float l1v = fabsf(diff);
+            float lossv;
+            if (p.l1) { lossv = l1v; dl = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f); }
+            else {                                               // SmoothL1Loss(beta = 0.5), vilbert.py:1528
+                const float beta = 0.5f;
+                if (l1v < beta) { lossv = 0.5f * diff * diff / beta; dl = diff / beta; }
+                else { lossv = l1v - 0.5f * beta; dl = diff > 0.f ? 1.f : -1.f; }
+            }
+            float dist = l1v / fabsf(tgt);                       // vilbert.py:1632-1636
+            if (tgt == 0.f) dist = 1.f;
+            const bool both0 = (pred == 0.f) && (tgt == 0.f);
+            if (both0) dist = 0.f;
+            if (dist <= 0.05f || both0) s_r5 += 1.f;
+            if (l1v <= p.tol_margin) s_rt += 1.f;
+            bool live = true;
+            if (p.smooth_kind && fabsf(tgt) > 1.f) live = false;  // kind != 'L1' zeroes impossible targets, vilbert.py:1639-1641
+            out_pred = pred * scale; out_l1 = l1v; out_dist = dist;
+            if (live) out_loss = lossv; else dl = 0.f;
+        }
+        p.reg_pred[b] = out_pred; p.reg_loss[b] = out_loss; p.reg_l1[b] = out_l1; p.reg_dist[b] = out_dist;
+        s_reg += out_loss;
+        if (p.dpre) p.dpre[b] = (p.unit_grads ? dl : p.reg_coeff * dl / (float)p.B) * (1.f - pred * pred);   // through tanh (regressor.py:33)
+        if (p.labels) {
+            const long long lab = p.labels[b];
+            const float z0 = p.logits[b * 2], z1 = p.logits[b * 2 + 1];
+            const float mx = fmaxf(z0, z1);
+            const float lse = mx + logf(expf(z0 - mx) + expf(z1 - mx));
+            if (lab != -1) { s_nsp += lse - (lab == 0 ? z0 : z1); s_valid += 1.f; }
+        }
+    }
+    red[0][threadIdx.x] = s_nsp; red[1][threadIdx.x] = s_valid; red[2][threadIdx.x] = s_reg; red[3][threadIdx.x] = s_r5; red[4][threadIdx.x] = s_rt;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + o];
+        __syncthreads();
+    }
+    const float nvalid = fmaxf(red[1][0], 1.f);
+    const float nsp = red[0][0] / nvalid, mreg = red[2][0] / (float)p.B;
+    if (threadIdx.x == 0) {
+        p.scalars[0] = p.labels ? p.nsp_coeff * nsp + p.reg_coeff * mreg : 0.f;   // encoder_decorator.py:144-153
+        p.scalars[1] = nsp; p.scalars[2] = mreg; p.scalars[3] = red[3][0]; p.scalars[4] = red[4][0];
+    }
+    if (p.labels && p.dlogits) {
+        for (int b = threadIdx.x; b < p.B; b += 256) {
+            const long long lab = p.labels[b];
+            const float z0 = p.logits[b * 2], z1 = p.logits[b * 2 + 1];
+            const float mx = fmaxf(z0, z1);
+            const float e0 = expf(z0 - mx), e1 = expf(z1 - mx), inv = 1.f / (e0 + e1);
+            const float w = lab != -1 ? (p.unit_grads ? 1.f : p.nsp_coeff) / nvalid : 0.f;
+            p.dlogits[b * 2] = w * (e0 * inv - (lab == 0 ? 1.f : 0.f));
+            p.dlogits[b * 2 + 1] = w * (e1 * inv - (lab == 1 ? 1.f : 0.f));
+        }
+    }
+}
+
+// fused multi-tensor AdamW over the flat parameter arena (f1: CRCT/utils.py:228-249 + torch.optim.AdamW semantics),
+// refreshing the bf16 operand copy in the same pass.  Every 64-element block of the arena carries a group id that
+// selects (lr, weight_decay): language vs vision learning rate x decay vs no-decay (bias / LayerNorm).
+struct AdamParams {
+    float* w; const float* g; float* m; float* v; bf16* w16; const uint8_t* group; size_t n;
+    float lr[4], wd[4];
+    float beta1, beta2, eps, bc1, bc2_sqrt, gscale;
+};
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamParams p) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (size_t)gridDim.x * blockDim.x) {
+        const int grp = p.group ? (p.group[i >> 6] & 3) : 0;
+        const float lr = p.lr[grp], wd = p.wd[grp];
+        const float gr = p.g[i] * p.gscale;
+        float wi = p.w[i];
+        wi *= 1.f - lr * wd;
+        const float mi = p.beta1 * p.m[i] + (1.f - p.beta1) * gr;
+        const float vi = p.beta2 * p.v[i] + (1.f - p.beta2) * gr * gr;
+        p.m[i] = mi; p.v[i] = vi;
+        wi -= lr / p.bc1 * mi / (sqrtf(vi) / p.bc2_sqrt + p.eps);
+        p.w[i] = wi;
+        if (p.w16) p.w16[i] = __float2bfloat16(wi);
+    }
+}
+
+}  // namespace
+
+extern "C" CRCT_API int crct_linear_f32(const crct_linear_t* a, crct_stream_t s) {
+    if (!a || !a->A || !a->B || !a->C) CRCT_FAIL(CRCT_ERR_ARG, "crct_linear_f32: null pointer");
+    if (a->M <= 0 || a->N <= 0 || a->K <= 0) return CRCT_OK;
+    if (a->act < 0 || a->act > 3) CRCT_FAIL(CRCT_ERR_ARG, "crct_linear_f32: unknown activation %d", a->act);
+    LinParams p;
+    p.A = a->A; p.sa_m = a->sa_m; p.sa_k = a->sa_k; p.B = a->B; p.sb_k = a->sb_k; p.sb_n = a->sb_n;
+    p.C = a->C; p.ldc = a->ldc; p.bias = a->bias; p.dmask = a->dmask; p.ldm = a->ldm;
+    p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->act; p.slope = a->slope; p.accumulate = a->accumulate;
+    dim3 grid((a->N + BN - 1) / BN, (a->M + BM - 1) / BM);
+    linear_f32_kernel<<<grid, LIN_THREADS, 0, as_stream(s)>>>(p);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_gather_first(const void* src, long long row_stride, float* out, int B, int H, crct_stream_t s) {
+    if (!src || !out || B <= 0 || H <= 0) CRCT_FAIL(CRCT_ERR_ARG, "crct_gather_first: bad argument");
+    gather_first_kernel<<<(B * H + 255) / 256, 256, 0, as_stream(s)>>>(reinterpret_cast<const bf16*>(src), row_stride, out, B, H);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_scatter_first(const float* g, void* dst, long long row_stride, int B, int H, crct_stream_t s) {
+    if (!g || !dst || B <= 0 || H <= 0) CRCT_FAIL(CRCT_ERR_ARG, "crct_scatter_first: bad argument");
+    scatter_first_kernel<<<(B * H + 255) / 256, 256, 0, as_stream(s)>>>(g, reinterpret_cast<bf16*>(dst), row_stride, B, H);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_colsum_f32(const float* x, float* out, int M, int N, long long ld, crct_stream_t s) {
+    if (!x || !out) CRCT_FAIL(CRCT_ERR_ARG, "crct_colsum_f32: null pointer");
+    if (M <= 0 || N <= 0) return CRCT_OK;
+    colsum_f32_kernel<<<(N + 127) / 128, 128, 0, as_stream(s)>>>(x, out, M, N, ld);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_pool_mul_fwd(const float* pt, const float* pv, float* out, int n, float p, uint64_t seed, crct_stream_t s) {
+    if (!pt || !pv || !out || n <= 0) CRCT_FAIL(CRCT_ERR_ARG, "crct_pool_mul_fwd: bad argument");
+    pool_mul_fwd_kernel<<<(n + 255) / 256, 256, 0, as_stream(s)>>>(pt, pv, out, n, crct_drop_threshold(p), p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_pool_mul_bwd(const float* dpooled, const float* pt, const float* pv, float* dut, float* duv, int n, float p,
+                                 uint64_t seed, crct_stream_t s) {
+    if (!dpooled || !pt || !pv || !dut || !duv || n <= 0) CRCT_FAIL(CRCT_ERR_ARG, "crct_pool_mul_bwd: bad argument");
+    pool_mul_bwd_kernel<<<(n + 255) / 256, 256, 0, as_stream(s)>>>(dpooled, pt, pv, dut, duv, n, crct_drop_threshold(p),
+                                                                 p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_hybrid_loss(const crct_loss_t* a, crct_stream_t s) {
+    if (!a || !a->logits || !a->reg || !a->R || !a->reg_pred || !a->reg_loss || !a->reg_l1 || !a->reg_dist || !a->scalars)
+        CRCT_FAIL(CRCT_ERR_ARG, "crct_hybrid_loss: null pointer");
+    if (a->B <= 0) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_hybrid_loss: empty batch");
+    LossParams p;
+    p.logits = a->logits; p.reg = a->reg; p.labels = reinterpret_cast<const long long*>(a->labels); p.R = a->R;
+    p.reg_pred = a->reg_pred; p.reg_loss = a->reg_loss; p.reg_l1 = a->reg_l1; p.reg_dist = a->reg_dist; p.scalars = a->scalars;
+    p.dlogits = a->dlogits; p.dpre = a->dpre; p.B = a->B; p.l1 = a->l1; p.smooth_kind = a->zero_impossible; p.unit_grads = a->unit_grads;
+    p.tol_margin = a->tol_margin; p.nsp_coeff = a->nsp_coeff; p.reg_coeff = a->reg_coeff;
+    loss_kernel<<<1, 256, 0, as_stream(s)>>>(p);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_adamw(const crct_adamw_t* a, crct_stream_t s) {
+    if (!a || !a->w || !a->g || !a->m || !a->v) CRCT_FAIL(CRCT_ERR_ARG, "crct_adamw: null pointer");
+    if (a->n == 0) return CRCT_OK;
+    if (a->step < 1) CRCT_FAIL(CRCT_ERR_ARG, "crct_adamw: step counts from 1");
+    AdamParams p;
+    p.w = a->w; p.g = a->g; p.m = a->m; p.v = a->v; p.w16 = reinterpret_cast<bf16*>(a->w_bf16); p.group = a->group_of_block64; p.n = a->n;
+    for (int i = 0; i < 4; ++i) { p.lr[i] = a->lr[i]; p.wd[i] = a->weight_decay[i]; }
+    p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps;
+    p.bc1 = 1.f - powf(a->beta1, (float)a->step);
+    p.bc2_sqrt = sqrtf(1.f - powf(a->beta2, (float)a->step));
+    p.gscale = a->grad_scale;
+    size_t blocks = (a->n + 255) / 256;
+    const size_t cap = (size_t)crct_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    adamw_kernel<<<(unsigned)blocks, 256, 0, as_stream(s)>>>(p);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+namespace {
+// out[b,j] = x[b,j] * s[b]  (s_stride = 1)  or  x[b,j] * s[0]  (s_stride = 0): upstream gradient of the loss outputs
+__global__ void scale_rows_kernel(const float* __restrict__ x, const float* __restrict__ s, int s_stride, float* __restrict__ out, int B, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * n) return;
+    out[i] = x[i] * s[(i / n) * s_stride];
+}
+}  // namespace
+
+extern "C" CRCT_API int crct_scale_rows(const float* x, const float* s, int s_stride, float* out, int B, int n, crct_stream_t st) {
+    if (!x || !s || !out || B <= 0 || n <= 0 || (s_stride != 0 && s_stride != 1)) CRCT_FAIL(CRCT_ERR_ARG, "crct_scale_rows: bad argument");
+    scale_rows_kernel<<<(B * n + 255) / 256, 256, 0, as_stream(st)>>>(x, s, s_stride, out, B, n);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}

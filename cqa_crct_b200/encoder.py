@@ -1,0 +1,699 @@
+"""Host side of the B200-native CRCT question-answering stage.
+
+`VisualDialogEncoder` mirrors the reference wrapper (CRCT/backbone/encoder_decorator.py:9-54) and the
+model under it (CRCT/backbone/vilbert.py:1499-1661): same constructor argument (`params` dict), same
+`forward(...)` signature and return tuple, same `state_dict()` keys / `named_parameters()` order, same
+branch selection by kwargs.  Every arithmetic step is a kernel of libcrct_b200 reached through the C ABI
+(include/crct_b200.h); PyTorch only owns memory, streams and the autograd hook that lets
+`loss.backward()` (CRCT/train.py:208) drive the hand-written backward.  There is no CPU / eager fallback.
+
+Data layout (all in HBM, caller = PyTorch allocator):
+  * parameters: ONE flat fp32 arena (master weights) + ONE flat fp32 gradient arena + ONE flat bf16 operand
+    copy, tensors ordered by `spec.arena_order` (forward execution order, fused q|k|v adjacent, dead
+    tensors last); every nn.Parameter / .grad is a view into them;
+  * activations: bf16 row-major [B*T, H] / [B*R, Hv]; packed projections [rows, 3H]; LayerNorm statistics,
+    attention log-sum-exp, head activations and losses in fp32.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .spec import ModelConfig, P, TIED, arena_offsets, arena_order, param_spec
+
+_SITE = {  # dropout stream ids (one counter-based stream per dropout call site of the reference)
+    'emb_t': 1, 'emb_v': 2, 'attn': 3, 'attn_out': 4, 'ffn_out': 5, 'co_attn1': 6, 'co_attn2': 7, 'co_out_v': 8,
+    'co_out_t': 9, 'co_ffn_v': 10, 'co_ffn_t': 11, 'cls': 12}
+
+
+def _seed(step_seed: int, site: str, layer: int = 0) -> int:
+    x = (step_seed * 0x9E3779B97F4A7C15 + _SITE[site] * 0xBF58476D1CE4E5B9 + layer * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 31
+    return (x * 0xD6E8FEB86659FD93) & 0xFFFFFFFFFFFFFFFF
+
+
+class ParamArena:
+    """Flat fp32 master / fp32 gradient / bf16 operand storage with per-tensor views."""
+
+    def __init__(self, cfg: ModelConfig, categories: int):
+        self.spec: List[P] = param_spec(cfg, categories)
+        self.order: List[P] = arena_order(cfg, self.spec)
+        self.offsets, self.live_end, self.total = arena_offsets(self.order)
+        self.by_name: Dict[str, P] = {p.name: p for p in self.spec}
+        self.w32 = torch.zeros(self.total, dtype=torch.float32)
+        self.g32: Optional[torch.Tensor] = None
+        self.w16: Optional[torch.Tensor] = None
+        self._w16_version = -1
+
+    def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        p = self.by_name[name]
+        o = self.offsets[name]
+        return flat[o:o + p.numel].view(p.shape)
+
+    def fused(self, flat: torch.Tensor, names: List[str], suffix: str) -> torch.Tensor:
+        """Zero-copy view of adjacent tensors (q|k|v weights -> [3*out, in], biases -> [3*out])."""
+        ps = [self.by_name[n + suffix] for n in names]
+        o0 = self.offsets[ps[0].name]
+        cur = o0
+        for p in ps:
+            if self.offsets[p.name] != cur:
+                raise RuntimeError(f'{p.name} is not adjacent to its fusion group in the arena')
+            cur += p.numel
+        shape = (sum(p.shape[0] for p in ps),) + tuple(ps[0].shape[1:])
+        return flat[o0:cur].view(shape)
+
+    def ensure_device_buffers(self):
+        if self.g32 is None or self.g32.device != self.w32.device:
+            self.g32 = torch.zeros_like(self.w32)
+        if self.w32.is_cuda and (self.w16 is None or self.w16.device != self.w32.device):
+            self.w16 = torch.empty(self.total, dtype=torch.bfloat16, device=self.w32.device)
+            self._w16_version = -1
+
+    def refresh_bf16(self):
+        """Re-cast the operand copy if any master weight changed since the last cast."""
+        if self._w16_version != self.w32._version:
+            L.cast_f32_to_bf16(self.w32, self.w16)
+            self._w16_version = self.w32._version
+
+    def mark_bf16_fresh(self):
+        self._w16_version = self.w32._version
+
+
+class _Node(nn.Module):
+    """Plain container used to rebuild the reference's module tree (names only; no arithmetic)."""
+
+
+def _attach(root: nn.Module, dotted: str, param: nn.Parameter):
+    parts = dotted.split('.')
+    mod = root
+    for part in parts[:-1]:
+        if part not in mod._modules:
+            mod.add_module(part, _Node())
+        mod = mod._modules[part]
+    mod.register_parameter(parts[-1], param)
+
+
+class _Saved:
+    """Activations a forward keeps for its backward."""
+    pass
+
+
+class _CrctFunction(torch.autograd.Function):
+    """Ties the hand-written forward/backward into autograd: inputs = one anchor parameter, outputs =
+    (nsp_loss[1], reg_loss[B]); backward runs the whole CUDA backward and accumulates into the gradient arena."""
+
+    @staticmethod
+    def forward(ctx, anchor, enc, saved):
+        ctx.enc, ctx.saved = enc, saved
+        return saved.nsp_loss, saved.reg_loss
+
+    @staticmethod
+    def backward(ctx, d_nsp, d_reg):
+        enc, saved = ctx.enc, ctx.saved
+        ctx.saved = None
+        enc._backward(saved, d_nsp, d_reg)
+        return None, None, None
+
+
+class VisualDialogEncoder(nn.Module):
+    """Drop-in for CRCT/backbone/encoder_decorator.py:9 `VisualDialogEncoder(params)`."""
+
+    def __init__(self, params: dict):
+        super().__init__()
+        config_path = params['model_config']
+        assert os.path.exists(config_path), "model_config file not found"      # encoder_decorator.py:13
+        self.params = params
+        self.cfg = ModelConfig(config_path)
+        if params.get('dataset', 'plotqa') in ('figure_qa', 'dvqa') or params.get('CE_REG') or params.get('binary_answers'):
+            raise NotImplementedError('only the PlotQA regression path (PlotQA_Regressor_v20) is implemented')
+        if params.get('mask_prob_img', 0) > 0:
+            raise NotImplementedError('mask_prob_img > 0 is not implemented (default 0, CRCT/options.py:33)')
+        self.arena = ParamArena(self.cfg, params['categories'])
+        self._init_reference_distributions()
+        root = _Node()
+        self._params_by_name: Dict[str, nn.Parameter] = {}
+        for p in self.arena.spec:
+            prm = nn.Parameter(self.arena.view(self.arena.w32, p.name), requires_grad=p.live)
+            self._params_by_name[p.name] = prm
+            _attach(root, p.name, prm)
+        for alias, src in TIED.items():
+            _attach(root, alias, self._params_by_name[src])
+        self.bert_pretrained = root
+        self._step = 0
+        self.grad_ready_hook = None          # set by cqa_crct_b200.parallel.DistributedDataParallel
+        self.train()                         # encoder_decorator.py:17
+
+    # ------------------------------------------------------------------ parameters / devices
+    def _init_reference_distributions(self):
+        """vilbert.py:1099-1110: N(0, initializer_range) weights, zero biases, unit LayerNorm; regressor keeps
+        nn.Linear's default init (it is constructed after `apply(init)`, vilbert.py:1510 vs 1523)."""
+        g = torch.Generator().manual_seed(torch.initial_seed() & 0x7FFFFFFF)
+        for p in self.arena.spec:
+            v = self.arena.view(self.arena.w32, p.name)
+            if p.kind in ('w', 'emb'):
+                v.normal_(0.0, self.cfg.initializer_range, generator=g)
+            elif p.kind == 'lnw':
+                v.fill_(1.0)
+            elif p.kind in ('rw', 'rb'):
+                fan_in = p.shape[1] if p.kind == 'rw' else self.arena.by_name[p.name[:-4] + 'weight'].shape[1]
+                v.uniform_(-1.0 / fan_in ** 0.5, 1.0 / fan_in ** 0.5, generator=g)
+
+    def _apply(self, fn, recurse=True):
+        new = fn(self.arena.w32)
+        if new.dtype != torch.float32:
+            raise TypeError('master parameters stay fp32; bf16 operands are derived inside the library')
+        old_g = self.arena.g32
+        self.arena.w32 = new
+        self.arena.g32 = None if old_g is None else fn(old_g)
+        self.arena.w16 = None
+        for name, prm in self._params_by_name.items():
+            prm.data = self.arena.view(self.arena.w32, name)
+            if prm.grad is not None:
+                prm.grad = self.arena.view(self.arena.g32, name) if self.arena.g32 is not None else None
+        return self
+
+    def _bind_grads(self):
+        self.arena.ensure_device_buffers()
+        for name, prm in self._params_by_name.items():
+            if prm.requires_grad and (prm.grad is None or prm.grad.data_ptr() != self.arena.view(self.arena.g32, name).data_ptr()):
+                prm.grad = self.arena.view(self.arena.g32, name)
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Gradients live in the arena: zeroing is one memset; `set_to_none` is ignored on purpose."""
+        if self.arena.g32 is not None:
+            self.arena.g32[:self.arena.live_end].zero_()
+
+    def flat_parameters(self):
+        return self.arena.w32, self.arena.g32, self.arena.w16
+
+    # ------------------------------------------------------------------ small helpers
+    def _w(self, name):      # bf16 operand view
+        return self.arena.view(self.arena.w16, name)
+
+    def _p(self, name):      # fp32 master view
+        return self.arena.view(self.arena.w32, name)
+
+    def _g(self, name):      # fp32 gradient view
+        return self.arena.view(self.arena.g32, name)
+
+    def _drop(self, p):
+        return float(p) if self.training else 0.0
+
+    # ------------------------------------------------------------------ building blocks (forward)
+    def _linear(self, x, W, bias, M, epilogue=L.EPI_BIAS, aux=None, D2=None, p=0.0, seed=0):
+        N, K = W.shape
+        D = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
+        L.gemm(x, W, D, M=M, N=N, K=K, bias=bias, epilogue=epilogue, aux=aux, D2=D2, dropout_p=p, seed=seed)
+        return D
+
+    def _ln(self, z, pre, keep):
+        rows, H = z.shape
+        y = torch.empty_like(z)
+        mean = rstd = None
+        if keep:
+            mean = torch.empty(rows, dtype=torch.float32, device=z.device)
+            rstd = torch.empty(rows, dtype=torch.float32, device=z.device)
+        L.layernorm_fwd(z, self._p(pre + '.weight'), self._p(pre + '.bias'), y, mean, rstd)
+        return y, mean, rstd
+
+    def _ffn_fwd(self, a, pre_i, pre_o, p_drop, seed, keep):
+        """intermediate + output blocks (vilbert.py:454-457,467-471 / 585-588,598-602)."""
+        M = a.shape[0]
+        W1, W2 = self._w(pre_i + '.dense.weight'), self._w(pre_o + '.dense.weight')
+        u = torch.empty(M, W1.shape[0], dtype=torch.bfloat16, device=a.device) if keep else None
+        h = self._linear(a, W1, self._p(pre_i + '.dense.bias'), M, L.EPI_BIAS_GELU, D2=u)
+        z = self._linear(h, W2, self._p(pre_o + '.dense.bias'), M, L.EPI_BIAS_RES, aux=a, p=p_drop, seed=seed)
+        y, mean, rstd = self._ln(z, pre_o + '.LayerNorm', keep)
+        s = None
+        if keep:
+            s = _Saved()
+            s.a, s.u, s.h, s.z, s.mean, s.rstd, s.p, s.seed = a, u, h, z, mean, rstd, p_drop, seed
+        return y, s
+
+    def _ffn_bwd(self, dy, s, pre_i, pre_o):
+        M, H = dy.shape
+        dz = torch.empty_like(dy)
+        dzm = torch.empty_like(dy) if s.p > 0 else None
+        L.layernorm_bwd(dy, s.z, s.mean, s.rstd, self._p(pre_o + '.LayerNorm.weight'), dz, self._g(pre_o + '.LayerNorm.weight'),
+                        self._g(pre_o + '.LayerNorm.bias'), dbias=self._g(pre_o + '.dense.bias'), dzm=dzm, p_out=s.p, seed_out=s.seed)
+        gz = dzm if dzm is not None else dz
+        W1, W2 = self._w(pre_i + '.dense.weight'), self._w(pre_o + '.dense.weight')
+        I = W1.shape[0]
+        self._wgrad(gz, s.h, self._g(pre_o + '.dense.weight'))
+        du = torch.empty(M, I, dtype=torch.bfloat16, device=dy.device)
+        L.gemm(gz, W2, du, M=M, N=I, K=H, b_major=1, epilogue=L.EPI_DGELU, aux=s.u)
+        L.colsum_bf16(du, self._g(pre_i + '.dense.bias'))
+        self._wgrad(du, s.a, self._g(pre_i + '.dense.weight'))
+        da = torch.empty_like(dy)
+        L.gemm(du, W1, da, M=M, N=H, K=I, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz)
+        return da
+
+    def _wgrad(self, dy, x, gW):
+        """gW[out,in] += dy^T x  (fp32 accumulate, split-K)."""
+        rows, No = dy.shape
+        Ki = x.shape[1]
+        L.gemm(dy, x, gW, M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, lda=dy.stride(0),
+               ldb=x.stride(0), ldd=Ki)
+
+    def _attn_out_fwd(self, ctx, x, pre_dense, pre_ln, p_drop, seed, keep):
+        """dense + dropout + residual + LayerNorm (vilbert.py:424-428 / 555-559 / 749-756)."""
+        M = x.shape[0]
+        z = self._linear(ctx, self._w(pre_dense + '.weight'), self._p(pre_dense + '.bias'), M, L.EPI_BIAS_RES, aux=x, p=p_drop, seed=seed)
+        a, mean, rstd = self._ln(z, pre_ln, keep)
+        s = None
+        if keep:
+            s = _Saved()
+            s.ctx, s.z, s.mean, s.rstd, s.p, s.seed = ctx, z, mean, rstd, p_drop, seed
+        return a, s
+
+    def _attn_out_bwd(self, da, s, pre_dense, pre_ln):
+        """returns (dz for the residual path, dctx)."""
+        M, H = da.shape
+        dz = torch.empty_like(da)
+        dzm = torch.empty_like(da) if s.p > 0 else None
+        L.layernorm_bwd(da, s.z, s.mean, s.rstd, self._p(pre_ln + '.weight'), dz, self._g(pre_ln + '.weight'), self._g(pre_ln + '.bias'),
+                        dbias=self._g(pre_dense + '.bias'), dzm=dzm, p_out=s.p, seed_out=s.seed)
+        gz = dzm if dzm is not None else dz
+        W = self._w(pre_dense + '.weight')
+        self._wgrad(gz, s.ctx, self._g(pre_dense + '.weight'))
+        dctx = torch.empty(M, W.shape[1], dtype=torch.bfloat16, device=da.device)
+        L.gemm(gz, W, dctx, M=M, N=W.shape[1], K=H, b_major=1)
+        return dz, dctx
+
+    def _self_layer_fwd(self, x, mask_add, B, Lseq, nh, pre, names, drops, layer, keep):
+        """BertLayer / BertImageLayer (vilbert.py:474-485, 605-616)."""
+        M, H = x.shape
+        dh = H // nh
+        step = self._step
+        Wqkv = self.arena.fused(self.arena.w16, [pre + '.attention.self.' + n for n in names], '.weight')
+        bqkv = self.arena.fused(self.arena.w32, [pre + '.attention.self.' + n for n in names], '.bias')
+        qkv = self._linear(x, Wqkv, bqkv, M)
+        ctx = torch.empty(M, H, dtype=torch.bfloat16, device=x.device)
+        lse = torch.empty(B, nh, Lseq, dtype=torch.float32, device=x.device) if keep else None
+        p_att, s_att = self._drop(drops[0]), _seed(step, 'attn', layer)
+        L.attn_fwd(qkv, qkv[:, H:], qkv[:, 2 * H:], mask_add, ctx, lse, B=B, nh=nh, dh=dh, Lq=Lseq, Lk=Lseq, ldq=3 * H, ldk=3 * H,
+                   ldv=3 * H, ldo=H, dropout_p=p_att, seed=s_att)
+        a, s_out = self._attn_out_fwd(ctx, x, pre + '.attention.output.dense', pre + '.attention.output.LayerNorm',
+                                      self._drop(drops[1]), _seed(step, 'attn_out', layer), keep)
+        y, s_ffn = self._ffn_fwd(a, pre + '.intermediate', pre + '.output', self._drop(drops[1]), _seed(step, 'ffn_out', layer), keep)
+        s = None
+        if keep:
+            s = _Saved()
+            s.x, s.qkv, s.lse, s.out, s.ffn, s.p_att, s.s_att = x, qkv, lse, s_out, s_ffn, p_att, s_att
+            s.B, s.L, s.nh, s.mask = B, Lseq, nh, mask_add
+        return y, s
+
+    def _self_layer_bwd(self, dy, s, pre, names):
+        M, H = dy.shape
+        dh = H // s.nh
+        da = self._ffn_bwd(dy, s.ffn, pre + '.intermediate', pre + '.output')
+        dz1, dctx = self._attn_out_bwd(da, s.out, pre + '.attention.output.dense', pre + '.attention.output.LayerNorm')
+        dqkv = torch.empty_like(s.qkv)
+        L.attn_bwd(s.qkv, s.qkv[:, H:], s.qkv[:, 2 * H:], s.mask, s.out.ctx, dctx, s.lse, dqkv, dqkv[:, H:], dqkv[:, 2 * H:],
+                   B=s.B, nh=s.nh, dh=dh, Lq=s.L, Lk=s.L, ldq=3 * H, ldk=3 * H, ldv=3 * H, ldo=H, lddo=H, lddq=3 * H, lddk=3 * H,
+                   lddv=3 * H, dropout_p=s.p_att, seed=s.s_att)
+        mods = [pre + '.attention.self.' + n for n in names]
+        L.colsum_bf16(dqkv, self.arena.fused(self.arena.g32, mods, '.bias'))
+        self._wgrad(dqkv, s.x, self.arena.fused(self.arena.g32, mods, '.weight'))
+        Wqkv = self.arena.fused(self.arena.w16, mods, '.weight')
+        dx = torch.empty_like(dy)
+        L.gemm(dqkv, Wqkv, dx, M=M, N=H, K=3 * H, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz1)
+        return dx
+
+    def _co_layer_fwd(self, v, t, v_mask, t_mask, B, T, R, pre, layer, keep):
+        """BertConnectionLayer (vilbert.py:774-788); stream 1 = visual, stream 2 = text."""
+        cfg, step = self.cfg, self._step
+        Mv, Hv = v.shape
+        Mt, H = t.shape
+        nh, Hb = cfg.bi_num_attention_heads, cfg.bi_hidden_size
+        dh = Hb // nh
+        m1 = [pre + '.biattention.' + n for n in ('query1', 'key1', 'value1')]
+        m2 = [pre + '.biattention.' + n for n in ('query2', 'key2', 'value2')]
+        qkv1 = self._linear(v, self.arena.fused(self.arena.w16, m1, '.weight'), self.arena.fused(self.arena.w32, m1, '.bias'), Mv)
+        qkv2 = self._linear(t, self.arena.fused(self.arena.w16, m2, '.weight'), self.arena.fused(self.arena.w32, m2, '.bias'), Mt)
+        ctx1 = torch.empty(Mt, Hb, dtype=torch.bfloat16, device=t.device)          # text queries over visual keys/values
+        ctx2 = torch.empty(Mv, Hb, dtype=torch.bfloat16, device=t.device)          # visual queries over text keys/values
+        lse1 = torch.empty(B, nh, T, dtype=torch.float32, device=t.device) if keep else None
+        lse2 = torch.empty(B, nh, R, dtype=torch.float32, device=t.device) if keep else None
+        p1, s1 = self._drop(cfg.v_attention_probs_dropout_prob), _seed(step, 'co_attn1', layer)      # dropout1, vilbert.py:642,696
+        p2, s2 = self._drop(cfg.attention_probs_dropout_prob), _seed(step, 'co_attn2', layer)        # dropout2, vilbert.py:649,718
+        ld = 3 * Hb
+        L.attn_fwd(qkv2, qkv1[:, Hb:], qkv1[:, 2 * Hb:], v_mask, ctx1, lse1, B=B, nh=nh, dh=dh, Lq=T, Lk=R, ldq=ld, ldk=ld, ldv=ld,
+                   ldo=Hb, dropout_p=p1, seed=s1)
+        L.attn_fwd(qkv1, qkv2[:, Hb:], qkv2[:, 2 * Hb:], t_mask, ctx2, lse2, B=B, nh=nh, dh=dh, Lq=R, Lk=T, ldq=ld, ldk=ld, ldv=ld,
+                   ldo=Hb, dropout_p=p2, seed=s2)
+        # biOutput is called with crossed arguments (vilbert.py:780): visual <- ctx2 via dense1/LayerNorm1, text <- ctx1 via dense2/LayerNorm2
+        av, so_v = self._attn_out_fwd(ctx2, v, pre + '.biOutput.dense1', pre + '.biOutput.LayerNorm1',
+                                      self._drop(cfg.v_hidden_dropout_prob), _seed(step, 'co_out_v', layer), keep)
+        at, so_t = self._attn_out_fwd(ctx1, t, pre + '.biOutput.dense2', pre + '.biOutput.LayerNorm2',
+                                      self._drop(cfg.hidden_dropout_prob), _seed(step, 'co_out_t', layer), keep)
+        yv, sf_v = self._ffn_fwd(av, pre + '.v_intermediate', pre + '.v_output', self._drop(cfg.v_hidden_dropout_prob),
+                                 _seed(step, 'co_ffn_v', layer), keep)
+        yt, sf_t = self._ffn_fwd(at, pre + '.t_intermediate', pre + '.t_output', self._drop(cfg.hidden_dropout_prob),
+                                 _seed(step, 'co_ffn_t', layer), keep)
+        s = None
+        if keep:
+            s = _Saved()
+            s.v, s.t, s.qkv1, s.qkv2, s.lse1, s.lse2 = v, t, qkv1, qkv2, lse1, lse2
+            s.so_v, s.so_t, s.sf_v, s.sf_t = so_v, so_t, sf_v, sf_t
+            s.p1, s.s1, s.p2, s.s2, s.v_mask, s.t_mask, s.B, s.T, s.R = p1, s1, p2, s2, v_mask, t_mask, B, T, R
+        return yv, yt, s
+
+    def _co_layer_bwd(self, dyv, dyt, s, pre):
+        cfg = self.cfg
+        Mv, Hv = dyv.shape
+        Mt, H = dyt.shape
+        nh, Hb = cfg.bi_num_attention_heads, cfg.bi_hidden_size
+        dh, ld = Hb // nh, 3 * Hb
+        dav = self._ffn_bwd(dyv, s.sf_v, pre + '.v_intermediate', pre + '.v_output')
+        dat = self._ffn_bwd(dyt, s.sf_t, pre + '.t_intermediate', pre + '.t_output')
+        dzv, dctx2 = self._attn_out_bwd(dav, s.so_v, pre + '.biOutput.dense1', pre + '.biOutput.LayerNorm1')
+        dzt, dctx1 = self._attn_out_bwd(dat, s.so_t, pre + '.biOutput.dense2', pre + '.biOutput.LayerNorm2')
+        dqkv1, dqkv2 = torch.empty_like(s.qkv1), torch.empty_like(s.qkv2)
+        # direction 1: q = text (qkv2[:, :Hb]), k/v = visual  -> dq2, dk1, dv1
+        L.attn_bwd(s.qkv2, s.qkv1[:, Hb:], s.qkv1[:, 2 * Hb:], s.v_mask, s.so_t.ctx, dctx1, s.lse1, dqkv2, dqkv1[:, Hb:], dqkv1[:, 2 * Hb:],
+                   B=s.B, nh=nh, dh=dh, Lq=s.T, Lk=s.R, ldq=ld, ldk=ld, ldv=ld, ldo=Hb, lddo=Hb, lddq=ld, lddk=ld, lddv=ld,
+                   dropout_p=s.p1, seed=s.s1)
+        # direction 2: q = visual (qkv1[:, :Hb]), k/v = text -> dq1, dk2, dv2
+        L.attn_bwd(s.qkv1, s.qkv2[:, Hb:], s.qkv2[:, 2 * Hb:], s.t_mask, s.so_v.ctx, dctx2, s.lse2, dqkv1, dqkv2[:, Hb:], dqkv2[:, 2 * Hb:],
+                   B=s.B, nh=nh, dh=dh, Lq=s.R, Lk=s.T, ldq=ld, ldk=ld, ldv=ld, ldo=Hb, lddo=Hb, lddq=ld, lddk=ld, lddv=ld,
+                   dropout_p=s.p2, seed=s.s2)
+        m1 = [pre + '.biattention.' + n for n in ('query1', 'key1', 'value1')]
+        m2 = [pre + '.biattention.' + n for n in ('query2', 'key2', 'value2')]
+        L.colsum_bf16(dqkv1, self.arena.fused(self.arena.g32, m1, '.bias'))
+        L.colsum_bf16(dqkv2, self.arena.fused(self.arena.g32, m2, '.bias'))
+        self._wgrad(dqkv1, s.v, self.arena.fused(self.arena.g32, m1, '.weight'))
+        self._wgrad(dqkv2, s.t, self.arena.fused(self.arena.g32, m2, '.weight'))
+        dv = torch.empty_like(dyv)
+        dt = torch.empty_like(dyt)
+        L.gemm(dqkv1, self.arena.fused(self.arena.w16, m1, '.weight'), dv, M=Mv, N=Hv, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzv)
+        L.gemm(dqkv2, self.arena.fused(self.arena.w16, m2, '.weight'), dt, M=Mt, N=H, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzt)
+        return dv, dt
+
+    # ------------------------------------------------------------------ heads (fp32, CUDA cores)
+    def _lin32(self, x, name, act=L.ACT_NONE, out=None, ldc=None):
+        W, b = self._p(name + '.weight'), self._p(name + '.bias')
+        M, (N, K) = x.shape[0], W.shape
+        if out is None:
+            out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+            ldc = N
+        L.linear_f32(x, x.stride(0), 1, W, 1, K, out, ldc, M, N, K, bias=b, act=act)
+        return out
+
+    def _lin32_bwd(self, dy, ldy, x, name, dmask=None, slope=0.0, dx_out=None, accumulate_dx=0, need_dx=True):
+        """dy: [M,N] (row stride ldy) gradient of the PRE-activation output of Linear `name` applied to x [M,K]."""
+        W = self._p(name + '.weight')
+        N, K = W.shape
+        M = x.shape[0]
+        L.linear_f32(dy, 1, ldy, x, x.stride(0), 1, self._g(name + '.weight'), K, N, K, M, accumulate=1)
+        L.colsum_f32(dy, self._g(name + '.bias'), M, N, ldy)
+        if not need_dx:
+            return None
+        if dx_out is None:
+            dx_out = torch.empty(M, K, dtype=torch.float32, device=x.device)
+        L.linear_f32(dy, ldy, 1, W, K, 1, dx_out, K, M, K, N, dmask=dmask, ldm=(dmask.stride(0) if dmask is not None else 0), slope=slope,
+                     accumulate=accumulate_dx)
+        return dx_out
+
+    def _mlp4_fwd(self, x, pre, out=None, ldc=None, last_act=L.ACT_NONE):
+        acts = [x]
+        h = x
+        for i, idx in enumerate((0, 2, 4, 6)):
+            if i < 3:
+                h = self._lin32(h, f'{pre}.{idx}', L.ACT_LEAKY)
+            else:
+                h = self._lin32(h, f'{pre}.{idx}', last_act, out=out, ldc=ldc)
+            acts.append(h)
+        return h, acts
+
+    def _mlp4_bwd(self, d_last, ld_last, acts, pre, dx_out=None, accumulate_dx=0):
+        """d_last = gradient of the pre-activation output of the last Linear."""
+        d, ldd = d_last, ld_last
+        for i, idx in reversed(list(enumerate((0, 2, 4, 6)))):
+            x = acts[i]
+            if i > 0:      # x is the LeakyReLU output of the previous Linear: fold its derivative into dx
+                d = self._lin32_bwd(d, ldd, x, f'{pre}.{idx}', dmask=x, slope=0.01)
+                ldd = d.stride(0)
+            else:
+                d = self._lin32_bwd(d, ldd, x, f'{pre}.{idx}', dx_out=dx_out, accumulate_dx=accumulate_dx)
+        return d
+
+    def _heads_fwd(self, t, v, B, T, R, labels, Rt, kind, keep):
+        cfg, dev = self.cfg, t.device
+        H, Hv, Hb = cfg.hidden_size, cfg.v_hidden_size, cfg.bi_hidden_size
+        hw0 = torch.empty(B, H, dtype=torch.float32, device=dev)
+        hv0 = torch.empty(B, Hv, dtype=torch.float32, device=dev)
+        L.gather_first(t, T * H, hw0)          # vilbert.py:958 / 1600
+        L.gather_first(v, R * Hv, hv0)         # vilbert.py:973 / 1599
+        pt = self._lin32(hw0, 'bert.t_pooler.dense', L.ACT_RELU)
+        pv = self._lin32(hv0, 'bert.v_pooler.dense', L.ACT_RELU)
+        pooled = torch.empty_like(pt)
+        p_cls, s_cls = self._drop(0.1), _seed(self._step, 'cls')      # nn.Dropout(0.1), vilbert.py:1045
+        L.pool_mul_fwd(pt, pv, pooled, p_cls, s_cls)
+        logits = self._lin32(pooled, 'cls.bi_seq_relationship')
+        prefusion = torch.empty(B, 512, dtype=torch.float32, device=dev)          # cat((hv, hw), -1), regressor.py:40
+        _, acts_v = self._mlp4_fwd(hv0, 'regressor.vis_pipe', out=prefusion, ldc=512)
+        _, acts_t = self._mlp4_fwd(hw0, 'regressor.txt_pipe', out=prefusion[:, 256:], ldc=512)
+        reg, acts_f = self._mlp4_fwd(prefusion, 'regressor.fusion', last_act=L.ACT_TANH)
+        outs = [torch.empty(B, dtype=torch.float32, device=dev) for _ in range(4)]
+        scalars = torch.empty(5, dtype=torch.float32, device=dev)
+        dlogits = torch.empty(B, 2, dtype=torch.float32, device=dev) if keep else None
+        dpre = torch.empty(B, 1, dtype=torch.float32, device=dev) if keep else None
+        L.hybrid_loss(logits, reg, labels, Rt, *outs, scalars, dlogits, dpre, l1=bool(self.params['L1']),
+                      zero_impossible=(kind != 'L1'), tol_margin=float(self.params['tol_margin']),
+                      nsp_coeff=float(self.params.get('nsp_loss_coeff', 1.0)), reg_coeff=float(self.params.get('reg_loss_coeff', 1.0)),
+                      unit_grads=1)
+        s = None
+        if keep:
+            s = _Saved()
+            s.hw0, s.hv0, s.pt, s.pv, s.pooled, s.p_cls, s.s_cls = hw0, hv0, pt, pv, pooled, p_cls, s_cls
+            s.acts_v, s.acts_t, s.acts_f, s.prefusion, s.dlogits, s.dpre = acts_v, acts_t, acts_f, prefusion, dlogits, dpre
+        return logits, outs, scalars, s
+
+    def _heads_bwd(self, s, d_nsp, d_reg, B, T, R):
+        cfg, dev = self.cfg, s.hw0.device
+        H, Hv = cfg.hidden_size, cfg.v_hidden_size
+        dlogits, dpre = torch.empty_like(s.dlogits), torch.empty_like(s.dpre)
+        L.scale_rows(s.dlogits, d_nsp.reshape(-1)[:1].contiguous().float(), dlogits)
+        L.scale_rows(s.dpre, d_reg.reshape(-1).contiguous().float(), dpre)
+        dpooled = self._lin32_bwd(dlogits, 2, s.pooled, 'cls.bi_seq_relationship')
+        dut, duv = torch.empty_like(s.pt), torch.empty_like(s.pv)
+        L.pool_mul_bwd(dpooled, s.pt, s.pv, dut, duv, s.p_cls, s.s_cls)
+        dhw0 = self._lin32_bwd(dut, dut.stride(0), s.hw0, 'bert.t_pooler.dense')
+        dhv0 = self._lin32_bwd(duv, duv.stride(0), s.hv0, 'bert.v_pooler.dense')
+        dpref = self._mlp4_bwd(dpre, 1, s.acts_f, 'regressor.fusion')
+        self._mlp4_bwd(dpref, 512, s.acts_v, 'regressor.vis_pipe', dx_out=dhv0, accumulate_dx=1)
+        self._mlp4_bwd(dpref[:, 256:], 512, s.acts_t, 'regressor.txt_pipe', dx_out=dhw0, accumulate_dx=1)
+        dt = torch.zeros(B * T, H, dtype=torch.bfloat16, device=dev)
+        dv = torch.zeros(B * R, Hv, dtype=torch.bfloat16, device=dev)
+        L.scatter_first(dhw0, dt, T * H)
+        L.scatter_first(dhv0, dv, R * Hv)
+        return dt, dv
+
+    # ------------------------------------------------------------------ whole model
+    def _run_forward(self, ids, types, loc, feat, box, cls, amask, imask, labels, Rt, kind, keep):
+        cfg, arena = self.cfg, self.arena
+        L.device_check()
+        self._bind_grads()
+        arena.refresh_bf16()
+        dev = ids.device
+        B, T = ids.shape
+        R, F = feat.shape[1], feat.shape[2]
+        H, Hv = cfg.hidden_size, cfg.v_hidden_size
+        if F != cfg.v_feature_size:
+            raise ValueError(f'image_feat has {F} features, config says {cfg.v_feature_size}')
+        if box.shape[-1] != 4:
+            raise ValueError('image_loc must be [B,R,4] (CRCT/fig_dataloader.py:346 strips the 5th column)')
+        step = self._step
+        t_mask = torch.empty(B, T, dtype=torch.float32, device=dev)
+        v_mask = torch.empty(B, R, dtype=torch.float32, device=dev)
+        L.additive_mask(amask, t_mask)
+        L.additive_mask(imask, v_mask)
+        sv = _Saved() if keep else None
+        # --- embeddings (vilbert.py:1412-1413)
+        e = 'bert.embeddings'
+        t = torch.empty(B * T, H, dtype=torch.bfloat16, device=dev)
+        zt = torch.empty_like(t) if keep else None
+        mt = torch.empty(B * T, dtype=torch.float32, device=dev) if keep else None
+        rt = torch.empty(B * T, dtype=torch.float32, device=dev) if keep else None
+        p_et, s_et = self._drop(cfg.hidden_dropout_prob), _seed(step, 'emb_t')
+        L.embed_text_fwd(ids, types, loc, self._p(e + '.word_embeddings.weight'), self._p(e + '.position_embeddings.weight'),
+                         self._p(e + '.plotqa_type_embeddings.weight'), self._p(e + '.txt_location_embeddings.weight'),
+                         self._p(e + '.txt_location_embeddings.bias'), self._p(e + '.LayerNorm.weight'), self._p(e + '.LayerNorm.bias'),
+                         t, zt, mt, rt, dropout_p=p_et, seed=s_et)
+        e = 'bert.v_embeddings'
+        feat2 = feat.reshape(B * R, F)
+        probs = torch.empty(B * R, F, dtype=torch.bfloat16, device=dev)
+        L.softmax_rows(feat2, probs)
+        gimg = self._linear(probs, self._w(e + '.new_image_embeddings.weight'), self._p(e + '.new_image_embeddings.bias'), B * R)
+        v = torch.empty(B * R, Hv, dtype=torch.bfloat16, device=dev)
+        zv = torch.empty_like(v) if keep else None
+        mv = torch.empty(B * R, dtype=torch.float32, device=dev) if keep else None
+        rv = torch.empty(B * R, dtype=torch.float32, device=dev) if keep else None
+        p_ev, s_ev = self._drop(cfg.hidden_dropout_prob), _seed(step, 'emb_v')      # nn.Dropout(config.hidden_dropout_prob), vilbert.py:1470
+        box2, cls2 = box.reshape(B * R, 4), cls.reshape(B * R)
+        L.embed_vis_fwd(gimg, box2, cls2, self._p(e + '.new_loc_emb.weight'), self._p(e + '.new_loc_emb.bias'),
+                        self._p(e + '.color_emb.weight'), self._p(e + '.LayerNorm.weight'), self._p(e + '.LayerNorm.bias'),
+                        v, zv, mv, rv, dropout_p=p_ev, seed=s_ev)
+        # --- encoder (vilbert.py:852-939)
+        layers = []
+        for kind_, i in cfg.schedule():
+            if kind_ == 't':
+                t, s = self._self_layer_fwd(t, t_mask, B, T, cfg.num_attention_heads, f'bert.encoder.layer.{i}', ('query', 'key', 'value'),
+                                            (cfg.attention_probs_dropout_prob, cfg.hidden_dropout_prob), i, keep)
+            elif kind_ == 'v':
+                v, s = self._self_layer_fwd(v, v_mask, B, R, cfg.v_num_attention_heads, f'bert.encoder.v_layer.{i}', ('query', 'key', 'value'),
+                                            (cfg.v_attention_probs_dropout_prob, cfg.v_hidden_dropout_prob), 100 + i, keep)
+            else:
+                v, t, s = self._co_layer_fwd(v, t, v_mask, t_mask, B, T, R, f'bert.encoder.c_layer.{i}', 200 + i, keep)
+            layers.append(s)
+        logits, outs, scalars, s_heads = self._heads_fwd(t, v, B, T, R, labels, Rt, kind, keep)
+        if keep:
+            sv.B, sv.T, sv.R = B, T, R
+            sv.ids, sv.types, sv.loc, sv.box2, sv.cls2, sv.probs = ids, types, loc, box2, cls2, probs
+            sv.zt, sv.mt, sv.rt, sv.p_et, sv.s_et = zt, mt, rt, p_et, s_et
+            sv.zv, sv.mv, sv.rv, sv.p_ev, sv.s_ev = zv, mv, rv, p_ev, s_ev
+            sv.layers, sv.heads = layers, s_heads
+        return logits, outs, scalars, t, sv
+
+    def _backward(self, sv, d_nsp, d_reg):
+        cfg, arena = self.cfg, self.arena
+        B, T, R = sv.B, sv.T, sv.R
+        hook = self.grad_ready_hook
+        dt, dv = self._heads_bwd(sv.heads, d_nsp, d_reg, B, T, R)
+        if hook:
+            hook(arena.offsets['bert.t_pooler.dense.weight'], arena.live_end)
+        sched = cfg.schedule()
+        for (kind_, i), s in reversed(list(zip(sched, sv.layers))):
+            if kind_ == 't':
+                pre = f'bert.encoder.layer.{i}'
+                dt = self._self_layer_bwd(dt, s, pre, ('query', 'key', 'value'))
+            elif kind_ == 'v':
+                pre = f'bert.encoder.v_layer.{i}'
+                dv = self._self_layer_bwd(dv, s, pre, ('query', 'key', 'value'))
+            else:
+                pre = f'bert.encoder.c_layer.{i}'
+                dv, dt = self._co_layer_bwd(dv, dt, s, pre)
+            if hook:
+                lo, hi = self._block_range(pre)
+                hook(lo, hi)
+        # embeddings
+        e = 'bert.embeddings'
+        dzt = torch.empty_like(dt)
+        L.layernorm_bwd(dt, sv.zt, sv.mt, sv.rt, self._p(e + '.LayerNorm.weight'), dzt, self._g(e + '.LayerNorm.weight'),
+                        self._g(e + '.LayerNorm.bias'), p_in=sv.p_et, seed_in=sv.s_et)
+        L.embed_text_bwd(sv.ids, sv.types, sv.loc, dzt, self._g(e + '.word_embeddings.weight'), self._g(e + '.position_embeddings.weight'),
+                         self._g(e + '.plotqa_type_embeddings.weight'), self._g(e + '.txt_location_embeddings.weight'),
+                         self._g(e + '.txt_location_embeddings.bias'))
+        e = 'bert.v_embeddings'
+        dzv = torch.empty_like(dv)
+        L.layernorm_bwd(dv, sv.zv, sv.mv, sv.rv, self._p(e + '.LayerNorm.weight'), dzv, self._g(e + '.LayerNorm.weight'),
+                        self._g(e + '.LayerNorm.bias'), dbias=self._g(e + '.new_image_embeddings.bias'), p_in=sv.p_ev, seed_in=sv.s_ev)
+        L.colsum_bf16(dzv, self._g(e + '.new_loc_emb.bias'))
+        self._wgrad(dzv, sv.probs, self._g(e + '.new_image_embeddings.weight'))
+        L.embed_vis_bwd(dzv, sv.box2, sv.cls2, self._g(e + '.color_emb.weight'), self._g(e + '.new_loc_emb.weight'))
+        if hook:
+            hook(0, self._block_range('bert.v_embeddings')[1])
+            hook(None, None)         # backward finished
+
+    def _block_range(self, prefix):
+        """[lo, hi) element range of the live arena tensors under `prefix` (contiguous by construction)."""
+        names = [p.name for p in self.arena.order if p.live and p.name.startswith(prefix + '.')]
+        lo = self.arena.offsets[names[0]]
+        last = self.arena.by_name[names[-1]]
+        hi = self.arena.offsets[last.name] + (last.numel + 63) // 64 * 64
+        return lo, hi
+
+    def forward(self, input_ids, txt_loc, image_feat, image_loc, sep_indices=None, sep_len=None, token_type_ids=None,
+                attention_mask=None, masked_lm_labels=None, next_sentence_label=None, head_mask=None, random_round_indices=None,
+                output_nsp_scores=False, output_lm_scores=False, image_attention_mask=None, image_label=None, image_target=None,
+                gt_reg=None, areas=None, legend_pred=None):
+        """Same signature and return tuple as encoder_decorator.py:19-54.  `sep_indices`, `sep_len`, `masked_lm_labels`
+        (presence only), `image_label`, `head_mask`, `random_round_indices`, `legend_pred` take no part in the arithmetic
+        (SURVEY.md §8b); `areas` is FigureQA/DVQA-only."""
+        dev = self.arena.w32.device
+        if dev.type != 'cuda':
+            raise L.CrctError('cqa_crct_b200 has no CPU path: move the model to a B200 with .to("cuda")')
+        if areas is not None:
+            raise NotImplementedError('`areas` is only used by the FigureQA / DVQA configurations')
+        if gt_reg is None:
+            raise ValueError('gt_reg=[R, kind] is required (vilbert.py:1586)')
+        train_branch = next_sentence_label is not None and masked_lm_labels is not None and image_target is not None   # :31-32
+        cvt = lambda x, dt=None: None if x is None else x.to(device=dev, dtype=dt, non_blocking=True).contiguous()
+        ids = cvt(input_ids, torch.int64)
+        B, T = ids.shape
+        types = cvt(token_type_ids, torch.int64) if token_type_ids is not None else torch.zeros_like(ids)           # vilbert.py:1368-1369
+        loc = cvt(txt_loc, torch.float32)
+        feat = cvt(image_feat, torch.float32)
+        box = cvt(image_loc, torch.float32)
+        R = feat.shape[1]
+        if image_target is None:
+            raise ValueError('image_target (RoI class ids for color_emb, vilbert.py:1479) is required')
+        cls = cvt(image_target, torch.int64)
+        amask = cvt(attention_mask) if attention_mask is not None else torch.ones(B, T, dtype=torch.int64, device=dev)   # :1366-1367
+        imask = cvt(image_attention_mask) if image_attention_mask is not None else torch.ones(B, R, dtype=torch.int64, device=dev)
+        if amask.dtype not in (torch.bool, torch.uint8, torch.int64, torch.float32):
+            amask = amask.to(torch.int64)
+        if imask.dtype not in (torch.bool, torch.uint8, torch.int64, torch.float32):
+            imask = imask.to(torch.int64)
+        Rt, kind = gt_reg[0], gt_reg[1]
+        Rt = cvt(Rt, torch.float32)
+        labels = cvt(next_sentence_label, torch.int64).view(-1) if train_branch else None
+        keep = train_branch and torch.is_grad_enabled()
+        if self.training:
+            self._step += 1
+        logits, outs, scalars, seq_t, sv = self._run_forward(ids, types, loc, feat, box, cls, amask, imask, labels, Rt, kind, keep)
+        reg_pred, reg_loss, reg_l1, reg_dist = outs
+        nsp_loss = scalars[1:2]
+        if keep:
+            sv.nsp_loss, sv.reg_loss = nsp_loss, reg_loss
+            anchor = self._params_by_name['bert.embeddings.word_embeddings.weight']
+            nsp_loss, reg_loss = _CrctFunction.apply(anchor, self, sv)
+        reg = [reg_pred, reg_loss, reg_l1, (scalars[3], scalars[4]), reg_dist]          # vilbert.py:1590-1648 (counts stay on device)
+        legend_loss = torch.zeros(1, dtype=torch.float32, device=dev)                   # vilbert.py:1583
+        if train_branch:
+            zero = torch.zeros(1, 1, dtype=torch.float32, device=dev)                   # vilbert.py:1652-1653
+            out = (zero, zero.clone(), nsp_loss)
+        else:
+            out = (None, None, None)
+        out = out + (logits,)
+        if output_lm_scores:
+            out = out + (None,)                                                          # prediction_scores_t is None, vilbert.py:1059
+        return out + (reg, legend_loss)
+
+
+def glue_forward(dialog_encoder, batch, params, output_nsp_scores=False, output_lm_scores=False, evaluation=False, sample_ids=None):
+    """Same contract as the module-level `forward` of CRCT/backbone/encoder_decorator.py:73-158 (the function
+    train.py:173 / evaluation.py:247 call): slices the batch, builds the text mask from sep_indices/hist_len, calls the
+    model, combines the losses.  Index / mask bookkeeping on [B,T] integers stays in torch (host glue, not arithmetic)."""
+    dev = params['device']
+    idx = slice(None) if sample_ids is None else sample_ids
+    take = lambda k: batch[k][idx]
+    tokens, txt_loc, segments = take('tokens'), take('loc'), take('segments')
+    sep_indices, mask, hist_len = take('sep_indices'), take('mask'), take('hist_len')
+    regression_target = take('R')
+    if not evaluation:
+        next_sentence_labels = take('next_sentence_labels')
+        image_label = take('image_label')
+        regression_target = [regression_target, 'L1_smooth']                 # encoder_decorator.py:104
+    else:
+        next_sentence_labels, image_label = None, None
+        regression_target = [regression_target, 'L1']                        # encoder_decorator.py:106
+    seq_len = torch.gather(sep_indices, 1, hist_len.view(-1, 1)).squeeze(1) + 1                    # :118-119
+    attention_mask = torch.arange(tokens.shape[1], device=seq_len.device).unsqueeze(0) < seq_len.unsqueeze(1)   # sequence_mask :57-70
+    lm_loss, img_loss, nsp_loss, nsp_scores, regression, legend_loss = dialog_encoder(
+        tokens, txt_loc, take('image_feat'), take('image_loc'), sep_indices=sep_indices, sep_len=hist_len + 1,
+        token_type_ids=segments, masked_lm_labels=mask, attention_mask=attention_mask, next_sentence_label=next_sentence_labels,
+        output_nsp_scores=output_nsp_scores, output_lm_scores=output_lm_scores, image_attention_mask=take('image_mask'),
+        image_label=image_label, image_target=take('image_target'), gt_reg=regression_target,
+        areas=batch['areas'][idx] if 'areas' in batch else None)
+    reg_loss = regression[1].mean()
+    loss = None
+    if not evaluation:
+        loss = ((params['nsp_loss_coeff'] * nsp_loss) + (params['reg_loss_coeff'] * reg_loss)).sum()   # :144-153
+        return loss, lm_loss, nsp_loss, img_loss, nsp_scores, regression, legend_loss
+    return loss, lm_loss, nsp_loss, img_loss, nsp_scores, regression

@@ -81,6 +81,188 @@ typedef struct {
 
 int crct_gemm_bf16(const crct_gemm_t* args, crct_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K4  row kernels (HBM-bound, one warp per row, fp32 statistics).  Row width H: multiple of 8, <= 1024.
+ * -------------------------------------------------------------------------------------------- */
+/* fp32 master weights -> bf16 operand arena (n multiple of 8).  Replaces autocast's per-op casts, train.py:172. */
+int crct_cast_f32_to_bf16(const float* src, void* dst_bf16, size_t n, crct_stream_t stream);
+/* out[i] = (1 - mask[i]) * -10000  (vilbert.py:1380-1396).  kind: 0 = bool/uint8, 1 = int64, 2 = fp32. */
+int crct_additive_mask(const void* mask, int kind, float* out, int n, crct_stream_t stream);
+/* y = LayerNorm(z) with eps = 1e-12 inside the sqrt (vilbert.py:281-294).  z,y bf16 [rows,H]; mean/rstd fp32 [rows]
+ * or both NULL (inference). */
+int crct_layernorm_fwd(const void* z, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                       int rows, int H, crct_stream_t stream);
+/* LayerNorm backward.  dy may carry the dropout that FOLLOWED the LayerNorm in the forward (embeddings:
+ * p_in, seed_in); dzm is dz with the dropout that PRECEDED the residual add re-applied (p_out, seed_out; element
+ * counter row*H+col — the same stream the CRCT_EPI_BIAS_RES epilogue used), i.e. the gradient of the dense output. */
+typedef struct {
+    const void* dy;      /* bf16 [rows,H] */
+    const void* z;       /* bf16 [rows,H] pre-LayerNorm input saved by the forward */
+    const float* mean;   /* [rows] */
+    const float* rstd;   /* [rows] */
+    const float* gamma;  /* [H] */
+    void* dz;            /* bf16 [rows,H] */
+    void* dzm;           /* bf16 [rows,H] or NULL (ignored when p_out == 0: dzm == dz) */
+    float* dgamma;       /* [H] += */
+    float* dbeta;        /* [H] += */
+    float* dbias;        /* [H] += column sums of dzm (dz when p_out == 0), or NULL */
+    int32_t rows, H;
+    float p_in;  uint64_t seed_in;
+    float p_out; uint64_t seed_out;
+} crct_ln_bwd_t;
+int crct_layernorm_bwd(const crct_ln_bwd_t* args, crct_stream_t stream);
+/* out[n] += sum_rows x[row,n]   (bias gradients).  x bf16 [rows,N], row stride ld. */
+int crct_colsum_bf16(const void* x, float* out, int rows, int N, int ld, crct_stream_t stream);
+/* softmax over the RoI feature axis, fp32 in -> bf16 GEMM operand (vilbert.py:1476). */
+int crct_softmax_rows(const float* x, void* out_bf16, int rows, int F, crct_stream_t stream);
+
+/* K5  text embedding (vilbert.py:320-358): word + position (question/answer tokens only, counted from the first
+ * such token) + plotqa type (-1 -> 0, none for type 0) + Linear(4->H)(box) (none, bias included, for an all-zero
+ * box) -> LayerNorm -> dropout.  z/mean/rstd may be NULL for inference. */
+typedef struct {
+    const int64_t* ids;    /* [B,T] */
+    const int64_t* types;  /* [B,T] in {-1,0..11} */
+    const float* loc;      /* [B,T,4] */
+    const float* word; const float* pos; const float* type;  /* fp32 tables [V,H] [P,H] [12,H] */
+    const float* w_loc; const float* b_loc;                  /* [H,4] [H] */
+    const float* gamma; const float* beta;
+    void* y; void* z; float* mean; float* rstd;              /* bf16 [B*T,H] x2, fp32 [B*T] x2 */
+    int32_t B, T, H, max_pos;
+    float dropout_p; uint64_t seed;
+} crct_embed_text_t;
+int crct_embed_text_fwd(const crct_embed_text_t* args, crct_stream_t stream);
+/* scatter of dz (after crct_layernorm_bwd) into the tables; all outputs += . */
+typedef struct {
+    const int64_t* ids; const int64_t* types; const float* loc;
+    const void* dz;        /* bf16 [B*T,H] */
+    float* g_word; float* g_pos; float* g_type; float* g_wloc; float* g_bloc;
+    int32_t B, T, H;
+} crct_embed_text_bwd_t;
+int crct_embed_text_bwd(const crct_embed_text_bwd_t* args, crct_stream_t stream);
+
+/* K6  visual embedding tail (vilbert.py:1478-1496): g = softmax(feat) W_img^T + b_img comes from K1;
+ * z = g + Linear(4->Hv)(box) + color_emb[class] -> LayerNorm -> dropout. */
+typedef struct {
+    const void* g;         /* bf16 [rows,H] */
+    const float* box;      /* [rows,4] */
+    const int64_t* cls;    /* [rows] */
+    const float* w_loc; const float* b_loc; const float* color; const float* gamma; const float* beta;
+    void* y; void* z; float* mean; float* rstd;
+    int32_t rows, H;
+    float dropout_p; uint64_t seed;
+} crct_embed_vis_t;
+int crct_embed_vis_fwd(const crct_embed_vis_t* args, crct_stream_t stream);
+typedef struct {
+    const void* dz; const float* box; const int64_t* cls;
+    float* g_color; float* g_wloc;   /* += ; the two bias gradients are crct_colsum_bf16(dz) */
+    int32_t rows, H;
+} crct_embed_vis_bwd_t;
+int crct_embed_vis_bwd(const crct_embed_vis_bwd_t* args, crct_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2/K3  fused attention: ctx = dropout(softmax(q k^T / sqrt(dh) + mask_add)) v, one CTA per (sample, head).
+ * Replaces vilbert.py:397-412 (text, 16 x 48), :527-543 (visual, 16 x 64) and both directions of the
+ * co-attention :684-723 (32 x 32; call once with q = text / k,v = visual and once crossed).
+ * Element (b, i, h, d) of q lives at q[(b*Lq + i)*ldq + h*dh + d]; k, v likewise with Lk.  dh in {32,48,64}.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* q; const void* k; const void* v;  /* bf16 */
+    int32_t ldq, ldk, ldv;
+    const float* mask_add;  /* [B,Lk] additive key mask (0 / -10000) */
+    void* out;              /* bf16 [B*Lq, nh*dh], row stride ldo */
+    int32_t ldo;
+    float* lse;             /* [B,nh,Lq] log-sum-exp of the masked scores, or NULL (inference) */
+    int32_t B, nh, dh, Lq, Lk;
+    float dropout_p;        /* on the probabilities; element counter ((b*nh+h)*Lq+i)*Lk+j */
+    uint64_t seed;
+} crct_attn_fwd_t;
+int crct_attn_fwd(const crct_attn_fwd_t* args, crct_stream_t stream);
+
+typedef struct {
+    const void* q; const void* k; const void* v;
+    int32_t ldq, ldk, ldv;
+    const float* mask_add;
+    const void* out; int32_t ldo;     /* forward output */
+    const void* dout; int32_t lddo;   /* bf16 gradient of out */
+    const float* lse;
+    void* dq; void* dk; void* dv;     /* bf16, same indexing as q/k/v with strides lddq/lddk/lddv; overwritten */
+    int32_t lddq, lddk, lddv;
+    int32_t B, nh, dh, Lq, Lk;
+    float dropout_p;
+    uint64_t seed;
+} crct_attn_bwd_t;
+int crct_attn_bwd(const crct_attn_bwd_t* args, crct_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7/K8  heads in fp32 on CUDA cores (M = batch size): poolers vilbert.py:955-976, classifier :1052-1060,
+ * regressor regressor.py:36-42, hybrid loss vilbert.py:1586-1657 + encoder_decorator.py:144-153.
+ * -------------------------------------------------------------------------------------------- */
+/* C[m*ldc+n] (+)= dact( act( sum_k A[m*sa_m+k*sa_k] * B[k*sb_k+n*sb_n] + bias[n] ) )
+ *   act: 0 none, 1 ReLU, 2 LeakyReLU(0.01), 3 tanh;  dact: multiply by (dmask[m*ldm+n] > 0 ? 1 : slope) when dmask.
+ *   forward y = x W^T + b : A = x (sa_m=ldx, sa_k=1), B = W (sb_k=1, sb_n=ldw)
+ *   dgrad   dx = dy W     : A = dy,                    B = W (sb_k=ldw, sb_n=1), dmask = post-activation of x
+ *   wgrad   dW += dy^T x  : A = dy (sa_m=1, sa_k=ldy), B = x (sb_k=ldx, sb_n=1), accumulate = 1 */
+typedef struct {
+    const float* A; int64_t sa_m, sa_k;
+    const float* B; int64_t sb_k, sb_n;
+    float* C; int64_t ldc;
+    const float* bias;
+    const float* dmask; int64_t ldm;
+    int32_t M, N, K;
+    int32_t act;
+    float slope;
+    int32_t accumulate;
+} crct_linear_t;
+int crct_linear_f32(const crct_linear_t* args, crct_stream_t stream);
+/* out[b,:] = float(src_bf16[b*row_stride + :]) — hidden state of the first token / region (vilbert.py:958,973,1599-1600) */
+int crct_gather_first(const void* src_bf16, long long row_stride, float* out, int B, int H, crct_stream_t stream);
+/* dst_bf16[b*row_stride + :] = g[b,:]; all other rows of dst must be zero (caller memsets) */
+int crct_scatter_first(const float* g, void* dst_bf16, long long row_stride, int B, int H, crct_stream_t stream);
+/* out[n] += sum_m x[m*ld+n] */
+int crct_colsum_f32(const float* x, float* out, int M, int N, long long ld, crct_stream_t stream);
+/* pooled = dropout_p(pt * pv)  (vilbert.py:1055) and its backward through the two ReLU poolers */
+int crct_pool_mul_fwd(const float* pt, const float* pv, float* out, int n, float p, uint64_t seed, crct_stream_t stream);
+int crct_pool_mul_bwd(const float* dpooled, const float* pt, const float* pv, float* dut, float* duv, int n, float p,
+                      uint64_t seed, crct_stream_t stream);
+/* Hybrid loss, metrics and (when dlogits/dpre are given) the gradients of
+ *   loss = nsp_coeff * CE(logits, labels; ignore -1) + reg_coeff * mean_B(reg_loss)
+ * R[b] = (value, needs_regression, tolerance, scale).  labels NULL = inference (no CE).  Outputs are dense [B]
+ * vectors with zeros on rows that need no regression, exactly the `reg` list of vilbert.py:1590-1648.
+ * scalars = {loss, nsp_loss, mean reg loss, #(+-5 %), #(<= tol_margin)}. */
+typedef struct {
+    const float* logits;   /* [B,2] */
+    const float* reg;      /* [B] tanh output */
+    const int64_t* labels; /* [B] or NULL */
+    const float* R;        /* [B,4] */
+    float* reg_pred; float* reg_loss; float* reg_l1; float* reg_dist;  /* [B] each */
+    float* scalars;        /* [5] */
+    float* dlogits;        /* [B,2] or NULL */
+    float* dpre;           /* [B] gradient w.r.t. the pre-tanh regressor output, or NULL */
+    int32_t B;
+    int32_t l1;               /* 1 = L1Loss (-L1 flag), 0 = SmoothL1Loss(beta=0.5)   vilbert.py:1525-1528 */
+    int32_t zero_impossible;  /* 1 = loss kind 'L1_smooth' (training glue): zero loss where |target| > 1   vilbert.py:1639-1641 */
+    int32_t unit_grads;       /* 1 = dlogits = d nsp_loss / d logits, dpre[b] = d reg_loss[b] / d pre[b] (autograd chains the rest);
+                                 0 = gradients of the combined loss (coefficients and the 1/B of the mean folded in) */
+    float tol_margin, nsp_coeff, reg_coeff;
+} crct_loss_t;
+int crct_hybrid_loss(const crct_loss_t* args, crct_stream_t stream);
+/* out[b,j] = x[b,j] * s[b*s_stride], s_stride in {0,1}: chains the upstream gradient of nsp_loss / reg_loss[b] */
+int crct_scale_rows(const float* x, const float* s, int s_stride, float* out, int B, int n, crct_stream_t stream);
+
+/* f1  fused AdamW over the flat arena (torch.optim.AdamW semantics, CRCT/utils.py:228-249 param groups):
+ * group_of_block64[i/64] in 0..3 selects (lr, weight_decay); also rewrites the bf16 operand copy. */
+typedef struct {
+    float* w; const float* g; float* m; float* v;
+    void* w_bf16;                       /* or NULL */
+    const uint8_t* group_of_block64;    /* or NULL (group 0) */
+    size_t n;
+    float lr[4], weight_decay[4];
+    float beta1, beta2, eps;
+    int32_t step;                       /* 1-based */
+    float grad_scale;                   /* e.g. 1/world_size after a sum all-reduce */
+} crct_adamw_t;
+int crct_adamw(const crct_adamw_t* args, crct_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
