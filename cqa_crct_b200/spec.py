@@ -215,11 +215,14 @@ def synth_tensor(p: P, seed: int, style: str, init_range: float = 0.02) -> torch
     nn.Linear's default U(-1/sqrt(fan_in), 1/sqrt(fan_in)) because it is built after `apply(init)`,
     vilbert.py:1510 vs 1518-1523).
     style 'trained': same plus non-trivial biases / LayerNorm affine and 2x wider weights, so that
-    bias-, gamma- and beta-paths cannot hide behind zeros in the parity tests."""
+    bias-, gamma- and beta-paths cannot hide behind zeros in the parity tests (a deliberately ill-conditioned
+    stress point: a random network this wide amplifies bf16 rounding ~45x into its gradients).
+    style 'mild': non-trivial biases / LayerNorm affine on top of the reference's N(0, 0.02) weights."""
     g = torch.Generator().manual_seed((zlib.crc32(p.name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
-    trained = style == 'trained'
+    trained = style in ('trained', 'mild')
+    wide = 2.0 if style == 'trained' else 1.0
     if p.kind in ('w', 'emb'):
-        return torch.randn(p.shape, generator=g) * (init_range * (2.0 if trained and p.kind == 'w' else 1.0))
+        return torch.randn(p.shape, generator=g) * (init_range * (wide if p.kind == 'w' else 1.0))
     if p.kind == 'b':
         return torch.randn(p.shape, generator=g) * 0.02 if trained else torch.zeros(p.shape)
     if p.kind == 'lnw':

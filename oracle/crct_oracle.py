@@ -69,6 +69,32 @@ def layer_schedule(cfg: Config) -> List[Tuple[str, int]]:
 
 
 # --------------------------------------------------------------------------------------
+# optional storage-precision emulation
+# --------------------------------------------------------------------------------------
+# The reference arithmetic is the default (`_q` / `_qw` are identities).  Inside `bf16_emulation()` the
+# restatement additionally rounds to bf16 exactly where the CUDA path STORES bf16: tensor-core GEMM operands
+# (weights `_qw`, activations `_q`) and every activation / gradient tensor that goes through HBM.  All
+# reductions, statistics, softmax, the heads and the losses stay fp32/fp64, as in the kernels.  Comparing the
+# CUDA path with this mode separates implementation error from the operand quantisation every bf16
+# tensor-core path has (tests/test_model_gpu.py states both tolerances).
+_EMU = [False]
+
+
+class bf16_emulation:
+    def __enter__(self):
+        _EMU[0] = True
+
+    def __exit__(self, *a):
+        _EMU[0] = False
+
+
+def _q(x):
+    return x.to(torch.bfloat16).to(x.dtype) if _EMU[0] else x
+
+
+_qw = _q
+
+# --------------------------------------------------------------------------------------
 # primitive ops (each = one CUDA kernel or GEMM epilogue)
 # --------------------------------------------------------------------------------------
 def gelu(x):                      # vilbert.py:111-117, exact erf form
@@ -110,8 +136,8 @@ def attn_fwd(q, k, v, add_mask, nh, drop=None):
     s = qh @ kh.transpose(-1, -2) / math.sqrt(d) + add_mask[:, None, None, :]
     p = torch.softmax(s, dim=-1)
     pd = p if drop is None else p * drop
-    ctx = (pd @ vh).permute(0, 2, 1, 3).reshape(B, Lq, H)
-    return ctx, p, pd
+    ctx = (_q(pd) @ vh).permute(0, 2, 1, 3).reshape(B, Lq, H)
+    return _q(ctx), p, pd
 
 
 def attn_bwd(dctx, q, k, v, p, pd, nh, drop=None):
@@ -120,13 +146,13 @@ def attn_bwd(dctx, q, k, v, p, pd, nh, drop=None):
     d = H // nh
     qh, kh, vh = split_heads(q, B, Lq, nh), split_heads(k, B, Lk, nh), split_heads(v, B, Lk, nh)
     do = split_heads(dctx, B, Lq, nh)
-    dv = pd.transpose(-1, -2) @ do
+    dv = _q(pd).transpose(-1, -2) @ do
     dpd = do @ vh.transpose(-1, -2)
     dp = dpd if drop is None else dpd * drop
-    ds = p * (dp - (dp * p).sum(-1, keepdim=True))
-    dq = ds @ kh / math.sqrt(d)
-    dk = ds.transpose(-1, -2) @ qh / math.sqrt(d)
-    merge = lambda t, L: t.permute(0, 2, 1, 3).reshape(B, L, H)
+    ds = _q(p * (dp - (dp * p).sum(-1, keepdim=True)) / math.sqrt(d))
+    dq = ds @ kh
+    dk = ds.transpose(-1, -2) @ qh
+    merge = lambda t, L: _q(t.permute(0, 2, 1, 3).reshape(B, L, H))
     return merge(dq, Lq), merge(dk, Lk), merge(dv, Lk)
 
 
@@ -138,6 +164,16 @@ def lin_bwd(dy, x, W):
     """dY -> (dX, dW, db) for y = x W^T + b: the dgrad GEMM, the wgrad GEMM and the column sum."""
     dy2, x2 = dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1])
     return dy @ W, dy2.t() @ x2, dy2.sum(0)
+
+
+def tlin(x, W, b):
+    """Linear on the tensor-core path (bf16 operands in emulation mode)."""
+    return x @ _qw(W).t() + b
+
+
+def tlin_bwd(dy, x, W):
+    dy2, x2 = dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1])
+    return dy @ _qw(W), dy2.t() @ x2, dy2.sum(0)
 
 
 class _Grads(dict):
@@ -170,13 +206,14 @@ def embed_text_fwd(w, ids, types, loc, pre='bert.embeddings.'):
     ty[ty == -1] = 0
     ty_on = (types != 0).unsqueeze(-1)
     te = w[pre + 'plotqa_type_embeddings.weight'][ty] * ty_on
-    z = we + pe + te + le
+    z = _q(we + pe + te + le)
     y, mean, rstd = ln_fwd(z, w[pre + 'LayerNorm.weight'], w[pre + 'LayerNorm.bias'])
-    return y, dict(z=z, mean=mean, rstd=rstd, pos=pos, qa=qa, loc_on=loc_on, ty=ty, ty_on=ty_on)
+    return _q(y), dict(z=z, mean=mean, rstd=rstd, pos=pos, qa=qa, loc_on=loc_on, ty=ty, ty_on=ty_on)
 
 
 def embed_text_bwd(w, g, dy, c, ids, loc, pre='bert.embeddings.'):
     dz, dg, db = ln_bwd(dy, c['z'], c['mean'], c['rstd'], w[pre + 'LayerNorm.weight'])
+    dz = _q(dz)
     g.add(pre + 'LayerNorm.weight', dg)
     g.add(pre + 'LayerNorm.bias', db)
     H = dz.shape[-1]
@@ -197,16 +234,17 @@ def embed_text_bwd(w, g, dy, c, ids, loc, pre='bert.embeddings.'):
 
 def embed_vis_fwd(w, feat, box, cls, pre='bert.v_embeddings.'):
     """vilbert.py:1474-1496 (PlotQA branch: img + loc + color, no areas, mask_prob_img = 0)."""
-    p = torch.softmax(feat, dim=-1)
-    z = (lin(p, w[pre + 'new_image_embeddings.weight'], w[pre + 'new_image_embeddings.bias'])
-         + lin(box, w[pre + 'new_loc_emb.weight'], w[pre + 'new_loc_emb.bias'])
-         + w[pre + 'color_emb.weight'][cls])
+    p = _q(torch.softmax(feat, dim=-1))
+    z = _q(_q(tlin(p, w[pre + 'new_image_embeddings.weight'], w[pre + 'new_image_embeddings.bias']))
+           + lin(box, w[pre + 'new_loc_emb.weight'], w[pre + 'new_loc_emb.bias'])
+           + w[pre + 'color_emb.weight'][cls])
     y, mean, rstd = ln_fwd(z, w[pre + 'LayerNorm.weight'], w[pre + 'LayerNorm.bias'])
-    return y, dict(p=p, z=z, mean=mean, rstd=rstd)
+    return _q(y), dict(p=p, z=z, mean=mean, rstd=rstd)
 
 
 def embed_vis_bwd(w, g, dy, c, box, cls, pre='bert.v_embeddings.'):
     dz, dg, db = ln_bwd(dy, c['z'], c['mean'], c['rstd'], w[pre + 'LayerNorm.weight'])
+    dz = _q(dz)
     g.add(pre + 'LayerNorm.weight', dg)
     g.add(pre + 'LayerNorm.bias', db)
     H = dz.shape[-1]
@@ -228,37 +266,39 @@ def _qkv(w, pre, names):
 
 def ffn_fwd(w, a, pre_i, pre_o):
     """intermediate (vilbert.py:454-457 / 585-588) + output (vilbert.py:467-471 / 598-602)."""
-    u = lin(a, w[pre_i + 'dense.weight'], w[pre_i + 'dense.bias'])
-    h = gelu(u)
-    z = lin(h, w[pre_o + 'dense.weight'], w[pre_o + 'dense.bias']) + a
+    u = tlin(a, w[pre_i + 'dense.weight'], w[pre_i + 'dense.bias'])
+    h = _q(gelu(u))
+    z = _q(tlin(h, w[pre_o + 'dense.weight'], w[pre_o + 'dense.bias']) + a)
     y, mean, rstd = ln_fwd(z, w[pre_o + 'LayerNorm.weight'], w[pre_o + 'LayerNorm.bias'])
-    return y, dict(a=a, u=u, h=h, z=z, mean=mean, rstd=rstd)
+    return _q(y), dict(a=a, u=_q(u), h=h, z=z, mean=mean, rstd=rstd)
 
 
 def ffn_bwd(w, g, dy, c, pre_i, pre_o):
     dz, dg, db = ln_bwd(dy, c['z'], c['mean'], c['rstd'], w[pre_o + 'LayerNorm.weight'])
     g.add(pre_o + 'LayerNorm.weight', dg)
     g.add(pre_o + 'LayerNorm.bias', db)
-    dh, dW, dbias = lin_bwd(dz, c['h'], w[pre_o + 'dense.weight'])
+    g.add(pre_o + 'dense.bias', dz.reshape(-1, dz.shape[-1]).sum(0))      # summed before the bf16 store
+    dz = _q(dz)
+    dh, dW, _ = tlin_bwd(dz, c['h'], w[pre_o + 'dense.weight'])
     g.add(pre_o + 'dense.weight', dW)
-    g.add(pre_o + 'dense.bias', dbias)
-    du = dh * gelu_grad(c['u'])
-    da, dW, dbias = lin_bwd(du, c['a'], w[pre_i + 'dense.weight'])
+    du = _q(dh * gelu_grad(c['u']))
+    da, dW, dbias = tlin_bwd(du, c['a'], w[pre_i + 'dense.weight'])
     g.add(pre_i + 'dense.weight', dW)
     g.add(pre_i + 'dense.bias', dbias)
-    return da + dz
+    return _q(da + dz)
 
 
 def self_layer_fwd(w, x, add_mask, nh, pre):
     """BertLayer / BertImageLayer (vilbert.py:474-485, 605-616)."""
     H = x.shape[-1]
     Wqkv, bqkv = _qkv(w, pre + 'attention.self.', ['query', 'key', 'value'])
-    qkv = lin(x, Wqkv, bqkv)
+    qkv = _q(tlin(x, Wqkv, bqkv))
     q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
     ctx, p, pd = attn_fwd(q, k, v, add_mask, nh)
     po = pre + 'attention.output.'
-    z1 = lin(ctx, w[po + 'dense.weight'], w[po + 'dense.bias']) + x
+    z1 = _q(tlin(ctx, w[po + 'dense.weight'], w[po + 'dense.bias']) + x)
     a, mean1, rstd1 = ln_fwd(z1, w[po + 'LayerNorm.weight'], w[po + 'LayerNorm.bias'])
+    a = _q(a)
     y, cf = ffn_fwd(w, a, pre + 'intermediate.', pre + 'output.')
     return y, dict(x=x, q=q, k=k, v=v, p=p, pd=pd, ctx=ctx, z1=z1, mean1=mean1, rstd1=rstd1, ffn=cf, nh=nh)
 
@@ -269,18 +309,20 @@ def self_layer_bwd(w, g, dy, c, pre):
     dz1, dg, db = ln_bwd(da, c['z1'], c['mean1'], c['rstd1'], w[po + 'LayerNorm.weight'])
     g.add(po + 'LayerNorm.weight', dg)
     g.add(po + 'LayerNorm.bias', db)
-    dctx, dW, dbias = lin_bwd(dz1, c['ctx'], w[po + 'dense.weight'])
+    g.add(po + 'dense.bias', dz1.reshape(-1, dz1.shape[-1]).sum(0))
+    dz1 = _q(dz1)
+    dctx, dW, _ = tlin_bwd(dz1, c['ctx'], w[po + 'dense.weight'])
+    dctx = _q(dctx)
     g.add(po + 'dense.weight', dW)
-    g.add(po + 'dense.bias', dbias)
     dq, dk, dv = attn_bwd(dctx, c['q'], c['k'], c['v'], c['p'], c['pd'], c['nh'])
     dqkv = torch.cat([dq, dk, dv], -1)
     Wqkv, _ = _qkv(w, pre + 'attention.self.', ['query', 'key', 'value'])
-    dx, dW, dbias = lin_bwd(dqkv, c['x'], Wqkv)
+    dx, dW, dbias = tlin_bwd(dqkv, c['x'], Wqkv)
     H = c['x'].shape[-1]
     for i, n in enumerate(['query', 'key', 'value']):
         g.add(pre + f'attention.self.{n}.weight', dW[i * H:(i + 1) * H])
         g.add(pre + f'attention.self.{n}.bias', dbias[i * H:(i + 1) * H])
-    return dx + dz1
+    return _q(dx + dz1)
 
 
 def co_layer_fwd(w, v, t, v_mask, t_mask, nh, pre):
@@ -291,16 +333,17 @@ def co_layer_fwd(w, v, t, v_mask, t_mask, nh, pre):
     W1, b1 = _qkv(w, pb, ['query1', 'key1', 'value1'])
     W2, b2 = _qkv(w, pb, ['query2', 'key2', 'value2'])
     Hb = W1.shape[0] // 3
-    qkv1, qkv2 = lin(v, W1, b1), lin(t, W2, b2)
+    qkv1, qkv2 = _q(tlin(v, W1, b1)), _q(tlin(t, W2, b2))
     q1, k1, v1 = qkv1[..., :Hb], qkv1[..., Hb:2 * Hb], qkv1[..., 2 * Hb:]
     q2, k2, v2 = qkv2[..., :Hb], qkv2[..., Hb:2 * Hb], qkv2[..., 2 * Hb:]
     ctx1, p1, pd1 = attn_fwd(q2, k1, v1, v_mask, nh)       # [B,T,Hb]
     ctx2, p2, pd2 = attn_fwd(q1, k2, v2, t_mask, nh)       # [B,R,Hb]
     po = pre + 'biOutput.'
-    zv = lin(ctx2, w[po + 'dense1.weight'], w[po + 'dense1.bias']) + v
+    zv = _q(tlin(ctx2, w[po + 'dense1.weight'], w[po + 'dense1.bias']) + v)
     av, mv, rv = ln_fwd(zv, w[po + 'LayerNorm1.weight'], w[po + 'LayerNorm1.bias'])
-    zt = lin(ctx1, w[po + 'dense2.weight'], w[po + 'dense2.bias']) + t
+    zt = _q(tlin(ctx1, w[po + 'dense2.weight'], w[po + 'dense2.bias']) + t)
     at, mt, rt = ln_fwd(zt, w[po + 'LayerNorm2.weight'], w[po + 'LayerNorm2.bias'])
+    av, at = _q(av), _q(at)
     yv, cfv = ffn_fwd(w, av, pre + 'v_intermediate.', pre + 'v_output.')
     yt, cft = ffn_fwd(w, at, pre + 't_intermediate.', pre + 't_output.')
     c = dict(v=v, t=t, q1=q1, k1=k1, v1=v1, q2=q2, k2=k2, v2=v2, p1=p1, pd1=pd1, p2=p2, pd2=pd2,
@@ -318,27 +361,29 @@ def co_layer_bwd(w, g, dyv, dyt, c, pre):
     dzt, dg, db = ln_bwd(dat, c['zt'], c['mt'], c['rt'], w[po + 'LayerNorm2.weight'])
     g.add(po + 'LayerNorm2.weight', dg)
     g.add(po + 'LayerNorm2.bias', db)
-    dctx2, dW, dbias = lin_bwd(dzv, c['ctx2'], w[po + 'dense1.weight'])
+    g.add(po + 'dense1.bias', dzv.reshape(-1, dzv.shape[-1]).sum(0))
+    g.add(po + 'dense2.bias', dzt.reshape(-1, dzt.shape[-1]).sum(0))
+    dzv, dzt = _q(dzv), _q(dzt)
+    dctx2, dW, _ = tlin_bwd(dzv, c['ctx2'], w[po + 'dense1.weight'])
     g.add(po + 'dense1.weight', dW)
-    g.add(po + 'dense1.bias', dbias)
-    dctx1, dW, dbias = lin_bwd(dzt, c['ctx1'], w[po + 'dense2.weight'])
+    dctx1, dW, _ = tlin_bwd(dzt, c['ctx1'], w[po + 'dense2.weight'])
     g.add(po + 'dense2.weight', dW)
-    g.add(po + 'dense2.bias', dbias)
+    dctx1, dctx2 = _q(dctx1), _q(dctx2)
     dq2, dk1, dv1 = attn_bwd(dctx1, c['q2'], c['k1'], c['v1'], c['p1'], c['pd1'], c['nh'])
     dq1, dk2, dv2 = attn_bwd(dctx2, c['q1'], c['k2'], c['v2'], c['p2'], c['pd2'], c['nh'])
     pb = pre + 'biattention.'
     W1, _ = _qkv(w, pb, ['query1', 'key1', 'value1'])
     W2, _ = _qkv(w, pb, ['query2', 'key2', 'value2'])
     Hb = W1.shape[0] // 3
-    dv_in, dW, dbias = lin_bwd(torch.cat([dq1, dk1, dv1], -1), c['v'], W1)
+    dv_in, dW, dbias = tlin_bwd(torch.cat([dq1, dk1, dv1], -1), c['v'], W1)
     for i, n in enumerate(['query1', 'key1', 'value1']):
         g.add(pb + n + '.weight', dW[i * Hb:(i + 1) * Hb])
         g.add(pb + n + '.bias', dbias[i * Hb:(i + 1) * Hb])
-    dt_in, dW, dbias = lin_bwd(torch.cat([dq2, dk2, dv2], -1), c['t'], W2)
+    dt_in, dW, dbias = tlin_bwd(torch.cat([dq2, dk2, dv2], -1), c['t'], W2)
     for i, n in enumerate(['query2', 'key2', 'value2']):
         g.add(pb + n + '.weight', dW[i * Hb:(i + 1) * Hb])
         g.add(pb + n + '.bias', dbias[i * Hb:(i + 1) * Hb])
-    return dv_in + dzv, dt_in + dzt
+    return _q(dv_in + dzv), _q(dt_in + dzt)
 
 
 def leaky(x):
@@ -405,7 +450,7 @@ def heads_bwd(w, g, dlogits, dreg, c, T, R):
     dhw0 = dhw0 + mlp4_bwd(w, g, dpre[:, nv:], c['ct'], 'regressor.txt_pipe.')
     dt = torch.zeros(B, T, dhw0.shape[-1], dtype=dhw0.dtype)
     dv = torch.zeros(B, R, dhv0.shape[-1], dtype=dhv0.dtype)
-    dt[:, 0], dv[:, 0] = dhw0, dhv0
+    dt[:, 0], dv[:, 0] = _q(dhw0), _q(dhv0)
     return dt, dv
 
 

@@ -32,6 +32,9 @@ CASES = [
     ('tiny_ragged', 'tiny.json', 3, 19, 5, True, 3, 14, True),     # odd T/R: padding paths
     ('full_eval_b8', 'vilbert.json', 8, 124, 44, True, 1, 21, False),   # BASELINE configs[0]
     ('full_train_b4', 'vilbert.json', 4, 124, 44, True, 1, 22, True),
+    # same shapes at a better-conditioned operating point (reference-scale weights): tighter tolerances apply
+    ('full_eval_b8_mild', 'vilbert.json', 8, 124, 44, True, 1, 21, False, 'mild'),
+    ('full_train_b4_mild', 'vilbert.json', 4, 124, 44, True, 1, 22, True, 'mild'),
 ]
 
 
@@ -48,17 +51,17 @@ def grad_summary(named_grads) -> dict:
     return out
 
 
-def run_case(name, cfg_file, B, T, R, l1, wseed, bseed, train):
+def run_case(name, cfg_file, B, T, R, l1, wseed, bseed, train, style='trained'):
     cfg_path = os.path.join(ROOT, 'cqa_crct_b200', 'config', cfg_file)
     cfg = ModelConfig(cfg_path)
     params = default_params(cfg_path, max_seq_len=T, max_vis_features=R, L1=l1)
     enc = ref_shim.RefEncoder(cfg_path, params, seed=0)
     m = enc.module
-    m.bert_pretrained.load_state_dict(synth_state_dict(cfg, params['categories'], wseed, 'trained'), strict=True)
+    m.bert_pretrained.load_state_dict(synth_state_dict(cfg, params['categories'], wseed, style), strict=True)
     m.eval()                      # dropout off; the train/eval BRANCH is chosen by kwargs (encoder_decorator.py:31-32)
     batch = make_batch(B, T, R, cfg.v_feature_size, seed=bseed, vocab_size=cfg.vocab_size)
     rec = dict(name=name, config=cfg_file, B=B, T=T, R=R, l1=l1, weight_seed=wseed, batch_seed=bseed,
-               weight_style='trained', train=train, torch=torch.__version__)
+               weight_style=style, train=train, torch=torch.__version__)
     if train:
         loss, _, nsp, _, scores, reg, _ = enc.glue_forward(m, batch, params)
         loss.backward()
@@ -75,7 +78,10 @@ def run_case(name, cfg_file, B, T, R, l1, wseed, bseed, train):
 def main():
     out_dir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
+    only = sys.argv[1:]
     for case in CASES:
+        if only and case[0] not in only:
+            continue
         rec = run_case(*case)
         path = os.path.join(out_dir, case[0] + '.pt')
         torch.save(rec, path)

@@ -1,0 +1,119 @@
+"""CPU-side checks: C-ABI exports, host logic (arena, module tree, optimizer grouping), loud failure without CUDA."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from cqa_crct_b200 import _lib as L
+from cqa_crct_b200.spec import ModelConfig, param_spec, arena_order, arena_offsets, fused_groups, synth_state_dict
+from cqa_crct_b200.synthetic import default_params, make_batch
+from tests.helpers import CONFIG_DIR, ROOT
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'crct_b200.h')).read()
+    declared = set(re.findall(r'\b(crct_[a-z0-9_]+)\s*\(', hdr))
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(L.EXPORTS)
+    assert L.lib().crct_version() >= 100
+
+
+def test_no_cuda_means_loud_failure_not_fallback():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from cqa_crct_b200.encoder import VisualDialogEncoder, glue_forward
+    cfg_path = os.path.join(CONFIG_DIR, 'tiny.json')
+    params = default_params(cfg_path, max_seq_len=16, max_vis_features=6)
+    m = VisualDialogEncoder(params)
+    batch = make_batch(2, 16, 6, 128, vocab_size=2048)
+    with pytest.raises(L.CrctError):
+        glue_forward(m, batch, params, evaluation=True)
+    with pytest.raises(L.CrctError):
+        L.device_check()
+
+
+@pytest.mark.parametrize('cfg_file', ['tiny.json', 'vilbert.json'])
+def test_arena_layout(cfg_file):
+    cfg = ModelConfig(os.path.join(CONFIG_DIR, cfg_file))
+    spec = param_spec(cfg)
+    order = arena_order(cfg, spec)
+    off, live_end, total = arena_offsets(order)
+    assert sorted(p.name for p in order) == sorted(p.name for p in spec)
+    assert all(o % 64 == 0 for o in off.values())
+    seen_dead = False
+    for p in order:                                   # live tensors first, dead tensors last
+        seen_dead |= not p.live
+        assert not (seen_dead and p.live)
+    by = {p.name: p for p in spec}
+    for grp in fused_groups(cfg):                     # q|k|v weights and biases back to back
+        for suffix in ('.weight', '.bias'):
+            cur = off[grp[0] + suffix]
+            for mname in grp:
+                assert off[mname + suffix] == cur
+                cur += by[mname + suffix].numel
+    # forward-execution order: backward finishes the arena from the tail towards the head
+    first = [off[f'bert.encoder.{k}.{i}.attention.self.query.weight' if k != 'c_layer' else f'bert.encoder.c_layer.{i}.biattention.query1.weight']
+             for k, i in [({'t': 'layer', 'v': 'v_layer', 'c': 'c_layer'}[kk], ii) for kk, ii in cfg.schedule()]]
+    assert first == sorted(first)
+
+
+def test_module_tree_and_state_dict_roundtrip():
+    from cqa_crct_b200.encoder import VisualDialogEncoder
+    cfg_path = os.path.join(CONFIG_DIR, 'tiny.json')
+    m = VisualDialogEncoder(default_params(cfg_path))
+    cfg = ModelConfig(cfg_path)
+    sd = synth_state_dict(cfg, 228, 4, 'trained')
+    m.load_state_dict({'bert_pretrained.' + k: v for k, v in sd.items()}, strict=True)
+    names = [k for k, _ in m.named_parameters()]
+    assert names == ['bert_pretrained.' + p.name for p in param_spec(cfg)]
+    out = m.state_dict()
+    assert set(out) == {'bert_pretrained.' + k for k in sd}
+    for k, v in sd.items():
+        assert torch.equal(out['bert_pretrained.' + k], v)
+    dead = [k for k, p in m.named_parameters() if not p.requires_grad]
+    assert len(dead) == 20
+    # parameters are views of one flat arena
+    base = m.arena.w32.data_ptr()
+    for k, p in m.named_parameters():
+        assert base <= p.data_ptr() < base + m.arena.total * 4
+    with pytest.raises(TypeError):
+        m.half()
+
+
+def test_reference_init_distributions():
+    from cqa_crct_b200.encoder import VisualDialogEncoder
+    torch.manual_seed(0)
+    m = VisualDialogEncoder(default_params(os.path.join(CONFIG_DIR, 'tiny.json')))
+    sd = m.state_dict()
+    w = sd['bert_pretrained.bert.encoder.layer.0.intermediate.dense.weight']
+    assert abs(float(w.std()) - 0.02) < 2e-3 and abs(float(w.mean())) < 1e-3            # vilbert.py:1105
+    assert float(sd['bert_pretrained.bert.encoder.layer.0.intermediate.dense.bias'].abs().sum()) == 0
+    assert torch.equal(sd['bert_pretrained.bert.embeddings.LayerNorm.weight'], torch.ones(192))
+    rw = sd['bert_pretrained.regressor.fusion.0.weight']
+    assert float(rw.abs().max()) <= 1 / 512 ** 0.5 + 1e-6 and float(rw.std()) > 0.02     # nn.Linear default, fan_in 512
+
+
+def test_dropout_hash_reference_values_and_rate():
+    """The counter-based keep/drop decision is a pure function of (seed, index); pin it so forward and backward
+    kernels (and future refactors) cannot drift apart."""
+    def h(seed, idx):
+        M = 0xFFFFFFFF
+        x = (idx & M) * 0x9E3779B1 & M
+        x ^= ((idx >> 32) & M) * 0x85EBCA77 & M
+        x ^= seed & M
+        x ^= x >> 16; x = x * 0x85EBCA6B & M
+        x ^= x >> 13; x = x * 0xC2B2AE35 & M
+        x ^= x >> 16
+        x = (x + (seed >> 32)) & M
+        x ^= x >> 15; x = x * 0x2C1B3C6D & M
+        x ^= x >> 12
+        return x
+    vals = [h(12345, i) for i in range(20000)]
+    thr = int(0.1 * 2 ** 32)
+    rate = sum(v >= thr for v in vals) / len(vals)
+    assert abs(rate - 0.9) < 0.01
+    assert len(set(vals)) > 19990

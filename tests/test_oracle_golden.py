@@ -7,7 +7,7 @@ from oracle import crct_oracle as O
 from tests.helpers import load_golden, golden_inputs, sample_idx
 
 TRAIN = ['tiny_train_l1', 'tiny_train_smooth', 'tiny_ragged']
-EVAL = ['tiny_eval', 'full_eval_b8']
+EVAL = ['tiny_eval', 'full_eval_b8', 'full_eval_b8_mild']
 
 
 def _check_outputs(rec, out, tol=2e-5):
