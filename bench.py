@@ -1,0 +1,298 @@
+"""Benchmark of the CRCT question-answering hot path (BASELINE.json metric: train samples/s at B=80 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|eval|stress]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one pass of the hot path over one synthetic PlotQA-shaped batch: forward + backward (+ bucketed gradient
+all-reduce overlapped with backward for N > 1) + fused AdamW, dropout ON, B = 80 sequences per GPU (weak scaling).
+  value : whole-job samples/s with the batches already resident in HBM (CUDA events, max over ranks)
+  e2e   : same metric through the reference-facing API (`glue_forward(model, batch, params)`) with HOST batches:
+          pinned host -> device copies of every input and a device -> host read of the loss inside the timed region
+  roofline : the tcgen05 GEMM kernel (dominant: 97.7 % of the FLOPs): algorithmic FLOPs of all GEMM launches of one
+          step / their summed CUDA-event durations, against the measured bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline : the CPU restatement of the reference (oracle/, kind "port" — /root/reference does not exist on the
+          GPU box) timed on the host cores on a bounded sample of the same workload (rank 0, N = 1 only)
+`--impl reference` times that CPU path alone (all host threads) and prints the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch                      # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+CFG = os.path.join(ROOT, 'cqa_crct_b200', 'config', 'vilbert.json')
+WORKLOADS = {   # name -> (B per GPU, T, R, train?)  — BASELINE.json configs[1] / [3] / [4]
+    'train': (80, 124, 44, True),
+    'eval': (512, 124, 44, False),
+    'stress': (80, 248, 88, True),
+}
+FWD_GFLOP_PER_SAMPLE = {(124, 44): 40.396, (248, 88): 82.547}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1365.6), d.get('bf16_tflops', 1624.7), d.get('hbm_gbs', 6548.8), 'measured'
+    return 1400.0, 1590.0, 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace('.', '').isdigit()]
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_run(B, T, R, train, steps, warmup, budget_s=200.0):
+    """The reference algorithm on the host cores (oracle port, fp32, all threads).  Each step processes a bounded
+    sample of `Bs` sequences of the workload's shape; returns (samples/s, Bs, seconds per step, threads)."""
+    from oracle import crct_oracle as O
+    from cqa_crct_b200.spec import ModelConfig, synth_state_dict
+    from cqa_crct_b200.synthetic import make_batch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = ModelConfig(CFG)
+    ocfg = O.Config(cfg.__dict__)
+    sd = synth_state_dict(cfg, 228, 0, 'mild')
+
+    def one(bs, seed):
+        batch = make_batch(bs, T, R, cfg.v_feature_size, seed=seed)
+        t0 = time.perf_counter()
+        if train:
+            out, cache = O.forward(sd, ocfg, batch, train=True, l1=True)
+            O.backward(cache)
+        else:
+            with torch.no_grad():
+                O.forward(sd, ocfg, batch, train=False, keep_cache=False)
+        return time.perf_counter() - t0
+
+    t_probe = one(2, 1)                                   # calibrate: seconds for 2 sequences (includes first-touch)
+    t_probe = min(t_probe, one(2, 2))
+    per_seq = t_probe / 2
+    total_steps = steps + warmup
+    bs = int(max(2, min(B, budget_s / max(1, total_steps) / per_seq)))
+    for i in range(warmup):
+        one(bs, 10 + i)
+    times = [one(bs, 100 + i) for i in range(steps)]
+    sec = sum(times) / len(times)
+    return bs / sec, bs, sec, threads
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='train', choices=list(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    B, T, R, train = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    metric = 'crct_train_samples_per_sec' if train else 'crct_eval_sequences_per_sec'
+    config = {'workload': f'CRCT {"train step (fwd+bwd+allreduce+AdamW, dropout on, L1 regression loss)" if train else "eval forward (hybrid head argmax + regression)"}'
+                          f', B={B}/GPU, T={T}, R={R}, full vilbert.json model (252.7M params), random-init weights',
+              'per_gpu_batch': B, 'global_batch': B * max(1, args.gpus), 'text_len': T, 'regions': R, 'parallelism': f'dp{max(1, args.gpus)}',
+              'l2': 'working set per step (0.5 GB bf16 weights + >4 GB activations) exceeds the 126 MB L2; inputs rotate over 4 batches'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        v, bs, sec, threads = cpu_reference_run(B, T, R, train, max(1, args.steps), max(0, args.warmup))
+        line = {'impl': 'reference', 'metric': metric, 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+                                 'sample': f'{bs} sequences per step of the same shape (T={T}, R={R}), {"fwd+bwd" if train else "fwd"}, fp32, torch CPU ops'},
+                'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a B200; there is no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from cqa_crct_b200 import _lib as L
+    from cqa_crct_b200.encoder import VisualDialogEncoder, glue_forward
+    from cqa_crct_b200.optim import FusedAdamW, WarmupLinearScheduleNonZero
+    from cqa_crct_b200.parallel import DistributedDataParallel
+    from cqa_crct_b200.synthetic import default_params, make_batch
+    L.device_check()
+    dev = torch.device('cuda', local_rank)
+    params = default_params(CFG, device=str(dev), max_seq_len=T, max_vis_features=R, L1=True)
+    torch.manual_seed(0)
+    enc = VisualDialogEncoder(params).to(dev)
+    model = DistributedDataParallel(enc) if world > 1 else enc
+    opt = sched = None
+    if train:
+        enc.train()
+        opt = FusedAdamW(model, lr=2e-5, image_lr=2e-5, weight_decay=0.01)
+        sched = WarmupLinearScheduleNonZero(opt, warmup_steps=3000, t_total=200000, min_lr=1.3e-5)
+    else:
+        enc.eval()
+    host = [make_batch(B, T, R, 1024, seed=1234 + 17 * rank + i) for i in range(4)]
+    pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items() if k != 'needs_reg')
+
+    def step(batch, read_loss=False):
+        if train:
+            opt.zero_grad()
+            loss = glue_forward(model, batch, params)[0]
+            loss.backward()
+            opt.step()
+            sched.step()
+            return float(loss) if read_loss else None
+        with torch.no_grad():
+            out = glue_forward(model, batch, params, evaluation=True)
+        scores, reg = out[4], out[5]
+        if read_loss:
+            pick = torch.softmax(scores, 1)[:, 0].argmax()           # evaluation.py:254-258,287-296 on one candidate group
+            return float(reg[0][pick])
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, read_loss):
+        for i in range(args.warmup):
+            step(batches[i % 4], read_loss)
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        l0 = L.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            # e2e (read_loss): the batch is HOST memory; glue_forward / the encoder copy every input to the device
+            # inside this region and the loss is read back every step
+            step(batches[i % 4], read_loss)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = L.LAUNCHES - l0
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches, clocks
+
+    ms, launches, clocks = timed(resident, False)
+    ms_step = ms / args.steps
+    value = B * world / (ms_step / 1e3)
+    e2e = None
+    if not args.no_e2e:
+        ms2, _, _ = timed(pinned, True)
+        e2e = {'value': B * world / (ms2 / args.steps / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+               'ms_per_step': ms2 / args.steps}
+
+    # ---- roofline of the dominant kernel: every GEMM launch of ONE more step, timed with CUDA events on the launch stream
+    roof = None
+    if rank == 0:
+        sustained, burst, hbm, src = load_peaks()
+        events, flops = [], []
+        orig = L.gemm
+
+        def timed_gemm(A, Bm, D, **kw):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            orig(A, Bm, D, **kw)
+            b.record()
+            events.append((a, b))
+            flops.append(2.0 * kw['M'] * kw['N'] * kw['K'])
+
+        L.gemm = timed_gemm
+        import cqa_crct_b200.encoder as E
+        E.L.gemm = timed_gemm
+        require = getattr(model, 'require_sync', None)
+        if require is not None:
+            model.require_sync = False            # rank 0 alone runs this extra step: no collective
+        try:
+            if train:
+                enc.zero_grad()
+                glue_forward(enc, resident[0], params)[0].backward()
+            else:
+                with torch.no_grad():
+                    glue_forward(enc, resident[0], params, evaluation=True)
+            torch.cuda.synchronize()
+        finally:
+            L.gemm = orig
+            E.L.gemm = orig
+            if require is not None:
+                model.require_sync = True
+        gemm_ms = sum(a.elapsed_time(b) for a, b in events)
+        achieved = sum(flops) / (gemm_ms / 1e3) / 1e12
+        roof = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel', 'achieved': achieved, 'peak': sustained, 'unit': 'TFLOP/s',
+                'frac': achieved / sustained, 'traffic': None, 'peak_source': f'{src} (bf16_tflops_sustained; burst {burst})',
+                'launches_per_step': len(events), 'gemm_ms_per_step': gemm_ms, 'gemm_share_of_step': gemm_ms / ms_step,
+                'algorithmic_tflop_per_step': sum(flops) / 1e12,
+                'model_tflops_whole_step': (FWD_GFLOP_PER_SAMPLE.get((T, R), 40.396) * (3 if train else 1) * B / 1e3) / (ms_step / 1e3)}
+    if world > 1:
+        dist.barrier()
+
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        v, bs, sec, threads = cpu_reference_run(B, T, R, train, 1, 0, budget_s=20.0)
+        cpu = {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+               'sample': f'1 step of {bs} sequences of the same shape, {"fwd+bwd" if train else "fwd"}, fp32 oracle port on torch CPU ops ({sec:.1f} s)'}
+
+    if rank == 0:
+        line = {'metric': metric, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+                'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
+                'gpu_launches_per_step': launches / args.steps, 'roofline': roof, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -137,7 +137,7 @@ class VisualDialogEncoder(nn.Module):
         root = _Node()
         self._params_by_name: Dict[str, nn.Parameter] = {}
         for p in self.arena.spec:
-            prm = nn.Parameter(self.arena.view(self.arena.w32, p.name), requires_grad=p.live)
+            prm = nn.Parameter(self.arena.view(self.arena.w32, p.name))     # all require grad, as in the reference
             self._params_by_name[p.name] = prm
             _attach(root, p.name, prm)
         for alias, src in TIED.items():
@@ -179,7 +179,7 @@ class VisualDialogEncoder(nn.Module):
     def _bind_grads(self):
         self.arena.ensure_device_buffers()
         for name, prm in self._params_by_name.items():
-            if prm.requires_grad and (prm.grad is None or prm.grad.data_ptr() != self.arena.view(self.arena.g32, name).data_ptr()):
+            if self.arena.by_name[name].live and (prm.grad is None or prm.grad.data_ptr() != self.arena.view(self.arena.g32, name).data_ptr()):
                 prm.grad = self.arena.view(self.arena.g32, name)
 
     def zero_grad(self, set_to_none: bool = False):

@@ -1,0 +1,102 @@
+"""f1 — optimizer step of the training path: one fused multi-tensor AdamW kernel over the flat arena.
+
+Mirrors `get_optimizer` (CRCT/utils.py:228-249: one param group per tensor, `-lr` for the names listed in
+config/language_weights.json and `-image_lr` for the rest, weight decay 0 for names containing 'bias',
+'LayerNorm.bias' or 'LayerNorm.weight') with torch.optim.AdamW defaults (betas 0.9/0.999, eps 1e-8), and
+`WarmupLinearScheduleNonZero` (CRCT/utils.py:11-29).  The same kernel rewrites the bf16 operand copy, so the next
+forward needs no cast pass; the GradScaler of CRCT/train.py:157,212-214 has no bf16 counterpart (fp32 exponent range).
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_NO_DECAY = ('bias', 'LayerNorm.bias', 'LayerNorm.weight')          # CRCT/utils.py:229
+
+
+class FusedAdamW:
+    def __init__(self, model, lr: float = 2e-5, image_lr: float = 2e-5, weight_decay: float = 0.01,
+                 betas=(0.9, 0.999), eps: float = 1e-8, language_weights: Optional[str] = None):
+        enc = getattr(model, 'module', model)
+        self.enc = enc
+        arena = enc.arena
+        if language_weights is None:
+            language_weights = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'config', 'language_weights.json')
+        with open(language_weights) as f:
+            lang = set(json.load(f))
+        self.base_lr = [lr, lr, image_lr, image_lr]            # groups: lang+wd, lang no-wd, image+wd, image no-wd
+        self.wd = [weight_decay, 0.0, weight_decay, 0.0]
+        self.betas, self.eps = betas, eps
+        self.n = arena.live_end
+        group = torch.zeros(self.n // 64, dtype=torch.uint8)
+        for p in arena.order:
+            if not p.live:
+                continue
+            key = 'bert_pretrained.' + p.name
+            gid = (0 if key in lang else 2) + (1 if any(nd in key for nd in _NO_DECAY) else 0)
+            o = arena.offsets[p.name]
+            group[o // 64:(o + p.numel + 63) // 64] = gid
+        dev = arena.w32.device
+        self.group = group.to(dev)
+        self.m = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.step_count = 0
+        self.lr_factor = 1.0
+        self.min_lr = 0.0
+
+    def current_lrs(self):
+        return [max(b * self.lr_factor, self.min_lr) if b * self.lr_factor > self.min_lr else self.min_lr for b in self.base_lr]
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.enc.zero_grad()
+
+    def step(self, grad_scale: float = 1.0):
+        arena = self.enc.arena
+        self.step_count += 1
+        arena.ensure_device_buffers()
+        L.adamw(arena.w32, arena.g32, self.m, self.v, arena.w16, self.group, self.n, self.current_lrs(), self.wd,
+                self.betas[0], self.betas[1], self.eps, self.step_count, grad_scale)
+        arena.mark_bf16_fresh()
+
+    def state_dict(self):
+        return {'step': self.step_count, 'exp_avg': self.m, 'exp_avg_sq': self.v, 'lr_factor': self.lr_factor, 'min_lr': self.min_lr}
+
+    def load_state_dict(self, sd):
+        self.step_count, self.lr_factor, self.min_lr = sd['step'], sd['lr_factor'], sd['min_lr']
+        self.m.copy_(sd['exp_avg'])
+        self.v.copy_(sd['exp_avg_sq'])
+
+
+class WarmupLinearScheduleNonZero:
+    """CRCT/utils.py:11-29: linear warm-up to the base lr over `warmup_steps`, linear decay to zero at `t_total`,
+    clamped from below at `min_lr`."""
+
+    def __init__(self, optimizer: FusedAdamW, warmup_steps: int, t_total: int, min_lr: float = 1.3e-5, last_epoch: int = -1):
+        self.opt, self.warmup_steps, self.t_total = optimizer, warmup_steps, t_total
+        optimizer.min_lr = min_lr
+        self.last_epoch = last_epoch
+        self.step()
+
+    def factor(self, step: int) -> float:
+        if step < self.warmup_steps:
+            return float(step) / float(max(1, self.warmup_steps))
+        return max(0.0, float(self.t_total - step) / float(max(1.0, self.t_total - self.warmup_steps)))
+
+    def step(self):
+        self.last_epoch += 1
+        self.opt.lr_factor = self.factor(self.last_epoch)
+
+    def get_last_lr(self):
+        return self.opt.current_lrs()
+
+    def state_dict(self):
+        return {'last_epoch': self.last_epoch, 'warmup_steps': self.warmup_steps, 't_total': self.t_total}
+
+    def load_state_dict(self, sd):
+        self.last_epoch = sd['last_epoch']
+        self.opt.lr_factor = self.factor(self.last_epoch)

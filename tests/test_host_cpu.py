@@ -74,8 +74,7 @@ def test_module_tree_and_state_dict_roundtrip():
     assert set(out) == {'bert_pretrained.' + k for k in sd}
     for k, v in sd.items():
         assert torch.equal(out['bert_pretrained.' + k], v)
-    dead = [k for k, p in m.named_parameters() if not p.requires_grad]
-    assert len(dead) == 20
+    assert all(p.requires_grad for _, p in m.named_parameters())          # like the reference; dead tensors just never get .grad
     # parameters are views of one flat arena
     base = m.arena.w32.data_ptr()
     for k, p in m.named_parameters():
