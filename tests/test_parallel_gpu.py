@@ -1,0 +1,69 @@
+"""Data-parallel equivalence on real GPUs (needs >= 2): gradients after the overlapped bucketed NCCL all-reduce on two
+ranks, each holding half of a batch, equal the single-GPU gradients of the whole batch (to bf16 noise)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from cqa_crct_b200.encoder import VisualDialogEncoder, glue_forward
+    from cqa_crct_b200.parallel import DistributedDataParallel
+    from cqa_crct_b200.spec import ModelConfig, synth_state_dict
+    from cqa_crct_b200.synthetic import default_params, make_batch
+    from tests.helpers import CONFIG_DIR
+    cfg_path = os.path.join(CONFIG_DIR, 'tiny.json')
+    cfg = ModelConfig(cfg_path)
+    params = default_params(cfg_path, device=f'cuda:{rank}', max_seq_len=32, max_vis_features=12)
+    enc = VisualDialogEncoder(params)
+    if rank == 0:      # only rank 0 holds the real weights: the wrapper must broadcast them
+        enc.load_state_dict({'bert_pretrained.' + k: v for k, v in synth_state_dict(cfg, 228, 7, 'mild').items()})
+    enc.to(f'cuda:{rank}').eval()
+    ddp = DistributedDataParallel(enc, bucket_cap_mb=1.0)
+    B = 8
+    full = make_batch(B, 32, 12, cfg.v_feature_size, seed=31, vocab_size=cfg.vocab_size)
+    half = {k: v[rank * B // world:(rank + 1) * B // world].to(f'cuda:{rank}') for k, v in full.items()}
+    enc.zero_grad()
+    glue_forward(ddp, half, params)[0].backward()
+    torch.cuda.synchronize()
+    g_ddp = enc.arena.g32[:enc.arena.live_end].clone()
+    nb = len(ddp.buckets_last_step)
+    # single-GPU reference on the same device, whole batch, no exchange
+    ddp.require_sync = False
+    enc.zero_grad()
+    glue_forward(enc, {k: v.to(f'cuda:{rank}') for k, v in full.items()}, params)[0].backward()
+    torch.cuda.synchronize()
+    g_one = enc.arena.g32[:enc.arena.live_end].clone()
+    rel = float((g_ddp - g_one).norm() / g_one.norm())
+    gathered = [torch.zeros_like(g_ddp) for _ in range(world)]
+    dist.all_gather(gathered, g_ddp)
+    same = all(torch.equal(gathered[0], x) for x in gathered)
+    if rank == 0:
+        torch.save({'rel': rel, 'same': same, 'buckets': nb}, out_path)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_gpu_gradients_equal_single_gpu_full_batch(tmp_path):
+    out = str(tmp_path / 'r.pt')
+    mp.spawn(_run, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r['same']                       # every rank ends with identical gradients
+    assert r['buckets'] >= 2               # the exchange really was bucketed
+    assert r['rel'] < 3e-2, r              # = full-batch gradients up to bf16 noise
