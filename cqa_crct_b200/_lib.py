@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
     _fields_ = [('A', vp), ('B', vp), ('D', vp), ('D2', vp), ('bias', vp), ('aux', vp),
                 ('M', i32), ('N', i32), ('K', i32), ('lda', i32), ('ldb', i32), ('ldd', i32), ('ldaux', i32),
                 ('a_major', i32), ('b_major', i32), ('epilogue', i32), ('accumulate', i32), ('split_k', i32),
-                ('block_n', i32), ('dropout_p', f32), ('seed', u64), ('max_ctas', i32), ('dbg', i32 * 7)]
+                ('block_n', i32), ('dropout_p', f32), ('seed', u64), ('max_ctas', i32), ('cta_group', i32), ('dbg', i32 * 7)]
 
 
 class LnBwdArgs(C.Structure):
@@ -160,7 +160,7 @@ def _f32(t, what):
 
 def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None, aux=None, D2=None,
          lda=None, ldb=None, ldd=None, ldaux=None, accumulate=0, split_k=0, block_n=0, dropout_p=0.0, seed=0,
-         max_ctas=0, dbg=None):
+         max_ctas=0, dbg=None, cta_group=0):
     """D[M,N] = epilogue(A·Bᵀ) — see include/crct_b200.h for operand majors."""
     _bf16(A, 'A'); _bf16(B, 'B'); _bf16(aux, 'aux'); _bf16(D2, 'D2'); _f32(bias, 'bias')
     if epilogue == EPI_F32:
@@ -176,7 +176,7 @@ def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None
     a.ldaux = ldaux if ldaux is not None else (aux.stride(0) if aux is not None else 0)
     a.a_major, a.b_major, a.epilogue = a_major, b_major, epilogue
     a.accumulate, a.split_k, a.block_n = accumulate, split_k, block_n
-    a.dropout_p, a.seed, a.max_ctas = dropout_p, seed, max_ctas
+    a.dropout_p, a.seed, a.max_ctas, a.cta_group = dropout_p, seed, max_ctas, cta_group
     if dbg is not None:
         for i, v in enumerate(dbg):
             a.dbg[i] = v

@@ -19,6 +19,7 @@ namespace {
 constexpr int ATT_THREADS = 128;
 constexpr int NWARPS = ATT_THREADS / 32;
 constexpr int KB = 64;                      // keys (pass B / forward) or queries (pass A) per inner block
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -97,10 +98,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
     load_tile<DH>(Qs, p.q + (size_t)b * p.Lq * p.ldq + h * DH, p.ldq, p.Lq, LQP);
     load_tile<DH>(Ks, p.k + (size_t)b * p.Lk * p.ldk + h * DH, p.ldk, p.Lk, LKP);
     load_tile<DH>(Vs, p.v + (size_t)b * p.Lk * p.ldv + h * DH, p.ldv, p.Lk, LKP);
-    for (int i = threadIdx.x; i < LKP; i += ATT_THREADS) mask_s[i] = i < p.Lk ? p.mask_add[(size_t)b * p.Lk + i] : -INFINITY;
+    // scores are kept in the log2 domain: s2 = s * scale * log2(e) + mask * log2(e), p = 2^(s2 - m2)  (one MUFU.EX2 per element)
+    for (int i = threadIdx.x; i < LKP; i += ATT_THREADS) mask_s[i] = i < p.Lk ? p.mask_add[(size_t)b * p.Lk + i] * LOG2E : -INFINITY;
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float scale2 = p.scale * LOG2E;
     for (int q0 = warp * 16; q0 < LQP; q0 += NWARPS * 16) {
         uint32_t aq[DH / 16][4];
 #pragma unroll
@@ -125,9 +128,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
             float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
             for (int j = 0; j < KB / 8; ++j) {
-                const float ma = mask_s[kb + j * 8 + 2 * t], mb = mask_s[kb + j * 8 + 2 * t + 1];
-                s[j][0] = s[j][0] * p.scale + ma; s[j][1] = s[j][1] * p.scale + mb;
-                s[j][2] = s[j][2] * p.scale + ma; s[j][3] = s[j][3] * p.scale + mb;
+                const float2 mk = *reinterpret_cast<const float2*>(&mask_s[kb + j * 8 + 2 * t]);
+                s[j][0] = fmaf(s[j][0], scale2, mk.x); s[j][1] = fmaf(s[j][1], scale2, mk.y);
+                s[j][2] = fmaf(s[j][2], scale2, mk.x); s[j][3] = fmaf(s[j][3], scale2, mk.y);
                 mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
                 mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
             }
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
                 mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
                 mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
                 const float m_new = fmaxf(m_run[r], mx[r]);
-                corr[r] = __expf(m_run[r] - m_new);
+                corr[r] = fast_exp2(m_run[r] - m_new);
                 m_run[r] = m_new;
                 l_run[r] *= corr[r];
             }
@@ -145,8 +148,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
             for (int j = 0; j < DH / 8; ++j) { o[j][0] *= corr[0]; o[j][1] *= corr[0]; o[j][2] *= corr[1]; o[j][3] *= corr[1]; }
 #pragma unroll
             for (int j = 0; j < KB / 8; ++j) {
-                s[j][0] = __expf(s[j][0] - m_run[0]); s[j][1] = __expf(s[j][1] - m_run[0]);
-                s[j][2] = __expf(s[j][2] - m_run[1]); s[j][3] = __expf(s[j][3] - m_run[1]);
+                s[j][0] = fast_exp2(s[j][0] - m_run[0]); s[j][1] = fast_exp2(s[j][1] - m_run[0]);
+                s[j][2] = fast_exp2(s[j][2] - m_run[1]); s[j][3] = fast_exp2(s[j][3] - m_run[1]);
                 l_run[0] += s[j][0] + s[j][1];
                 l_run[1] += s[j][2] + s[j][3];
             }
@@ -156,10 +159,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
                 for (int j = 0; j < KB / 8; ++j) {
                     const int key = kb + j * 8 + 2 * t;
                     const uint64_t i0 = base + (uint64_t)(q0 + g) * p.Lk + key, i1 = base + (uint64_t)(q0 + g + 8) * p.Lk + key;
-                    s[j][0] = crct_keep(p.seed, i0, p.thr) ? s[j][0] * p.dscale : 0.f;
-                    s[j][1] = crct_keep(p.seed, i0 + 1, p.thr) ? s[j][1] * p.dscale : 0.f;
-                    s[j][2] = crct_keep(p.seed, i1, p.thr) ? s[j][2] * p.dscale : 0.f;
-                    s[j][3] = crct_keep(p.seed, i1 + 1, p.thr) ? s[j][3] * p.dscale : 0.f;
+                    bool k0, k1, k2, k3;
+                    crct_keep2(p.seed, i0, p.thr, k0, k1);
+                    crct_keep2(p.seed, i1, p.thr, k2, k3);
+                    s[j][0] = k0 ? s[j][0] * p.dscale : 0.f; s[j][1] = k1 ? s[j][1] * p.dscale : 0.f;
+                    s[j][2] = k2 ? s[j][2] * p.dscale : 0.f; s[j][3] = k3 ? s[j][3] * p.dscale : 0.f;
                 }
             }
 #pragma unroll
@@ -192,8 +196,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
             if (r1 < p.Lq) *reinterpret_cast<uint32_t*>(p.out + ((size_t)b * p.Lq + r1) * p.ldo + col) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
         }
         if (p.lse != nullptr && t == 0) {
-            if (r0 < p.Lq) p.lse[(size_t)blockIdx.x * p.Lq + r0] = m_run[0] + __logf(l_run[0]);
-            if (r1 < p.Lq) p.lse[(size_t)blockIdx.x * p.Lq + r1] = m_run[1] + __logf(l_run[1]);
+            if (r0 < p.Lq) p.lse[(size_t)blockIdx.x * p.Lq + r0] = (m_run[0] + __log2f(l_run[0])) * LN2;
+            if (r1 < p.Lq) p.lse[(size_t)blockIdx.x * p.Lq + r1] = (m_run[1] + __log2f(l_run[1])) * LN2;
         }
     }
 }
@@ -212,7 +216,7 @@ struct BwdParams {
     uint32_t thr; float dscale; uint64_t seed;
 };
 
-template <int DH>
+template <int DH, int PASS>     // PASS 0: this warp owns 16 keys -> dK, dV ; PASS 1: this warp owns 16 queries -> dQ
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p) {
     constexpr int LD = Smem<DH>::LD;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
     load_tile<DH>(dOs, p.dout + (size_t)b * p.Lq * p.lddo + h * DH, p.lddo, p.Lq, LQP);
     load_tile<DH>(Ks, p.k + (size_t)b * p.Lk * p.ldk + h * DH, p.ldk, p.Lk, LKP);
     load_tile<DH>(Vs, p.v + (size_t)b * p.Lk * p.ldv + h * DH, p.ldv, p.Lk, LKP);
-    for (int i = threadIdx.x; i < LKP; i += ATT_THREADS) mask_s[i] = i < p.Lk ? p.mask_add[(size_t)b * p.Lk + i] : -INFINITY;
+    for (int i = threadIdx.x; i < LKP; i += ATT_THREADS) mask_s[i] = i < p.Lk ? p.mask_add[(size_t)b * p.Lk + i] * LOG2E : -INFINITY;
     // D[q] = sum_d dO[q,d] * O[q,d]; padded queries get lse = +inf so their probabilities vanish
     for (int i = threadIdx.x; i < LQP; i += ATT_THREADS) {
         float d = 0.f, l = INFINITY;
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
 #pragma unroll
                 for (int j = 0; j < 8; ++j) d += fo[j] * fd[j];
             }
-            l = p.lse[(size_t)blockIdx.x * p.Lq + i];
+            l = p.lse[(size_t)blockIdx.x * p.Lq + i] * LOG2E;
         }
         D_s[i] = d;
         lse_s[i] = l;
@@ -254,8 +258,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const uint64_t drop_base = ((uint64_t)blockIdx.x * p.Lq) * (uint64_t)p.Lk;
+    const float scale2 = p.scale * LOG2E;
 
     // ---------------- pass A: this warp owns 16 keys -> dK, dV ----------------
+    if constexpr (PASS == 0)
     for (int k0 = warp * 16; k0 < LKP && k0 < ((p.Lk + 15) & ~15); k0 += NWARPS * 16) {
         uint32_t ak[DH / 16][4], av[DH / 16][4];
 #pragma unroll
@@ -284,15 +290,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
             // P^T, dS^T in place: st <- P^T (dropped, for dV), dpt <- dS^T * scale (for dK)
 #pragma unroll
             for (int j = 0; j < KB / 8; ++j) {
+                const int qi0 = qb + j * 8 + 2 * t;
+                const float2 ls = *reinterpret_cast<const float2*>(&lse_s[qi0]);
+                const float2 dd = *reinterpret_cast<const float2*>(&D_s[qi0]);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int qi = qb + j * 8 + 2 * t + (c & 1);
                     const int r = c >> 1;
-                    const float pr = __expf(st[j][c] * p.scale + mrow[r] - lse_s[qi]);
+                    const float pr = fast_exp2(fmaf(st[j][c], scale2, mrow[r]) - ((c & 1) ? ls.y : ls.x));
                     float fac = 1.f;
-                    if (p.thr != 0u) fac = crct_keep(p.seed, drop_base + (uint64_t)qi * p.Lk + (k0 + g + 8 * r), p.thr) ? p.dscale : 0.f;
+                    if (p.thr != 0u) fac = crct_keep(p.seed, drop_base + (uint64_t)(qi0 + (c & 1)) * p.Lk + (k0 + g + 8 * r), p.thr) ? p.dscale : 0.f;
                     st[j][c] = pr * fac;
-                    dpt[j][c] = pr * (dpt[j][c] * fac - D_s[qi]) * p.scale;
+                    dpt[j][c] = pr * (dpt[j][c] * fac - ((c & 1) ? dd.y : dd.x)) * p.scale;
                 }
             }
 #pragma unroll
@@ -330,6 +338,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
     }
 
     // ---------------- pass B: this warp owns 16 queries -> dQ ----------------
+    if constexpr (PASS == 1)
     for (int q0 = warp * 16; q0 < ((p.Lq + 15) & ~15); q0 += NWARPS * 16) {
         uint32_t aq[DH / 16][4], ado[DH / 16][4];
 #pragma unroll
@@ -358,14 +367,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
                 }
 #pragma unroll
             for (int j = 0; j < KB / 8; ++j) {
+                const int key0 = kb + j * 8 + 2 * t;
+                const float2 mk = *reinterpret_cast<const float2*>(&mask_s[key0]);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int key = kb + j * 8 + 2 * t + (c & 1);
-                    const int r = c >> 1;
-                    const float pr = __expf(s[j][c] * p.scale + mask_s[key] - lrow[r]);
-                    float fac = 1.f;
-                    if (p.thr != 0u) fac = crct_keep(p.seed, drop_base + (uint64_t)(q0 + g + 8 * r) * p.Lk + key, p.thr) ? p.dscale : 0.f;
-                    dp[j][c] = pr * (dp[j][c] * fac - drow[r]) * p.scale;
+                for (int r = 0; r < 2; ++r) {
+                    bool k0 = true, k1 = true;
+                    if (p.thr != 0u) crct_keep2(p.seed, drop_base + (uint64_t)(q0 + g + 8 * r) * p.Lk + key0, p.thr, k0, k1);
+                    const float pr0 = fast_exp2(fmaf(s[j][2 * r], scale2, mk.x) - lrow[r]);
+                    const float pr1 = fast_exp2(fmaf(s[j][2 * r + 1], scale2, mk.y) - lrow[r]);
+                    dp[j][2 * r] = pr0 * ((k0 ? dp[j][2 * r] * p.dscale : 0.f) - drow[r]) * p.scale;
+                    dp[j][2 * r + 1] = pr1 * ((k1 ? dp[j][2 * r + 1] * p.dscale : 0.f) - drow[r]) * p.scale;
                 }
             }
 #pragma unroll
@@ -416,10 +427,13 @@ int launch_bwd(const BwdParams& p, cudaStream_t st) {
     if (smem > 200 * 1024) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_bwd: Lq=%d Lk=%d do not fit in shared memory", p.Lq, p.Lk);
     static size_t configured = 0;
     if (smem > configured) {
-        CRCT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CRCT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CRCT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    attn_bwd_kernel<DH><<<p.B * p.nh, ATT_THREADS, smem, st>>>(p);
+    attn_bwd_kernel<DH, 0><<<p.B * p.nh, ATT_THREADS, smem, st>>>(p);      // dK, dV
+    CRCT_LAUNCH_CHECK();
+    attn_bwd_kernel<DH, 1><<<p.B * p.nh, ATT_THREADS, smem, st>>>(p);      // dQ
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }

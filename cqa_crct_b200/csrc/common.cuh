@@ -29,43 +29,73 @@ static inline cudaStream_t as_stream(crct_stream_t s) { return reinterpret_cast<
 int crct_num_sms();
 
 // ---------------------------------------------------------------------------------------------
-// counter-based dropout RNG: one 32-bit hash per element, identical in forward and backward.
-// keep(idx) <=> uniform(idx) >= p ; kept values are scaled by 1/(1-p)  (torch.nn.Dropout semantics;
-// reference call sites vilbert.py:315,377,422,465,506,553,596,642,649,734,741,1045).
+// counter-based dropout RNG, identical in forward and backward and never stored.
+// One 32-bit hash serves the element pair (2i, 2i+1): element idx keeps iff its 16-bit half >= threshold, with
+// threshold = round(p * 65536) (0 => keep everything); kept values are scaled by 1/(1-p)
+// (torch.nn.Dropout semantics; reference call sites vilbert.py:315,377,422,465,506,553,596,642,649,734,741,1045).
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t crct_hash32(uint64_t seed, uint64_t idx) {
-    uint32_t h = (uint32_t)idx * 0x9E3779B1u;
-    h ^= (uint32_t)(idx >> 32) * 0x85EBCA77u;
-    h ^= (uint32_t)seed;
-    h ^= h >> 16; h *= 0x85EBCA6Bu;
+__host__ __device__ __forceinline__ uint32_t crct_hash_pair(uint64_t seed, uint64_t idx) {
+    const uint64_t pair = idx >> 1;
+    uint32_t h = (uint32_t)pair * 0x9E3779B1u + (uint32_t)seed;
+    h ^= (uint32_t)(pair >> 32) * 0x85EBCA77u + (uint32_t)(seed >> 32) * 0x27D4EB2Fu;
+    h ^= h >> 15; h *= 0x85EBCA6Bu;
     h ^= h >> 13; h *= 0xC2B2AE35u;
     h ^= h >> 16;
-    h += (uint32_t)(seed >> 32);
-    h ^= h >> 15; h *= 0x2C1B3C6Du;
-    h ^= h >> 12;
     return h;
 }
-// threshold = round(p * 2^32) (0 => keep everything)
 __host__ __device__ __forceinline__ bool crct_keep(uint64_t seed, uint64_t idx, uint32_t threshold) {
-    return crct_hash32(seed, idx) >= threshold;
+    const uint32_t h = crct_hash_pair(seed, idx);
+    return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= threshold;
+}
+// decisions for idx and idx+1 (one hash when idx is even)
+__host__ __device__ __forceinline__ void crct_keep2(uint64_t seed, uint64_t idx, uint32_t threshold, bool& k0, bool& k1) {
+    const uint32_t h = crct_hash_pair(seed, idx);
+    if ((idx & 1) == 0) {
+        k0 = (h & 0xFFFFu) >= threshold;
+        k1 = (h >> 16) >= threshold;
+    } else {
+        k0 = (h >> 16) >= threshold;
+        k1 = (crct_hash_pair(seed, idx + 1) & 0xFFFFu) >= threshold;
+    }
 }
 static inline uint32_t crct_drop_threshold(float p) {
     if (p <= 0.f) return 0u;
-    double t = (double)p * 4294967296.0;
-    return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    double t = (double)p * 65536.0 + 0.5;
+    return t >= 65535.0 ? 0xFFFFu : (uint32_t)t;
 }
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // math
 // ---------------------------------------------------------------------------------------------
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below one bf16 ulp of the result): one MUFU.RCP + one
+// MUFU.EX2 instead of erff()'s ~40-instruction branchy polynomial — the GELU epilogues are issue-bound otherwise.
+// e = exp(-x^2/2) is shared between erf(x/sqrt2) = 1 - poly(t) e and the Gaussian pdf of the derivative.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
+    const float ax = fabsf(x) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    e = __expf(-ax * ax);
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erf_abs = 1.0f - poly * t * e;
+    cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+}
 __device__ __forceinline__ float gelu_f(float x) {            // vilbert.py:111-117 (exact erf form)
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    float cdf, e;
+    gelu_parts(x, cdf, e);
+    return x * cdf;
 }
 __device__ __forceinline__ float gelu_grad_f(float x) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    float cdf, e;
+    gelu_parts(x, cdf, e);
+    return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -100,6 +130,17 @@ __device__ __forceinline__ void store8_bf16(bf16* p, const float (&f)[8]) {
 __device__ __forceinline__ void load8_f32(const float* p, float (&f)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// dropout on 8 consecutive elements (4 hashes when e0 is even)
+__device__ __forceinline__ void dropout8(float (&f)[8], uint64_t seed, uint64_t e0, uint32_t thr, float scale) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        bool k0, k1;
+        crct_keep2(seed, e0 + j, thr, k0, k1);
+        f[j] = k0 ? f[j] * scale : 0.f;
+        f[j + 1] = k1 ? f[j + 1] * scale : 0.f;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,6 +214,52 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
+}
+// ---- cta_group::2 (CTA pair) forms
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are signalled on the LEADER CTA's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+// commit: arrive (once the pair's MMAs retire) on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_2cta(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}" :: "r"(bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

@@ -32,7 +32,8 @@ struct Cfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+    static constexpr int BIAS_BYTES = 2 * 256 * 4;              // per accumulator stage: the tile's bias slice
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 };
 
 struct KParams {
@@ -65,8 +66,32 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
+constexpr bool epi_uses_aux(int epi) { return epi == CRCT_EPI_BIAS_RES || epi == CRCT_EPI_DGELU; }
+
+// aux (residual / addend / pre-activation) for one row x 32 columns, fetched ahead of the accumulator load
+struct AuxRegs {
+    uint4 v[4];
+};
 template <int EPI>
-__device__ __forceinline__ void epilogue_row32(const KParams& p, int row, int col0, const uint32_t (&v)[32]) {
+__device__ __forceinline__ void prefetch_aux(const KParams& p, int row, int col0, bool valid, AuxRegs& r) {
+    if constexpr (epi_uses_aux(EPI)) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            r.v[g] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid && p.aux != nullptr && col0 + g * 8 < p.N)
+                r.v[g] = *reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col0 + g * 8);
+        }
+    }
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// one accumulator row x 32 columns: bias (from the CTA's smem copy) / GELU / dropout + residual / GELU' -> global
+template <int EPI>
+__device__ __forceinline__ void epilogue_row32(const KParams& p, int row, int col0, const uint32_t (&v)[32], const float* bias_s,
+                                               const AuxRegs& aux) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const int col = col0 + g * 8;
@@ -87,10 +112,10 @@ __device__ __forceinline__ void epilogue_row32(const KParams& p, int row, int co
         } else {
             if constexpr (EPI != CRCT_EPI_DGELU) {
                 if (p.bias != nullptr) {
-                    float b[8];
-                    load8_f32(p.bias + col, b);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] += b[j];
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + g * 8);         // smem broadcast
+                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + g * 8 + 4);
+                    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                 }
             }
             if constexpr (EPI == CRCT_EPI_BIAS_GELU) {
@@ -99,26 +124,51 @@ __device__ __forceinline__ void epilogue_row32(const KParams& p, int row, int co
                 for (int j = 0; j < 8; ++j) f[j] = gelu_f(f[j]);
             }
             if constexpr (EPI == CRCT_EPI_BIAS_RES) {
-                if (p.drop_thr != 0u) {
-                    const uint64_t e0 = (uint64_t)row * (uint64_t)p.N + (uint64_t)col;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = crct_keep(p.seed, e0 + j, p.drop_thr) ? f[j] * p.drop_scale : 0.f;
-                }
+                if (p.drop_thr != 0u) dropout8(f, p.seed, (uint64_t)row * (uint64_t)p.N + (uint64_t)col, p.drop_thr, p.drop_scale);
                 if (p.aux != nullptr) {
                     float a[8];
-                    load8_bf16(p.aux + (size_t)row * p.ldaux + col, a);
+                    unpack8(aux.v[g], a);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] += a[j];
                 }
             }
             if constexpr (EPI == CRCT_EPI_DGELU) {
                 float a[8];
-                load8_bf16(p.aux + (size_t)row * p.ldaux + col, a);
+                unpack8(aux.v[g], a);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] *= gelu_grad_f(a[j]);
             }
             store8_bf16(reinterpret_cast<bf16*>(p.D) + off, f);
         }
+    }
+}
+
+// Epilogue of one tile for one warp: stage the tile's bias slice in smem (all 8 epilogue warps, named barrier 1),
+// then per 32-column chunk: aux prefetch (one chunk ahead) -> tcgen05.ld -> fused math -> global store.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_acc, int m0, int n0, int warp, int lane, float* bias_s) {
+    const int lane_grp = warp & 3;                          // TMEM lanes [32*lane_grp, +32) are this warp's
+    const int col_half = (warp - EPI_WARP0) >> 2;
+    if constexpr (EPI != CRCT_EPI_F32 && EPI != CRCT_EPI_DGELU) {
+        if (p.bias != nullptr) {
+            const int t = (warp - EPI_WARP0) * 32 + lane;   // 0..255
+            if (t < BN) bias_s[t] = (n0 + t < p.N) ? p.bias[n0 + t] : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    const int row = m0 + lane_grp * 32 + lane;
+    const bool row_ok = row < p.M;
+    AuxRegs aux[2];
+    prefetch_aux<EPI>(p, row, n0 + col_half * (BN / 2), row_ok, aux[0]);
+#pragma unroll
+    for (int c = 0; c < BN / 64; ++c) {
+        const int cc = col_half * (BN / 2) + c * 32;
+        if (c + 1 < BN / 64) prefetch_aux<EPI>(p, row, n0 + cc + 32, row_ok, aux[(c + 1) & 1]);
+        const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cc;
+        uint32_t v[32];
+        ptx::tc_ld_32x32(taddr, v);
+        ptx::tc_wait_ld();
+        if (row_ok && n0 + cc < p.N) epilogue_row32<EPI>(p, row, n0 + cc, v, bias_s + cc, aux[c & 1]);
     }
 }
 
@@ -234,8 +284,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue =====================
-        const int lane_grp = warp & 3;                          // TMEM lanes [32*lane_grp, +32) are this warp's
-        const int col_half = (warp - EPI_WARP0) >> 2;
+        float* bias_s = reinterpret_cast<float*>(gbase + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int mn = tile / p.split_k;
@@ -245,16 +294,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            const int row = m0 + lane_grp * 32 + lane;
-#pragma unroll 1
-            for (int c = 0; c < BN / 64; ++c) {
-                const int cc = col_half * (BN / 2) + c * 32;
-                const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN + cc);
-                uint32_t v[32];
-                ptx::tc_ld_32x32(taddr, v);
-                ptx::tc_wait_ld();
-                if (row < p.M && n0 + cc < p.N) epilogue_row32<EPI>(p, row, n0 + cc, v);
-            }
+            epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m0, n0, warp, lane, bias_s + acc * 256);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
@@ -265,6 +305,174 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.  Each CTA stages its own
+// 128 rows of A and only HALF of the B tile (BN/2 rows); one tcgen05.mma.cta_group::2 (M = 256) issued by the leader
+// CTA drives both SMs' tensor cores and reads B from both shared memories.  Per SM and per k-block that is 32 KB of TMA
+// writes and 8 KB of operand reads per MMA instead of 48 KB / 12 KB — the single-CTA kernel is shared-memory-bandwidth
+// bound (96 B/clk of MMA reads + 96 B/clk of TMA writes against a 128 B/clk port), this one is not.
+//   full[s]    (leader)  : 1 arrival (leader's expect_tx of both CTAs' bytes); both CTAs' TMA complete_tx land here
+//   empty[s]   (each CTA): 1 arrival = multicast tcgen05.commit after the pair's MMAs on stage s retire
+//   tfull[i]   (each CTA): 1 arrival = multicast commit after the last k-block of a tile
+//   tempty[i]  (leader)  : 2 x 8 arrivals = every epilogue warp of both CTAs (remote mbarrier.arrive)
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct Cfg2 {
+    static constexpr int STAGES = (BN == 256) ? 6 : 8;
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
+    static constexpr int BIAS_BYTES = 2 * 256 * 4;              // per accumulator stage: the tile's bias slice
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__device__ __forceinline__ constexpr uint32_t make_idesc_2cta() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+    using C = Cfg2<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - raw_addr);
+    const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
+    auto smem_a = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
+    auto smem_b = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES + C::A_BYTES; };
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * C::STAGES + i); };
+    auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * C::STAGES + 2 + i); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        ptx::tma_prefetch_desc(&tmA);
+        ptx::tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(tfull_bar(i), 1);
+            ptx::mbar_init(tempty_bar(i), 2 * NUM_EPI_WARPS);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc_2cta(tmem_slot, C::TMEM_COLS);
+        ptx::tmem_relinquish_2cta();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();                                   // barriers of BOTH CTAs initialised before any remote arrive
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+                const int ks = tile % p.split_k;
+                const int mn = tile / p.split_k;
+                const int m0 = (mn / p.num_n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+                const int n0 = (mn % p.num_n_tiles) * BN + (int)rank * (BN / 2);
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                    const int k0 = kb * BLOCK_K;
+                    if constexpr (!A_MN) {
+                        ptx::tma_load_2d_2cta(smem_a(stage), &tmA, full_bar(stage), k0, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_M / 64; ++j)
+                            ptx::tma_load_2d_2cta(smem_a(stage) + j * (BLOCK_K * 128), &tmA, full_bar(stage), m0 + j * 64, k0);
+                    }
+                    if constexpr (!B_MN) {
+                        ptx::tma_load_2d_2cta(smem_b(stage), &tmB, full_bar(stage), k0, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 128; ++j)
+                            ptx::tma_load_2d_2cta(smem_b(stage) + j * (BLOCK_K * 128), &tmB, full_bar(stage), n0 + j * 64, k0);
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only; one instruction drives both SMs) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_2cta<BN, A_MN, B_MN>();
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+                const int ks = tile % p.split_k;
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t adesc = make_smem_desc(smem_a(stage) + k * p.a_kstep, p.a_lbo, p.a_sbo);
+                        const uint64_t bdesc = make_smem_desc(smem_b(stage) + k * p.b_kstep, p.b_lbo, p.b_sbo);
+                        ptx::tc_mma_bf16_2cta(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    ptx::tc_commit_2cta(empty_bar(stage), 0x3);       // both CTAs' producers may refill stage
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+                ptx::tc_commit_2cta(tfull_bar(acc), 0x3);             // both CTAs' epilogues may drain their half
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue (each CTA drains its own 128 accumulator rows) =====================
+        float* bias_s = reinterpret_cast<float*>(gbase + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
+        int it = 0;
+        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+            const int mn = tile / p.split_k;
+            const int m0 = (mn / p.num_n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+            const int n0 = (mn % p.num_n_tiles) * BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m0, n0, warp, lane, bias_s + acc * 256);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_remote(tempty_bar(acc), 0);
+        }
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync();                                   // the peer's smem / TMEM stay alive until the leader is done
+    ptx::tc_fence_after();
+    if (warp == 2) ptx::tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -314,6 +522,35 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int
     return CRCT_OK;
 }
 
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int grid, cudaStream_t st) {
+    auto kern = gemm_tcgen05_2cta_kernel<BN, A_MN, B_MN, EPI>;
+    static bool configured = false;       // per instantiation
+    if (!configured) {
+        CRCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM_BYTES));
+        configured = true;
+    }
+    kern<<<grid, NUM_THREADS, Cfg2<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);     // __cluster_dims__(2,1,1): grid is even
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+template <int BN>
+int dispatch2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int grid, cudaStream_t st) {
+    if (!a_mn && !b_mn) {
+        if (epi == CRCT_EPI_BIAS) return launch2<BN, false, false, CRCT_EPI_BIAS>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_BIAS_GELU) return launch2<BN, false, false, CRCT_EPI_BIAS_GELU>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_BIAS_RES) return launch2<BN, false, false, CRCT_EPI_BIAS_RES>(tmA, tmB, p, grid, st);
+    } else if (!a_mn && b_mn) {
+        if (epi == CRCT_EPI_BIAS) return launch2<BN, false, true, CRCT_EPI_BIAS>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_BIAS_RES) return launch2<BN, false, true, CRCT_EPI_BIAS_RES>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_DGELU) return launch2<BN, false, true, CRCT_EPI_DGELU>(tmA, tmB, p, grid, st);
+    } else if (a_mn && b_mn) {
+        if (epi == CRCT_EPI_F32) return launch2<BN, true, true, CRCT_EPI_F32>(tmA, tmB, p, grid, st);
+    }
+    CRCT_FAIL(CRCT_ERR_ARG, "unsupported GEMM variant a_major=%d b_major=%d epilogue=%d", a_mn, b_mn, epi);
+}
+
 template <int BN>
 int dispatch(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int grid, cudaStream_t st) {
     if (!a_mn && !b_mn) {
@@ -332,6 +569,11 @@ int dispatch(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensor
 
 }  // namespace
 
+// auto policy for cta_group == 0
+static bool crct_gemm_auto_pair(const crct_gemm_t* a) {
+    return false;
+}
+
 extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t stream) {
     if (!a || !a->A || !a->B || !a->D) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: null pointer");
     if (a->M <= 0 || a->N <= 0 || a->K <= 0) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_gemm_bf16: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
@@ -347,23 +589,30 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     const int sms = a->max_ctas > 0 ? a->max_ctas : crct_num_sms();
     if (sms <= 0) return CRCT_ERR_CUDA;
 
+    const bool pair = a->cta_group == 2 || (a->cta_group == 0 && crct_gemm_auto_pair(a));
+    const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
     int bn = a->block_n;
     if (bn == 0) {
         auto cost = [&](int b) {
-            long tiles = (long)((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + b - 1) / b);
-            return ((tiles + sms - 1) / sms) * (long)b;
+            long tiles = (long)((a->M + tile_m - 1) / tile_m) * ((a->N + b - 1) / b);
+            const long slots = pair ? sms / 2 : sms;
+            return ((tiles + slots - 1) / slots) * (long)b;
         };
-        bn = (cost(128) < cost(256)) ? 128 : 256;
-        if (f32) bn = 128;             // wgrad: more, smaller tiles + split-K fill the SMs better
+        // 128x256 tiles move 1.33x fewer operand bytes per FLOP through L2/smem than 128x128 (measured faster on every
+        // CRCT shape); 128-wide only when it removes a mostly-empty tile column or for the fp32 split-K wgrad
+        bn = (a->N <= 128 || cost(128) * 5 < cost(256) * 4) ? 128 : 256;
+        if (f32) bn = 128;
     }
     if (bn != 128 && bn != 256) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: block_n must be 0, 128 or 256");
-    const int num_m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+    const int num_m_tiles = (a->M + tile_m - 1) / tile_m;
     const int num_n_tiles = (a->N + bn - 1) / bn;
+    const int slots = pair ? sms / 2 : sms;          // concurrently resident tiles
+    if (pair && slots < 1) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: cta_group 2 needs at least 2 CTAs");
     if (split_k <= 0) {
         split_k = 1;
         if (f32 && a->accumulate) {
             const int mn = num_m_tiles * num_n_tiles;
-            split_k = sms / mn;
+            split_k = slots / mn;
             if (split_k > kb_total / 4) split_k = kb_total / 4;
             if (split_k < 1) split_k = 1;
         }
@@ -402,12 +651,17 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     if (!a->a_major) rc = make_tmap(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BLOCK_K, BLOCK_M);
     else             rc = make_tmap(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BLOCK_K);
     if (rc) return rc;
-    if (!a->b_major) rc = make_tmap(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)bn);
+    if (!a->b_major) rc = make_tmap(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)(pair ? bn / 2 : bn));
     else             rc = make_tmap(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K);
     if (rc) return rc;
 
-    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
     cudaStream_t st = as_stream(stream);
+    if (pair) {
+        const int grid2 = 2 * (p.num_tiles < slots ? p.num_tiles : slots);
+        if (bn == 256) return dispatch2<256>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid2, st);
+        return dispatch2<128>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid2, st);
+    }
+    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
     if (bn == 256) return dispatch<256>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
     return dispatch<128>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
 }

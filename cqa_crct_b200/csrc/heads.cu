@@ -10,7 +10,7 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, LIN_THREADS = 256;
+constexpr int BM = 64, BN = 64, BK = 32, LIN_THREADS = 256;
 
 struct LinParams {
     const float* A; long long sa_m, sa_k;     // A(m,k) = A[m*sa_m + k*sa_k]
@@ -24,9 +24,12 @@ struct LinParams {
     int accumulate;
 };
 
+// 64x64 output tile per CTA, 4x4 per thread, K in slabs of 32 with the next slab's global loads issued before the
+// current slab's FMAs (the problems are tiny — M = batch — so the kernel is latency- not throughput-bound)
 __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinParams p) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
+    constexpr int PER = (BM * BK) / LIN_THREADS;       // 8 elements of A and of B per thread per slab
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     float acc[4][4];
@@ -35,31 +38,34 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinParams
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const bool a_kfast = p.sa_k == 1, b_nfast = p.sb_n == 1;
-    for (int k0 = 0; k0 < p.K; k0 += BK) {
+    float ra[PER], rb[PER];
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < (BM * BK) / LIN_THREADS; ++i) {
+        for (int i = 0; i < PER; ++i) {
             const int e = tid + i * LIN_THREADS;
             const int kk = a_kfast ? (e % BK) : (e / BM), m = a_kfast ? (e / BK) : (e % BM);
-            float v = 0.f;
-            if (m0 + m < p.M && k0 + kk < p.K) v = p.A[(long long)(m0 + m) * p.sa_m + (long long)(k0 + kk) * p.sa_k];
-            As[kk][m] = v;
+            ra[i] = (m0 + m < p.M && k0 + kk < p.K) ? p.A[(long long)(m0 + m) * p.sa_m + (long long)(k0 + kk) * p.sa_k] : 0.f;
+            const int kb = b_nfast ? (e / BN) : (e % BK), n = b_nfast ? (e % BN) : (e / BK);
+            rb[i] = (n0 + n < p.N && k0 + kb < p.K) ? p.B[(long long)(k0 + kb) * p.sb_k + (long long)(n0 + n) * p.sb_n] : 0.f;
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
 #pragma unroll
-        for (int i = 0; i < (BN * BK) / LIN_THREADS; ++i) {
+        for (int i = 0; i < PER; ++i) {
             const int e = tid + i * LIN_THREADS;
-            const int kk = b_nfast ? (e / BN) : (e % BK), n = b_nfast ? (e % BN) : (e / BK);
-            float v = 0.f;
-            if (n0 + n < p.N && k0 + kk < p.K) v = p.B[(long long)(k0 + kk) * p.sb_k + (long long)(n0 + n) * p.sb_n];
-            Bs[kk][n] = v;
+            const int kk = a_kfast ? (e % BK) : (e / BM), m = a_kfast ? (e / BK) : (e % BM);
+            As[kk][m] = ra[i];
+            const int kb = b_nfast ? (e / BN) : (e % BK), n = b_nfast ? (e % BN) : (e / BK);
+            Bs[kb][n] = rb[i];
         }
         __syncthreads();
+        if (k0 + BK < p.K) fetch(k0 + BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll

@@ -47,10 +47,8 @@ __device__ __forceinline__ void ln_write(const Row& z, int nchunks, int lane, fl
             load8_f32(gamma + ch * 8, g);
             load8_f32(beta + ch * 8, b);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                o[j] = (z.v[c][j] - mean) * rstd * g[j] + b[j];
-                if (thr != 0u) o[j] = crct_keep(seed, row_idx0 + ch * 8 + j, thr) ? o[j] * scale : 0.f;
-            }
+            for (int j = 0; j < 8; ++j) o[j] = (z.v[c][j] - mean) * rstd * g[j] + b[j];
+            if (thr != 0u) dropout8(o, seed, row_idx0 + ch * 8, thr, scale);
             store8_bf16(y_row + ch * 8, o);
         }
     }
@@ -95,92 +93,99 @@ layernorm_fwd_kernel(const bf16* __restrict__ z, const float* __restrict__ gamma
 
 // dz = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)), dxh = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dbias += sum_rows dzm (optional)
-// dy may carry an input dropout mask (seed_in), dzm = dz * keep(seed_out) * scale (optional second output)
-__global__ void __launch_bounds__(ROW_THREADS)
+// dy may carry an input dropout mask (seed_in), dzm = dz * keep(seed_out) * scale (optional second output).
+// The three column sums are accumulated in per-warp shared-memory rows (registers hold only the current row), so two
+// CTAs fit per SM; they meet in one atomic per column per CTA at the end.
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS, 2)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, const float* __restrict__ gamma, bf16* __restrict__ dz,
                      bf16* __restrict__ dzm, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                      int rows, int H, uint32_t thr_in, float scale_in, uint64_t seed_in, uint32_t thr_out, float scale_out,
                      uint64_t seed_out) {
-    extern __shared__ float red[];                       // [8 warps][H]
+    extern __shared__ __align__(16) float acc_s[];       // [3][8 warps][H]
+    constexpr int NW = ROW_THREADS / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = H >> 3;
-    Row ag, ab, abias;
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { ag.v[c][j] = 0.f; ab.v[c][j] = 0.f; abias.v[c][j] = 0.f; }
-
-    for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < rows; row += gridDim.x * (ROW_THREADS / 32)) {
+    float* my_g = acc_s + (size_t)(0 * NW + warp) * H;
+    float* my_b = acc_s + (size_t)(1 * NW + warp) * H;
+    float* my_d = acc_s + (size_t)(2 * NW + warp) * H;
+    for (int i = lane; i < H; i += 32) { my_g[i] = 0.f; my_b[i] = 0.f; my_d[i] = 0.f; }
+    __syncwarp();
+    const float invH = 1.0f / (float)H;
+    for (int row = blockIdx.x * NW + warp; row < rows; row += gridDim.x * NW) {
         const float mean = mean_in[row], rstd = rstd_in[row];
-        Row g, x;                                         // g: dy then dxh ; x: xhat
-        float s1 = 0.f, s2 = 0.f;
+        float g[NCH][8], x[NCH][8];                      // g: dy then dxh ; x: z then xhat
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
+        for (int c = 0; c < NCH; ++c) {                  // all loads of the row first (memory-level parallelism)
             const int ch = lane + 32 * c;
             if (ch < nchunks) {
-                float gm[8];
-                load8_bf16(dy + (size_t)row * H + ch * 8, g.v[c]);
-                load8_bf16(z + (size_t)row * H + ch * 8, x.v[c]);
-                load8_f32(gamma + ch * 8, gm);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float d = g.v[c][j];
-                    if (thr_in != 0u) d = crct_keep(seed_in, (uint64_t)row * H + ch * 8 + j, thr_in) ? d * scale_in : 0.f;
-                    const float xh = (x.v[c][j] - mean) * rstd;
-                    ag.v[c][j] += d * xh;
-                    ab.v[c][j] += d;
-                    const float dxh = d * gm[j];
-                    s1 += dxh;
-                    s2 += dxh * xh;
-                    g.v[c][j] = dxh;
-                    x.v[c][j] = xh;
-                }
+                load8_bf16(dy + (size_t)row * H + ch * 8, g[c]);
+                load8_bf16(z + (size_t)row * H + ch * 8, x[c]);
             }
         }
-        const float m1 = warp_sum(s1) / (float)H, m2 = warp_sum(s2) / (float)H;
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
+        for (int c = 0; c < NCH; ++c) {
+            const int ch = lane + 32 * c;
+            if (ch < nchunks) {
+                float gm[8], pg[8], pb[8];
+                load8_f32(gamma + ch * 8, gm);
+                load8_f32(my_g + ch * 8, pg);
+                load8_f32(my_b + ch * 8, pb);
+                if (thr_in != 0u) dropout8(g[c], seed_in, (uint64_t)row * H + ch * 8, thr_in, scale_in);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = g[c][j];
+                    const float xh = (x[c][j] - mean) * rstd;
+                    pg[j] = fmaf(d, xh, pg[j]);
+                    pb[j] += d;
+                    const float dxh = d * gm[j];
+                    s1 += dxh;
+                    s2 = fmaf(dxh, xh, s2);
+                    g[c][j] = dxh;
+                    x[c][j] = xh;
+                }
+                *reinterpret_cast<float4*>(my_g + ch * 8) = make_float4(pg[0], pg[1], pg[2], pg[3]);
+                *reinterpret_cast<float4*>(my_g + ch * 8 + 4) = make_float4(pg[4], pg[5], pg[6], pg[7]);
+                *reinterpret_cast<float4*>(my_b + ch * 8) = make_float4(pb[0], pb[1], pb[2], pb[3]);
+                *reinterpret_cast<float4*>(my_b + ch * 8 + 4) = make_float4(pb[4], pb[5], pb[6], pb[7]);
+            }
+        }
+        const float m1 = warp_sum(s1) * invH, m2 = warp_sum(s2) * invH;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
             const int ch = lane + 32 * c;
             if (ch < nchunks) {
                 float o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = rstd * (g.v[c][j] - m1 - x.v[c][j] * m2);
+                for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] - m1 - x[c][j] * m2);
                 store8_bf16(dz + (size_t)row * H + ch * 8, o);
                 if (dzm != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        o[j] = crct_keep(seed_out, (uint64_t)row * H + ch * 8 + j, thr_out) ? o[j] * scale_out : 0.f;
+                    dropout8(o, seed_out, (uint64_t)row * H + ch * 8, thr_out, scale_out);
                     store8_bf16(dzm + (size_t)row * H + ch * 8, o);
                 }
                 if (dbias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) abias.v[c][j] += o[j];
+                    float pd[8];
+                    load8_f32(my_d + ch * 8, pd);
+                    *reinterpret_cast<float4*>(my_d + ch * 8) = make_float4(pd[0] + o[0], pd[1] + o[1], pd[2] + o[2], pd[3] + o[3]);
+                    *reinterpret_cast<float4*>(my_d + ch * 8 + 4) = make_float4(pd[4] + o[4], pd[5] + o[5], pd[6] + o[6], pd[7] + o[7]);
                 }
             }
         }
     }
-    // cross-warp reduction of the three column sums, one array at a time through smem
-    for (int which = 0; which < 3; ++which) {
-        float* out = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
-        if (out == nullptr) continue;                      // uniform across the CTA
-        const Row& a = which == 0 ? ag : (which == 1 ? ab : abias);
-        __syncthreads();
+    __syncthreads();
+    for (int col = threadIdx.x; col < H; col += ROW_THREADS) {
+        float sg = 0.f, sb = 0.f, sd = 0.f;
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-            const int ch = lane + 32 * c;
-            if (ch < nchunks) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) red[warp * H + ch * 8 + j] = a.v[c][j];
-            }
+        for (int w = 0; w < NW; ++w) {
+            sg += acc_s[(size_t)(0 * NW + w) * H + col];
+            sb += acc_s[(size_t)(1 * NW + w) * H + col];
+            sd += acc_s[(size_t)(2 * NW + w) * H + col];
         }
-        __syncthreads();
-        for (int col = threadIdx.x; col < H; col += ROW_THREADS) {
-            float s = 0.f;
-#pragma unroll
-            for (int w = 0; w < ROW_THREADS / 32; ++w) s += red[w * H + col];
-            atomicAdd(out + col, s);
-        }
+        if (dgamma != nullptr) atomicAdd(dgamma + col, sg);
+        if (dbeta != nullptr) atomicAdd(dbeta + col, sb);
+        if (dbias != nullptr) atomicAdd(dbias + col, sd);
     }
 }
 
@@ -192,7 +197,18 @@ colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows, int
     const int col = blockIdx.x * 256 + lane * 8;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (col < N) {
-        for (int row = blockIdx.y * (ROW_THREADS / 32) + warp; row < rows; row += gridDim.y * (ROW_THREADS / 32)) {
+        const int stride = gridDim.y * (ROW_THREADS / 32);
+        int row = blockIdx.y * (ROW_THREADS / 32) + warp;
+        for (; row + 3 * stride < rows; row += 4 * stride) {          // 4 independent 16-byte loads in flight
+            float f0[8], f1[8], f2[8], f3[8];
+            load8_bf16(x + (size_t)row * ld + col, f0);
+            load8_bf16(x + (size_t)(row + stride) * ld + col, f1);
+            load8_bf16(x + (size_t)(row + 2 * stride) * ld + col, f2);
+            load8_bf16(x + (size_t)(row + 3 * stride) * ld + col, f3);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+        }
+        for (; row < rows; row += stride) {
             float f[8];
             load8_bf16(x + (size_t)row * ld + col, f);
 #pragma unroll
@@ -535,15 +551,29 @@ extern "C" CRCT_API int crct_layernorm_bwd(const crct_ln_bwd_t* a, crct_stream_t
     if (!a || !a->dy || !a->z || !a->mean || !a->rstd || !a->gamma || !a->dz) CRCT_FAIL(CRCT_ERR_ARG, "crct_layernorm_bwd: null pointer");
     if (int rc = check_row_width(a->H, "crct_layernorm_bwd")) return rc;
     if (a->rows <= 0) return CRCT_OK;
-    int grid = crct_num_sms();
+    int grid = 2 * crct_num_sms();
     if (grid > row_grid(a->rows)) grid = row_grid(a->rows);
-    const size_t smem = (size_t)(ROW_THREADS / 32) * a->H * sizeof(float);
+    const size_t smem = (size_t)3 * (ROW_THREADS / 32) * a->H * sizeof(float);
     const bool dzm = a->dzm != nullptr && a->p_out > 0.f;
-    layernorm_bwd_kernel<<<grid, ROW_THREADS, smem, as_stream(s)>>>(
-        reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), a->mean, a->rstd, a->gamma,
-        reinterpret_cast<bf16*>(a->dz), dzm ? reinterpret_cast<bf16*>(a->dzm) : nullptr, a->dgamma, a->dbeta, a->dbias,
-        a->rows, a->H, crct_drop_threshold(a->p_in), a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, a->seed_in,
-        crct_drop_threshold(a->p_out), a->p_out > 0.f ? 1.f / (1.f - a->p_out) : 1.f, a->seed_out);
+    const int nch = (a->H / 8 + 31) / 32;
+    auto launch = [&](auto kern) {
+        static bool configured[MAXC + 1] = {};    // all instantiations share one pointer type: track per chunk count
+        if (!configured[nch]) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (ROW_THREADS / 32) * MAXC * 256 * (int)sizeof(float));
+            configured[nch] = true;
+        }
+        kern<<<grid, ROW_THREADS, smem, as_stream(s)>>>(
+            reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), a->mean, a->rstd, a->gamma,
+            reinterpret_cast<bf16*>(a->dz), dzm ? reinterpret_cast<bf16*>(a->dzm) : nullptr, a->dgamma, a->dbeta, a->dbias,
+            a->rows, a->H, crct_drop_threshold(a->p_in), a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, a->seed_in,
+            crct_drop_threshold(a->p_out), a->p_out > 0.f ? 1.f / (1.f - a->p_out) : 1.f, a->seed_out);
+    };
+    switch (nch) {
+        case 1: launch(layernorm_bwd_kernel<1>); break;
+        case 2: launch(layernorm_bwd_kernel<2>); break;
+        case 3: launch(layernorm_bwd_kernel<3>); break;
+        default: launch(layernorm_bwd_kernel<4>); break;
+    }
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }

@@ -76,6 +76,7 @@ typedef struct {
     float dropout_p;    /* CRCT_EPI_BIAS_RES: 0 = off */
     uint64_t seed;      /* dropout stream; element counter = m * N + n */
     int32_t max_ctas;   /* 0 = one persistent CTA per SM; else cap (tests) */
+    int32_t cta_group;  /* 0 = choose; 1 = one CTA per 128 x BN tile; 2 = CTA pair (tcgen05 cta_group::2) per 256 x BN tile */
     int32_t dbg[7];     /* descriptor overrides for bring-up; must be 0 in production */
 } crct_gemm_t;
 

@@ -97,22 +97,31 @@ def test_reference_init_distributions():
 
 
 def test_dropout_hash_reference_values_and_rate():
-    """The counter-based keep/drop decision is a pure function of (seed, index); pin it so forward and backward
-    kernels (and future refactors) cannot drift apart."""
-    def h(seed, idx):
-        M = 0xFFFFFFFF
-        x = (idx & M) * 0x9E3779B1 & M
-        x ^= ((idx >> 32) & M) * 0x85EBCA77 & M
-        x ^= seed & M
-        x ^= x >> 16; x = x * 0x85EBCA6B & M
-        x ^= x >> 13; x = x * 0xC2B2AE35 & M
-        x ^= x >> 16
-        x = (x + (seed >> 32)) & M
-        x ^= x >> 15; x = x * 0x2C1B3C6D & M
-        x ^= x >> 12
-        return x
-    vals = [h(12345, i) for i in range(20000)]
-    thr = int(0.1 * 2 ** 32)
-    rate = sum(v >= thr for v in vals) / len(vals)
-    assert abs(rate - 0.9) < 0.01
-    assert len(set(vals)) > 19990
+    """The counter-based keep/drop decision is a pure function of (seed, index) — csrc/common.cuh `crct_keep`: one
+    32-bit hash per element pair, 16 bits per element.  Restated here so forward and backward kernels (and future
+    refactors) cannot drift apart; the GPU tests check fwd/bwd mask agreement on the device."""
+    M = 0xFFFFFFFF
+
+    def hpair(seed, idx):
+        pair = idx >> 1
+        h = ((pair & M) * 0x9E3779B1 + (seed & M)) & M
+        h ^= (((pair >> 32) & M) * 0x85EBCA77 + ((seed >> 32) & M) * 0x27D4EB2F) & M
+        h ^= h >> 15; h = h * 0x85EBCA6B & M
+        h ^= h >> 13; h = h * 0xC2B2AE35 & M
+        h ^= h >> 16
+        return h
+
+    def keep(seed, idx, thr):
+        h = hpair(seed, idx)
+        return ((h >> 16) if idx & 1 else (h & 0xFFFF)) >= thr
+
+    for p in (0.1, 0.5):
+        thr = int(p * 65536 + 0.5)
+        for seed in (12345, 0xDEADBEEFCAFE1234):
+            n = 40000
+            rate = sum(keep(seed, i, thr) for i in range(n)) / n
+            assert abs(rate - (1 - p)) < 0.01, (p, seed, rate)
+    # the two halves of a pair and neighbouring pairs are uncorrelated enough for dropout
+    thr = int(0.5 * 65536 + 0.5)
+    both = sum(keep(7, 2 * i, thr) and keep(7, 2 * i + 1, thr) for i in range(20000)) / 20000
+    assert abs(both - 0.25) < 0.02

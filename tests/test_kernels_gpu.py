@@ -32,47 +32,50 @@ GEMM_SHAPES = [(128, 128, 64), (200, 192, 192), (992, 576, 192), (1000, 768, 307
 
 @pytest.mark.parametrize('M,N,K', GEMM_SHAPES)
 @pytest.mark.parametrize('bn', [0, 128, 256])
-def test_gemm_forward_epilogues(M, N, K, bn):
+@pytest.mark.parametrize('cg', [1, 2])
+def test_gemm_forward_epilogues(M, N, K, bn, cg):
     torch.manual_seed(M + N + K)
     A, B = bf(torch.randn(M, K, device=DEV) * 0.5), bf(torch.randn(N, K, device=DEV) * 0.5)
     bias, aux = torch.randn(N, device=DEV), bf(torch.randn(M, N, device=DEV))
     ref = A.float() @ B.float().t() + bias
     D = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-    L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, block_n=bn)
+    L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, block_n=bn, cta_group=cg)
     assert relmax(D.float(), ref) < 6e-3
     D2 = torch.empty_like(D)
-    L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_GELU, D2=D2, block_n=bn)
+    L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_GELU, D2=D2, block_n=bn, cta_group=cg)
     assert relmax(D2.float(), ref) < 6e-3
     assert relmax(D.float(), torch.nn.functional.gelu(ref)) < 6e-3
-    L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES, aux=aux, block_n=bn)
+    L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES, aux=aux, block_n=bn, cta_group=cg)
     assert relmax(D.float(), ref + aux.float()) < 6e-3
 
 
+@pytest.mark.parametrize('cg', [1, 2])
 @pytest.mark.parametrize('M,N,K', [(128, 128, 64), (1000, 192, 576), (9920, 768, 2304), (3520, 1024, 3072)])
-def test_gemm_dgrad_forms(M, N, K):
+def test_gemm_dgrad_forms(M, N, K, cg):
     """dx = dy W with W stored [K_gemm, N_gemm] = [out, in] (b_major = 1)."""
     torch.manual_seed(1)
     dy, W = bf(torch.randn(M, K, device=DEV) * 0.5), bf(torch.randn(K, N, device=DEV) * 0.5)
     aux = bf(torch.randn(M, N, device=DEV))
     ref = dy.float() @ W.float()
     D = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-    L.gemm(dy, W, D, M=M, N=N, K=K, b_major=1)
+    L.gemm(dy, W, D, M=M, N=N, K=K, b_major=1, cta_group=cg)
     assert relmax(D.float(), ref) < 6e-3
-    L.gemm(dy, W, D, M=M, N=N, K=K, b_major=1, epilogue=L.EPI_BIAS_RES, aux=aux)
+    L.gemm(dy, W, D, M=M, N=N, K=K, b_major=1, epilogue=L.EPI_BIAS_RES, aux=aux, cta_group=cg)
     assert relmax(D.float(), ref + aux.float()) < 6e-3
-    L.gemm(dy, W, D, M=M, N=N, K=K, b_major=1, epilogue=L.EPI_DGELU, aux=aux)
+    L.gemm(dy, W, D, M=M, N=N, K=K, b_major=1, epilogue=L.EPI_DGELU, aux=aux, cta_group=cg)
     assert relmax(D.float(), ref * O.gelu_grad(aux.float())) < 6e-3
 
 
 @pytest.mark.parametrize('rows,No,Ki', [(128, 128, 64), (1000, 576, 192), (9920, 768, 768), (9920, 3072, 768), (3520, 1024, 1024), (992, 768, 3072)])
 @pytest.mark.parametrize('split', [0, 1, 5])
-def test_gemm_wgrad_accumulates_fp32(rows, No, Ki, split):
+@pytest.mark.parametrize('cg', [1, 2])
+def test_gemm_wgrad_accumulates_fp32(rows, No, Ki, split, cg):
     """dW[out,in] += dy^T x with both operands MN-major; split-K partial sums meet through fp32 atomics."""
     torch.manual_seed(2)
     dy, x = bf(torch.randn(rows, No, device=DEV) * 0.5), bf(torch.randn(rows, Ki, device=DEV) * 0.5)
     ref = dy.float().t() @ x.float()
     dW = torch.full((No, Ki), 1.0, device=DEV)
-    L.gemm(dy, x, dW, M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, split_k=split)
+    L.gemm(dy, x, dW, M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, split_k=split, cta_group=cg)
     assert relmax(dW - 1.0, ref) < 1e-4
 
 
@@ -85,6 +88,8 @@ def test_gemm_persistent_schedule_and_dropout():
     for bn in (128, 256):
         D = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
         L.gemm(A, B, D, M=M, N=N, K=K, block_n=bn, max_ctas=3)
+        assert relmax(D.float(), ref) < 6e-3
+        L.gemm(A, B, D, M=M, N=N, K=K, block_n=bn, max_ctas=4, cta_group=2)       # 2 clusters, several tiles each
         assert relmax(D.float(), ref) < 6e-3
     D = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
     L.gemm(A, B, D, M=M, N=N, K=K, epilogue=L.EPI_BIAS_RES, dropout_p=0.25, seed=77)

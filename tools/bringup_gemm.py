@@ -120,16 +120,16 @@ def perf():
     for (M, N, K) in shapes:
         A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
         D = torch.empty(M, N, device=dev).bfloat16(); bias = torch.zeros(N, device=dev)
-        for bn in (128, 256):
+        for bn, cg in ((128, 1), (256, 1), (128, 2), (256, 2)):
             for _ in range(3):
-                L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, block_n=bn)
+                L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, block_n=bn, cta_group=cg)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             for _ in range(20):
-                L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, block_n=bn)
+                L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, block_n=bn, cta_group=cg)
             e.record(); torch.cuda.synchronize()
             ms = s.elapsed_time(e) / 20
-            print(f'perf M={M} N={N} K={K} BN={bn}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s', flush=True)
+            print(f'perf M={M} N={N} K={K} BN={bn} cta_group={cg}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s', flush=True)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3): torch.matmul(A, B.t())
         s.record()
