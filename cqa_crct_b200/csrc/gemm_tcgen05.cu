@@ -33,7 +33,7 @@ struct Cfg {
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
     static constexpr int BIAS_BYTES = 2 * 256 * 4;              // per accumulator stage: the tile's bias slice
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 20480 + 1024;   // + OUT_STAGE_BYTES
 };
 
 struct KParams {
@@ -88,28 +88,57 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-// one accumulator row x 32 columns: bias (from the CTA's smem copy) / GELU / dropout + residual / GELU' -> global
+constexpr int OUT_PITCH = 80;                      // bytes per staged row: 64 B of bf16 + 16 B pad (conflict-free 128-bit stores)
+constexpr int OUT_STAGE_BYTES = NUM_EPI_WARPS * 32 * OUT_PITCH;
+
+// Warp-cooperative store of a 32-row x 32-column bf16 block: every lane holds one row (4 x 16 B); the block is
+// transposed through the warp's smem staging area so that one store instruction writes 8 rows x 64 contiguous bytes
+// (full 32-byte sectors) instead of 32 rows x 16 bytes.
+__device__ __forceinline__ void store_block_bf16(bf16* __restrict__ dst, int ld, int row0, int col0, int M, int N, int lane,
+                                                 const uint4 (&o)[4], uint8_t* stage) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stage + lane * OUT_PITCH + g * 16) = o[g];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = lane + 32 * i, r = q >> 2, seg = q & 3;
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + r * OUT_PITCH + seg * 16);
+        const int row = row0 + r, col = col0 + seg * 8;
+        if (row < M && col < N) *reinterpret_cast<uint4*>(dst + (size_t)row * ld + col) = v;
+    }
+    __syncwarp();
+}
+
+// one accumulator row x 32 columns per lane: bias (smem copy) / GELU / dropout + residual / GELU' -> global
 template <int EPI>
-__device__ __forceinline__ void epilogue_row32(const KParams& p, int row, int col0, const uint32_t (&v)[32], const float* bias_s,
-                                               const AuxRegs& aux) {
+__device__ __forceinline__ void epilogue_chunk(const KParams& p, int row0, int lane, int col0, const uint32_t (&v)[32],
+                                               const float* bias_s, const AuxRegs& aux, uint8_t* stage) {
+    const int row = row0 + lane;
+    if constexpr (EPI == CRCT_EPI_F32) {
+        if (row >= p.M) return;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const int col = col0 + g * 8;
-        if (col >= p.N) break;                       // N % 8 == 0: a group is entirely in or out
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-        const size_t off = (size_t)row * p.ldd + col;
-        if constexpr (EPI == CRCT_EPI_F32) {
-            float* d = reinterpret_cast<float*>(p.D) + off;
+        for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col >= p.N) break;
+            float* d = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col;
+            const float f0 = __uint_as_float(v[g * 8]), f1 = __uint_as_float(v[g * 8 + 1]), f2 = __uint_as_float(v[g * 8 + 2]),
+                        f3 = __uint_as_float(v[g * 8 + 3]), f4 = __uint_as_float(v[g * 8 + 4]), f5 = __uint_as_float(v[g * 8 + 5]),
+                        f6 = __uint_as_float(v[g * 8 + 6]), f7 = __uint_as_float(v[g * 8 + 7]);
             if (p.accumulate) {
-                ptx::red_add_f32x4(d, f[0], f[1], f[2], f[3]);
-                ptx::red_add_f32x4(d + 4, f[4], f[5], f[6], f[7]);
+                ptx::red_add_f32x4(d, f0, f1, f2, f3);
+                ptx::red_add_f32x4(d + 4, f4, f5, f6, f7);
             } else {
-                *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                *reinterpret_cast<float4*>(d) = make_float4(f0, f1, f2, f3);
+                *reinterpret_cast<float4*>(d + 4) = make_float4(f4, f5, f6, f7);
             }
-        } else {
+        }
+    } else {
+        uint4 o[4], o2[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
             if constexpr (EPI != CRCT_EPI_DGELU) {
                 if (p.bias != nullptr) {
                     const float4 b0 = *reinterpret_cast<const float4*>(bias_s + g * 8);         // smem broadcast
@@ -119,12 +148,13 @@ __device__ __forceinline__ void epilogue_row32(const KParams& p, int row, int co
                 }
             }
             if constexpr (EPI == CRCT_EPI_BIAS_GELU) {
-                if (p.D2 != nullptr) store8_bf16(reinterpret_cast<bf16*>(p.D2) + off, f);
+                o2[g] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = gelu_f(f[j]);
             }
             if constexpr (EPI == CRCT_EPI_BIAS_RES) {
-                if (p.drop_thr != 0u) dropout8(f, p.seed, (uint64_t)row * (uint64_t)p.N + (uint64_t)col, p.drop_thr, p.drop_scale);
+                if (p.drop_thr != 0u)
+                    dropout8(f, p.seed, (uint64_t)row * (uint64_t)p.N + (uint64_t)(col0 + g * 8), p.drop_thr, p.drop_scale);
                 if (p.aux != nullptr) {
                     float a[8];
                     unpack8(aux.v[g], a);
@@ -138,17 +168,23 @@ __device__ __forceinline__ void epilogue_row32(const KParams& p, int row, int co
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] *= gelu_grad_f(a[j]);
             }
-            store8_bf16(reinterpret_cast<bf16*>(p.D) + off, f);
+            o[g] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
+        if constexpr (EPI == CRCT_EPI_BIAS_GELU) {
+            if (p.D2 != nullptr) store_block_bf16(reinterpret_cast<bf16*>(p.D2), p.ldd, row0, col0, p.M, p.N, lane, o2, stage);
+        }
+        store_block_bf16(reinterpret_cast<bf16*>(p.D), p.ldd, row0, col0, p.M, p.N, lane, o, stage);
     }
 }
 
 // Epilogue of one tile for one warp: stage the tile's bias slice in smem (all 8 epilogue warps, named barrier 1),
-// then per 32-column chunk: aux prefetch (one chunk ahead) -> tcgen05.ld -> fused math -> global store.
+// then per 32-column chunk: aux prefetch (one chunk ahead) -> tcgen05.ld -> fused math -> coalesced global store.
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_acc, int m0, int n0, int warp, int lane, float* bias_s) {
+__device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_acc, int m0, int n0, int warp, int lane, float* bias_s,
+                                              uint8_t* stage_all) {
     const int lane_grp = warp & 3;                          // TMEM lanes [32*lane_grp, +32) are this warp's
     const int col_half = (warp - EPI_WARP0) >> 2;
+    uint8_t* stage = stage_all + (warp - EPI_WARP0) * 32 * OUT_PITCH;
     if constexpr (EPI != CRCT_EPI_F32 && EPI != CRCT_EPI_DGELU) {
         if (p.bias != nullptr) {
             const int t = (warp - EPI_WARP0) * 32 + lane;   // 0..255
@@ -156,7 +192,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    const int row = m0 + lane_grp * 32 + lane;
+    const int row0 = m0 + lane_grp * 32;
+    const int row = row0 + lane;
     const bool row_ok = row < p.M;
     AuxRegs aux[2];
     prefetch_aux<EPI>(p, row, n0 + col_half * (BN / 2), row_ok, aux[0]);
@@ -168,7 +205,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
         uint32_t v[32];
         ptx::tc_ld_32x32(taddr, v);
         ptx::tc_wait_ld();
-        if (row_ok && n0 + cc < p.N) epilogue_row32<EPI>(p, row, n0 + cc, v, bias_s + cc, aux[c & 1]);
+        if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row0, lane, n0 + cc, v, bias_s + cc, aux[c & 1], stage);     // warp-uniform
     }
 }
 
@@ -294,7 +331,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m0, n0, warp, lane, bias_s + acc * 256);
+            epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m0, n0, warp, lane, bias_s + acc * 256,
+                                   reinterpret_cast<uint8_t*>(bias_s + 512));
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
@@ -327,7 +365,7 @@ struct Cfg2 {
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
     static constexpr int BIAS_BYTES = 2 * 256 * 4;              // per accumulator stage: the tile's bias slice
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 20480 + 1024;   // + OUT_STAGE_BYTES
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -462,7 +500,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m0, n0, warp, lane, bias_s + acc * 256);
+            epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m0, n0, warp, lane, bias_s + acc * 256,
+                                   reinterpret_cast<uint8_t*>(bias_s + 512));
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_remote(tempty_bar(acc), 0);
@@ -571,7 +610,9 @@ int dispatch(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensor
 
 // auto policy for cta_group == 0
 static bool crct_gemm_auto_pair(const crct_gemm_t* a) {
-    return false;
+    // measured on B200 (profiles/r01_gemm_shapes.log): the CTA pair wins ~4 % once there are >= 8 tile columns to
+    // share; narrower outputs quantise worse on 256-row tiles
+    return a->epilogue != CRCT_EPI_F32 && a->N >= 2048 && a->M >= 1024;
 }
 
 extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t stream) {
