@@ -261,6 +261,15 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
         "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
         "}" :: "r"(bar), "r"(cta) : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

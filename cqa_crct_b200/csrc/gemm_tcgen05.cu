@@ -20,9 +20,10 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;           // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;       // 4 per SMSP: the fused epilogues are issue/latency-bound with fewer
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
+constexpr int EPI_COLS = 16;            // accumulator columns per epilogue step
 
 template <int BN>
 struct Cfg {
@@ -33,7 +34,7 @@ struct Cfg {
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
     static constexpr int BIAS_BYTES = 2 * 256 * 4;              // per accumulator stage: the tile's bias slice
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 20480 + 1024;   // + OUT_STAGE_BYTES
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 24576 + 1024;   // + OUT_STAGE_BYTES
 };
 
 struct KParams {
@@ -68,15 +69,15 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 
 constexpr bool epi_uses_aux(int epi) { return epi == CRCT_EPI_BIAS_RES || epi == CRCT_EPI_DGELU; }
 
-// aux (residual / addend / pre-activation) for one row x 32 columns, fetched ahead of the accumulator load
+// aux (residual / addend / pre-activation) for one row x EPI_COLS columns, fetched one step ahead of the accumulator
 struct AuxRegs {
-    uint4 v[4];
+    uint4 v[EPI_COLS / 8];
 };
 template <int EPI>
 __device__ __forceinline__ void prefetch_aux(const KParams& p, int row, int col0, bool valid, AuxRegs& r) {
     if constexpr (epi_uses_aux(EPI)) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < EPI_COLS / 8; ++g) {
             r.v[g] = make_uint4(0u, 0u, 0u, 0u);
             if (valid && p.aux != nullptr && col0 + g * 8 < p.N)
                 r.v[g] = *reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col0 + g * 8);
@@ -88,20 +89,20 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-constexpr int OUT_PITCH = 80;                      // bytes per staged row: 64 B of bf16 + 16 B pad (conflict-free 128-bit stores)
+constexpr int OUT_PITCH = EPI_COLS * 2 + 16;       // bytes per staged row: 32 B of bf16 + 16 B pad
 constexpr int OUT_STAGE_BYTES = NUM_EPI_WARPS * 32 * OUT_PITCH;
 
-// Warp-cooperative store of a 32-row x 32-column bf16 block: every lane holds one row (4 x 16 B); the block is
-// transposed through the warp's smem staging area so that one store instruction writes 8 rows x 64 contiguous bytes
-// (full 32-byte sectors) instead of 32 rows x 16 bytes.
+// Warp-cooperative store of a 32-row x 16-column bf16 block: every lane holds one row (2 x 16 B); the block is
+// transposed through the warp's smem staging area so that one store instruction writes 16 rows x 32 contiguous bytes
+// (full sectors) instead of 32 rows x 16 bytes.
 __device__ __forceinline__ void store_block_bf16(bf16* __restrict__ dst, int ld, int row0, int col0, int M, int N, int lane,
-                                                 const uint4 (&o)[4], uint8_t* stage) {
+                                                 const uint4 (&o)[EPI_COLS / 8], uint8_t* stage) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stage + lane * OUT_PITCH + g * 16) = o[g];
+    for (int g = 0; g < EPI_COLS / 8; ++g) *reinterpret_cast<uint4*>(stage + lane * OUT_PITCH + g * 16) = o[g];
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int q = lane + 32 * i, r = q >> 2, seg = q & 3;
+    for (int i = 0; i < EPI_COLS / 8; ++i) {
+        const int q = lane + 32 * i, r = q >> 1, seg = q & 1;
         const uint4 v = *reinterpret_cast<const uint4*>(stage + r * OUT_PITCH + seg * 16);
         const int row = row0 + r, col = col0 + seg * 8;
         if (row < M && col < N) *reinterpret_cast<uint4*>(dst + (size_t)row * ld + col) = v;
@@ -109,15 +110,15 @@ __device__ __forceinline__ void store_block_bf16(bf16* __restrict__ dst, int ld,
     __syncwarp();
 }
 
-// one accumulator row x 32 columns per lane: bias (smem copy) / GELU / dropout + residual / GELU' -> global
+// one accumulator row x EPI_COLS columns per lane: bias (smem copy) / GELU / dropout + residual / GELU' -> global
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const KParams& p, int row0, int lane, int col0, const uint32_t (&v)[32],
+__device__ __forceinline__ void epilogue_chunk(const KParams& p, int row0, int lane, int col0, const uint32_t (&v)[EPI_COLS],
                                                const float* bias_s, const AuxRegs& aux, uint8_t* stage) {
     const int row = row0 + lane;
     if constexpr (EPI == CRCT_EPI_F32) {
         if (row >= p.M) return;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < EPI_COLS / 8; ++g) {
             const int col = col0 + g * 8;
             if (col >= p.N) break;
             float* d = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col;
@@ -133,9 +134,9 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row0, int l
             }
         }
     } else {
-        uint4 o[4], o2[4];
+        uint4 o[EPI_COLS / 8], o2[EPI_COLS / 8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < EPI_COLS / 8; ++g) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
@@ -177,33 +178,36 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row0, int l
     }
 }
 
-// Epilogue of one tile for one warp: stage the tile's bias slice in smem (all 8 epilogue warps, named barrier 1),
-// then per 32-column chunk: aux prefetch (one chunk ahead) -> tcgen05.ld -> fused math -> coalesced global store.
+// Epilogue of one tile for one warp (16 epilogue warps: 4 TMEM lane groups x 4 column quarters): stage the tile's bias
+// slice in smem (named barrier 1), then per 16-column step: aux prefetch (one step ahead) -> tcgen05.ld -> fused math
+// -> coalesced global store.
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_acc, int m0, int n0, int warp, int lane, float* bias_s,
                                               uint8_t* stage_all) {
     const int lane_grp = warp & 3;                          // TMEM lanes [32*lane_grp, +32) are this warp's
-    const int col_half = (warp - EPI_WARP0) >> 2;
+    const int col_q = (warp - EPI_WARP0) >> 2;              // column quarter
     uint8_t* stage = stage_all + (warp - EPI_WARP0) * 32 * OUT_PITCH;
     if constexpr (EPI != CRCT_EPI_F32 && EPI != CRCT_EPI_DGELU) {
         if (p.bias != nullptr) {
-            const int t = (warp - EPI_WARP0) * 32 + lane;   // 0..255
+            const int t = (warp - EPI_WARP0) * 32 + lane;   // 0..511
             if (t < BN) bias_s[t] = (n0 + t < p.N) ? p.bias[n0 + t] : 0.f;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" :: "n"(NUM_EPI_WARPS * 32) : "memory");
     }
     const int row0 = m0 + lane_grp * 32;
     const int row = row0 + lane;
     const bool row_ok = row < p.M;
+    constexpr int STEPS = (BN / 4) / EPI_COLS;
+    const int cbase = col_q * (BN / 4);
     AuxRegs aux[2];
-    prefetch_aux<EPI>(p, row, n0 + col_half * (BN / 2), row_ok, aux[0]);
+    prefetch_aux<EPI>(p, row, n0 + cbase, row_ok, aux[0]);
 #pragma unroll
-    for (int c = 0; c < BN / 64; ++c) {
-        const int cc = col_half * (BN / 2) + c * 32;
-        if (c + 1 < BN / 64) prefetch_aux<EPI>(p, row, n0 + cc + 32, row_ok, aux[(c + 1) & 1]);
+    for (int c = 0; c < STEPS; ++c) {
+        const int cc = cbase + c * EPI_COLS;
+        if (c + 1 < STEPS) prefetch_aux<EPI>(p, row, n0 + cc + EPI_COLS, row_ok, aux[(c + 1) & 1]);
         const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cc;
-        uint32_t v[32];
-        ptx::tc_ld_32x32(taddr, v);
+        uint32_t v[EPI_COLS];
+        ptx::tc_ld_32x16(taddr, v);
         ptx::tc_wait_ld();
         if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row0, lane, n0 + cc, v, bias_s + cc, aux[c & 1], stage);     // warp-uniform
     }
@@ -365,7 +369,7 @@ struct Cfg2 {
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
     static constexpr int BIAS_BYTES = 2 * 256 * 4;              // per accumulator stage: the tile's bias slice
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 20480 + 1024;   // + OUT_STAGE_BYTES
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 24576 + 1024;   // + OUT_STAGE_BYTES
 };
 
 template <int BN, bool A_MN, bool B_MN>
