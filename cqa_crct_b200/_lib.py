@@ -92,7 +92,7 @@ class AdamWArgs(C.Structure):
 EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf16', 'crct_cast_f32_to_bf16',
            'crct_additive_mask', 'crct_layernorm_fwd', 'crct_layernorm_bwd', 'crct_colsum_bf16', 'crct_softmax_rows',
            'crct_embed_text_fwd', 'crct_embed_text_bwd', 'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd',
-           'crct_attn_bwd', 'crct_linear_f32', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
+           'crct_attn_bwd', 'crct_linear_f32', 'crct_linear_f32_batched', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
            'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw']
 
 _lib = None
@@ -117,6 +117,7 @@ def lib():
         _lib.crct_gather_first.argtypes = [vp, C.c_longlong, vp, C.c_int, C.c_int, vp]
         _lib.crct_scatter_first.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, vp]
         _lib.crct_colsum_f32.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, vp]
+        _lib.crct_linear_f32_batched.argtypes = [vp, C.c_int, vp]
         _lib.crct_scale_rows.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp]
         _lib.crct_pool_mul_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp]
         _lib.crct_pool_mul_bwd.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp]
@@ -291,6 +292,20 @@ def linear_f32(A, sa_m, sa_k, B, sb_k, sb_n, Cout, ldc, M, N, K, bias=None, act=
     a.bias, a.dmask, a.ldm = ptr(bias), ptr(dmask), ldm
     a.M, a.N, a.K, a.act, a.slope, a.accumulate = M, N, K, act, slope, accumulate
     check(lib().crct_linear_f32(C.byref(a), stream_ptr()))
+
+
+def lin_problem(A, sa_m, sa_k, B, sb_k, sb_n, Cout, ldc, M, N, K, bias=None, act=ACT_NONE, dmask=None, ldm=0, slope=0.0, accumulate=0):
+    a = LinearArgs()
+    a.A, a.sa_m, a.sa_k, a.B, a.sb_k, a.sb_n, a.C, a.ldc = ptr(A), sa_m, sa_k, ptr(B), sb_k, sb_n, ptr(Cout), ldc
+    a.bias, a.dmask, a.ldm = ptr(bias), ptr(dmask), ldm
+    a.M, a.N, a.K, a.act, a.slope, a.accumulate = M, N, K, act, slope, accumulate
+    return a
+
+
+def linear_f32_batched(problems):
+    """Independent small fp32 problems in one launch (include/crct_b200.h: crct_linear_f32_batched)."""
+    arr = (LinearArgs * len(problems))(*problems)
+    check(lib().crct_linear_f32_batched(arr, len(problems), stream_ptr()))
 
 
 def gather_first(src, row_stride, out):

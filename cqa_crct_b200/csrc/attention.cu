@@ -65,12 +65,16 @@ template <int DH>
 __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int ld, int rows, int rows_pad) {
     constexpr int LD = Smem<DH>::LD;
     constexpr int CH = DH / 8;
+    // cp.async (LDGSTS): fire-and-forget 16-byte copies, all in flight at once; rows beyond `rows` are zero-filled
     for (int i = threadIdx.x; i < rows_pad * CH; i += ATT_THREADS) {
         const int r = i / CH, c = i % CH;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < rows) v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld + c * 8);
-        *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+        const bf16* g = src + (size_t)(r < rows ? r : 0) * ld + c * 8;
+        const uint32_t nbytes = r < rows ? 16u : 0u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(ptx::smem_u32(dst + r * LD + c * 8)), "l"(g), "r"(nbytes) : "memory");
     }
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 struct FwdParams {
@@ -100,6 +104,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
     load_tile<DH>(Vs, p.v + (size_t)b * p.Lk * p.ldv + h * DH, p.ldv, p.Lk, LKP);
     // scores are kept in the log2 domain: s2 = s * scale * log2(e) + mask * log2(e), p = 2^(s2 - m2)  (one MUFU.EX2 per element)
     for (int i = threadIdx.x; i < LKP; i += ATT_THREADS) mask_s[i] = i < p.Lk ? p.mask_add[(size_t)b * p.Lk + i] * LOG2E : -INFINITY;
+    cp_async_wait_all();
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
         D_s[i] = d;
         lse_s[i] = l;
     }
+    cp_async_wait_all();
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;

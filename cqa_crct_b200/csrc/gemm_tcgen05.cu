@@ -73,14 +73,17 @@ constexpr bool epi_uses_aux(int epi) { return epi == CRCT_EPI_BIAS_RES || epi ==
 struct AuxRegs {
     uint4 v[EPI_COLS / 8];
 };
+// Coalesced fetch in the "transposed" mapping: piece q = lane + 32 i covers row row0 + q/2, 16-byte segment q%2, so one
+// load instruction reads 16 rows x 32 contiguous bytes (full sectors).  `aux_to_rows` turns it into one row per lane.
 template <int EPI>
-__device__ __forceinline__ void prefetch_aux(const KParams& p, int row, int col0, bool valid, AuxRegs& r) {
+__device__ __forceinline__ void prefetch_aux(const KParams& p, int row0, int lane, int col0, AuxRegs& r) {
     if constexpr (epi_uses_aux(EPI)) {
 #pragma unroll
-        for (int g = 0; g < EPI_COLS / 8; ++g) {
-            r.v[g] = make_uint4(0u, 0u, 0u, 0u);
-            if (valid && p.aux != nullptr && col0 + g * 8 < p.N)
-                r.v[g] = *reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col0 + g * 8);
+        for (int i = 0; i < EPI_COLS / 8; ++i) {
+            const int q = lane + 32 * i, row = row0 + (q >> 1), col = col0 + (q & 1) * 8;
+            r.v[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (p.aux != nullptr && row < p.M && col < p.N)
+                r.v[i] = *reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col);
         }
     }
 }
@@ -91,6 +94,21 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 
 constexpr int OUT_PITCH = EPI_COLS * 2 + 16;       // bytes per staged row: 32 B of bf16 + 16 B pad
 constexpr int OUT_STAGE_BYTES = NUM_EPI_WARPS * 32 * OUT_PITCH;
+
+template <int EPI>
+__device__ __forceinline__ void aux_to_rows(AuxRegs& r, int lane, uint8_t* stage) {
+    if constexpr (epi_uses_aux(EPI)) {
+#pragma unroll
+        for (int i = 0; i < EPI_COLS / 8; ++i) {
+            const int q = lane + 32 * i;
+            *reinterpret_cast<uint4*>(stage + (q >> 1) * OUT_PITCH + (q & 1) * 16) = r.v[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < EPI_COLS / 8; ++g) r.v[g] = *reinterpret_cast<const uint4*>(stage + lane * OUT_PITCH + g * 16);
+        __syncwarp();
+    }
+}
 
 // Warp-cooperative store of a 32-row x 16-column bf16 block: every lane holds one row (2 x 16 B); the block is
 // transposed through the warp's smem staging area so that one store instruction writes 16 rows x 32 contiguous bytes
@@ -195,19 +213,18 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
         asm volatile("bar.sync 1, %0;" :: "n"(NUM_EPI_WARPS * 32) : "memory");
     }
     const int row0 = m0 + lane_grp * 32;
-    const int row = row0 + lane;
-    const bool row_ok = row < p.M;
     constexpr int STEPS = (BN / 4) / EPI_COLS;
     const int cbase = col_q * (BN / 4);
     AuxRegs aux[2];
-    prefetch_aux<EPI>(p, row, n0 + cbase, row_ok, aux[0]);
+    prefetch_aux<EPI>(p, row0, lane, n0 + cbase, aux[0]);
 #pragma unroll
     for (int c = 0; c < STEPS; ++c) {
         const int cc = cbase + c * EPI_COLS;
-        if (c + 1 < STEPS) prefetch_aux<EPI>(p, row, n0 + cc + EPI_COLS, row_ok, aux[(c + 1) & 1]);
+        if (c + 1 < STEPS) prefetch_aux<EPI>(p, row0, lane, n0 + cc + EPI_COLS, aux[(c + 1) & 1]);
         const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cc;
         uint32_t v[EPI_COLS];
         ptx::tc_ld_32x16(taddr, v);
+        aux_to_rows<EPI>(aux[c & 1], lane, stage);
         ptx::tc_wait_ld();
         if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row0, lane, n0 + cc, v, bias_s + cc, aux[c & 1], stage);     // warp-uniform
     }

@@ -26,7 +26,16 @@ struct LinParams {
 
 // 64x64 output tile per CTA, 4x4 per thread, K in slabs of 32 with the next slab's global loads issued before the
 // current slab's FMAs (the problems are tiny — M = batch — so the kernel is latency- not throughput-bound)
-__global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinParams p) {
+constexpr int MAX_BATCH = 12;
+struct LinBatch {
+    LinParams p[MAX_BATCH];
+};
+
+// blockIdx.z selects one of several INDEPENDENT small problems (e.g. wgrad + dgrad + bias-grad of one head layer, or
+// the same layer of the two regressor pipes): one launch instead of up to 8 latency-bound ones.
+__global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinBatch batch) {
+    const LinParams& p = batch.p[blockIdx.z];
+    if ((int)blockIdx.y * BM >= p.M || (int)blockIdx.x * BN >= p.N) return;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     constexpr int PER = (BM * BK) / LIN_THREADS;       // 8 elements of A and of B per thread per slab
@@ -44,7 +53,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinParams
         for (int i = 0; i < PER; ++i) {
             const int e = tid + i * LIN_THREADS;
             const int kk = a_kfast ? (e % BK) : (e / BM), m = a_kfast ? (e / BK) : (e % BM);
-            ra[i] = (m0 + m < p.M && k0 + kk < p.K) ? p.A[(long long)(m0 + m) * p.sa_m + (long long)(k0 + kk) * p.sa_k] : 0.f;
+            ra[i] = (m0 + m < p.M && k0 + kk < p.K) ? (p.A ? p.A[(long long)(m0 + m) * p.sa_m + (long long)(k0 + kk) * p.sa_k] : 1.f) : 0.f;
             const int kb = b_nfast ? (e / BN) : (e % BK), n = b_nfast ? (e % BN) : (e / BK);
             rb[i] = (n0 + n < p.N && k0 + kb < p.K) ? p.B[(long long)(k0 + kb) * p.sb_k + (long long)(n0 + n) * p.sb_n] : 0.f;
         }
@@ -239,18 +248,36 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams p) {
 
 }  // namespace
 
-extern "C" CRCT_API int crct_linear_f32(const crct_linear_t* a, crct_stream_t s) {
-    if (!a || !a->A || !a->B || !a->C) CRCT_FAIL(CRCT_ERR_ARG, "crct_linear_f32: null pointer");
-    if (a->M <= 0 || a->N <= 0 || a->K <= 0) return CRCT_OK;
+static int fill_lin(LinParams& p, const crct_linear_t* a) {
+    if (!a->B || !a->C) CRCT_FAIL(CRCT_ERR_ARG, "crct_linear_f32: null pointer");
     if (a->act < 0 || a->act > 3) CRCT_FAIL(CRCT_ERR_ARG, "crct_linear_f32: unknown activation %d", a->act);
-    LinParams p;
     p.A = a->A; p.sa_m = a->sa_m; p.sa_k = a->sa_k; p.B = a->B; p.sb_k = a->sb_k; p.sb_n = a->sb_n;
     p.C = a->C; p.ldc = a->ldc; p.bias = a->bias; p.dmask = a->dmask; p.ldm = a->ldm;
     p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->act; p.slope = a->slope; p.accumulate = a->accumulate;
-    dim3 grid((a->N + BN - 1) / BN, (a->M + BM - 1) / BM);
-    linear_f32_kernel<<<grid, LIN_THREADS, 0, as_stream(s)>>>(p);
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_linear_f32_batched(const crct_linear_t* problems, int count, crct_stream_t s) {
+    if (!problems || count < 1 || count > MAX_BATCH) CRCT_FAIL(CRCT_ERR_ARG, "crct_linear_f32_batched: 1..%d problems", MAX_BATCH);
+    LinBatch b;
+    memset(&b, 0, sizeof(b));
+    int gx = 0, gy = 0, n = 0;
+    for (int i = 0; i < count; ++i) {
+        if (problems[i].M <= 0 || problems[i].N <= 0 || problems[i].K <= 0) continue;
+        if (int rc = fill_lin(b.p[n], &problems[i])) return rc;
+        gx = max(gx, (problems[i].N + BN - 1) / BN);
+        gy = max(gy, (problems[i].M + BM - 1) / BM);
+        ++n;
+    }
+    if (n == 0) return CRCT_OK;
+    linear_f32_kernel<<<dim3(gx, gy, n), LIN_THREADS, 0, as_stream(s)>>>(b);
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_linear_f32(const crct_linear_t* a, crct_stream_t s) {
+    if (!a || !a->A) CRCT_FAIL(CRCT_ERR_ARG, "crct_linear_f32: null pointer");
+    return crct_linear_f32_batched(a, 1, s);
 }
 
 extern "C" CRCT_API int crct_gather_first(const void* src, long long row_stride, float* out, int B, int H, crct_stream_t s) {

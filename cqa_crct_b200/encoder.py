@@ -395,52 +395,30 @@ class VisualDialogEncoder(nn.Module):
         return dv, dt
 
     # ------------------------------------------------------------------ heads (fp32, CUDA cores)
-    def _lin32(self, x, name, act=L.ACT_NONE, out=None, ldc=None):
+    # Every Linear of the heads is a tiny latency-bound problem (M = batch size); independent ones are issued as ONE
+    # batched launch (crct_linear_f32_batched): the two regressor pipes and the poolers side by side in the forward,
+    # {wgrad, bias-grad, dgrad} of a layer (of both pipes) in the backward.
+    def _fwd_problem(self, x, name, act, out=None, ldc=None):
         W, b = self._p(name + '.weight'), self._p(name + '.bias')
         M, (N, K) = x.shape[0], W.shape
         if out is None:
             out = torch.empty(M, N, dtype=torch.float32, device=x.device)
             ldc = N
-        L.linear_f32(x, x.stride(0), 1, W, 1, K, out, ldc, M, N, K, bias=b, act=act)
-        return out
+        return L.lin_problem(x, x.stride(0), 1, W, 1, K, out, ldc, M, N, K, bias=b, act=act), out
 
-    def _lin32_bwd(self, dy, ldy, x, name, dmask=None, slope=0.0, dx_out=None, accumulate_dx=0, need_dx=True):
-        """dy: [M,N] (row stride ldy) gradient of the PRE-activation output of Linear `name` applied to x [M,K]."""
+    def _bwd_problems(self, dy, ldy, x, name, dx=None, dmask=None, slope=0.0, accumulate_dx=0):
+        """dy [M,N] (row stride ldy) = gradient of the PRE-activation output of Linear `name` applied to x [M,K].
+        Returns ([wgrad, bias-grad, dgrad] problems, dx); dx = (dy W) * (dmask > 0 ? 1 : slope)."""
         W = self._p(name + '.weight')
         N, K = W.shape
         M = x.shape[0]
-        L.linear_f32(dy, 1, ldy, x, x.stride(0), 1, self._g(name + '.weight'), K, N, K, M, accumulate=1)
-        L.colsum_f32(dy, self._g(name + '.bias'), M, N, ldy)
-        if not need_dx:
-            return None
-        if dx_out is None:
-            dx_out = torch.empty(M, K, dtype=torch.float32, device=x.device)
-        L.linear_f32(dy, ldy, 1, W, K, 1, dx_out, K, M, K, N, dmask=dmask, ldm=(dmask.stride(0) if dmask is not None else 0), slope=slope,
-                     accumulate=accumulate_dx)
-        return dx_out
-
-    def _mlp4_fwd(self, x, pre, out=None, ldc=None, last_act=L.ACT_NONE):
-        acts = [x]
-        h = x
-        for i, idx in enumerate((0, 2, 4, 6)):
-            if i < 3:
-                h = self._lin32(h, f'{pre}.{idx}', L.ACT_LEAKY)
-            else:
-                h = self._lin32(h, f'{pre}.{idx}', last_act, out=out, ldc=ldc)
-            acts.append(h)
-        return h, acts
-
-    def _mlp4_bwd(self, d_last, ld_last, acts, pre, dx_out=None, accumulate_dx=0):
-        """d_last = gradient of the pre-activation output of the last Linear."""
-        d, ldd = d_last, ld_last
-        for i, idx in reversed(list(enumerate((0, 2, 4, 6)))):
-            x = acts[i]
-            if i > 0:      # x is the LeakyReLU output of the previous Linear: fold its derivative into dx
-                d = self._lin32_bwd(d, ldd, x, f'{pre}.{idx}', dmask=x, slope=0.01)
-                ldd = d.stride(0)
-            else:
-                d = self._lin32_bwd(d, ldd, x, f'{pre}.{idx}', dx_out=dx_out, accumulate_dx=accumulate_dx)
-        return d
+        probs = [L.lin_problem(dy, 1, ldy, x, x.stride(0), 1, self._g(name + '.weight'), K, N, K, M, accumulate=1),
+                 L.lin_problem(None, 0, 0, dy, ldy, 1, self._g(name + '.bias'), N, 1, N, M, accumulate=1)]
+        if dx is None:
+            dx = torch.empty(M, K, dtype=torch.float32, device=x.device)
+        probs.append(L.lin_problem(dy, ldy, 1, W, K, 1, dx, K, M, K, N, dmask=dmask, ldm=(dmask.stride(0) if dmask is not None else 0),
+                                   slope=slope, accumulate=accumulate_dx))
+        return probs, dx
 
     def _heads_fwd(self, t, v, B, T, R, labels, Rt, kind, keep):
         cfg, dev = self.cfg, t.device
@@ -449,16 +427,33 @@ class VisualDialogEncoder(nn.Module):
         hv0 = torch.empty(B, Hv, dtype=torch.float32, device=dev)
         L.gather_first(t, T * H, hw0)          # vilbert.py:958 / 1600
         L.gather_first(v, R * Hv, hv0)         # vilbert.py:973 / 1599
-        pt = self._lin32(hw0, 'bert.t_pooler.dense', L.ACT_RELU)
-        pv = self._lin32(hv0, 'bert.v_pooler.dense', L.ACT_RELU)
+        prefusion = torch.empty(B, 512, dtype=torch.float32, device=dev)          # cat((hv, hw), -1), regressor.py:40
+        p_t, pt = self._fwd_problem(hw0, 'bert.t_pooler.dense', L.ACT_RELU)
+        p_v, pv = self._fwd_problem(hv0, 'bert.v_pooler.dense', L.ACT_RELU)
+        acts_v, acts_t = [hv0], [hw0]
+        probs = [p_t, p_v]
+        for i, idx in enumerate((0, 2, 4, 6)):
+            last = i == 3
+            pr_v, ov = self._fwd_problem(acts_v[-1], f'regressor.vis_pipe.{idx}', L.ACT_NONE if last else L.ACT_LEAKY,
+                                         out=prefusion if last else None, ldc=512 if last else None)
+            pr_t, ot = self._fwd_problem(acts_t[-1], f'regressor.txt_pipe.{idx}', L.ACT_NONE if last else L.ACT_LEAKY,
+                                         out=prefusion[:, 256:] if last else None, ldc=512 if last else None)
+            L.linear_f32_batched(probs + [pr_v, pr_t])
+            probs = []
+            acts_v.append(ov)
+            acts_t.append(ot)
         pooled = torch.empty_like(pt)
         p_cls, s_cls = self._drop(0.1), _seed(self._step, 'cls')      # nn.Dropout(0.1), vilbert.py:1045
         L.pool_mul_fwd(pt, pv, pooled, p_cls, s_cls)
-        logits = self._lin32(pooled, 'cls.bi_seq_relationship')
-        prefusion = torch.empty(B, 512, dtype=torch.float32, device=dev)          # cat((hv, hw), -1), regressor.py:40
-        _, acts_v = self._mlp4_fwd(hv0, 'regressor.vis_pipe', out=prefusion, ldc=512)
-        _, acts_t = self._mlp4_fwd(hw0, 'regressor.txt_pipe', out=prefusion[:, 256:], ldc=512)
-        reg, acts_f = self._mlp4_fwd(prefusion, 'regressor.fusion', last_act=L.ACT_TANH)
+        pr_c, logits = self._fwd_problem(pooled, 'cls.bi_seq_relationship', L.ACT_NONE)
+        acts_f = [prefusion]
+        probs = [pr_c]
+        for i, idx in enumerate((0, 2, 4, 6)):
+            pr_f, of = self._fwd_problem(acts_f[-1], f'regressor.fusion.{idx}', L.ACT_TANH if i == 3 else L.ACT_LEAKY)
+            L.linear_f32_batched(probs + [pr_f])
+            probs = []
+            acts_f.append(of)
+        reg = acts_f[-1]
         outs = [torch.empty(B, dtype=torch.float32, device=dev) for _ in range(4)]
         scalars = torch.empty(5, dtype=torch.float32, device=dev)
         dlogits = torch.empty(B, 2, dtype=torch.float32, device=dev) if keep else None
@@ -480,14 +475,34 @@ class VisualDialogEncoder(nn.Module):
         dlogits, dpre = torch.empty_like(s.dlogits), torch.empty_like(s.dpre)
         L.scale_rows(s.dlogits, d_nsp.reshape(-1)[:1].contiguous().float(), dlogits)
         L.scale_rows(s.dpre, d_reg.reshape(-1).contiguous().float(), dpre)
-        dpooled = self._lin32_bwd(dlogits, 2, s.pooled, 'cls.bi_seq_relationship')
+        # classifier + last fusion layer
+        pc, dpooled = self._bwd_problems(dlogits, 2, s.pooled, 'cls.bi_seq_relationship')
+        pf, d = self._bwd_problems(dpre, 1, s.acts_f[3], 'regressor.fusion.6', dmask=s.acts_f[3], slope=0.01)
+        L.linear_f32_batched(pc + pf)
         dut, duv = torch.empty_like(s.pt), torch.empty_like(s.pv)
         L.pool_mul_bwd(dpooled, s.pt, s.pv, dut, duv, s.p_cls, s.s_cls)
-        dhw0 = self._lin32_bwd(dut, dut.stride(0), s.hw0, 'bert.t_pooler.dense')
-        dhv0 = self._lin32_bwd(duv, duv.stride(0), s.hv0, 'bert.v_pooler.dense')
-        dpref = self._mlp4_bwd(dpre, 1, s.acts_f, 'regressor.fusion')
-        self._mlp4_bwd(dpref, 512, s.acts_v, 'regressor.vis_pipe', dx_out=dhv0, accumulate_dx=1)
-        self._mlp4_bwd(dpref[:, 256:], 512, s.acts_t, 'regressor.txt_pipe', dx_out=dhw0, accumulate_dx=1)
+        # poolers + fusion.4
+        pt_, dhw0 = self._bwd_problems(dut, dut.stride(0), s.hw0, 'bert.t_pooler.dense')
+        pv_, dhv0 = self._bwd_problems(duv, duv.stride(0), s.hv0, 'bert.v_pooler.dense')
+        pf, d = self._bwd_problems(d, d.stride(0), s.acts_f[2], 'regressor.fusion.4', dmask=s.acts_f[2], slope=0.01)
+        L.linear_f32_batched(pt_ + pv_ + pf)
+        pf, d = self._bwd_problems(d, d.stride(0), s.acts_f[1], 'regressor.fusion.2', dmask=s.acts_f[1], slope=0.01)
+        L.linear_f32_batched(pf)
+        pf, dpref = self._bwd_problems(d, d.stride(0), s.acts_f[0], 'regressor.fusion.0')      # input = cat(pipe outputs): no activation
+        L.linear_f32_batched(pf)
+        # the two pipes, layer by layer, side by side
+        dv_, dt_ = dpref, dpref[:, 256:]
+        ldv = ldt = 512
+        for i, idx in reversed(list(enumerate((0, 2, 4, 6)))):
+            xv, xt = s.acts_v[i], s.acts_t[i]
+            if i > 0:      # x is the LeakyReLU output of the previous Linear: fold its derivative into dx
+                pv_, nv = self._bwd_problems(dv_, ldv, xv, f'regressor.vis_pipe.{idx}', dmask=xv, slope=0.01)
+                pt_, nt = self._bwd_problems(dt_, ldt, xt, f'regressor.txt_pipe.{idx}', dmask=xt, slope=0.01)
+            else:          # first layer: its input gradient joins the pooler's (first-token hidden state)
+                pv_, nv = self._bwd_problems(dv_, ldv, xv, f'regressor.vis_pipe.{idx}', dx=dhv0, accumulate_dx=1)
+                pt_, nt = self._bwd_problems(dt_, ldt, xt, f'regressor.txt_pipe.{idx}', dx=dhw0, accumulate_dx=1)
+            L.linear_f32_batched(pv_ + pt_)
+            dv_, dt_, ldv, ldt = nv, nt, nv.stride(0), nt.stride(0)
         dt = torch.zeros(B * T, H, dtype=torch.bfloat16, device=dev)
         dv = torch.zeros(B * R, Hv, dtype=torch.bfloat16, device=dev)
         L.scatter_first(dhw0, dt, T * H)

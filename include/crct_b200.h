@@ -215,6 +215,9 @@ typedef struct {
     int32_t accumulate;
 } crct_linear_t;
 int crct_linear_f32(const crct_linear_t* args, crct_stream_t stream);
+/* up to 12 independent problems in one launch (blockIdx.z); a NULL `A` stands for all-ones, which makes a bias gradient
+ * `db += colsum(dy)` the problem {A = NULL, M = 1, B = dy (sb_k = ldy, sb_n = 1), K = rows, accumulate = 1}. */
+int crct_linear_f32_batched(const crct_linear_t* problems, int count, crct_stream_t stream);
 /* out[b,:] = float(src_bf16[b*row_stride + :]) — hidden state of the first token / region (vilbert.py:958,973,1599-1600) */
 int crct_gather_first(const void* src_bf16, long long row_stride, float* out, int B, int H, crct_stream_t stream);
 /* dst_bf16[b*row_stride + :] = g[b,:]; all other rows of dst must be zero (caller memsets) */
