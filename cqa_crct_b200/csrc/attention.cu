@@ -33,6 +33,11 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t sad
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+
 template <int DH>
 struct Smem {
     static constexpr int LD = DH + 8;       // +16 B per row: conflict-free fragment reads, 16 B aligned rows
@@ -40,11 +45,15 @@ struct Smem {
 
 // A fragment (16 rows x 16 k) of a row-major smem tile X[row][k]
 template <int LD>
-__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], const bf16* X, int r0, int k0, int g, int t) {
-    a[0] = *reinterpret_cast<const uint32_t*>(X + (r0 + g) * LD + k0 + 2 * t);
-    a[1] = *reinterpret_cast<const uint32_t*>(X + (r0 + g + 8) * LD + k0 + 2 * t);
-    a[2] = *reinterpret_cast<const uint32_t*>(X + (r0 + g) * LD + k0 + 8 + 2 * t);
-    a[3] = *reinterpret_cast<const uint32_t*>(X + (r0 + g + 8) * LD + k0 + 8 + 2 * t);
+__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], const bf16* X, int r0, int k0, int lane) {
+    const int m = lane >> 3, rr = lane & 7;           // one ldmatrix.x4: (rows r0.., k0..) (rows r0+8.., k0..) (rows r0.., k0+8..) (rows r0+8.., k0+8..)
+    ldmatrix_x4(a, ptx::smem_u32(X + (r0 + rr + (m & 1) * 8) * LD + k0 + (m >> 1) * 8));
+}
+// B fragments of n-tiles n0 and n0+8 for one 16-wide k-step, B[k][n] = Y[n][k] (k contiguous): r[0],r[1] -> n0 ; r[2],r[3] -> n0+8
+template <int LD>
+__device__ __forceinline__ void load_b_frag_x2(uint32_t (&r)[4], const bf16* Y, int n0, int k0, int lane) {
+    const int m = lane >> 3, rr = lane & 7;
+    ldmatrix_x4(r, ptx::smem_u32(Y + (n0 + rr + (m >> 1) * 8) * LD + k0 + (m & 1) * 8));
 }
 // B fragment (16 k x 8 n) where B[k][n] = Y[n][k], Y row-major in smem (k contiguous)
 template <int LD>
@@ -109,10 +118,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const float scale2 = p.scale * LOG2E;
+    const CrctDrop32 drop = crct_drop32(p.seed, p.thr);
     for (int q0 = warp * 16; q0 < LQP; q0 += NWARPS * 16) {
         uint32_t aq[DH / 16][4];
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) load_a_frag<LD>(aq[kk], Qs, q0, kk * 16, g, t);
+        for (int kk = 0; kk < DH / 16; ++kk) load_a_frag<LD>(aq[kk], Qs, q0, kk * 16, lane);
         float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
         float o[DH / 8][4];
 #pragma unroll
@@ -125,10 +135,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
 #pragma unroll
             for (int kk = 0; kk < DH / 16; ++kk)
 #pragma unroll
-                for (int j = 0; j < KB / 8; ++j) {
-                    uint32_t b0, b1;
-                    load_b_frag<LD>(b0, b1, Ks, kb + j * 8, kk * 16, g, t);
-                    mma16816(s[j], aq[kk], b0, b1);
+                for (int j = 0; j < KB / 8; j += 2) {
+                    uint32_t r[4];
+                    load_b_frag_x2<LD>(r, Ks, kb + j * 8, kk * 16, lane);
+                    mma16816(s[j], aq[kk], r[0], r[1]);
+                    mma16816(s[j + 1], aq[kk], r[2], r[3]);
                 }
             float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
@@ -159,14 +170,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
                 l_run[1] += s[j][2] + s[j][3];
             }
             if (p.thr != 0u) {                 // dropout on the probabilities (vilbert.py:407); l_run stays undropped
-                const uint64_t base = ((uint64_t)blockIdx.x * p.Lq) * (uint64_t)p.Lk;
+                const uint32_t i0b = (blockIdx.x * p.Lq + q0 + g) * p.Lk + kb + 2 * t, i1b = i0b + 8u * p.Lk;
 #pragma unroll
                 for (int j = 0; j < KB / 8; ++j) {
-                    const int key = kb + j * 8 + 2 * t;
-                    const uint64_t i0 = base + (uint64_t)(q0 + g) * p.Lk + key, i1 = base + (uint64_t)(q0 + g + 8) * p.Lk + key;
                     bool k0, k1, k2, k3;
-                    crct_keep2(p.seed, i0, p.thr, k0, k1);
-                    crct_keep2(p.seed, i1, p.thr, k2, k3);
+                    crct_keep2_32(drop, i0b + j * 8, k0, k1);
+                    crct_keep2_32(drop, i1b + j * 8, k2, k3);
                     s[j][0] = k0 ? s[j][0] * p.dscale : 0.f; s[j][1] = k1 ? s[j][1] * p.dscale : 0.f;
                     s[j][2] = k2 ? s[j][2] * p.dscale : 0.f; s[j][3] = k3 ? s[j][3] * p.dscale : 0.f;
                 }
@@ -263,7 +272,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const uint64_t drop_base = ((uint64_t)blockIdx.x * p.Lq) * (uint64_t)p.Lk;
+    const uint32_t drop_base = blockIdx.x * (uint32_t)p.Lq * (uint32_t)p.Lk;
+    const CrctDrop32 drop = crct_drop32(p.seed, p.thr);
     const float scale2 = p.scale * LOG2E;
 
     // ---------------- pass A: this warp owns 16 keys -> dK, dV ----------------
@@ -272,8 +282,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
         uint32_t ak[DH / 16][4], av[DH / 16][4];
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) {
-            load_a_frag<LD>(ak[kk], Ks, k0, kk * 16, g, t);
-            load_a_frag<LD>(av[kk], Vs, k0, kk * 16, g, t);
+            load_a_frag<LD>(ak[kk], Ks, k0, kk * 16, lane);
+            load_a_frag<LD>(av[kk], Vs, k0, kk * 16, lane);
         }
         const float mrow[2] = {mask_s[k0 + g], mask_s[k0 + g + 8]};
         float dk[DH / 8][4], dv[DH / 8][4];
@@ -286,12 +296,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
 #pragma unroll
             for (int kk = 0; kk < DH / 16; ++kk)
 #pragma unroll
-                for (int j = 0; j < KB / 8; ++j) {
-                    uint32_t b0, b1;
-                    load_b_frag<LD>(b0, b1, Qs, qb + j * 8, kk * 16, g, t);
-                    mma16816(st[j], ak[kk], b0, b1);                 // S^T = K Q^T
-                    load_b_frag<LD>(b0, b1, dOs, qb + j * 8, kk * 16, g, t);
-                    mma16816(dpt[j], av[kk], b0, b1);                // dP^T = V dO^T
+                for (int j = 0; j < KB / 8; j += 2) {
+                    uint32_t r[4];
+                    load_b_frag_x2<LD>(r, Qs, qb + j * 8, kk * 16, lane);
+                    mma16816(st[j], ak[kk], r[0], r[1]);             // S^T = K Q^T
+                    mma16816(st[j + 1], ak[kk], r[2], r[3]);
+                    load_b_frag_x2<LD>(r, dOs, qb + j * 8, kk * 16, lane);
+                    mma16816(dpt[j], av[kk], r[0], r[1]);            // dP^T = V dO^T
+                    mma16816(dpt[j + 1], av[kk], r[2], r[3]);
                 }
             // P^T, dS^T in place: st <- P^T (dropped, for dV), dpt <- dS^T * scale (for dK)
 #pragma unroll
@@ -304,7 +316,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
                     const int r = c >> 1;
                     const float pr = fast_exp2(fmaf(st[j][c], scale2, mrow[r]) - ((c & 1) ? ls.y : ls.x));
                     float fac = 1.f;
-                    if (p.thr != 0u) fac = crct_keep(p.seed, drop_base + (uint64_t)(qi0 + (c & 1)) * p.Lk + (k0 + g + 8 * r), p.thr) ? p.dscale : 0.f;
+                    if (p.thr != 0u) fac = crct_keep32(drop, drop_base + (uint32_t)(qi0 + (c & 1)) * p.Lk + (k0 + g + 8 * r)) ? p.dscale : 0.f;
                     st[j][c] = pr * fac;
                     dpt[j][c] = pr * (dpt[j][c] * fac - ((c & 1) ? dd.y : dd.x)) * p.scale;
                 }
@@ -349,8 +361,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
         uint32_t aq[DH / 16][4], ado[DH / 16][4];
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) {
-            load_a_frag<LD>(aq[kk], Qs, q0, kk * 16, g, t);
-            load_a_frag<LD>(ado[kk], dOs, q0, kk * 16, g, t);
+            load_a_frag<LD>(aq[kk], Qs, q0, kk * 16, lane);
+            load_a_frag<LD>(ado[kk], dOs, q0, kk * 16, lane);
         }
         const float lrow[2] = {lse_s[q0 + g], lse_s[q0 + g + 8]};
         const float drow[2] = {D_s[q0 + g], D_s[q0 + g + 8]};
@@ -364,12 +376,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
 #pragma unroll
             for (int kk = 0; kk < DH / 16; ++kk)
 #pragma unroll
-                for (int j = 0; j < KB / 8; ++j) {
-                    uint32_t b0, b1;
-                    load_b_frag<LD>(b0, b1, Ks, kb + j * 8, kk * 16, g, t);
-                    mma16816(s[j], aq[kk], b0, b1);                  // S = Q K^T
-                    load_b_frag<LD>(b0, b1, Vs, kb + j * 8, kk * 16, g, t);
-                    mma16816(dp[j], ado[kk], b0, b1);                // dP = dO V^T
+                for (int j = 0; j < KB / 8; j += 2) {
+                    uint32_t r[4];
+                    load_b_frag_x2<LD>(r, Ks, kb + j * 8, kk * 16, lane);
+                    mma16816(s[j], aq[kk], r[0], r[1]);              // S = Q K^T
+                    mma16816(s[j + 1], aq[kk], r[2], r[3]);
+                    load_b_frag_x2<LD>(r, Vs, kb + j * 8, kk * 16, lane);
+                    mma16816(dp[j], ado[kk], r[0], r[1]);            // dP = dO V^T
+                    mma16816(dp[j + 1], ado[kk], r[2], r[3]);
                 }
 #pragma unroll
             for (int j = 0; j < KB / 8; ++j) {
@@ -378,7 +392,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     bool k0 = true, k1 = true;
-                    if (p.thr != 0u) crct_keep2(p.seed, drop_base + (uint64_t)(q0 + g + 8 * r) * p.Lk + key0, p.thr, k0, k1);
+                    if (p.thr != 0u) crct_keep2_32(drop, drop_base + (uint32_t)(q0 + g + 8 * r) * p.Lk + key0, k0, k1);
                     const float pr0 = fast_exp2(fmaf(s[j][2 * r], scale2, mk.x) - lrow[r]);
                     const float pr1 = fast_exp2(fmaf(s[j][2 * r + 1], scale2, mk.y) - lrow[r]);
                     dp[j][2 * r] = pr0 * ((k0 ? dp[j][2 * r] * p.dscale : 0.f) - drow[r]) * p.scale;
@@ -453,6 +467,7 @@ extern "C" CRCT_API int crct_attn_fwd(const crct_attn_fwd_t* a, crct_stream_t s)
     if (a->B <= 0 || a->nh <= 0 || a->Lq <= 0 || a->Lk <= 0) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_fwd: empty problem");
     if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8) || !aligned16(a->q) || !aligned16(a->k) || !aligned16(a->v) || !aligned16(a->out))
         CRCT_FAIL(CRCT_ERR_ARG, "crct_attn_fwd: operands must be 16-byte aligned with leading dimensions multiple of 8");
+    if ((double)a->B * a->nh * a->Lq * a->Lk >= 4294967296.0) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_fwd: B*nh*Lq*Lk must stay below 2^32");
     FwdParams p;
     p.q = reinterpret_cast<const bf16*>(a->q); p.k = reinterpret_cast<const bf16*>(a->k); p.v = reinterpret_cast<const bf16*>(a->v);
     p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.mask_add = a->mask_add;
@@ -475,6 +490,7 @@ extern "C" CRCT_API int crct_attn_bwd(const crct_attn_bwd_t* a, crct_stream_t s)
     if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8) || (a->lddo % 8) || (a->lddq % 2) || (a->lddk % 2) || (a->lddv % 2) ||
         !aligned16(a->q) || !aligned16(a->k) || !aligned16(a->v) || !aligned16(a->out) || !aligned16(a->dout))
         CRCT_FAIL(CRCT_ERR_ARG, "crct_attn_bwd: operands must be 16-byte aligned with leading dimensions multiple of 8");
+    if ((double)a->B * a->nh * a->Lq * a->Lk >= 4294967296.0) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_bwd: B*nh*Lq*Lk must stay below 2^32");
     BwdParams p;
     p.q = reinterpret_cast<const bf16*>(a->q); p.k = reinterpret_cast<const bf16*>(a->k); p.v = reinterpret_cast<const bf16*>(a->v);
     p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.mask_add = a->mask_add;

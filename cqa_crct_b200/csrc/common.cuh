@@ -58,6 +58,39 @@ __host__ __device__ __forceinline__ void crct_keep2(uint64_t seed, uint64_t idx,
         k1 = (crct_hash_pair(seed, idx + 1) & 0xFFFFu) >= threshold;
     }
 }
+// 32-bit fast path (element counters below 2^32): same decisions as crct_keep, with the seed mixing hoisted
+struct CrctDrop32 {
+    uint32_t sm, sh, thr;
+};
+__host__ __device__ __forceinline__ CrctDrop32 crct_drop32(uint64_t seed, uint32_t thr) {
+    CrctDrop32 d;
+    d.sm = (uint32_t)seed;
+    d.sh = (uint32_t)(seed >> 32) * 0x27D4EB2Fu;
+    d.thr = thr;
+    return d;
+}
+__host__ __device__ __forceinline__ uint32_t crct_hash_pair32(const CrctDrop32& d, uint32_t pair) {
+    uint32_t h = pair * 0x9E3779B1u + d.sm;
+    h ^= d.sh;
+    h ^= h >> 15; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+__host__ __device__ __forceinline__ bool crct_keep32(const CrctDrop32& d, uint32_t idx) {
+    const uint32_t h = crct_hash_pair32(d, idx >> 1);
+    return ((idx & 1u) ? (h >> 16) : (h & 0xFFFFu)) >= d.thr;
+}
+__host__ __device__ __forceinline__ void crct_keep2_32(const CrctDrop32& d, uint32_t idx, bool& k0, bool& k1) {
+    const uint32_t h = crct_hash_pair32(d, idx >> 1);
+    if ((idx & 1u) == 0u) {
+        k0 = (h & 0xFFFFu) >= d.thr;
+        k1 = (h >> 16) >= d.thr;
+    } else {
+        k0 = (h >> 16) >= d.thr;
+        k1 = (crct_hash_pair32(d, (idx + 1u) >> 1) & 0xFFFFu) >= d.thr;
+    }
+}
 static inline uint32_t crct_drop_threshold(float p) {
     if (p <= 0.f) return 0u;
     double t = (double)p * 65536.0 + 0.5;

@@ -661,9 +661,8 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
             return ((tiles + slots - 1) / slots) * (long)b;
         };
         // 128x256 tiles move 1.33x fewer operand bytes per FLOP through L2/smem than 128x128 (measured faster on every
-        // CRCT shape); 128-wide only when it removes a mostly-empty tile column or for the fp32 split-K wgrad
-        bn = (a->N <= 128 || cost(128) * 5 < cost(256) * 4) ? 128 : 256;
-        if (f32) bn = 128;
+        // CRCT shape, wgrad included: profiles/r01_wgrad_shapes.log); 128-wide only when it removes a mostly-empty tile column
+        bn = (a->N <= 128 || cost(128) * 5 < cost(256) * 4) ? 128 : 256;       // also for the split-K wgrad (measured)
     }
     if (bn != 128 && bn != 256) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: block_n must be 0, 128 or 256");
     const int num_m_tiles = (a->M + tile_m - 1) / tile_m;

@@ -144,5 +144,31 @@ if __name__ == '__main__':
         child([int(x) for x in sys.argv[2:]])
     elif len(sys.argv) > 1 and sys.argv[1] == 'perf':
         perf()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'perf_wgrad':
+        pass
     else:
         main()
+
+
+def perf_wgrad():
+    import torch
+    from cqa_crct_b200 import _lib as L
+    dev = 'cuda'
+    for (rows, No, Ki) in [(9920, 3072, 768), (9920, 768, 3072), (9920, 768, 768), (9920, 2304, 768), (3520, 1024, 1024), (3520, 3072, 1024), (9920, 1024, 768)]:
+        dy = torch.randn(rows, No, device=dev).bfloat16(); x = torch.randn(rows, Ki, device=dev).bfloat16()
+        dW = torch.zeros(No, Ki, device=dev)
+        for bn, cg, sk in ((128, 1, 0), (256, 1, 0), (128, 2, 0), (256, 2, 0), (256, 2, 1), (256, 2, 2), (256, 2, 4)):
+            kw = dict(M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, block_n=bn, cta_group=cg, split_k=sk)
+            for _ in range(3):
+                L.gemm(dy, x, dW, **kw)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(20):
+                L.gemm(dy, x, dW, **kw)
+            e.record(); torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / 20
+            print(f'wgrad rows={rows} out={No} in={Ki} BN={bn} cta_group={cg} split_k={sk}: {ms*1e3:.1f} us  {2*rows*No*Ki/ms/1e9:.1f} TFLOP/s', flush=True)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'perf_wgrad':
+    perf_wgrad()
