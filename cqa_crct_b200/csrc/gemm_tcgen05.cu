@@ -14,6 +14,7 @@
 // descriptor major bits + transposed TMA boxes), so dgrad / wgrad need no transposed copies.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -633,7 +634,11 @@ int dispatch(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensor
 static bool crct_gemm_auto_pair(const crct_gemm_t* a) {
     // measured on B200 (profiles/r01_gemm_shapes.log): the CTA pair wins ~4 % once there are >= 8 tile columns to
     // share; narrower outputs quantise worse on 256-row tiles
-    return a->epilogue != CRCT_EPI_F32 && a->N >= 2048 && a->M >= 1024;
+    static const int policy = []() { const char* e = getenv("CRCT_GEMM_PAIR_POLICY"); return e ? atoi(e) : 0; }();   // tuning aid
+    if (a->epilogue == CRCT_EPI_F32) return (policy & 1) != 0;
+    if (policy & 2) return a->M >= 1024 && a->N >= 768;
+    if (policy & 4) return false;
+    return a->N >= 2048 && a->M >= 1024;
 }
 
 extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t stream) {
@@ -662,7 +667,8 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
         };
         // 128x256 tiles move 1.33x fewer operand bytes per FLOP through L2/smem than 128x128 (measured faster on every
         // CRCT shape, wgrad included: profiles/r01_wgrad_shapes.log); 128-wide only when it removes a mostly-empty tile column
-        bn = (a->N <= 128 || cost(128) * 5 < cost(256) * 4) ? 128 : 256;       // also for the split-K wgrad (measured)
+        bn = (a->N <= 128 || cost(128) * 5 < cost(256) * 4) ? 128 : 256;
+        if (f32 && a->accumulate && a->N >= 256) bn = 256;       // split-K refills the SMs: wave count is not the issue (measured)
     }
     if (bn != 128 && bn != 256) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: block_n must be 0, 128 or 256");
     const int num_m_tiles = (a->M + tile_m - 1) / tile_m;
