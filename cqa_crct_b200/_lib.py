@@ -27,19 +27,19 @@ class GemmArgs(C.Structure):
     _fields_ = [('A', vp), ('B', vp), ('D', vp), ('D2', vp), ('bias', vp), ('aux', vp),
                 ('M', i32), ('N', i32), ('K', i32), ('lda', i32), ('ldb', i32), ('ldd', i32), ('ldaux', i32),
                 ('a_major', i32), ('b_major', i32), ('epilogue', i32), ('accumulate', i32), ('split_k', i32),
-                ('block_n', i32), ('dropout_p', f32), ('seed', u64), ('max_ctas', i32), ('cta_group', i32), ('dbg', i32 * 7)]
+                ('block_n', i32), ('dropout_p', f32), ('seed', u64), ('max_ctas', i32), ('cta_group', i32), ('dbg', i32 * 7), ('salt', vp)]
 
 
 class LnBwdArgs(C.Structure):
     _fields_ = [('dy', vp), ('z', vp), ('mean', vp), ('rstd', vp), ('gamma', vp), ('dz', vp), ('dzm', vp),
                 ('dgamma', vp), ('dbeta', vp), ('dbias', vp), ('rows', i32), ('H', i32),
-                ('p_in', f32), ('seed_in', u64), ('p_out', f32), ('seed_out', u64)]
+                ('p_in', f32), ('seed_in', u64), ('p_out', f32), ('seed_out', u64), ('salt', vp)]
 
 
 class EmbedTextArgs(C.Structure):
     _fields_ = [('ids', vp), ('types', vp), ('loc', vp), ('word', vp), ('pos', vp), ('type', vp), ('w_loc', vp),
                 ('b_loc', vp), ('gamma', vp), ('beta', vp), ('y', vp), ('z', vp), ('mean', vp), ('rstd', vp),
-                ('B', i32), ('T', i32), ('H', i32), ('max_pos', i32), ('dropout_p', f32), ('seed', u64)]
+                ('B', i32), ('T', i32), ('H', i32), ('max_pos', i32), ('dropout_p', f32), ('seed', u64), ('salt', vp)]
 
 
 class EmbedTextBwdArgs(C.Structure):
@@ -50,7 +50,7 @@ class EmbedTextBwdArgs(C.Structure):
 class EmbedVisArgs(C.Structure):
     _fields_ = [('g', vp), ('box', vp), ('cls', vp), ('w_loc', vp), ('b_loc', vp), ('color', vp), ('gamma', vp),
                 ('beta', vp), ('y', vp), ('z', vp), ('mean', vp), ('rstd', vp), ('rows', i32), ('H', i32),
-                ('dropout_p', f32), ('seed', u64)]
+                ('dropout_p', f32), ('seed', u64), ('salt', vp)]
 
 
 class EmbedVisBwdArgs(C.Structure):
@@ -60,14 +60,14 @@ class EmbedVisBwdArgs(C.Structure):
 class AttnFwdArgs(C.Structure):
     _fields_ = [('q', vp), ('k', vp), ('v', vp), ('ldq', i32), ('ldk', i32), ('ldv', i32), ('mask_add', vp),
                 ('out', vp), ('ldo', i32), ('lse', vp), ('B', i32), ('nh', i32), ('dh', i32), ('Lq', i32), ('Lk', i32),
-                ('dropout_p', f32), ('seed', u64)]
+                ('dropout_p', f32), ('seed', u64), ('salt', vp)]
 
 
 class AttnBwdArgs(C.Structure):
     _fields_ = [('q', vp), ('k', vp), ('v', vp), ('ldq', i32), ('ldk', i32), ('ldv', i32), ('mask_add', vp),
                 ('out', vp), ('ldo', i32), ('dout', vp), ('lddo', i32), ('lse', vp), ('dq', vp), ('dk', vp), ('dv', vp),
                 ('lddq', i32), ('lddk', i32), ('lddv', i32), ('B', i32), ('nh', i32), ('dh', i32), ('Lq', i32),
-                ('Lk', i32), ('dropout_p', f32), ('seed', u64)]
+                ('Lk', i32), ('dropout_p', f32), ('seed', u64), ('salt', vp)]
 
 
 class LinearArgs(C.Structure):
@@ -85,7 +85,7 @@ class LossArgs(C.Structure):
 class AdamWArgs(C.Structure):
     _fields_ = [('w', vp), ('g', vp), ('m', vp), ('v', vp), ('w_bf16', vp), ('group_of_block64', vp), ('n', C.c_size_t),
                 ('lr', f32 * 4), ('weight_decay', f32 * 4), ('beta1', f32), ('beta2', f32), ('eps', f32), ('step', i32),
-                ('grad_scale', f32)]
+                ('grad_scale', f32), ('dyn', vp)]
 
 
 # every symbol include/crct_b200.h declares (tests check the .so exports exactly these)
@@ -93,9 +93,10 @@ EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf
            'crct_additive_mask', 'crct_layernorm_fwd', 'crct_layernorm_bwd', 'crct_colsum_bf16', 'crct_softmax_rows',
            'crct_embed_text_fwd', 'crct_embed_text_bwd', 'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd',
            'crct_attn_bwd', 'crct_linear_f32', 'crct_linear_f32_batched', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
-           'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw']
+           'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_bump_salt', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw']
 
 _lib = None
+SALT = None         # device int64[1] tensor XOR-ed into every dropout seed on the device (set by the encoder); None = off
 LAUNCHES = 0          # kernels enqueued through this binding (bench.py reports it as gpu_launches)
 
 
@@ -119,8 +120,9 @@ def lib():
         _lib.crct_colsum_f32.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, vp]
         _lib.crct_linear_f32_batched.argtypes = [vp, C.c_int, vp]
         _lib.crct_scale_rows.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp]
-        _lib.crct_pool_mul_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp]
-        _lib.crct_pool_mul_bwd.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp]
+        _lib.crct_pool_mul_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
+        _lib.crct_pool_mul_bwd.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
+        _lib.crct_bump_salt.argtypes = [vp, vp]
         for name in ('crct_gemm_bf16', 'crct_layernorm_bwd', 'crct_embed_text_fwd', 'crct_embed_text_bwd',
                      'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd', 'crct_attn_bwd', 'crct_linear_f32',
                      'crct_hybrid_loss', 'crct_adamw'):
@@ -178,6 +180,7 @@ def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None
     a.a_major, a.b_major, a.epilogue = a_major, b_major, epilogue
     a.accumulate, a.split_k, a.block_n = accumulate, split_k, block_n
     a.dropout_p, a.seed, a.max_ctas, a.cta_group = dropout_p, seed, max_ctas, cta_group
+    a.salt = ptr(SALT)
     if dbg is not None:
         for i, v in enumerate(dbg):
             a.dbg[i] = v
@@ -210,6 +213,7 @@ def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias=None, dzm=N
     a.dgamma, a.dbeta, a.dbias = ptr(dgamma), ptr(dbeta), ptr(dbias)
     a.rows, a.H = z.shape
     a.p_in, a.seed_in, a.p_out, a.seed_out = p_in, seed_in, p_out, seed_out
+    a.salt = ptr(SALT)
     check(lib().crct_layernorm_bwd(C.byref(a), stream_ptr()))
 
 
@@ -235,7 +239,7 @@ def embed_text_fwd(ids, types, loc, word, pos, type_, w_loc, b_loc, gamma, beta,
     a.y, a.z, a.mean, a.rstd = ptr(y), ptr(z), ptr(mean), ptr(rstd)
     a.B, a.T = ids.shape
     a.H, a.max_pos = word.shape[1], pos.shape[0]
-    a.dropout_p, a.seed = dropout_p, seed
+    a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
     check(lib().crct_embed_text_fwd(C.byref(a), stream_ptr()))
 
 
@@ -254,7 +258,7 @@ def embed_vis_fwd(g, box, cls, w_loc, b_loc, color, gamma, beta, y, z=None, mean
                                                                      ptr(color), ptr(gamma), ptr(beta))
     a.y, a.z, a.mean, a.rstd = ptr(y), ptr(z), ptr(mean), ptr(rstd)
     a.rows, a.H = g.shape
-    a.dropout_p, a.seed = dropout_p, seed
+    a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
     check(lib().crct_embed_vis_fwd(C.byref(a), stream_ptr()))
 
 
@@ -270,7 +274,7 @@ def attn_fwd(q, k, v, mask_add, out, lse, *, B, nh, dh, Lq, Lk, ldq, ldk, ldv, l
     a.q, a.k, a.v, a.mask_add, a.out, a.lse = ptr(q), ptr(k), ptr(v), ptr(mask_add), ptr(out), ptr(lse)
     a.ldq, a.ldk, a.ldv, a.ldo = ldq, ldk, ldv, ldo
     a.B, a.nh, a.dh, a.Lq, a.Lk = B, nh, dh, Lq, Lk
-    a.dropout_p, a.seed = dropout_p, seed
+    a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
     check(lib().crct_attn_fwd(C.byref(a), stream_ptr()))
 
 
@@ -281,7 +285,7 @@ def attn_bwd(q, k, v, mask_add, out, dout, lse, dq, dk, dv, *, B, nh, dh, Lq, Lk
     a.dq, a.dk, a.dv = ptr(dq), ptr(dk), ptr(dv)
     a.ldq, a.ldk, a.ldv, a.ldo, a.lddo, a.lddq, a.lddk, a.lddv = ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv
     a.B, a.nh, a.dh, a.Lq, a.Lk = B, nh, dh, Lq, Lk
-    a.dropout_p, a.seed = dropout_p, seed
+    a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
     check(lib().crct_attn_bwd(C.byref(a), stream_ptr()))
 
 
@@ -323,11 +327,11 @@ def colsum_f32(x, out, M, N, ld):
 
 
 def pool_mul_fwd(pt, pv, out, p=0.0, seed=0):
-    check(lib().crct_pool_mul_fwd(ptr(pt), ptr(pv), ptr(out), pt.numel(), p, seed, stream_ptr()))
+    check(lib().crct_pool_mul_fwd(ptr(pt), ptr(pv), ptr(out), pt.numel(), p, seed, ptr(SALT), stream_ptr()))
 
 
 def pool_mul_bwd(dpooled, pt, pv, dut, duv, p=0.0, seed=0):
-    check(lib().crct_pool_mul_bwd(ptr(dpooled), ptr(pt), ptr(pv), ptr(dut), ptr(duv), pt.numel(), p, seed, stream_ptr()))
+    check(lib().crct_pool_mul_bwd(ptr(dpooled), ptr(pt), ptr(pv), ptr(dut), ptr(duv), pt.numel(), p, seed, ptr(SALT), stream_ptr()))
 
 
 def hybrid_loss(logits, reg, labels, R, reg_pred, reg_loss, reg_l1, reg_dist, scalars, dlogits=None, dpre=None, *, l1,
@@ -346,10 +350,14 @@ def scale_rows(x, s, out):
     check(lib().crct_scale_rows(ptr(x), ptr(s), 1 if s.numel() == B else 0, ptr(out), B, n, stream_ptr()))
 
 
-def adamw(w, g, m, v, w_bf16, group, n, lr4, wd4, beta1, beta2, eps, step, grad_scale=1.0):
+def bump_salt(salt):
+    check(lib().crct_bump_salt(ptr(salt), stream_ptr()))
+
+
+def adamw(w, g, m, v, w_bf16, group, n, lr4, wd4, beta1, beta2, eps, step, grad_scale=1.0, dyn=None):
     a = AdamWArgs()
     a.w, a.g, a.m, a.v, a.w_bf16, a.group_of_block64, a.n = ptr(w), ptr(g), ptr(m), ptr(v), ptr(w_bf16), ptr(group), n
     for i in range(4):
         a.lr[i], a.weight_decay[i] = lr4[i], wd4[i]
-    a.beta1, a.beta2, a.eps, a.step, a.grad_scale = beta1, beta2, eps, step, grad_scale
+    a.beta1, a.beta2, a.eps, a.step, a.grad_scale, a.dyn = beta1, beta2, eps, step, grad_scale, ptr(dyn)
     check(lib().crct_adamw(C.byref(a), stream_ptr()))

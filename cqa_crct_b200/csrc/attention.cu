@@ -94,7 +94,7 @@ struct FwdParams {
     float* lse;
     int B, nh, Lq, Lk;
     float scale;
-    uint32_t thr; float dscale; uint64_t seed;
+    uint32_t thr; float dscale; uint64_t seed; const unsigned long long* salt;
 };
 
 template <int DH>
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const float scale2 = p.scale * LOG2E;
-    const CrctDrop32 drop = crct_drop32(p.seed, p.thr);
+    const CrctDrop32 drop = crct_drop32((p.thr != 0u && p.salt) ? (p.seed ^ __ldg(p.salt)) : p.seed, p.thr);
     for (int q0 = warp * 16; q0 < LQP; q0 += NWARPS * 16) {
         uint32_t aq[DH / 16][4];
 #pragma unroll
@@ -227,7 +227,7 @@ struct BwdParams {
     int lddq, lddk, lddv;
     int B, nh, Lq, Lk;
     float scale;
-    uint32_t thr; float dscale; uint64_t seed;
+    uint32_t thr; float dscale; uint64_t seed; const unsigned long long* salt;
 };
 
 template <int DH, int PASS>     // PASS 0: this warp owns 16 keys -> dK, dV ; PASS 1: this warp owns 16 queries -> dQ
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const uint32_t drop_base = blockIdx.x * (uint32_t)p.Lq * (uint32_t)p.Lk;
-    const CrctDrop32 drop = crct_drop32(p.seed, p.thr);
+    const CrctDrop32 drop = crct_drop32((p.thr != 0u && p.salt) ? (p.seed ^ __ldg(p.salt)) : p.seed, p.thr);
     const float scale2 = p.scale * LOG2E;
 
     // ---------------- pass A: this warp owns 16 keys -> dK, dV ----------------
@@ -475,6 +475,7 @@ extern "C" CRCT_API int crct_attn_fwd(const crct_attn_fwd_t* a, crct_stream_t s)
     p.B = a->B; p.nh = a->nh; p.Lq = a->Lq; p.Lk = a->Lk;
     p.scale = 1.0f / sqrtf((float)a->dh);
     p.thr = crct_drop_threshold(a->dropout_p); p.dscale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; p.seed = a->seed;
+    p.salt = reinterpret_cast<const unsigned long long*>(a->salt);
     switch (a->dh) {
         case 32: return launch_fwd<32>(p, as_stream(s));
         case 48: return launch_fwd<48>(p, as_stream(s));
@@ -501,6 +502,7 @@ extern "C" CRCT_API int crct_attn_bwd(const crct_attn_bwd_t* a, crct_stream_t s)
     p.B = a->B; p.nh = a->nh; p.Lq = a->Lq; p.Lk = a->Lk;
     p.scale = 1.0f / sqrtf((float)a->dh);
     p.thr = crct_drop_threshold(a->dropout_p); p.dscale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; p.seed = a->seed;
+    p.salt = reinterpret_cast<const unsigned long long*>(a->salt);
     switch (a->dh) {
         case 32: return launch_bwd<32>(p, as_stream(s));
         case 48: return launch_bwd<48>(p, as_stream(s));

@@ -50,6 +50,7 @@ struct KParams {
     uint32_t drop_thr;
     float drop_scale;
     uint64_t seed;
+    const unsigned long long* salt;
     uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;   // bytes
 };
 
@@ -132,7 +133,7 @@ __device__ __forceinline__ void store_block_bf16(bf16* __restrict__ dst, int ld,
 // one accumulator row x EPI_COLS columns per lane: bias (smem copy) / GELU / dropout + residual / GELU' -> global
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row0, int lane, int col0, const uint32_t (&v)[EPI_COLS],
-                                               const float* bias_s, const AuxRegs& aux, uint8_t* stage) {
+                                               const float* bias_s, const AuxRegs& aux, uint8_t* stage, uint64_t seed) {
     const int row = row0 + lane;
     if constexpr (EPI == CRCT_EPI_F32) {
         if (row >= p.M) return;
@@ -174,7 +175,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row0, int l
             }
             if constexpr (EPI == CRCT_EPI_BIAS_RES) {
                 if (p.drop_thr != 0u)
-                    dropout8(f, p.seed, (uint64_t)row * (uint64_t)p.N + (uint64_t)(col0 + g * 8), p.drop_thr, p.drop_scale);
+                    dropout8(f, seed, (uint64_t)row * (uint64_t)p.N + (uint64_t)(col0 + g * 8), p.drop_thr, p.drop_scale);
                 if (p.aux != nullptr) {
                     float a[8];
                     unpack8(aux.v[g], a);
@@ -213,6 +214,10 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
         }
         asm volatile("bar.sync 1, %0;" :: "n"(NUM_EPI_WARPS * 32) : "memory");
     }
+    uint64_t seed = p.seed;
+    if constexpr (EPI == CRCT_EPI_BIAS_RES) {
+        if (p.drop_thr != 0u && p.salt != nullptr) seed ^= __ldg(p.salt);
+    }
     const int row0 = m0 + lane_grp * 32;
     constexpr int STEPS = (BN / 4) / EPI_COLS;
     const int cbase = col_q * (BN / 4);
@@ -227,7 +232,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
         ptx::tc_ld_32x16(taddr, v);
         aux_to_rows<EPI>(aux[c & 1], lane, stage);
         ptx::tc_wait_ld();
-        if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row0, lane, n0 + cc, v, bias_s + cc, aux[c & 1], stage);     // warp-uniform
+        if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row0, lane, n0 + cc, v, bias_s + cc, aux[c & 1], stage, seed);     // warp-uniform
     }
 }
 
@@ -703,6 +708,7 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     p.drop_thr = crct_drop_threshold(a->dropout_p);
     p.drop_scale = a->dropout_p > 0.f ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
     p.seed = a->seed;
+    p.salt = reinterpret_cast<const unsigned long long*>(a->salt);
     // K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO); LBO unused; +32 B per UMMA_K step.
     // MN-major, SWIZZLE_128B: one TMA box = 64 (MN) x BLOCK_K (K) -> K-groups of 8 rows 1024 B apart (SBO),
     //                         64-wide MN atoms BLOCK_K*128 B apart (LBO); +16 rows * 128 B per UMMA_K step.

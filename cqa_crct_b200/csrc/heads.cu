@@ -125,18 +125,21 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict
 }
 // pooled = dropout(pt * pv)   (vilbert.py:1055)
 __global__ void pool_mul_fwd_kernel(const float* __restrict__ pt, const float* __restrict__ pv, float* __restrict__ out, int n,
-                                    uint32_t thr, float scale, uint64_t seed) {
+                                    uint32_t thr, float scale, uint64_t seed, const unsigned long long* __restrict__ salt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (thr != 0u && salt) seed ^= __ldg(salt);
     float v = pt[i] * pv[i];
     if (thr != 0u) v = crct_keep(seed, (uint64_t)i, thr) ? v * scale : 0.f;
     out[i] = v;
 }
 // dut = dpooled * keep * pv * [pt > 0] ; duv = dpooled * keep * pt * [pv > 0]   (ReLU poolers, vilbert.py:959-960,974-975)
 __global__ void pool_mul_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ pt, const float* __restrict__ pv,
-                                    float* __restrict__ dut, float* __restrict__ duv, int n, uint32_t thr, float scale, uint64_t seed) {
+                                    float* __restrict__ dut, float* __restrict__ duv, int n, uint32_t thr, float scale, uint64_t seed,
+                                    const unsigned long long* __restrict__ salt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (thr != 0u && salt) seed ^= __ldg(salt);
     float d = dpooled[i];
     if (thr != 0u) d = crct_keep(seed, (uint64_t)i, thr) ? d * scale : 0.f;
     const float a = pt[i], b = pv[i];
@@ -229,18 +232,20 @@ struct AdamParams {
     float* w; const float* g; float* m; float* v; bf16* w16; const uint8_t* group; size_t n;
     float lr[4], wd[4];
     float beta1, beta2, eps, bc1, bc2_sqrt, gscale;
+    const float* dyn;          // device {lr[4], bc1, bc2_sqrt} overriding the by-value fields (graph replay)
 };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams p) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (size_t)gridDim.x * blockDim.x) {
         const int grp = p.group ? (p.group[i >> 6] & 3) : 0;
-        const float lr = p.lr[grp], wd = p.wd[grp];
+        const float lr = p.dyn ? __ldg(p.dyn + grp) : p.lr[grp], wd = p.wd[grp];
+        const float bc1 = p.dyn ? __ldg(p.dyn + 4) : p.bc1, bc2_sqrt = p.dyn ? __ldg(p.dyn + 5) : p.bc2_sqrt;
         const float gr = p.g[i] * p.gscale;
         float wi = p.w[i];
         wi *= 1.f - lr * wd;
         const float mi = p.beta1 * p.m[i] + (1.f - p.beta1) * gr;
         const float vi = p.beta2 * p.v[i] + (1.f - p.beta2) * gr * gr;
         p.m[i] = mi; p.v[i] = vi;
-        wi -= lr / p.bc1 * mi / (sqrtf(vi) / p.bc2_sqrt + p.eps);
+        wi -= lr / bc1 * mi / (sqrtf(vi) / bc2_sqrt + p.eps);
         p.w[i] = wi;
         if (p.w16) p.w16[i] = __float2bfloat16(wi);
     }
@@ -302,18 +307,21 @@ extern "C" CRCT_API int crct_colsum_f32(const float* x, float* out, int M, int N
     return CRCT_OK;
 }
 
-extern "C" CRCT_API int crct_pool_mul_fwd(const float* pt, const float* pv, float* out, int n, float p, uint64_t seed, crct_stream_t s) {
+extern "C" CRCT_API int crct_pool_mul_fwd(const float* pt, const float* pv, float* out, int n, float p, uint64_t seed, const uint64_t* salt,
+                                          crct_stream_t s) {
     if (!pt || !pv || !out || n <= 0) CRCT_FAIL(CRCT_ERR_ARG, "crct_pool_mul_fwd: bad argument");
-    pool_mul_fwd_kernel<<<(n + 255) / 256, 256, 0, as_stream(s)>>>(pt, pv, out, n, crct_drop_threshold(p), p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+    pool_mul_fwd_kernel<<<(n + 255) / 256, 256, 0, as_stream(s)>>>(pt, pv, out, n, crct_drop_threshold(p), p > 0.f ? 1.f / (1.f - p) : 1.f, seed,
+                                                                 reinterpret_cast<const unsigned long long*>(salt));
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }
 
 extern "C" CRCT_API int crct_pool_mul_bwd(const float* dpooled, const float* pt, const float* pv, float* dut, float* duv, int n, float p,
-                                 uint64_t seed, crct_stream_t s) {
+                                 uint64_t seed, const uint64_t* salt, crct_stream_t s) {
     if (!dpooled || !pt || !pv || !dut || !duv || n <= 0) CRCT_FAIL(CRCT_ERR_ARG, "crct_pool_mul_bwd: bad argument");
     pool_mul_bwd_kernel<<<(n + 255) / 256, 256, 0, as_stream(s)>>>(dpooled, pt, pv, dut, duv, n, crct_drop_threshold(p),
-                                                                 p > 0.f ? 1.f / (1.f - p) : 1.f, seed);
+                                                                 p > 0.f ? 1.f / (1.f - p) : 1.f, seed,
+                                                                 reinterpret_cast<const unsigned long long*>(salt));
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }
@@ -335,7 +343,7 @@ extern "C" CRCT_API int crct_hybrid_loss(const crct_loss_t* a, crct_stream_t s) 
 extern "C" CRCT_API int crct_adamw(const crct_adamw_t* a, crct_stream_t s) {
     if (!a || !a->w || !a->g || !a->m || !a->v) CRCT_FAIL(CRCT_ERR_ARG, "crct_adamw: null pointer");
     if (a->n == 0) return CRCT_OK;
-    if (a->step < 1) CRCT_FAIL(CRCT_ERR_ARG, "crct_adamw: step counts from 1");
+    if (a->step < 1 && !a->dyn) CRCT_FAIL(CRCT_ERR_ARG, "crct_adamw: step counts from 1");
     AdamParams p;
     p.w = a->w; p.g = a->g; p.m = a->m; p.v = a->v; p.w16 = reinterpret_cast<bf16*>(a->w_bf16); p.group = a->group_of_block64; p.n = a->n;
     for (int i = 0; i < 4; ++i) { p.lr[i] = a->lr[i]; p.wd[i] = a->weight_decay[i]; }
@@ -343,6 +351,7 @@ extern "C" CRCT_API int crct_adamw(const crct_adamw_t* a, crct_stream_t s) {
     p.bc1 = 1.f - powf(a->beta1, (float)a->step);
     p.bc2_sqrt = sqrtf(1.f - powf(a->beta2, (float)a->step));
     p.gscale = a->grad_scale;
+    p.dyn = a->dyn;
     size_t blocks = (a->n + 255) / 256;
     const size_t cap = (size_t)crct_num_sms() * 8;
     if (blocks > cap) blocks = cap;

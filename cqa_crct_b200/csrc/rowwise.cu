@@ -102,8 +102,9 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
                      const float* __restrict__ rstd_in, const float* __restrict__ gamma, bf16* __restrict__ dz,
                      bf16* __restrict__ dzm, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                      int rows, int H, uint32_t thr_in, float scale_in, uint64_t seed_in, uint32_t thr_out, float scale_out,
-                     uint64_t seed_out) {
-    extern __shared__ __align__(16) float acc_s[];       // [3][8 warps][H]
+                     uint64_t seed_out, const unsigned long long* __restrict__ salt) {
+    extern __shared__ __align__(16) float acc_s[];
+    if (salt != nullptr) { const unsigned long long sv = __ldg(salt); seed_in ^= sv; seed_out ^= sv; }       // [3][8 warps][H]
     constexpr int NW = ROW_THREADS / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = H >> 3;
@@ -270,7 +271,7 @@ struct TextEmbArgs {
     const float* gamma; const float* beta;
     bf16* y; bf16* z; float* mean; float* rstd;
     int B, T, H;
-    uint32_t thr; float scale; uint64_t seed;
+    uint32_t thr; float scale; uint64_t seed; const unsigned long long* salt;
 };
 
 __device__ __forceinline__ int first_qa_index(const long long* types_row, int T, int lane) {
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_text_fwd_kernel(const TextE
     }
     float mean, rstd;
     row_stats(r, nchunks, lane, H, mean, rstd);
-    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)row * H, a.thr, a.scale, a.seed);
+    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)row * H, a.thr, a.scale, a.salt ? (a.seed ^ __ldg(a.salt)) : a.seed);
     if (lane == 0 && a.mean) { a.mean[row] = mean; a.rstd[row] = rstd; }
 }
 
@@ -416,7 +417,7 @@ struct VisEmbArgs {
     const float* w_loc; const float* b_loc; const float* color; const float* gamma; const float* beta;
     bf16* y; bf16* z; float* mean; float* rstd;
     int rows, H;
-    uint32_t thr; float scale; uint64_t seed;
+    uint32_t thr; float scale; uint64_t seed; const unsigned long long* salt;
 };
 
 __global__ void __launch_bounds__(ROW_THREADS) embed_vis_fwd_kernel(const VisEmbArgs a) {
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_vis_fwd_kernel(const VisEmb
     }
     float mean, rstd;
     row_stats(r, nchunks, lane, H, mean, rstd);
-    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)row * H, a.thr, a.scale, a.seed);
+    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)row * H, a.thr, a.scale, a.salt ? (a.seed ^ __ldg(a.salt)) : a.seed);
     if (lane == 0 && a.mean) { a.mean[row] = mean; a.rstd[row] = rstd; }
 }
 
@@ -508,6 +509,13 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_vis_bwd_kernel(const VisEmb
     }
 }
 
+__global__ void bump_salt_kernel(unsigned long long* salt) {
+    unsigned long long z = *salt + 0x9E3779B97F4A7C15ull;          // splitmix64 step
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    *salt = z ^ (z >> 31);
+}
+
 inline int check_row_width(int H, const char* what) {
     if (H <= 0 || (H % 8) || H > MAXC * 256) CRCT_FAIL(CRCT_ERR_SHAPE, "%s: row width %d must be a multiple of 8 and <= %d", what, H, MAXC * 256);
     return CRCT_OK;
@@ -515,6 +523,13 @@ inline int check_row_width(int H, const char* what) {
 inline int row_grid(int rows) { return (rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32); }
 
 }  // namespace
+
+extern "C" CRCT_API int crct_bump_salt(uint64_t* salt, crct_stream_t s) {
+    if (!salt) CRCT_FAIL(CRCT_ERR_ARG, "crct_bump_salt: null pointer");
+    bump_salt_kernel<<<1, 1, 0, as_stream(s)>>>(reinterpret_cast<unsigned long long*>(salt));
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
 
 extern "C" CRCT_API int crct_cast_f32_to_bf16(const float* src, void* dst, size_t n, crct_stream_t s) {
     if (!src || !dst) CRCT_FAIL(CRCT_ERR_ARG, "crct_cast_f32_to_bf16: null pointer");
@@ -566,7 +581,8 @@ extern "C" CRCT_API int crct_layernorm_bwd(const crct_ln_bwd_t* a, crct_stream_t
             reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), a->mean, a->rstd, a->gamma,
             reinterpret_cast<bf16*>(a->dz), dzm ? reinterpret_cast<bf16*>(a->dzm) : nullptr, a->dgamma, a->dbeta, a->dbias,
             a->rows, a->H, crct_drop_threshold(a->p_in), a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, a->seed_in,
-            crct_drop_threshold(a->p_out), a->p_out > 0.f ? 1.f / (1.f - a->p_out) : 1.f, a->seed_out);
+            crct_drop_threshold(a->p_out), a->p_out > 0.f ? 1.f / (1.f - a->p_out) : 1.f, a->seed_out,
+            reinterpret_cast<const unsigned long long*>(a->salt));
     };
     switch (nch) {
         case 1: launch(layernorm_bwd_kernel<1>); break;
@@ -613,6 +629,7 @@ extern "C" CRCT_API int crct_embed_text_fwd(const crct_embed_text_t* a, crct_str
     k.y = reinterpret_cast<bf16*>(a->y); k.z = reinterpret_cast<bf16*>(a->z); k.mean = a->mean; k.rstd = a->rstd;
     k.B = a->B; k.T = a->T; k.H = a->H;
     k.thr = crct_drop_threshold(a->dropout_p); k.scale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; k.seed = a->seed;
+    k.salt = reinterpret_cast<const unsigned long long*>(a->salt);
     if (a->B * a->T <= 0) return CRCT_OK;
     embed_text_fwd_kernel<<<row_grid(a->B * a->T), ROW_THREADS, 0, as_stream(s)>>>(k);
     CRCT_LAUNCH_CHECK();
@@ -647,6 +664,7 @@ extern "C" CRCT_API int crct_embed_vis_fwd(const crct_embed_vis_t* a, crct_strea
     k.y = reinterpret_cast<bf16*>(a->y); k.z = reinterpret_cast<bf16*>(a->z); k.mean = a->mean; k.rstd = a->rstd;
     k.rows = a->rows; k.H = a->H;
     k.thr = crct_drop_threshold(a->dropout_p); k.scale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; k.seed = a->seed;
+    k.salt = reinterpret_cast<const unsigned long long*>(a->salt);
     if (a->rows <= 0) return CRCT_OK;
     embed_vis_fwd_kernel<<<row_grid(a->rows), ROW_THREADS, 0, as_stream(s)>>>(k);
     CRCT_LAUNCH_CHECK();

@@ -143,7 +143,8 @@ class VisualDialogEncoder(nn.Module):
         for alias, src in TIED.items():
             _attach(root, alias, self._params_by_name[src])
         self.bert_pretrained = root
-        self._step = 0
+        self._step = 0                       # site seeds are launch constants; per-step variation comes from the device salt
+        self._salt = None                    # int64[1] on the device, advanced by crct_bump_salt once per training forward
         self.grad_ready_hook = None          # set by cqa_crct_b200.parallel.DistributedDataParallel
         self.train()                         # encoder_decorator.py:17
 
@@ -577,6 +578,7 @@ class VisualDialogEncoder(nn.Module):
 
     def _backward(self, sv, d_nsp, d_reg):
         cfg, arena = self.cfg, self.arena
+        L.SALT = self._salt
         B, T, R = sv.B, sv.T, sv.R
         hook = self.grad_ready_hook
         dt, dv = self._heads_bwd(sv.heads, d_nsp, d_reg, B, T, R)
@@ -659,8 +661,11 @@ class VisualDialogEncoder(nn.Module):
         Rt = cvt(Rt, torch.float32)
         labels = cvt(next_sentence_label, torch.int64).view(-1) if train_branch else None
         keep = train_branch and torch.is_grad_enabled()
+        if self._salt is None or self._salt.device != dev:
+            self._salt = torch.full((1,), (torch.initial_seed() * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF, dtype=torch.int64, device=dev)
+        L.SALT = self._salt
         if self.training:
-            self._step += 1
+            L.bump_salt(self._salt)          # fresh dropout masks for this step (also on CUDA-graph replay)
         logits, outs, scalars, seq_t, sv = self._run_forward(ids, types, loc, feat, box, cls, amask, imask, labels, Rt, kind, keep)
         reg_pred, reg_loss, reg_l1, reg_dist = outs
         nsp_loss = scalars[1:2]

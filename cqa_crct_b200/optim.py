@@ -48,6 +48,8 @@ class FusedAdamW:
         self.step_count = 0
         self.lr_factor = 1.0
         self.min_lr = 0.0
+        self.dyn = None            # device {lr[4], 1-beta1^t, sqrt(1-beta2^t)} for CUDA-graph replay (see graph.py)
+        self._dyn_host = None
 
     def current_lrs(self):
         return [max(b * self.lr_factor, self.min_lr) if b * self.lr_factor > self.min_lr else self.min_lr for b in self.base_lr]
@@ -61,6 +63,29 @@ class FusedAdamW:
         arena.ensure_device_buffers()
         L.adamw(arena.w32, arena.g32, self.m, self.v, arena.w16, self.group, self.n, self.current_lrs(), self.wd,
                 self.betas[0], self.betas[1], self.eps, self.step_count, grad_scale)
+        arena.mark_bf16_fresh()
+
+    # ---- CUDA-graph support: the kernel reads lr / bias corrections from a device array refreshed before each replay
+    def enable_device_scalars(self):
+        dev = self.enc.arena.w32.device
+        self.dyn = torch.zeros(6, dtype=torch.float32, device=dev)
+        self._dyn_host = torch.zeros(6, dtype=torch.float32).pin_memory()
+
+    def push_device_scalars(self):
+        """Advance the step counter and upload {lr[4], bias corrections} (call right before replaying a captured step)."""
+        self.step_count += 1
+        lrs = self.current_lrs()
+        h = self._dyn_host
+        h[0], h[1], h[2], h[3] = lrs
+        h[4] = 1.0 - self.betas[0] ** self.step_count
+        h[5] = (1.0 - self.betas[1] ** self.step_count) ** 0.5
+        self.dyn.copy_(h, non_blocking=True)
+
+    def step_captured(self, grad_scale: float = 1.0):
+        """The launch to put INSIDE a CUDA graph: identical kernel, scalars taken from `self.dyn`."""
+        arena = self.enc.arena
+        L.adamw(arena.w32, arena.g32, self.m, self.v, arena.w16, self.group, self.n, self.base_lr, self.wd,
+                self.betas[0], self.betas[1], self.eps, 1, grad_scale, dyn=self.dyn)
         arena.mark_bf16_fresh()
 
     def state_dict(self):

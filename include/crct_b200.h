@@ -78,6 +78,7 @@ typedef struct {
     int32_t max_ctas;   /* 0 = one persistent CTA per SM; else cap (tests) */
     int32_t cta_group;  /* 0 = choose; 1 = one CTA per 128 x BN tile; 2 = CTA pair (tcgen05 cta_group::2) per 256 x BN tile */
     int32_t dbg[7];     /* descriptor overrides for bring-up; must be 0 in production */
+    const uint64_t* salt; /* optional DEVICE word XOR-ed into `seed` at run time (see crct_bump_salt), or NULL */
 } crct_gemm_t;
 
 int crct_gemm_bf16(const crct_gemm_t* args, crct_stream_t stream);
@@ -110,6 +111,7 @@ typedef struct {
     int32_t rows, H;
     float p_in;  uint64_t seed_in;
     float p_out; uint64_t seed_out;
+    const uint64_t* salt; /* optional device word XOR-ed into both seeds */
 } crct_ln_bwd_t;
 int crct_layernorm_bwd(const crct_ln_bwd_t* args, crct_stream_t stream);
 /* out[n] += sum_rows x[row,n]   (bias gradients).  x bf16 [rows,N], row stride ld. */
@@ -130,6 +132,7 @@ typedef struct {
     void* y; void* z; float* mean; float* rstd;              /* bf16 [B*T,H] x2, fp32 [B*T] x2 */
     int32_t B, T, H, max_pos;
     float dropout_p; uint64_t seed;
+    const uint64_t* salt;
 } crct_embed_text_t;
 int crct_embed_text_fwd(const crct_embed_text_t* args, crct_stream_t stream);
 /* scatter of dz (after crct_layernorm_bwd) into the tables; all outputs += . */
@@ -151,6 +154,7 @@ typedef struct {
     void* y; void* z; float* mean; float* rstd;
     int32_t rows, H;
     float dropout_p; uint64_t seed;
+    const uint64_t* salt;
 } crct_embed_vis_t;
 int crct_embed_vis_fwd(const crct_embed_vis_t* args, crct_stream_t stream);
 typedef struct {
@@ -176,6 +180,7 @@ typedef struct {
     int32_t B, nh, dh, Lq, Lk;
     float dropout_p;        /* on the probabilities; element counter ((b*nh+h)*Lq+i)*Lk+j */
     uint64_t seed;
+    const uint64_t* salt;
 } crct_attn_fwd_t;
 int crct_attn_fwd(const crct_attn_fwd_t* args, crct_stream_t stream);
 
@@ -191,6 +196,7 @@ typedef struct {
     int32_t B, nh, dh, Lq, Lk;
     float dropout_p;
     uint64_t seed;
+    const uint64_t* salt;
 } crct_attn_bwd_t;
 int crct_attn_bwd(const crct_attn_bwd_t* args, crct_stream_t stream);
 
@@ -225,9 +231,14 @@ int crct_scatter_first(const float* g, void* dst_bf16, long long row_stride, int
 /* out[n] += sum_m x[m*ld+n] */
 int crct_colsum_f32(const float* x, float* out, int M, int N, long long ld, crct_stream_t stream);
 /* pooled = dropout_p(pt * pv)  (vilbert.py:1055) and its backward through the two ReLU poolers */
-int crct_pool_mul_fwd(const float* pt, const float* pv, float* out, int n, float p, uint64_t seed, crct_stream_t stream);
+int crct_pool_mul_fwd(const float* pt, const float* pv, float* out, int n, float p, uint64_t seed, const uint64_t* salt,
+                      crct_stream_t stream);
 int crct_pool_mul_bwd(const float* dpooled, const float* pt, const float* pv, float* dut, float* duv, int n, float p,
-                      uint64_t seed, crct_stream_t stream);
+                      uint64_t seed, const uint64_t* salt, crct_stream_t stream);
+/* Dropout streams are counter-based: keep(element) = f(seed ^ *salt, element).  `seed` identifies the call site and is a
+ * launch constant; `salt` is one device word the training loop advances once per step with this kernel, so a step
+ * captured in a CUDA graph draws fresh masks on every replay while forward and backward of one step still agree. */
+int crct_bump_salt(uint64_t* salt, crct_stream_t stream);
 /* Hybrid loss, metrics and (when dlogits/dpre are given) the gradients of
  *   loss = nsp_coeff * CE(logits, labels; ignore -1) + reg_coeff * mean_B(reg_loss)
  * R[b] = (value, needs_regression, tolerance, scale).  labels NULL = inference (no CE).  Outputs are dense [B]
@@ -264,6 +275,7 @@ typedef struct {
     float beta1, beta2, eps;
     int32_t step;                       /* 1-based */
     float grad_scale;                   /* e.g. 1/world_size after a sum all-reduce */
+    const float* dyn;                   /* optional DEVICE array {lr[0..3], 1-beta1^t, sqrt(1-beta2^t)} overriding lr/step (CUDA-graph replay) */
 } crct_adamw_t;
 int crct_adamw(const crct_adamw_t* args, crct_stream_t stream);
 

@@ -178,3 +178,33 @@ def test_stress_shape_forward_backward_runs():
     loss.backward()
     torch.cuda.synchronize()
     assert torch.isfinite(loss) and torch.isfinite(m.arena.g32).all()
+
+
+def test_graphed_train_step_matches_eager_and_redraws_dropout():
+    """cqa_crct_b200.graph.GraphedTrainStep: the captured step updates the weights exactly like the eager calls
+    (dropout off), and with dropout on every replay draws new masks (device salt) — losses differ between replays."""
+    from cqa_crct_b200.graph import GraphedTrainStep
+    from cqa_crct_b200.optim import FusedAdamW
+    rec = load_golden('tiny_train_l1')
+    m1, params, cfg, sd, batch, gb = build(rec)
+    m2, *_ = build(rec)
+    o1, o2 = FusedAdamW(m1, lr=1e-3, image_lr=1e-3), FusedAdamW(m2, lr=1e-3, image_lr=1e-3)
+    g = GraphedTrainStep(m2, o2, params, gb, warmup_steps=1)          # 1 eager warm-up step applied; capture itself runs nothing
+    o1.zero_grad()
+    glue_forward(m1, gb, params)[0].backward()
+    o1.step()
+    assert rel_err(m2.arena.w32, m1.arena.w32) < 1e-5               # fp32 split-K atomics: not bit-identical
+    l_eager = None
+    for _ in range(3):
+        o1.zero_grad()
+        l_eager = glue_forward(m1, gb, params)[0]
+        l_eager.backward()
+        o1.step()
+        l_graph = g.step(gb)
+    torch.cuda.synchronize()
+    assert abs(float(l_eager) - float(l_graph)) < 1e-3
+    assert rel_err(m2.arena.w32, m1.arena.w32) < 1e-4
+    m2.train()                                                       # dropout on: a new graph, masks must change per replay
+    g2 = GraphedTrainStep(m2, o2, params, gb, warmup_steps=1)
+    losses = [float(g2.step(gb)) for _ in range(4)]
+    assert len(set(round(x, 6) for x in losses)) > 1 and all(x == x for x in losses)
