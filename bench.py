@@ -184,9 +184,8 @@ def main():
     captured_launches = 0
     if train and not args.no_graph:
         from cqa_crct_b200.graph import GraphedTrainStep
-        l0 = L.LAUNCHES
         gstep = GraphedTrainStep(model, opt, params, resident[0], scheduler=sched, warmup_steps=2)
-        captured_launches = (L.LAUNCHES - l0) // 3           # 2 eager warm-up steps + 1 captured step
+        captured_launches = gstep.launches_per_step
 
     def step(batch, read_loss=False):
         if gstep is not None:                                # captured step: copy inputs into the static buffers, replay

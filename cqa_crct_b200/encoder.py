@@ -577,13 +577,23 @@ class VisualDialogEncoder(nn.Module):
         return logits, outs, scalars, t, sv
 
     def _backward(self, sv, d_nsp, d_reg):
+        """Hand-written backward; reports every finished gradient range to `grad_ready_hook` (data-parallel exchange)."""
+        hook = self.grad_ready_hook
+        for lo, hi in self._backward_stages(sv, d_nsp, d_reg):
+            if hook:
+                hook(lo, hi)
+        if hook:
+            hook(None, None)         # backward finished
+
+    def _backward_stages(self, sv, d_nsp, d_reg):
+        """Generator form of the backward: yields the [lo, hi) arena range whose gradients have just become final,
+        from the tail of the arena (heads) to its head (embeddings).  `graph.GraphedTrainStep` drives it directly to
+        cut the captured step into segments between which the bucketed all-reduces are launched."""
         cfg, arena = self.cfg, self.arena
         L.SALT = self._salt
         B, T, R = sv.B, sv.T, sv.R
-        hook = self.grad_ready_hook
         dt, dv = self._heads_bwd(sv.heads, d_nsp, d_reg, B, T, R)
-        if hook:
-            hook(arena.offsets['bert.t_pooler.dense.weight'], arena.live_end)
+        yield arena.offsets['bert.t_pooler.dense.weight'], arena.live_end
         sched = cfg.schedule()
         for (kind_, i), s in reversed(list(zip(sched, sv.layers))):
             if kind_ == 't':
@@ -595,9 +605,7 @@ class VisualDialogEncoder(nn.Module):
             else:
                 pre = f'bert.encoder.c_layer.{i}'
                 dv, dt = self._co_layer_bwd(dv, dt, s, pre)
-            if hook:
-                lo, hi = self._block_range(pre)
-                hook(lo, hi)
+            yield self._block_range(pre)
         # embeddings
         e = 'bert.embeddings'
         dzt = torch.empty_like(dt)
@@ -613,9 +621,30 @@ class VisualDialogEncoder(nn.Module):
         L.colsum_bf16(dzv, self._g(e + '.new_loc_emb.bias'))
         self._wgrad(dzv, sv.probs, self._g(e + '.new_image_embeddings.weight'))
         L.embed_vis_bwd(dzv, sv.box2, sv.cls2, self._g(e + '.color_emb.weight'), self._g(e + '.new_loc_emb.weight'))
-        if hook:
-            hook(0, self._block_range('bert.v_embeddings')[1])
-            hook(None, None)         # backward finished
+        yield 0, self._block_range('bert.v_embeddings')[1]
+
+    def train_step_stages(self, batch, nsp_coeff: float = 1.0, reg_coeff: float = 1.0):
+        """Forward + backward of one training batch WITHOUT autograd (same kernels, same order as
+        `glue_forward(...)[0].backward()`), as a generator over finished gradient ranges.  After the first `next()`
+        the forward and the heads' backward have been enqueued; `self.last_scalars` = {loss, nsp, mean reg, counts},
+        `self.last_logits`, `self.last_reg` hold the (device) outputs."""
+        dev = self.arena.w32.device
+        ids = batch['tokens']
+        B, T = ids.shape
+        seq_len = torch.gather(batch['sep_indices'], 1, batch['hist_len'].view(-1, 1)).squeeze(1) + 1       # encoder_decorator.py:118-119
+        amask = torch.arange(T, device=dev).unsqueeze(0) < seq_len.unsqueeze(1)
+        if self._salt is None or self._salt.device != dev:
+            self._salt = torch.full((1,), (torch.initial_seed() * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF, dtype=torch.int64, device=dev)
+        L.SALT = self._salt
+        if self.training:
+            L.bump_salt(self._salt)
+        logits, outs, scalars, _, sv = self._run_forward(
+            ids, batch['segments'], batch['loc'], batch['image_feat'], batch['image_loc'], batch['image_target'], amask,
+            batch['image_mask'], batch['next_sentence_labels'].view(-1), batch['R'], 'L1_smooth', True)
+        self.last_scalars, self.last_logits, self.last_reg = scalars, logits, outs
+        d_nsp = torch.full((1,), float(nsp_coeff), dtype=torch.float32, device=dev)
+        d_reg = torch.full((B,), float(reg_coeff) / B, dtype=torch.float32, device=dev)      # d mean_B(reg_loss) / d reg_loss[b]
+        yield from self._backward_stages(sv, d_nsp, d_reg)
 
     def _block_range(self, prefix):
         """[lo, hi) element range of the live arena tensors under `prefix` (contiguous by construction)."""

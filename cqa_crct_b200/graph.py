@@ -3,59 +3,103 @@
 One training step of the reference loop (CRCT/train.py:167-215: forward glue, `loss.backward()`, optimizer step,
 `zero_grad`) is ~640 kernel launches here; enqueuing them from Python costs ~16 ms per step, and the reference
 additionally syncs the host six times per step for its statistics (train.py:178-183).  `GraphedTrainStep` captures the
-same calls (`glue_forward` -> `loss.backward()` -> `FusedAdamW`) once into a CUDA graph and replays it:
+same kernels in the same order (`VisualDialogEncoder.train_step_stages` = the body of `glue_forward` + the hand-written
+backward, then `FusedAdamW`) into CUDA graphs and replays them:
 
   * inputs live in static device buffers; `step(batch)` copies the batch (host-pinned or device) into them;
   * dropout stays random: every replay runs `crct_bump_salt`, and all dropout kernels XOR that device word into their
     call-site seed (include/crct_b200.h), so masks change per step while forward/backward agree;
   * the optimizer's per-step scalars (lr schedule, bias corrections) are read from a 6-float device array that is
     refreshed before the replay;
-  * with a `cqa_crct_b200.parallel.DistributedDataParallel` model the bucketed NCCL all-reduces are captured too.
+  * data parallel (model wrapped in `cqa_crct_b200.parallel.DistributedDataParallel`): the step is cut into one graph
+    per gradient bucket; after replaying segment i the bucket it finished is all-reduced (NCCL, average) asynchronously
+    while segment i+1 replays, so the exchange still overlaps the backward without capturing NCCL inside a graph.
 
-Outputs (`loss`, `nsp_scores`, regression list) are static tensors, overwritten by the next `step`: read or clone
-them before stepping again.
+`step()` returns the static loss tensor (overwritten by the next step): read or clone it before stepping again.
 """
 from __future__ import annotations
 
 from typing import Dict, Optional
 
 import torch
-
-from .encoder import glue_forward
+import torch.distributed as dist
 
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, params: dict, example_batch: Dict[str, torch.Tensor], scheduler=None,
                  warmup_steps: int = 2):
-        self.model, self.opt, self.params, self.sched = model, optimizer, params, scheduler
-        enc = getattr(model, 'module', model)
+        self.opt, self.params, self.sched = optimizer, params, scheduler
+        self.ddp = model if hasattr(model, 'module') else None
+        self.enc = enc = getattr(model, 'module', model)
+        self.world = self.ddp.world if self.ddp is not None else 1
         dev = enc.arena.w32.device
-        self.static = {k: v.to(dev).clone() for k, v in example_batch.items()}
+        self.static = {k: v.to(dev).clone() for k, v in example_batch.items() if k != 'needs_reg'}
+        self.nsp_coeff, self.reg_coeff = float(params.get('nsp_loss_coeff', 1.0)), float(params.get('reg_loss_coeff', 1.0))
         optimizer.enable_device_scalars()
-        self.stream = torch.cuda.Stream(device=dev)
-        self.graph = torch.cuda.CUDAGraph()
-        self.stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(self.stream):
-            for _ in range(max(1, warmup_steps)):       # eager warm-up on the side stream: allocator pools, lazy init, NCCL
+        self.segments = []                # [(graph, (lo, hi) bucket finished by this segment or None)]
+        self.launches_per_step = 0
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup_steps)):       # eager warm-up: allocator pools, lazy kernel attributes, NCCL
                 optimizer.push_device_scalars()
-                self._one_step()
+                self._eager_step()
             torch.cuda.synchronize(dev)
             optimizer.push_device_scalars()
-            with torch.cuda.graph(self.graph, stream=self.stream):
-                self.loss, self.out = self._one_step()
+            self._capture()
             optimizer.step_count -= 1                    # capture records the step, it does not run it
-        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
         if scheduler is not None:
             for _ in range(max(1, warmup_steps)):
                 scheduler.step()
 
-    def _one_step(self):
+    # -- one step, eagerly (warm-up): same calls as the captured version, exchange through the wrapper's hook logic
+    def _eager_step(self):
         self.opt.zero_grad()
-        out = glue_forward(self.model, self.static, self.params)
-        loss = out[0]
-        loss.backward()
+        works = []
+        for lo, hi in self._buckets(self.enc.train_step_stages(self.static, self.nsp_coeff, self.reg_coeff)):
+            if self.world > 1:
+                works.append(dist.all_reduce(self.enc.arena.g32[lo:hi], op=dist.ReduceOp.AVG, group=self.ddp.pg, async_op=True))
+        for w in works:
+            w.wait()
         self.opt.step_captured()
-        return loss.detach(), out
+
+    def _buckets(self, stages):
+        """Merge the finished ranges (descending, contiguous) into buckets of >= the wrapper's bucket size."""
+        cap = self.ddp.bucket_elems if self.ddp is not None else 1 << 62
+        pend = None
+        for lo, hi in stages:
+            pend = (lo, hi) if pend is None else (lo, pend[1])
+            if pend[1] - pend[0] >= cap:
+                yield pend
+                pend = None
+        if pend is not None:
+            yield pend
+
+    def _capture(self):
+        from . import _lib as L
+        l0 = L.LAUNCHES
+        pool = torch.cuda.graph_pool_handle()      # all segments share one memory pool (they replay in capture order)
+
+        def begin():
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(pool=pool)
+            return g
+
+        g = begin()
+        self.opt.zero_grad()
+        for lo, hi in self._buckets(self.enc.train_step_stages(self.static, self.nsp_coeff, self.reg_coeff)):
+            if self.world > 1:                   # cut here: the bucket [lo, hi) is final once this segment has run
+                g.capture_end()
+                self.segments.append((g, (lo, hi)))
+                g = begin()
+        self.opt.step_captured()
+        g.capture_end()
+        self.segments.append((g, None))
+        self.loss = self.enc.last_scalars[0:1]
+        self.logits, self.reg = self.enc.last_logits, self.enc.last_reg
+        self.launches_per_step = L.LAUNCHES - l0
 
     def step(self, batch: Optional[Dict[str, torch.Tensor]] = None):
         """Copy `batch` into the static inputs (if given), replay the captured step, return the (static) loss tensor."""
@@ -63,7 +107,15 @@ class GraphedTrainStep:
             for k, dst in self.static.items():
                 dst.copy_(batch[k], non_blocking=True)
         self.opt.push_device_scalars()
-        self.graph.replay()
+        works = []
+        for g, bucket in self.segments:
+            if bucket is None:
+                for w in works:
+                    w.wait()                     # compute stream waits for the exchanges before the optimizer segment
+            g.replay()
+            if bucket is not None:
+                works.append(dist.all_reduce(self.enc.arena.g32[bucket[0]:bucket[1]], op=dist.ReduceOp.AVG,
+                                             group=self.ddp.pg, async_op=True))
         if self.sched is not None:
             self.sched.step()
         return self.loss

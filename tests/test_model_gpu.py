@@ -188,12 +188,13 @@ def test_graphed_train_step_matches_eager_and_redraws_dropout():
     rec = load_golden('tiny_train_l1')
     m1, params, cfg, sd, batch, gb = build(rec)
     m2, *_ = build(rec)
-    o1, o2 = FusedAdamW(m1, lr=1e-3, image_lr=1e-3), FusedAdamW(m2, lr=1e-3, image_lr=1e-3)
+    o1, o2 = FusedAdamW(m1, lr=2e-5, image_lr=2e-5), FusedAdamW(m2, lr=2e-5, image_lr=2e-5)      # the reference's lr (options.py:21)
     g = GraphedTrainStep(m2, o2, params, gb, warmup_steps=1)          # 1 eager warm-up step applied; capture itself runs nothing
     o1.zero_grad()
     glue_forward(m1, gb, params)[0].backward()
     o1.step()
-    assert rel_err(m2.arena.w32, m1.arena.w32) < 1e-5               # fp32 split-K atomics: not bit-identical
+    e0 = rel_err(m2.arena.w32, m1.arena.w32)
+    assert e0 < 1e-5, e0               # fp32 split-K atomics: not bit-identical
     l_eager = None
     for _ in range(3):
         o1.zero_grad()
@@ -202,8 +203,9 @@ def test_graphed_train_step_matches_eager_and_redraws_dropout():
         o1.step()
         l_graph = g.step(gb)
     torch.cuda.synchronize()
-    assert abs(float(l_eager) - float(l_graph)) < 1e-3
-    assert rel_err(m2.arena.w32, m1.arena.w32) < 1e-4
+    assert abs(float(l_eager) - float(l_graph)) < 1e-3, (float(l_eager), float(l_graph))
+    e1 = rel_err(m2.arena.w32, m1.arena.w32)
+    assert e1 < 1e-4, e1
     m2.train()                                                       # dropout on: a new graph, masks must change per replay
     g2 = GraphedTrainStep(m2, o2, params, gb, warmup_steps=1)
     losses = [float(g2.step(gb)) for _ in range(4)]
