@@ -54,8 +54,21 @@ def _run(rank, world, port, out_path):
     gathered = [torch.zeros_like(g_ddp) for _ in range(world)]
     dist.all_gather(gathered, g_ddp)
     same = all(torch.equal(gathered[0], x) for x in gathered)
+    # the CUDA-graph step: one graph segment per bucket, NCCL launched between segments; ranks must stay in lock-step
+    from cqa_crct_b200.graph import GraphedTrainStep
+    from cqa_crct_b200.optim import FusedAdamW
+    ddp.require_sync = True
+    opt = FusedAdamW(ddp, lr=2e-5, image_lr=2e-5)
+    gs = GraphedTrainStep(ddp, opt, params, half, warmup_steps=1)
+    for _ in range(2):
+        gs.step(half)
+    torch.cuda.synchronize()
+    w = enc.arena.w32[:enc.arena.live_end].clone()
+    ws = [torch.zeros_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    graph_same = all(torch.equal(ws[0], x) for x in ws)
     if rank == 0:
-        torch.save({'rel': rel, 'same': same, 'buckets': nb}, out_path)
+        torch.save({'rel': rel, 'same': same, 'buckets': nb, 'graph_same': graph_same, 'segments': len(gs.segments)}, out_path)
     dist.destroy_process_group()
 
 
@@ -67,3 +80,4 @@ def test_two_gpu_gradients_equal_single_gpu_full_batch(tmp_path):
     assert r['same']                       # every rank ends with identical gradients
     assert r['buckets'] >= 2               # the exchange really was bucketed
     assert r['rel'] < 3e-2, r              # = full-batch gradients up to bf16 noise
+    assert r['graph_same'] and r['segments'] >= 3, r     # graphed data-parallel steps keep the replicas identical
