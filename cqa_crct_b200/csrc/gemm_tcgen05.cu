@@ -639,7 +639,8 @@ int dispatch(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensor
 static bool crct_gemm_auto_pair(const crct_gemm_t* a) {
     // measured on B200 (profiles/r01_gemm_shapes.log): the CTA pair wins ~4 % once there are >= 8 tile columns to
     // share; narrower outputs quantise worse on 256-row tiles
-    static const int policy = []() { const char* e = getenv("CRCT_GEMM_PAIR_POLICY"); return e ? atoi(e) : 0; }();   // tuning aid
+    const char* e = getenv("CRCT_GEMM_PAIR_POLICY");            // tuning aid (tools/ab_policy.py)
+    const int policy = e ? atoi(e) : 0;
     if (a->epilogue == CRCT_EPI_F32) return (policy & 1) != 0;
     if (policy & 2) return a->M >= 1024 && a->N >= 768;
     if (policy & 4) return false;
