@@ -97,6 +97,14 @@ def _attach(root: nn.Module, dotted: str, param: nn.Parameter):
     mod.register_parameter(parts[-1], param)
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class _Saved:
     """Activations a forward keeps for its backward."""
     pass
@@ -146,6 +154,10 @@ class VisualDialogEncoder(nn.Module):
         self._step = 0                       # site seeds are launch constants; per-step variation comes from the device salt
         self._salt = None                    # int64[1] on the device, advanced by crct_bump_salt once per training forward
         self.grad_ready_hook = None          # set by cqa_crct_b200.parallel.DistributedDataParallel
+        self.overlap_streams = True          # run independent visual / text layers on two streams, wgrads on a third
+        self._side_stream = None
+        self._wg_stream = None
+        self._wg_hold = []
         self.train()                         # encoder_decorator.py:17
 
     # ------------------------------------------------------------------ parameters / devices
@@ -204,6 +216,11 @@ class VisualDialogEncoder(nn.Module):
     def _drop(self, p):
         return float(p) if self.training else 0.0
 
+    def _side(self, dev):
+        if self._side_stream is None or self._side_stream.device != dev:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        return self._side_stream
+
     # ------------------------------------------------------------------ building blocks (forward)
     def _linear(self, x, W, bias, M, epilogue=L.EPI_BIAS, aux=None, D2=None, p=0.0, seed=0):
         N, K = W.shape
@@ -247,18 +264,38 @@ class VisualDialogEncoder(nn.Module):
         self._wgrad(gz, s.h, self._g(pre_o + '.dense.weight'))
         du = torch.empty(M, I, dtype=torch.bfloat16, device=dy.device)
         L.gemm(gz, W2, du, M=M, N=I, K=H, b_major=1, epilogue=L.EPI_DGELU, aux=s.u)
-        L.colsum_bf16(du, self._g(pre_i + '.dense.bias'))
-        self._wgrad(du, s.a, self._g(pre_i + '.dense.weight'))
+        self._wgrad(du, s.a, self._g(pre_i + '.dense.weight'), self._g(pre_i + '.dense.bias'))
         da = torch.empty_like(dy)
         L.gemm(du, W1, da, M=M, N=H, K=I, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz)
         return da
 
-    def _wgrad(self, dy, x, gW):
-        """gW[out,in] += dy^T x  (fp32 accumulate, split-K)."""
+    def _wgrad(self, dy, x, gW, gb=None):
+        """gW[out,in] += dy^T x  (fp32 accumulate, split-K) and, when `gb` is given, gb += colsum(dy).
+        Nothing in the backward chain waits for weight gradients, so they are issued on a second stream: their CTAs take
+        the SMs that the chain's kernels (partial last waves, small grids) leave idle.  `_wgrad_join` (called before a
+        gradient range is reported finished) makes the chain's stream wait for them and releases the operands."""
         rows, No = dy.shape
         Ki = x.shape[1]
-        L.gemm(dy, x, gW, M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, lda=dy.stride(0),
-               ldb=x.stride(0), ldd=Ki)
+        dev = dy.device
+        ws = None
+        if self.overlap_streams:
+            cur = torch.cuda.current_stream(dev)
+            if self._wg_stream is None or self._wg_stream.device != dev:
+                self._wg_stream = torch.cuda.Stream(device=dev)
+            ws = self._wg_stream
+            ws.wait_stream(cur)
+            self._wg_hold.append((dy, x, cur))
+        with torch.cuda.stream(ws) if ws is not None else _NullCtx():
+            if gb is not None:
+                L.colsum_bf16(dy, gb)
+            L.gemm(dy, x, gW, M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, lda=dy.stride(0),
+                   ldb=x.stride(0), ldd=Ki)
+
+    def _wgrad_join(self):
+        if self._wg_hold:
+            for cur in {id(c): c for _, _, c in self._wg_hold}.values():
+                cur.wait_stream(self._wg_stream)
+            self._wg_hold.clear()
 
     def _attn_out_fwd(self, ctx, x, pre_dense, pre_ln, p_drop, seed, keep):
         """dense + dropout + residual + LayerNorm (vilbert.py:424-428 / 555-559 / 749-756)."""
@@ -318,8 +355,7 @@ class VisualDialogEncoder(nn.Module):
                    B=s.B, nh=s.nh, dh=dh, Lq=s.L, Lk=s.L, ldq=3 * H, ldk=3 * H, ldv=3 * H, ldo=H, lddo=H, lddq=3 * H, lddk=3 * H,
                    lddv=3 * H, dropout_p=s.p_att, seed=s.s_att)
         mods = [pre + '.attention.self.' + n for n in names]
-        L.colsum_bf16(dqkv, self.arena.fused(self.arena.g32, mods, '.bias'))
-        self._wgrad(dqkv, s.x, self.arena.fused(self.arena.g32, mods, '.weight'))
+        self._wgrad(dqkv, s.x, self.arena.fused(self.arena.g32, mods, '.weight'), self.arena.fused(self.arena.g32, mods, '.bias'))
         Wqkv = self.arena.fused(self.arena.w16, mods, '.weight')
         dx = torch.empty_like(dy)
         L.gemm(dqkv, Wqkv, dx, M=M, N=H, K=3 * H, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz1)
@@ -385,10 +421,8 @@ class VisualDialogEncoder(nn.Module):
                    dropout_p=s.p2, seed=s.s2)
         m1 = [pre + '.biattention.' + n for n in ('query1', 'key1', 'value1')]
         m2 = [pre + '.biattention.' + n for n in ('query2', 'key2', 'value2')]
-        L.colsum_bf16(dqkv1, self.arena.fused(self.arena.g32, m1, '.bias'))
-        L.colsum_bf16(dqkv2, self.arena.fused(self.arena.g32, m2, '.bias'))
-        self._wgrad(dqkv1, s.v, self.arena.fused(self.arena.g32, m1, '.weight'))
-        self._wgrad(dqkv2, s.t, self.arena.fused(self.arena.g32, m2, '.weight'))
+        self._wgrad(dqkv1, s.v, self.arena.fused(self.arena.g32, m1, '.weight'), self.arena.fused(self.arena.g32, m1, '.bias'))
+        self._wgrad(dqkv2, s.t, self.arena.fused(self.arena.g32, m2, '.weight'), self.arena.fused(self.arena.g32, m2, '.bias'))
         dv = torch.empty_like(dyv)
         dt = torch.empty_like(dyt)
         L.gemm(dqkv1, self.arena.fused(self.arena.w16, m1, '.weight'), dv, M=Mv, N=Hv, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzv)
@@ -557,16 +591,36 @@ class VisualDialogEncoder(nn.Module):
                         v, zv, mv, rv, dropout_p=p_ev, seed=s_ev)
         # --- encoder (vilbert.py:852-939)
         layers = []
-        for kind_, i in cfg.schedule():
+        sched = cfg.schedule()
+        run_t = lambda x, i: self._self_layer_fwd(x, t_mask, B, T, cfg.num_attention_heads, f'bert.encoder.layer.{i}', ('query', 'key', 'value'),
+                                                  (cfg.attention_probs_dropout_prob, cfg.hidden_dropout_prob), i, keep)
+        run_v = lambda x, i: self._self_layer_fwd(x, v_mask, B, R, cfg.v_num_attention_heads, f'bert.encoder.v_layer.{i}', ('query', 'key', 'value'),
+                                                  (cfg.v_attention_probs_dropout_prob, cfg.v_hidden_dropout_prob), 100 + i, keep)
+        idx = 0
+        while idx < len(sched):
+            kind_, i = sched[idx]
+            if kind_ == 'v' and idx + 1 < len(sched) and sched[idx + 1][0] == 't' and self.overlap_streams:
+                # v_layer[k-1] and layer[5+k] are independent (vilbert.py:868-886): the 3520-row visual kernels fill the SMs
+                # the text kernels' partial waves leave idle.  Inputs stay referenced until the streams have joined.
+                cur, side = torch.cuda.current_stream(dev), self._side(dev)
+                hold = (v, t)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    v, s_v = run_v(v, i)
+                t, s_t = run_t(t, sched[idx + 1][1])
+                cur.wait_stream(side)
+                del hold
+                layers += [s_v, s_t]
+                idx += 2
+                continue
             if kind_ == 't':
-                t, s = self._self_layer_fwd(t, t_mask, B, T, cfg.num_attention_heads, f'bert.encoder.layer.{i}', ('query', 'key', 'value'),
-                                            (cfg.attention_probs_dropout_prob, cfg.hidden_dropout_prob), i, keep)
+                t, s = run_t(t, i)
             elif kind_ == 'v':
-                v, s = self._self_layer_fwd(v, v_mask, B, R, cfg.v_num_attention_heads, f'bert.encoder.v_layer.{i}', ('query', 'key', 'value'),
-                                            (cfg.v_attention_probs_dropout_prob, cfg.v_hidden_dropout_prob), 100 + i, keep)
+                v, s = run_v(v, i)
             else:
                 v, t, s = self._co_layer_fwd(v, t, v_mask, t_mask, B, T, R, f'bert.encoder.c_layer.{i}', 200 + i, keep)
             layers.append(s)
+            idx += 1
         logits, outs, scalars, s_heads = self._heads_fwd(t, v, B, T, R, labels, Rt, kind, keep)
         if keep:
             sv.B, sv.T, sv.R = B, T, R
@@ -594,8 +648,27 @@ class VisualDialogEncoder(nn.Module):
         B, T, R = sv.B, sv.T, sv.R
         dt, dv = self._heads_bwd(sv.heads, d_nsp, d_reg, B, T, R)
         yield arena.offsets['bert.t_pooler.dense.weight'], arena.live_end
-        sched = cfg.schedule()
-        for (kind_, i), s in reversed(list(zip(sched, sv.layers))):
+        dev = dt.device
+        items = list(reversed(list(zip(cfg.schedule(), sv.layers))))
+        idx = 0
+        while idx < len(items):
+            (kind_, i), s = items[idx]
+            if kind_ == 't' and idx + 1 < len(items) and items[idx + 1][0][0] == 'v' and self.overlap_streams:
+                (_, j), s2 = items[idx + 1]                     # text layer and the visual layer before it: independent
+                pre_t, pre_v = f'bert.encoder.layer.{i}', f'bert.encoder.v_layer.{j}'
+                cur, side = torch.cuda.current_stream(dev), self._side(dev)
+                hold = (dt, dv)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    dv = self._self_layer_bwd(dv, s2, pre_v, ('query', 'key', 'value'))
+                dt = self._self_layer_bwd(dt, s, pre_t, ('query', 'key', 'value'))
+                cur.wait_stream(side)
+                self._wgrad_join()
+                del hold
+                yield self._block_range(pre_t)
+                yield self._block_range(pre_v)
+                idx += 2
+                continue
             if kind_ == 't':
                 pre = f'bert.encoder.layer.{i}'
                 dt = self._self_layer_bwd(dt, s, pre, ('query', 'key', 'value'))
@@ -605,7 +678,9 @@ class VisualDialogEncoder(nn.Module):
             else:
                 pre = f'bert.encoder.c_layer.{i}'
                 dv, dt = self._co_layer_bwd(dv, dt, s, pre)
+            self._wgrad_join()
             yield self._block_range(pre)
+            idx += 1
         # embeddings
         e = 'bert.embeddings'
         dzt = torch.empty_like(dt)
@@ -618,9 +693,9 @@ class VisualDialogEncoder(nn.Module):
         dzv = torch.empty_like(dv)
         L.layernorm_bwd(dv, sv.zv, sv.mv, sv.rv, self._p(e + '.LayerNorm.weight'), dzv, self._g(e + '.LayerNorm.weight'),
                         self._g(e + '.LayerNorm.bias'), dbias=self._g(e + '.new_image_embeddings.bias'), p_in=sv.p_ev, seed_in=sv.s_ev)
-        L.colsum_bf16(dzv, self._g(e + '.new_loc_emb.bias'))
-        self._wgrad(dzv, sv.probs, self._g(e + '.new_image_embeddings.weight'))
+        self._wgrad(dzv, sv.probs, self._g(e + '.new_image_embeddings.weight'), self._g(e + '.new_loc_emb.bias'))
         L.embed_vis_bwd(dzv, sv.box2, sv.cls2, self._g(e + '.color_emb.weight'), self._g(e + '.new_loc_emb.weight'))
+        self._wgrad_join()
         yield 0, self._block_range('bert.v_embeddings')[1]
 
     def train_step_stages(self, batch, nsp_coeff: float = 1.0, reg_coeff: float = 1.0):
