@@ -105,6 +105,31 @@ class _NullCtx:
         return False
 
 
+class _Lanes:
+    """The two dataflow lanes of the two-stream encoder: text kernels run on the caller's stream, visual kernels on a
+    side stream; the lanes meet only where data crosses (co-attention, heads).  With one stream both lanes are the
+    caller's stream and every wait is a no-op."""
+
+    def __init__(self, text, vis):
+        self.t, self.v = text, vis
+        self.split = vis is not text
+
+    def vis(self):
+        return torch.cuda.stream(self.v) if self.split else _NullCtx()
+
+    def v_wait_t(self):
+        if self.split:
+            self.v.wait_stream(self.t)
+
+    def t_wait_v(self):
+        if self.split:
+            self.t.wait_stream(self.v)
+
+    def meet(self):
+        self.v_wait_t()
+        self.t_wait_v()
+
+
 class _Saved:
     """Activations a forward keeps for its backward."""
     pass
@@ -154,7 +179,9 @@ class VisualDialogEncoder(nn.Module):
         self._step = 0                       # site seeds are launch constants; per-step variation comes from the device salt
         self._salt = None                    # int64[1] on the device, advanced by crct_bump_salt once per training forward
         self.grad_ready_hook = None          # set by cqa_crct_b200.parallel.DistributedDataParallel
-        self.overlap_streams = True          # run independent visual / text layers on two streams, wgrads on a third
+        self.overlap_streams = True          # visual lane / text lane on two streams, weight gradients on a third
+        self.segment_ranges = False          # set by graph.GraphedTrainStep when it cuts the step at bucket boundaries
+        self._x_hold = None                  # tensors read across lanes, kept until the lanes have met again
         self._side_stream = None
         self._wg_stream = None
         self._wg_hold = []
@@ -216,10 +243,13 @@ class VisualDialogEncoder(nn.Module):
     def _drop(self, p):
         return float(p) if self.training else 0.0
 
-    def _side(self, dev):
+    def _lanes(self, dev):
+        cur = torch.cuda.current_stream(dev)
+        if not self.overlap_streams:
+            return _Lanes(cur, cur)
         if self._side_stream is None or self._side_stream.device != dev:
             self._side_stream = torch.cuda.Stream(device=dev)
-        return self._side_stream
+        return _Lanes(cur, self._side_stream)
 
     # ------------------------------------------------------------------ building blocks (forward)
     def _linear(self, x, W, bias, M, epilogue=L.EPI_BIAS, aux=None, D2=None, p=0.0, seed=0):
@@ -361,35 +391,40 @@ class VisualDialogEncoder(nn.Module):
         L.gemm(dqkv, Wqkv, dx, M=M, N=H, K=3 * H, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz1)
         return dx
 
-    def _co_layer_fwd(self, v, t, v_mask, t_mask, B, T, R, pre, layer, keep):
-        """BertConnectionLayer (vilbert.py:774-788); stream 1 = visual, stream 2 = text."""
+    def _co_layer_fwd(self, v, t, v_mask, t_mask, B, T, R, pre, layer, keep, lanes):
+        """BertConnectionLayer (vilbert.py:774-788); stream 1 = visual, stream 2 = text.  Each lane projects its own
+        q/k/v, the lanes meet once (each attention reads the other lane's keys/values), then run apart again."""
         cfg, step = self.cfg, self._step
         Mv, Hv = v.shape
         Mt, H = t.shape
         nh, Hb = cfg.bi_num_attention_heads, cfg.bi_hidden_size
         dh = Hb // nh
+        ld = 3 * Hb
         m1 = [pre + '.biattention.' + n for n in ('query1', 'key1', 'value1')]
         m2 = [pre + '.biattention.' + n for n in ('query2', 'key2', 'value2')]
-        qkv1 = self._linear(v, self.arena.fused(self.arena.w16, m1, '.weight'), self.arena.fused(self.arena.w32, m1, '.bias'), Mv)
+        with lanes.vis():
+            qkv1 = self._linear(v, self.arena.fused(self.arena.w16, m1, '.weight'), self.arena.fused(self.arena.w32, m1, '.bias'), Mv)
         qkv2 = self._linear(t, self.arena.fused(self.arena.w16, m2, '.weight'), self.arena.fused(self.arena.w32, m2, '.bias'), Mt)
-        ctx1 = torch.empty(Mt, Hb, dtype=torch.bfloat16, device=t.device)          # text queries over visual keys/values
-        ctx2 = torch.empty(Mv, Hb, dtype=torch.bfloat16, device=t.device)          # visual queries over text keys/values
-        lse1 = torch.empty(B, nh, T, dtype=torch.float32, device=t.device) if keep else None
-        lse2 = torch.empty(B, nh, R, dtype=torch.float32, device=t.device) if keep else None
+        lanes.meet()
+        self._x_hold = (qkv1, qkv2)        # replaces the previous layer's pair: both lanes are past its readers now
         p1, s1 = self._drop(cfg.v_attention_probs_dropout_prob), _seed(step, 'co_attn1', layer)      # dropout1, vilbert.py:642,696
         p2, s2 = self._drop(cfg.attention_probs_dropout_prob), _seed(step, 'co_attn2', layer)        # dropout2, vilbert.py:649,718
-        ld = 3 * Hb
+        # biOutput is called with crossed arguments (vilbert.py:780): visual <- ctx2 via dense1/LayerNorm1, text <- ctx1 via dense2/LayerNorm2
+        with lanes.vis():                  # visual queries over text keys/values
+            ctx2 = torch.empty(Mv, Hb, dtype=torch.bfloat16, device=t.device)
+            lse2 = torch.empty(B, nh, R, dtype=torch.float32, device=t.device) if keep else None
+            L.attn_fwd(qkv1, qkv2[:, Hb:], qkv2[:, 2 * Hb:], t_mask, ctx2, lse2, B=B, nh=nh, dh=dh, Lq=R, Lk=T, ldq=ld, ldk=ld, ldv=ld,
+                       ldo=Hb, dropout_p=p2, seed=s2)
+            av, so_v = self._attn_out_fwd(ctx2, v, pre + '.biOutput.dense1', pre + '.biOutput.LayerNorm1',
+                                          self._drop(cfg.v_hidden_dropout_prob), _seed(step, 'co_out_v', layer), keep)
+            yv, sf_v = self._ffn_fwd(av, pre + '.v_intermediate', pre + '.v_output', self._drop(cfg.v_hidden_dropout_prob),
+                                     _seed(step, 'co_ffn_v', layer), keep)
+        ctx1 = torch.empty(Mt, Hb, dtype=torch.bfloat16, device=t.device)          # text queries over visual keys/values
+        lse1 = torch.empty(B, nh, T, dtype=torch.float32, device=t.device) if keep else None
         L.attn_fwd(qkv2, qkv1[:, Hb:], qkv1[:, 2 * Hb:], v_mask, ctx1, lse1, B=B, nh=nh, dh=dh, Lq=T, Lk=R, ldq=ld, ldk=ld, ldv=ld,
                    ldo=Hb, dropout_p=p1, seed=s1)
-        L.attn_fwd(qkv1, qkv2[:, Hb:], qkv2[:, 2 * Hb:], t_mask, ctx2, lse2, B=B, nh=nh, dh=dh, Lq=R, Lk=T, ldq=ld, ldk=ld, ldv=ld,
-                   ldo=Hb, dropout_p=p2, seed=s2)
-        # biOutput is called with crossed arguments (vilbert.py:780): visual <- ctx2 via dense1/LayerNorm1, text <- ctx1 via dense2/LayerNorm2
-        av, so_v = self._attn_out_fwd(ctx2, v, pre + '.biOutput.dense1', pre + '.biOutput.LayerNorm1',
-                                      self._drop(cfg.v_hidden_dropout_prob), _seed(step, 'co_out_v', layer), keep)
         at, so_t = self._attn_out_fwd(ctx1, t, pre + '.biOutput.dense2', pre + '.biOutput.LayerNorm2',
                                       self._drop(cfg.hidden_dropout_prob), _seed(step, 'co_out_t', layer), keep)
-        yv, sf_v = self._ffn_fwd(av, pre + '.v_intermediate', pre + '.v_output', self._drop(cfg.v_hidden_dropout_prob),
-                                 _seed(step, 'co_ffn_v', layer), keep)
         yt, sf_t = self._ffn_fwd(at, pre + '.t_intermediate', pre + '.t_output', self._drop(cfg.hidden_dropout_prob),
                                  _seed(step, 'co_ffn_t', layer), keep)
         s = None
@@ -400,32 +435,41 @@ class VisualDialogEncoder(nn.Module):
             s.p1, s.s1, s.p2, s.s2, s.v_mask, s.t_mask, s.B, s.T, s.R = p1, s1, p2, s2, v_mask, t_mask, B, T, R
         return yv, yt, s
 
-    def _co_layer_bwd(self, dyv, dyt, s, pre):
+    def _co_layer_bwd(self, dyv, dyt, s, pre, lanes):
+        """Mirror of the forward's dataflow: each lane runs its FFN / output-block backward, the lanes meet, each runs
+        one attention direction (disjoint slices of dqkv1/dqkv2), they meet again, each lane finishes its projection."""
         cfg = self.cfg
         Mv, Hv = dyv.shape
         Mt, H = dyt.shape
         nh, Hb = cfg.bi_num_attention_heads, cfg.bi_hidden_size
         dh, ld = Hb // nh, 3 * Hb
-        dav = self._ffn_bwd(dyv, s.sf_v, pre + '.v_intermediate', pre + '.v_output')
+        m1 = [pre + '.biattention.' + n for n in ('query1', 'key1', 'value1')]
+        m2 = [pre + '.biattention.' + n for n in ('query2', 'key2', 'value2')]
+        with lanes.vis():
+            dav = self._ffn_bwd(dyv, s.sf_v, pre + '.v_intermediate', pre + '.v_output')
+            dzv, dctx2 = self._attn_out_bwd(dav, s.so_v, pre + '.biOutput.dense1', pre + '.biOutput.LayerNorm1')
+            dqkv1 = torch.empty_like(s.qkv1)
         dat = self._ffn_bwd(dyt, s.sf_t, pre + '.t_intermediate', pre + '.t_output')
-        dzv, dctx2 = self._attn_out_bwd(dav, s.so_v, pre + '.biOutput.dense1', pre + '.biOutput.LayerNorm1')
         dzt, dctx1 = self._attn_out_bwd(dat, s.so_t, pre + '.biOutput.dense2', pre + '.biOutput.LayerNorm2')
-        dqkv1, dqkv2 = torch.empty_like(s.qkv1), torch.empty_like(s.qkv2)
+        dqkv2 = torch.empty_like(s.qkv2)
+        lanes.meet()
         # direction 1: q = text (qkv2[:, :Hb]), k/v = visual  -> dq2, dk1, dv1
         L.attn_bwd(s.qkv2, s.qkv1[:, Hb:], s.qkv1[:, 2 * Hb:], s.v_mask, s.so_t.ctx, dctx1, s.lse1, dqkv2, dqkv1[:, Hb:], dqkv1[:, 2 * Hb:],
                    B=s.B, nh=nh, dh=dh, Lq=s.T, Lk=s.R, ldq=ld, ldk=ld, ldv=ld, ldo=Hb, lddo=Hb, lddq=ld, lddk=ld, lddv=ld,
                    dropout_p=s.p1, seed=s.s1)
-        # direction 2: q = visual (qkv1[:, :Hb]), k/v = text -> dq1, dk2, dv2
-        L.attn_bwd(s.qkv1, s.qkv2[:, Hb:], s.qkv2[:, 2 * Hb:], s.t_mask, s.so_v.ctx, dctx2, s.lse2, dqkv1, dqkv2[:, Hb:], dqkv2[:, 2 * Hb:],
-                   B=s.B, nh=nh, dh=dh, Lq=s.R, Lk=s.T, ldq=ld, ldk=ld, ldv=ld, ldo=Hb, lddo=Hb, lddq=ld, lddk=ld, lddv=ld,
-                   dropout_p=s.p2, seed=s.s2)
-        m1 = [pre + '.biattention.' + n for n in ('query1', 'key1', 'value1')]
-        m2 = [pre + '.biattention.' + n for n in ('query2', 'key2', 'value2')]
-        self._wgrad(dqkv1, s.v, self.arena.fused(self.arena.g32, m1, '.weight'), self.arena.fused(self.arena.g32, m1, '.bias'))
+        with lanes.vis():
+            # direction 2: q = visual (qkv1[:, :Hb]), k/v = text -> dq1, dk2, dv2
+            L.attn_bwd(s.qkv1, s.qkv2[:, Hb:], s.qkv2[:, 2 * Hb:], s.t_mask, s.so_v.ctx, dctx2, s.lse2, dqkv1, dqkv2[:, Hb:], dqkv2[:, 2 * Hb:],
+                       B=s.B, nh=nh, dh=dh, Lq=s.R, Lk=s.T, ldq=ld, ldk=ld, ldv=ld, ldo=Hb, lddo=Hb, lddq=ld, lddk=ld, lddv=ld,
+                       dropout_p=s.p2, seed=s.s2)
+        lanes.meet()
+        self._x_hold = (dqkv1, dqkv2, dctx1, dctx2)
+        with lanes.vis():
+            self._wgrad(dqkv1, s.v, self.arena.fused(self.arena.g32, m1, '.weight'), self.arena.fused(self.arena.g32, m1, '.bias'))
+            dv = torch.empty_like(dyv)
+            L.gemm(dqkv1, self.arena.fused(self.arena.w16, m1, '.weight'), dv, M=Mv, N=Hv, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzv)
         self._wgrad(dqkv2, s.t, self.arena.fused(self.arena.g32, m2, '.weight'), self.arena.fused(self.arena.g32, m2, '.bias'))
-        dv = torch.empty_like(dyv)
         dt = torch.empty_like(dyt)
-        L.gemm(dqkv1, self.arena.fused(self.arena.w16, m1, '.weight'), dv, M=Mv, N=Hv, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzv)
         L.gemm(dqkv2, self.arena.fused(self.arena.w16, m2, '.weight'), dt, M=Mt, N=H, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzt)
         return dv, dt
 
@@ -564,7 +608,9 @@ class VisualDialogEncoder(nn.Module):
         L.additive_mask(amask, t_mask)
         L.additive_mask(imask, v_mask)
         sv = _Saved() if keep else None
-        # --- embeddings (vilbert.py:1412-1413)
+        # --- embeddings (vilbert.py:1412-1413); from here to the heads the visual lane runs on its own stream
+        lanes = self._lanes(dev)
+        lanes.v_wait_t()
         e = 'bert.embeddings'
         t = torch.empty(B * T, H, dtype=torch.bfloat16, device=dev)
         zt = torch.empty_like(t) if keep else None
@@ -577,50 +623,37 @@ class VisualDialogEncoder(nn.Module):
                          t, zt, mt, rt, dropout_p=p_et, seed=s_et)
         e = 'bert.v_embeddings'
         feat2 = feat.reshape(B * R, F)
-        probs = torch.empty(B * R, F, dtype=torch.bfloat16, device=dev)
-        L.softmax_rows(feat2, probs)
-        gimg = self._linear(probs, self._w(e + '.new_image_embeddings.weight'), self._p(e + '.new_image_embeddings.bias'), B * R)
-        v = torch.empty(B * R, Hv, dtype=torch.bfloat16, device=dev)
-        zv = torch.empty_like(v) if keep else None
-        mv = torch.empty(B * R, dtype=torch.float32, device=dev) if keep else None
-        rv = torch.empty(B * R, dtype=torch.float32, device=dev) if keep else None
-        p_ev, s_ev = self._drop(cfg.hidden_dropout_prob), _seed(step, 'emb_v')      # nn.Dropout(config.hidden_dropout_prob), vilbert.py:1470
         box2, cls2 = box.reshape(B * R, 4), cls.reshape(B * R)
-        L.embed_vis_fwd(gimg, box2, cls2, self._p(e + '.new_loc_emb.weight'), self._p(e + '.new_loc_emb.bias'),
-                        self._p(e + '.color_emb.weight'), self._p(e + '.LayerNorm.weight'), self._p(e + '.LayerNorm.bias'),
-                        v, zv, mv, rv, dropout_p=p_ev, seed=s_ev)
-        # --- encoder (vilbert.py:852-939)
+        p_ev, s_ev = self._drop(cfg.hidden_dropout_prob), _seed(step, 'emb_v')      # nn.Dropout(config.hidden_dropout_prob), vilbert.py:1470
+        with lanes.vis():
+            probs = torch.empty(B * R, F, dtype=torch.bfloat16, device=dev)
+            L.softmax_rows(feat2, probs)
+            gimg = self._linear(probs, self._w(e + '.new_image_embeddings.weight'), self._p(e + '.new_image_embeddings.bias'), B * R)
+            v = torch.empty(B * R, Hv, dtype=torch.bfloat16, device=dev)
+            zv = torch.empty_like(v) if keep else None
+            mv = torch.empty(B * R, dtype=torch.float32, device=dev) if keep else None
+            rv = torch.empty(B * R, dtype=torch.float32, device=dev) if keep else None
+            L.embed_vis_fwd(gimg, box2, cls2, self._p(e + '.new_loc_emb.weight'), self._p(e + '.new_loc_emb.bias'),
+                            self._p(e + '.color_emb.weight'), self._p(e + '.LayerNorm.weight'), self._p(e + '.LayerNorm.bias'),
+                            v, zv, mv, rv, dropout_p=p_ev, seed=s_ev)
+        # --- encoder (vilbert.py:852-939): text layers on the text lane, visual layers on the visual lane (v_layer[k-1]
+        # and layer[5+k] are independent, vilbert.py:868-886; the 3520-row visual kernels fill the SMs the text kernels'
+        # partial waves leave idle); the lanes meet inside every connection layer.
         layers = []
-        sched = cfg.schedule()
-        run_t = lambda x, i: self._self_layer_fwd(x, t_mask, B, T, cfg.num_attention_heads, f'bert.encoder.layer.{i}', ('query', 'key', 'value'),
-                                                  (cfg.attention_probs_dropout_prob, cfg.hidden_dropout_prob), i, keep)
-        run_v = lambda x, i: self._self_layer_fwd(x, v_mask, B, R, cfg.v_num_attention_heads, f'bert.encoder.v_layer.{i}', ('query', 'key', 'value'),
-                                                  (cfg.v_attention_probs_dropout_prob, cfg.v_hidden_dropout_prob), 100 + i, keep)
-        idx = 0
-        while idx < len(sched):
-            kind_, i = sched[idx]
-            if kind_ == 'v' and idx + 1 < len(sched) and sched[idx + 1][0] == 't' and self.overlap_streams:
-                # v_layer[k-1] and layer[5+k] are independent (vilbert.py:868-886): the 3520-row visual kernels fill the SMs
-                # the text kernels' partial waves leave idle.  Inputs stay referenced until the streams have joined.
-                cur, side = torch.cuda.current_stream(dev), self._side(dev)
-                hold = (v, t)
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    v, s_v = run_v(v, i)
-                t, s_t = run_t(t, sched[idx + 1][1])
-                cur.wait_stream(side)
-                del hold
-                layers += [s_v, s_t]
-                idx += 2
-                continue
+        for kind_, i in cfg.schedule():
             if kind_ == 't':
-                t, s = run_t(t, i)
+                t, s = self._self_layer_fwd(t, t_mask, B, T, cfg.num_attention_heads, f'bert.encoder.layer.{i}', ('query', 'key', 'value'),
+                                            (cfg.attention_probs_dropout_prob, cfg.hidden_dropout_prob), i, keep)
             elif kind_ == 'v':
-                v, s = run_v(v, i)
+                with lanes.vis():
+                    v, s = self._self_layer_fwd(v, v_mask, B, R, cfg.v_num_attention_heads, f'bert.encoder.v_layer.{i}',
+                                                ('query', 'key', 'value'),
+                                                (cfg.v_attention_probs_dropout_prob, cfg.v_hidden_dropout_prob), 100 + i, keep)
             else:
-                v, t, s = self._co_layer_fwd(v, t, v_mask, t_mask, B, T, R, f'bert.encoder.c_layer.{i}', 200 + i, keep)
+                v, t, s = self._co_layer_fwd(v, t, v_mask, t_mask, B, T, R, f'bert.encoder.c_layer.{i}', 200 + i, keep, lanes)
             layers.append(s)
-            idx += 1
+        lanes.t_wait_v()
+        self._x_hold = None
         logits, outs, scalars, s_heads = self._heads_fwd(t, v, B, T, R, labels, Rt, kind, keep)
         if keep:
             sv.B, sv.T, sv.R = B, T, R
@@ -647,41 +680,56 @@ class VisualDialogEncoder(nn.Module):
         L.SALT = self._salt
         B, T, R = sv.B, sv.T, sv.R
         dt, dv = self._heads_bwd(sv.heads, d_nsp, d_reg, B, T, R)
-        yield arena.offsets['bert.t_pooler.dense.weight'], arena.live_end
         dev = dt.device
+        # Finished ranges are only reported one by one when somebody consumes them (the data-parallel hook, or a graph
+        # cut into per-bucket segments): reporting a range makes the caller's stream wait for both other streams.
+        fine = self.grad_ready_hook is not None or self.segment_ranges
+        lanes = self._lanes(dev)
+        if fine:
+            yield arena.offsets['bert.t_pooler.dense.weight'], arena.live_end
+        lanes.v_wait_t()
+        dv_heads = dv                      # allocated on the text lane, read on the visual lane: keep it until the end
+        pending = []                       # finished layers whose range has not been reported yet
+
+        def report():
+            self._wgrad_join()
+            lanes.t_wait_v()
+            out = list(pending)
+            pending.clear()
+            return out
+
+        def vis_embeddings_bwd(dv):
+            e = 'bert.v_embeddings'
+            with lanes.vis():
+                dzv = torch.empty_like(dv)
+                L.layernorm_bwd(dv, sv.zv, sv.mv, sv.rv, self._p(e + '.LayerNorm.weight'), dzv, self._g(e + '.LayerNorm.weight'),
+                                self._g(e + '.LayerNorm.bias'), dbias=self._g(e + '.new_image_embeddings.bias'), p_in=sv.p_ev,
+                                seed_in=sv.s_ev)
+                self._wgrad(dzv, sv.probs, self._g(e + '.new_image_embeddings.weight'), self._g(e + '.new_loc_emb.bias'))
+                L.embed_vis_bwd(dzv, sv.box2, sv.cls2, self._g(e + '.color_emb.weight'), self._g(e + '.new_loc_emb.weight'))
+
         items = list(reversed(list(zip(cfg.schedule(), sv.layers))))
-        idx = 0
-        while idx < len(items):
-            (kind_, i), s = items[idx]
-            if kind_ == 't' and idx + 1 < len(items) and items[idx + 1][0][0] == 'v' and self.overlap_streams:
-                (_, j), s2 = items[idx + 1]                     # text layer and the visual layer before it: independent
-                pre_t, pre_v = f'bert.encoder.layer.{i}', f'bert.encoder.v_layer.{j}'
-                cur, side = torch.cuda.current_stream(dev), self._side(dev)
-                hold = (dt, dv)
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    dv = self._self_layer_bwd(dv, s2, pre_v, ('query', 'key', 'value'))
-                dt = self._self_layer_bwd(dt, s, pre_t, ('query', 'key', 'value'))
-                cur.wait_stream(side)
-                self._wgrad_join()
-                del hold
-                yield self._block_range(pre_t)
-                yield self._block_range(pre_v)
-                idx += 2
-                continue
+        last_c = max((k for k, ((kind_, _), _) in enumerate(items) if kind_ == 'c'), default=-1)
+        for k, ((kind_, i), s) in enumerate(items):
             if kind_ == 't':
                 pre = f'bert.encoder.layer.{i}'
                 dt = self._self_layer_bwd(dt, s, pre, ('query', 'key', 'value'))
             elif kind_ == 'v':
                 pre = f'bert.encoder.v_layer.{i}'
-                dv = self._self_layer_bwd(dv, s, pre, ('query', 'key', 'value'))
+                with lanes.vis():
+                    dv = self._self_layer_bwd(dv, s, pre, ('query', 'key', 'value'))
             else:
                 pre = f'bert.encoder.c_layer.{i}'
-                dv, dt = self._co_layer_bwd(dv, dt, s, pre)
-            self._wgrad_join()
-            yield self._block_range(pre)
-            idx += 1
-        # embeddings
+                dv, dt = self._co_layer_bwd(dv, dt, s, pre, lanes)
+            pending.append(self._block_range(pre))
+            if k == last_c:
+                vis_embeddings_bwd(dv)     # nothing visual is left but the embeddings: next to the remaining text layers
+            if fine and (kind_ == 'c' or k > last_c):
+                for r in report():
+                    yield r
+                lanes.v_wait_t()           # a graph cut may follow a report: the visual lane re-forks from the text lane
+        if last_c < 0:
+            vis_embeddings_bwd(dv)
         e = 'bert.embeddings'
         dzt = torch.empty_like(dt)
         L.layernorm_bwd(dt, sv.zt, sv.mt, sv.rt, self._p(e + '.LayerNorm.weight'), dzt, self._g(e + '.LayerNorm.weight'),
@@ -689,14 +737,15 @@ class VisualDialogEncoder(nn.Module):
         L.embed_text_bwd(sv.ids, sv.types, sv.loc, dzt, self._g(e + '.word_embeddings.weight'), self._g(e + '.position_embeddings.weight'),
                          self._g(e + '.plotqa_type_embeddings.weight'), self._g(e + '.txt_location_embeddings.weight'),
                          self._g(e + '.txt_location_embeddings.bias'))
-        e = 'bert.v_embeddings'
-        dzv = torch.empty_like(dv)
-        L.layernorm_bwd(dv, sv.zv, sv.mv, sv.rv, self._p(e + '.LayerNorm.weight'), dzv, self._g(e + '.LayerNorm.weight'),
-                        self._g(e + '.LayerNorm.bias'), dbias=self._g(e + '.new_image_embeddings.bias'), p_in=sv.p_ev, seed_in=sv.s_ev)
-        self._wgrad(dzv, sv.probs, self._g(e + '.new_image_embeddings.weight'), self._g(e + '.new_loc_emb.bias'))
-        L.embed_vis_bwd(dzv, sv.box2, sv.cls2, self._g(e + '.color_emb.weight'), self._g(e + '.new_loc_emb.weight'))
-        self._wgrad_join()
-        yield 0, self._block_range('bert.v_embeddings')[1]
+        rest = report()
+        self._x_hold = None
+        del dv_heads
+        if fine:
+            for r in rest:
+                yield r
+            yield 0, self._block_range('bert.v_embeddings')[1]
+        else:
+            yield 0, arena.live_end
 
     def train_step_stages(self, batch, nsp_coeff: float = 1.0, reg_coeff: float = 1.0):
         """Forward + backward of one training batch WITHOUT autograd (same kernels, same order as

@@ -36,6 +36,7 @@ class GraphedTrainStep:
         self.static = {k: v.to(dev).clone() for k, v in example_batch.items() if k != 'needs_reg'}
         self.nsp_coeff, self.reg_coeff = float(params.get('nsp_loss_coeff', 1.0)), float(params.get('reg_loss_coeff', 1.0))
         optimizer.enable_device_scalars()
+        enc.segment_ranges = self.world > 1      # per-bucket ranges only when the step is cut for the exchange
         self.segments = []                # [(graph, (lo, hi) bucket finished by this segment or None)]
         self.launches_per_step = 0
         side = torch.cuda.Stream(device=dev)
