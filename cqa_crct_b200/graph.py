@@ -16,6 +16,11 @@ backward, then `FusedAdamW`) into CUDA graphs and replays them:
     while segment i+1 replays, so the exchange still overlaps the backward without capturing NCCL inside a graph.
 
 `step()` returns the static loss tensor (overwritten by the next step): read or clone it before stepping again.
+
+Input pipeline (the reference's loop copies the batch and `.item()`s its losses synchronously, train.py:167-183):
+`prefetch(host_batch)` stages the NEXT batch's host->device copies on a copy stream while the current step runs, and
+`step_async()` returns a handle whose `.item()` waits only for that step's own loss (copied to pinned host memory
+behind the step), so a loop that reads the loss of step i after enqueuing step i+1 never drains the GPU.
 """
 from __future__ import annotations
 
@@ -38,6 +43,12 @@ class GraphedTrainStep:
         optimizer.enable_device_scalars()
         enc.segment_ranges = self.world > 1      # per-bucket ranges only when the step is cut for the exchange
         self.segments = []                # [(graph, (lo, hi) bucket finished by this segment or None)]
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._staged = None               # device staging copy of the prefetched batch
+        self._staged_ready = None         # event: staging copy complete
+        self._staged_free = None          # event: staging buffers consumed by the step that used them
+        self._loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+        self._loss_slot = 0
         self.launches_per_step = 0
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -102,11 +113,44 @@ class GraphedTrainStep:
         self.logits, self.reg = self.enc.last_logits, self.enc.last_reg
         self.launches_per_step = L.LAUNCHES - l0
 
+    def prefetch(self, batch: Dict[str, torch.Tensor]):
+        """Start copying the next batch (pinned host or device tensors) into device staging buffers on the copy stream;
+        the next `step()` / `step_async()` without a batch consumes it."""
+        if self._staged is None:
+            self._staged = {k: torch.empty_like(v) for k, v in self.static.items()}
+        cs = self._copy_stream
+        if self._staged_free is not None:
+            cs.wait_event(self._staged_free)
+        with torch.cuda.stream(cs):
+            for k, dst in self._staged.items():
+                dst.copy_(batch[k], non_blocking=True)
+            self._staged_ready = torch.cuda.Event()
+            self._staged_ready.record(cs)
+
+    def step_async(self, batch: Optional[Dict[str, torch.Tensor]] = None):
+        """`step()` + an asynchronous copy of the loss to pinned host memory; returns a handle with `.item()`."""
+        self.step(batch)
+        slot = self._loss_slot
+        self._loss_slot = (slot + 1) % self._loss_host.numel()
+        self._loss_host[slot:slot + 1].copy_(self.loss, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return _PendingLoss(self._loss_host, slot, ev)
+
     def step(self, batch: Optional[Dict[str, torch.Tensor]] = None):
-        """Copy `batch` into the static inputs (if given), replay the captured step, return the (static) loss tensor."""
+        """Copy `batch` (or the prefetched batch) into the static inputs, replay the captured step, return the (static)
+        loss tensor."""
         if batch is not None:
             for k, dst in self.static.items():
                 dst.copy_(batch[k], non_blocking=True)
+        elif self._staged_ready is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._staged_ready)
+            for k, dst in self.static.items():
+                dst.copy_(self._staged[k], non_blocking=True)
+            self._staged_free = torch.cuda.Event()
+            self._staged_free.record(cur)
+            self._staged_ready = None
         self.opt.push_device_scalars()
         works = []
         for g, bucket in self.segments:
@@ -120,3 +164,14 @@ class GraphedTrainStep:
         if self.sched is not None:
             self.sched.step()
         return self.loss
+
+
+class _PendingLoss:
+    """Loss of one enqueued step: `.item()` blocks until that step (not the queue behind it) has finished."""
+
+    def __init__(self, buf, slot, event):
+        self.buf, self.slot, self.event = buf, slot, event
+
+    def item(self) -> float:
+        self.event.synchronize()
+        return float(self.buf[self.slot])

@@ -206,6 +206,16 @@ def test_graphed_train_step_matches_eager_and_redraws_dropout():
     assert abs(float(l_eager) - float(l_graph)) < 1e-3, (float(l_eager), float(l_graph))
     e1 = rel_err(m2.arena.w32, m1.arena.w32)
     assert e1 < 1e-4, e1
+    # input pipeline: a prefetched pinned host batch + asynchronous loss read give the same step
+    pinned = {k: v.cpu().pin_memory() for k, v in gb.items()}
+    g.prefetch(pinned)
+    h = g.step_async()
+    o1.zero_grad()
+    l_eager = glue_forward(m1, gb, params)[0]
+    l_eager.backward()
+    o1.step()
+    assert abs(float(l_eager) - h.item()) < 1e-3
+    assert rel_err(m2.arena.w32, m1.arena.w32) < 1e-4
     m2.train()                                                       # dropout on: a new graph, masks must change per replay
     g2 = GraphedTrainStep(m2, o2, params, gb, warmup_steps=1)
     losses = [float(g2.step(gb)) for _ in range(4)]
