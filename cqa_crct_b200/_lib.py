@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcrct_b200.so')
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_F32 = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL, EPI_F32 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
 
 vp, i32, i64, f32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64

@@ -104,31 +104,42 @@ static inline uint32_t crct_drop_threshold(float p) {
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below one bf16 ulp of the result): one MUFU.RCP + one
 // MUFU.EX2 instead of erff()'s ~40-instruction branchy polynomial — the GELU epilogues are issue-bound otherwise.
 // e = exp(-x^2/2) is shared between erf(x/sqrt2) = 1 - poly(t) e and the Gaussian pdf of the derivative.
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
-    const float ax = fabsf(x) * 0.70710678118654752f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-    e = __expf(-ax * ax);
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float erf_abs = 1.0f - poly * t * e;
-    cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
-}
-__device__ __forceinline__ float gelu_f(float x) {            // vilbert.py:111-117 (exact erf form)
-    float cdf, e;
-    gelu_parts(x, cdf, e);
-    return x * cdf;
-}
-__device__ __forceinline__ float gelu_grad_f(float x) {
-    float cdf, e;
-    gelu_parts(x, cdf, e);
-    return fmaf(x * 0.3989422804014327f, e, cdf);
-}
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// hq = Phi(-|x|) = erfc(|x|/sqrt 2)/2 (A&S 7.1.26 with the 1/2 folded into the coefficients), e = exp(-x^2/2).
+// Two MUFU operations per element (rcp, ex2); gelu and gelu' share them.
+__device__ __forceinline__ void gelu_parts(float x, float& hq, float& e) {
+    const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
+    e = fast_exp2(x * x * (-0.5f * 1.4426950408889634f));
+    float poly = fmaf(0.5f * 1.061405429f, t, -0.5f * 1.453152027f);
+    poly = fmaf(poly, t, 0.5f * 1.421413741f);
+    poly = fmaf(poly, t, -0.5f * 0.284496736f);
+    poly = fmaf(poly, t, 0.5f * 0.254829592f);
+    hq = poly * t * e;
+}
+// x Phi(x) = max(x, 0) - |x| Phi(-|x|)                               vilbert.py:111-117 (exact erf form)
+__device__ __forceinline__ float gelu_from_parts(float x, float hq) { return fmaf(-fabsf(x), hq, fmaxf(x, 0.f)); }
+// Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_grad_from_parts(float x, float hq, float e) {
+    return fmaf(x * 0.3989422804014327f, e, x >= 0.f ? 1.0f - hq : hq);
+}
+__device__ __forceinline__ float gelu_f(float x) {
+    float hq, e;
+    gelu_parts(x, hq, e);
+    return gelu_from_parts(x, hq);
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    float hq, e;
+    gelu_parts(x, hq, e);
+    return gelu_grad_from_parts(x, hq, e);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

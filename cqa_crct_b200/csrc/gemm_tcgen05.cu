@@ -35,7 +35,7 @@ struct Cfg {
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
     static constexpr int BIAS_BYTES = 2 * 256 * 4;              // per accumulator stage: the tile's bias slice
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 24576 + 1024;   // + OUT_STAGE_BYTES
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 };
 
 struct KParams {
@@ -46,6 +46,7 @@ struct KParams {
     const float* bias;
     const bf16* aux;
     int ldd, ldaux;
+    int wide;          // 1: D/D2/aux rows can be moved 32 bytes at a time (alignment, N % 16 == 0)
     int accumulate;
     uint32_t drop_thr;
     float drop_scale;
@@ -69,74 +70,59 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-constexpr bool epi_uses_aux(int epi) { return epi == CRCT_EPI_BIAS_RES || epi == CRCT_EPI_DGELU; }
+constexpr bool epi_uses_aux(int epi) { return epi == CRCT_EPI_BIAS_RES || epi == CRCT_EPI_MUL; }
 
-// aux (residual / addend / pre-activation) for one row x EPI_COLS columns, fetched one step ahead of the accumulator
+// ---------------------------------------------------------------------------------------------
+// Epilogue.  A lane owns one accumulator row; per step it handles EPI_COLS = 16 consecutive columns = 32 bytes of
+// bf16 = one DRAM sector, moved with ONE 256-bit global access (sm_100: ld/st.global.v8.b32), so every warp
+// instruction reads or writes 32 full sectors and nothing is staged through shared memory.  The four column-quarter
+// warps of a lane group fill each row's 128-byte lines between them.  Operands that are not 32-byte aligned / a
+// multiple of 16 columns take the 2 x 128-bit path (`wide` = 0).
+// ---------------------------------------------------------------------------------------------
 struct AuxRegs {
-    uint4 v[EPI_COLS / 8];
+    uint32_t v[EPI_COLS / 2];       // 16 bf16 of one row
 };
-// Coalesced fetch in the "transposed" mapping: piece q = lane + 32 i covers row row0 + q/2, 16-byte segment q%2, so one
-// load instruction reads 16 rows x 32 contiguous bytes (full sectors).  `aux_to_rows` turns it into one row per lane.
-template <int EPI>
-__device__ __forceinline__ void prefetch_aux(const KParams& p, int row0, int lane, int col0, AuxRegs& r) {
-    if constexpr (epi_uses_aux(EPI)) {
+
+__device__ __forceinline__ void ld_row32(const bf16* src, bool wide, int cols_left, uint32_t (&v)[8]) {
+    if (wide) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(src));
+    } else {
 #pragma unroll
-        for (int i = 0; i < EPI_COLS / 8; ++i) {
-            const int q = lane + 32 * i, row = row0 + (q >> 1), col = col0 + (q & 1) * 8;
-            r.v[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (p.aux != nullptr && row < p.M && col < p.N)
-                r.v[i] = *reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + col);
+        for (int h = 0; h < 2; ++h) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (h * 8 < cols_left) t = __ldg(reinterpret_cast<const uint4*>(src + h * 8));
+            v[h * 4] = t.x; v[h * 4 + 1] = t.y; v[h * 4 + 2] = t.z; v[h * 4 + 3] = t.w;
         }
     }
 }
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-    float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+__device__ __forceinline__ void st_row32(bf16* dst, bool wide, int cols_left, const uint32_t (&v)[8]) {
+    if (wide) {
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :: "l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+    } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (h * 8 < cols_left)
+                *reinterpret_cast<uint4*>(dst + h * 8) = make_uint4(v[h * 4], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
+    }
 }
 
-constexpr int OUT_PITCH = EPI_COLS * 2 + 16;       // bytes per staged row: 32 B of bf16 + 16 B pad
-constexpr int OUT_STAGE_BYTES = NUM_EPI_WARPS * 32 * OUT_PITCH;
-
 template <int EPI>
-__device__ __forceinline__ void aux_to_rows(AuxRegs& r, int lane, uint8_t* stage) {
+__device__ __forceinline__ void prefetch_aux(const KParams& p, int row, int col, AuxRegs& r) {
     if constexpr (epi_uses_aux(EPI)) {
 #pragma unroll
-        for (int i = 0; i < EPI_COLS / 8; ++i) {
-            const int q = lane + 32 * i;
-            *reinterpret_cast<uint4*>(stage + (q >> 1) * OUT_PITCH + (q & 1) * 16) = r.v[i];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int g = 0; g < EPI_COLS / 8; ++g) r.v[g] = *reinterpret_cast<const uint4*>(stage + lane * OUT_PITCH + g * 16);
-        __syncwarp();
+        for (int i = 0; i < EPI_COLS / 2; ++i) r.v[i] = 0u;
+        if (p.aux != nullptr && row < p.M && col < p.N) ld_row32(p.aux + (size_t)row * p.ldaux + col, p.wide != 0, p.N - col, r.v);
     }
 }
 
-// Warp-cooperative store of a 32-row x 16-column bf16 block: every lane holds one row (2 x 16 B); the block is
-// transposed through the warp's smem staging area so that one store instruction writes 16 rows x 32 contiguous bytes
-// (full sectors) instead of 32 rows x 16 bytes.
-__device__ __forceinline__ void store_block_bf16(bf16* __restrict__ dst, int ld, int row0, int col0, int M, int N, int lane,
-                                                 const uint4 (&o)[EPI_COLS / 8], uint8_t* stage) {
-#pragma unroll
-    for (int g = 0; g < EPI_COLS / 8; ++g) *reinterpret_cast<uint4*>(stage + lane * OUT_PITCH + g * 16) = o[g];
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < EPI_COLS / 8; ++i) {
-        const int q = lane + 32 * i, r = q >> 1, seg = q & 1;
-        const uint4 v = *reinterpret_cast<const uint4*>(stage + r * OUT_PITCH + seg * 16);
-        const int row = row0 + r, col = col0 + seg * 8;
-        if (row < M && col < N) *reinterpret_cast<uint4*>(dst + (size_t)row * ld + col) = v;
-    }
-    __syncwarp();
-}
-
-// one accumulator row x EPI_COLS columns per lane: bias (smem copy) / GELU / dropout + residual / GELU' -> global
+// one accumulator row x EPI_COLS columns: bias (smem copy) / GELU (+ GELU') / dropout + residual / multiply -> global
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const KParams& p, int row0, int lane, int col0, const uint32_t (&v)[EPI_COLS],
-                                               const float* bias_s, const AuxRegs& aux, uint8_t* stage, uint64_t seed) {
-    const int row = row0 + lane;
+__device__ __forceinline__ void epilogue_chunk(const KParams& p, int row, int col0, const uint32_t (&v)[EPI_COLS],
+                                               const float* bias_s, const AuxRegs& aux, uint64_t seed) {
+    if (row >= p.M) return;
     if constexpr (EPI == CRCT_EPI_F32) {
-        if (row >= p.M) return;
 #pragma unroll
         for (int g = 0; g < EPI_COLS / 8; ++g) {
             const int col = col0 + g * 8;
@@ -154,13 +140,13 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row0, int l
             }
         }
     } else {
-        uint4 o[EPI_COLS / 8], o2[EPI_COLS / 8];
+        uint32_t o[EPI_COLS / 2], o2[EPI_COLS / 2];
 #pragma unroll
         for (int g = 0; g < EPI_COLS / 8; ++g) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-            if constexpr (EPI != CRCT_EPI_DGELU) {
+            if constexpr (EPI != CRCT_EPI_MUL) {
                 if (p.bias != nullptr) {
                     const float4 b0 = *reinterpret_cast<const float4*>(bias_s + g * 8);         // smem broadcast
                     const float4 b1 = *reinterpret_cast<const float4*>(bias_s + g * 8 + 4);
@@ -169,70 +155,112 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row0, int l
                 }
             }
             if constexpr (EPI == CRCT_EPI_BIAS_GELU) {
-                o2[g] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                if (p.D2 != nullptr) {                      // training: also emit gelu'(u) for the backward (shares rcp/ex2)
+                    float d[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = gelu_f(f[j]);
+                    for (int j = 0; j < 8; ++j) {
+                        float hq, e;
+                        gelu_parts(f[j], hq, e);
+                        d[j] = gelu_grad_from_parts(f[j], hq, e);
+                        f[j] = gelu_from_parts(f[j], hq);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o2[g * 4 + j] = pack_bf16x2(d[2 * j], d[2 * j + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = gelu_f(f[j]);
+                }
             }
             if constexpr (EPI == CRCT_EPI_BIAS_RES) {
                 if (p.drop_thr != 0u)
                     dropout8(f, seed, (uint64_t)row * (uint64_t)p.N + (uint64_t)(col0 + g * 8), p.drop_thr, p.drop_scale);
+            }
+            if constexpr (epi_uses_aux(EPI)) {
                 if (p.aux != nullptr) {
-                    float a[8];
-                    unpack8(aux.v[g], a);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] += a[j];
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 a = unpack_bf16x2(aux.v[g * 4 + j]);
+                        if constexpr (EPI == CRCT_EPI_MUL) {
+                            f[2 * j] *= a.x; f[2 * j + 1] *= a.y;
+                        } else {
+                            f[2 * j] += a.x; f[2 * j + 1] += a.y;
+                        }
+                    }
                 }
             }
-            if constexpr (EPI == CRCT_EPI_DGELU) {
-                float a[8];
-                unpack8(aux.v[g], a);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] *= gelu_grad_f(a[j]);
-            }
-            o[g] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            for (int j = 0; j < 4; ++j) o[g * 4 + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
         }
+        const size_t off = (size_t)row * p.ldd + col0;
         if constexpr (EPI == CRCT_EPI_BIAS_GELU) {
-            if (p.D2 != nullptr) store_block_bf16(reinterpret_cast<bf16*>(p.D2), p.ldd, row0, col0, p.M, p.N, lane, o2, stage);
+            if (p.D2 != nullptr) st_row32(reinterpret_cast<bf16*>(p.D2) + off, p.wide != 0, p.N - col0, o2);
         }
-        store_block_bf16(reinterpret_cast<bf16*>(p.D), p.ldd, row0, col0, p.M, p.N, lane, o, stage);
+        st_row32(reinterpret_cast<bf16*>(p.D) + off, p.wide != 0, p.N - col0, o);
     }
 }
 
-// Epilogue of one tile for one warp (16 epilogue warps: 4 TMEM lane groups x 4 column quarters): stage the tile's bias
-// slice in smem (named barrier 1), then per 16-column step: aux prefetch (one step ahead) -> tcgen05.ld -> fused math
-// -> coalesced global store.
+__device__ __forceinline__ void reg_fence16(uint32_t (&v)[16]) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                      "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+}
+
+template <int BN>
+struct EpiGeom {
+    static constexpr int STEPS = (BN / 4) / EPI_COLS;
+};
+
+// aux (residual / multiplier) is fetched ONE TILE AHEAD: a lane keeps its row's BN/4 columns of the current tile in
+// registers (STEPS x 32 B); as soon as a step's 32 bytes are consumed, the same registers receive the next tile's
+// bytes, so every load has a whole tile time to arrive even when the epilogue is the critical path.
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_acc, int m0, int n0, int warp, int lane, float* bias_s,
-                                              uint8_t* stage_all) {
-    const int lane_grp = warp & 3;                          // TMEM lanes [32*lane_grp, +32) are this warp's
-    const int col_q = (warp - EPI_WARP0) >> 2;              // column quarter
-    uint8_t* stage = stage_all + (warp - EPI_WARP0) * 32 * OUT_PITCH;
-    if constexpr (EPI != CRCT_EPI_F32 && EPI != CRCT_EPI_DGELU) {
+__device__ __forceinline__ void aux_load_tile(const KParams& p, int m0, int n0, int warp, int lane, AuxRegs (&aux)[EpiGeom<BN>::STEPS]) {
+    const int row = m0 + (warp & 3) * 32 + lane;
+    const int cbase = n0 + ((warp - EPI_WARP0) >> 2) * (BN / 4);
+#pragma unroll
+    for (int c = 0; c < EpiGeom<BN>::STEPS; ++c) prefetch_aux<EPI>(p, row, cbase + c * EPI_COLS, aux[c]);
+}
+
+// Stage the tile's bias slice in smem (named barrier 1 among the epilogue warps); runs before the accumulator is ready.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_prepare(const KParams& p, int n0, int warp, int lane, float* bias_s) {
+    if constexpr (EPI != CRCT_EPI_F32 && EPI != CRCT_EPI_MUL) {
         if (p.bias != nullptr) {
             const int t = (warp - EPI_WARP0) * 32 + lane;   // 0..511
             if (t < BN) bias_s[t] = (n0 + t < p.N) ? p.bias[n0 + t] : 0.f;
         }
         asm volatile("bar.sync 1, %0;" :: "n"(NUM_EPI_WARPS * 32) : "memory");
     }
+}
+
+// Epilogue of one tile for one warp (16 epilogue warps: 4 TMEM lane groups x 4 column quarters); per 16-column step:
+// tcgen05.ld (next step's load in flight) -> fused math -> one 256-bit store per output -> aux refill for the next
+// tile (m0n, n0n; has_next = 0 on the CTA's last tile).
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_acc, int m0, int n0, int warp, int lane,
+                                              const float* bias_s, AuxRegs (&aux)[EpiGeom<BN>::STEPS], bool has_next, int m0n, int n0n) {
+    constexpr int STEPS = EpiGeom<BN>::STEPS;
+    const int lane_grp = warp & 3;                          // TMEM lanes [32*lane_grp, +32) are this warp's
+    const int col_q = (warp - EPI_WARP0) >> 2;              // column quarter
     uint64_t seed = p.seed;
     if constexpr (EPI == CRCT_EPI_BIAS_RES) {
         if (p.drop_thr != 0u && p.salt != nullptr) seed ^= __ldg(p.salt);
     }
-    const int row0 = m0 + lane_grp * 32;
-    constexpr int STEPS = (BN / 4) / EPI_COLS;
+    const int row = m0 + lane_grp * 32 + lane;
+    const int rown = m0n + lane_grp * 32 + lane;
     const int cbase = col_q * (BN / 4);
-    AuxRegs aux[2];
-    prefetch_aux<EPI>(p, row0, lane, n0 + cbase, aux[0]);
+    const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cbase;
+    uint32_t v[2][EPI_COLS];
+    ptx::tc_ld_32x16(taddr, v[0]);
 #pragma unroll
     for (int c = 0; c < STEPS; ++c) {
         const int cc = cbase + c * EPI_COLS;
-        if (c + 1 < STEPS) prefetch_aux<EPI>(p, row0, lane, n0 + cc + EPI_COLS, aux[(c + 1) & 1]);
-        const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cc;
-        uint32_t v[EPI_COLS];
-        ptx::tc_ld_32x16(taddr, v);
-        aux_to_rows<EPI>(aux[c & 1], lane, stage);
         ptx::tc_wait_ld();
-        if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row0, lane, n0 + cc, v, bias_s + cc, aux[c & 1], stage, seed);     // warp-uniform
+        reg_fence16(v[c & 1]);              // the loaded values exist from here on (tcgen05.ld is asynchronous)
+        if (c + 1 < STEPS) ptx::tc_ld_32x16(taddr + (uint32_t)((c + 1) * EPI_COLS), v[(c + 1) & 1]);
+        if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row, n0 + cc, v[c & 1], bias_s + cc, aux[c], seed);     // warp-uniform
+        if constexpr (epi_uses_aux(EPI)) {
+            if (has_next) prefetch_aux<EPI>(p, rown, n0n + cc, aux[c]);
+        }
     }
 }
 
@@ -350,16 +378,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ===================== epilogue =====================
         float* bias_s = reinterpret_cast<float*>(gbase + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        auto origin = [&](int tile, int& m0, int& n0) {
             const int mn = tile / p.split_k;
-            const int m0 = (mn / p.num_n_tiles) * BLOCK_M;
-            const int n0 = (mn % p.num_n_tiles) * BN;
+            m0 = (mn / p.num_n_tiles) * BLOCK_M;
+            n0 = (mn % p.num_n_tiles) * BN;
+        };
+        AuxRegs aux[EpiGeom<BN>::STEPS];
+        if (blockIdx.x < p.num_tiles) {
+            int m0, n0;
+            origin(blockIdx.x, m0, n0);
+            aux_load_tile<BN, EPI>(p, m0, n0, warp, lane, aux);
+        }
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            int m0, n0, m0n = 0, n0n = 0;
+            origin(tile, m0, n0);
+            const bool has_next = tile + (int)gridDim.x < p.num_tiles;
+            if (has_next) origin(tile + (int)gridDim.x, m0n, n0n);
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            epilogue_prepare<BN, EPI>(p, n0, warp, lane, bias_s + acc * 256);
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m0, n0, warp, lane, bias_s + acc * 256,
-                                   reinterpret_cast<uint8_t*>(bias_s + 512));
+            epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m0, n0, warp, lane, bias_s + acc * 256, aux, has_next, m0n, n0n);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
@@ -392,7 +432,7 @@ struct Cfg2 {
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
     static constexpr int BIAS_BYTES = 2 * 256 * 4;              // per accumulator stage: the tile's bias slice
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 24576 + 1024;   // + OUT_STAGE_BYTES
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -519,16 +559,28 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ===================== epilogue (each CTA drains its own 128 accumulator rows) =====================
         float* bias_s = reinterpret_cast<float*>(gbase + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
         int it = 0;
-        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+        auto origin = [&](int tile, int& m0, int& n0) {
             const int mn = tile / p.split_k;
-            const int m0 = (mn / p.num_n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
-            const int n0 = (mn % p.num_n_tiles) * BN;
+            m0 = (mn / p.num_n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+            n0 = (mn % p.num_n_tiles) * BN;
+        };
+        AuxRegs aux[EpiGeom<BN>::STEPS];
+        if (cluster_id < p.num_tiles) {
+            int m0, n0;
+            origin(cluster_id, m0, n0);
+            aux_load_tile<BN, EPI>(p, m0, n0, warp, lane, aux);
+        }
+        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+            int m0, n0, m0n = 0, n0n = 0;
+            origin(tile, m0, n0);
+            const bool has_next = tile + num_clusters < p.num_tiles;
+            if (has_next) origin(tile + num_clusters, m0n, n0n);
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            epilogue_prepare<BN, EPI>(p, n0, warp, lane, bias_s + acc * 256);
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m0, n0, warp, lane, bias_s + acc * 256,
-                                   reinterpret_cast<uint8_t*>(bias_s + 512));
+            epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m0, n0, warp, lane, bias_s + acc * 256, aux, has_next, m0n, n0n);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_remote(tempty_bar(acc), 0);
@@ -610,7 +662,7 @@ int dispatch2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtenso
     } else if (!a_mn && b_mn) {
         if (epi == CRCT_EPI_BIAS) return launch2<BN, false, true, CRCT_EPI_BIAS>(tmA, tmB, p, grid, st);
         if (epi == CRCT_EPI_BIAS_RES) return launch2<BN, false, true, CRCT_EPI_BIAS_RES>(tmA, tmB, p, grid, st);
-        if (epi == CRCT_EPI_DGELU) return launch2<BN, false, true, CRCT_EPI_DGELU>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_MUL) return launch2<BN, false, true, CRCT_EPI_MUL>(tmA, tmB, p, grid, st);
     } else if (a_mn && b_mn) {
         if (epi == CRCT_EPI_F32) return launch2<BN, true, true, CRCT_EPI_F32>(tmA, tmB, p, grid, st);
     }
@@ -626,7 +678,7 @@ int dispatch(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensor
     } else if (!a_mn && b_mn) {
         if (epi == CRCT_EPI_BIAS) return launch<BN, false, true, CRCT_EPI_BIAS>(tmA, tmB, p, grid, st);
         if (epi == CRCT_EPI_BIAS_RES) return launch<BN, false, true, CRCT_EPI_BIAS_RES>(tmA, tmB, p, grid, st);
-        if (epi == CRCT_EPI_DGELU) return launch<BN, false, true, CRCT_EPI_DGELU>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_MUL) return launch<BN, false, true, CRCT_EPI_MUL>(tmA, tmB, p, grid, st);
     } else if (a_mn && b_mn) {
         if (epi == CRCT_EPI_F32) return launch<BN, true, true, CRCT_EPI_F32>(tmA, tmB, p, grid, st);
     }
@@ -655,7 +707,7 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
         CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: leading dimensions must be multiples of 8 elements");
     if (((uintptr_t)a->A | (uintptr_t)a->B | (uintptr_t)a->D | (uintptr_t)a->D2 | (uintptr_t)a->aux | (uintptr_t)a->bias) & 15)
         CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: pointers must be 16-byte aligned");
-    if ((a->epilogue == CRCT_EPI_DGELU) && !a->aux) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: DGELU epilogue needs aux");
+    if ((a->epilogue == CRCT_EPI_MUL) && !a->aux) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: MUL epilogue needs aux");
     const bool f32 = a->epilogue == CRCT_EPI_F32;
     int split_k = a->split_k;
     const int kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
@@ -705,6 +757,10 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     p.kb_per_split = kb_per_split;
     p.D = a->D; p.D2 = a->D2; p.bias = a->bias; p.aux = reinterpret_cast<const bf16*>(a->aux);
     p.ldd = a->ldd; p.ldaux = a->ldaux;
+    {
+        auto ok32 = [](const void* q, int ld) { return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 31u) == 0 && ld % 16 == 0); };
+        p.wide = (!f32 && a->N % 16 == 0 && ok32(a->D, a->ldd) && ok32(a->D2, a->ldd) && ok32(a->aux, a->ldaux)) ? 1 : 0;
+    }
     p.accumulate = a->accumulate;
     p.drop_thr = crct_drop_threshold(a->dropout_p);
     p.drop_scale = a->dropout_p > 0.f ? 1.0f / (1.0f - a->dropout_p) : 1.0f;

@@ -7,10 +7,11 @@
 // reference: CRCT/backbone/vilbert.py:955-976 (poolers), :1052-1060 (classifier), CRCT/backbone/regressor.py:36-42,
 //            vilbert.py:1586-1657 (losses, metrics), CRCT/backbone/encoder_decorator.py:144-153 (loss combine).
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 32, LIN_THREADS = 256;
+constexpr int BM = 64, BN = 64, BK = 64, LIN_THREADS = 256;
 
 struct LinParams {
     const float* A; long long sa_m, sa_k;     // A(m,k) = A[m*sa_m + k*sa_k]
@@ -24,23 +25,35 @@ struct LinParams {
     int accumulate;
 };
 
-// 64x64 output tile per CTA, 4x4 per thread, K in slabs of 32 with the next slab's global loads issued before the
-// current slab's FMAs (the problems are tiny — M = batch — so the kernel is latency- not throughput-bound)
+// 64x64 output tile per CLUSTER, 4x4 per thread.  These problems are weight-streaming (M = batch, every weight used
+// M times) and far too small to fill the GPU along M and N alone, so a serial K loop is a chain of exposed DRAM
+// latencies (measured: 23-118 us per launch, 0.9 ms per step).  The K range is therefore split across the CTAs of a
+// thread-block cluster (grid.z = cluster size S <= 8): every CTA loads its K chunk (at most two 64-deep slabs, all
+// loads in flight at once), the partial tiles meet through distributed shared memory, and CTA r finishes rows
+// [64 r / S, 64 (r+1) / S) of the tile (bias, activation, mask, store) — deterministic, no workspace, no atomics.
 constexpr int MAX_BATCH = 12;
 struct LinBatch {
     LinParams p[MAX_BATCH];
+    int gy;            // M tiles per problem: blockIdx.y = problem * gy + m tile
 };
 
-// blockIdx.z selects one of several INDEPENDENT small problems (e.g. wgrad + dgrad + bias-grad of one head layer, or
-// the same layer of the two regressor pipes): one launch instead of up to 8 latency-bound ones.
+// blockIdx.y also selects one of several INDEPENDENT small problems (e.g. wgrad + dgrad + bias-grad of one head layer,
+// or the same layer of the two regressor pipes): one launch instead of up to 12 latency-bound ones.
 __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinBatch batch) {
-    const LinParams& p = batch.p[blockIdx.z];
-    if ((int)blockIdx.y * BM >= p.M || (int)blockIdx.x * BN >= p.N) return;
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN + 4];
-    constexpr int PER = (BM * BK) / LIN_THREADS;       // 8 elements of A and of B per thread per slab
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const LinParams& p = batch.p[blockIdx.y / batch.gy];
+    const int m0 = (int)(blockIdx.y % batch.gy) * BM, n0 = blockIdx.x * BN;
+    if (m0 >= p.M || n0 >= p.N) return;                 // the whole cluster shares (x, y): it leaves together
+    const int S = gridDim.z, r = blockIdx.z;
+    __shared__ float smem[2 * BK * (BM + 4)];
+    float (*As)[BM + 4] = reinterpret_cast<float (*)[BM + 4]>(smem);
+    float (*Bs)[BN + 4] = reinterpret_cast<float (*)[BN + 4]>(smem + BK * (BM + 4));
+    float (*Ps)[BN + 1] = reinterpret_cast<float (*)[BN + 1]>(smem);       // partial tile, reuses the slabs after the K loop
+    constexpr int PER = (BM * BK) / LIN_THREADS;        // 16 elements of A and of B per thread per slab
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kchunk = ((p.K + S - 1) / S + BK - 1) / BK * BK;
+    const int k_lo = r * kchunk, k_hi = min(p.K, k_lo + kchunk);
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -53,13 +66,13 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinBatch 
         for (int i = 0; i < PER; ++i) {
             const int e = tid + i * LIN_THREADS;
             const int kk = a_kfast ? (e % BK) : (e / BM), m = a_kfast ? (e / BK) : (e % BM);
-            ra[i] = (m0 + m < p.M && k0 + kk < p.K) ? (p.A ? p.A[(long long)(m0 + m) * p.sa_m + (long long)(k0 + kk) * p.sa_k] : 1.f) : 0.f;
+            ra[i] = (m0 + m < p.M && k0 + kk < k_hi) ? (p.A ? p.A[(long long)(m0 + m) * p.sa_m + (long long)(k0 + kk) * p.sa_k] : 1.f) : 0.f;
             const int kb = b_nfast ? (e / BN) : (e % BK), n = b_nfast ? (e % BN) : (e / BK);
-            rb[i] = (n0 + n < p.N && k0 + kb < p.K) ? p.B[(long long)(k0 + kb) * p.sb_k + (long long)(n0 + n) * p.sb_n] : 0.f;
+            rb[i] = (n0 + n < p.N && k0 + kb < k_hi) ? p.B[(long long)(k0 + kb) * p.sb_k + (long long)(n0 + n) * p.sb_n] : 0.f;
         }
     };
-    fetch(0);
-    for (int k0 = 0; k0 < p.K; k0 += BK) {
+    if (k_lo < k_hi) fetch(k_lo);
+    for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int e = tid + i * LIN_THREADS;
@@ -69,8 +82,8 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinBatch 
             Bs[kb][n] = rb[i];
         }
         __syncthreads();
-        if (k0 + BK < p.K) fetch(k0 + BK);
-#pragma unroll
+        if (k0 + BK < k_hi) fetch(k0 + BK);
+#pragma unroll 8
         for (int kk = 0; kk < BK; ++kk) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
             const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
@@ -83,23 +96,27 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinBatch 
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
-        if (m >= p.M) continue;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
-            if (n >= p.N) continue;
-            float v = acc[i][j];
-            if (p.bias) v += p.bias[n];
-            if (p.act == 1) v = fmaxf(v, 0.f);
-            else if (p.act == 2) v = v > 0.f ? v : 0.01f * v;
-            else if (p.act == 3) v = tanhf(v);
-            if (p.dmask) v *= (p.dmask[(long long)m * p.ldm + n] > 0.f ? 1.f : p.slope);
-            float* c = p.C + (long long)m * p.ldc + n;
-            if (p.accumulate) *c += v; else *c = v;
-        }
+        for (int j = 0; j < 4; ++j) Ps[ty * 4 + i][tx * 4 + j] = acc[i][j];
+    cluster.sync();                                      // every CTA's partial tile is complete and visible
+    const int rows = (BM + S - 1) / S;
+    const int r_lo = r * rows, r_hi = min(BM, r_lo + rows);
+    for (int e = tid; e < (r_hi - r_lo) * BN; e += LIN_THREADS) {
+        const int ml = r_lo + e / BN, nl = e % BN;
+        const int m = m0 + ml, n = n0 + nl;
+        if (m >= p.M || n >= p.N) continue;
+        float v = 0.f;
+        for (int s2 = 0; s2 < S; ++s2) v += cluster.map_shared_rank(smem, s2)[ml * (BN + 1) + nl];
+        if (p.bias) v += p.bias[n];
+        if (p.act == 1) v = fmaxf(v, 0.f);
+        else if (p.act == 2) v = v > 0.f ? v : 0.01f * v;
+        else if (p.act == 3) v = tanhf(v);
+        if (p.dmask) v *= (p.dmask[(long long)m * p.ldm + n] > 0.f ? 1.f : p.slope);
+        float* c = p.C + (long long)m * p.ldc + n;
+        if (p.accumulate) *c += v; else *c = v;
     }
+    cluster.sync();                                      // nobody leaves while its partial tile is still being read
 }
 
 // out[b, :] = float(src[b * row_stride + :])  (first token / region of every sample)
@@ -266,17 +283,30 @@ extern "C" CRCT_API int crct_linear_f32_batched(const crct_linear_t* problems, i
     if (!problems || count < 1 || count > MAX_BATCH) CRCT_FAIL(CRCT_ERR_ARG, "crct_linear_f32_batched: 1..%d problems", MAX_BATCH);
     LinBatch b;
     memset(&b, 0, sizeof(b));
-    int gx = 0, gy = 0, n = 0;
+    int gx = 0, gy = 0, n = 0, kmax = 0;
     for (int i = 0; i < count; ++i) {
         if (problems[i].M <= 0 || problems[i].N <= 0 || problems[i].K <= 0) continue;
         if (int rc = fill_lin(b.p[n], &problems[i])) return rc;
         gx = max(gx, (problems[i].N + BN - 1) / BN);
         gy = max(gy, (problems[i].M + BM - 1) / BM);
+        kmax = max(kmax, problems[i].K);
         ++n;
     }
     if (n == 0) return CRCT_OK;
-    linear_f32_kernel<<<dim3(gx, gy, n), LIN_THREADS, 0, as_stream(s)>>>(b);
-    CRCT_LAUNCH_CHECK();
+    b.gy = gy;
+    int S = 1;                                           // K split = cluster size: at most two 64-deep slabs per CTA
+    while (S < 8 && S * 2 * BK < kmax) S *= 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(gx, gy * n, S);
+    cfg.blockDim = dim3(LIN_THREADS, 1, 1);
+    cfg.stream = as_stream(s);
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 1; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = S;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    CRCT_CUDA(cudaLaunchKernelEx(&cfg, linear_f32_kernel, b));
     return CRCT_OK;
 }
 

@@ -272,14 +272,14 @@ class VisualDialogEncoder(nn.Module):
         """intermediate + output blocks (vilbert.py:454-457,467-471 / 585-588,598-602)."""
         M = a.shape[0]
         W1, W2 = self._w(pre_i + '.dense.weight'), self._w(pre_o + '.dense.weight')
-        u = torch.empty(M, W1.shape[0], dtype=torch.bfloat16, device=a.device) if keep else None
-        h = self._linear(a, W1, self._p(pre_i + '.dense.bias'), M, L.EPI_BIAS_GELU, D2=u)
+        dg = torch.empty(M, W1.shape[0], dtype=torch.bfloat16, device=a.device) if keep else None      # gelu'(u), for the backward
+        h = self._linear(a, W1, self._p(pre_i + '.dense.bias'), M, L.EPI_BIAS_GELU, D2=dg)
         z = self._linear(h, W2, self._p(pre_o + '.dense.bias'), M, L.EPI_BIAS_RES, aux=a, p=p_drop, seed=seed)
         y, mean, rstd = self._ln(z, pre_o + '.LayerNorm', keep)
         s = None
         if keep:
             s = _Saved()
-            s.a, s.u, s.h, s.z, s.mean, s.rstd, s.p, s.seed = a, u, h, z, mean, rstd, p_drop, seed
+            s.a, s.dg, s.h, s.z, s.mean, s.rstd, s.p, s.seed = a, dg, h, z, mean, rstd, p_drop, seed
         return y, s
 
     def _ffn_bwd(self, dy, s, pre_i, pre_o):
@@ -293,7 +293,7 @@ class VisualDialogEncoder(nn.Module):
         I = W1.shape[0]
         self._wgrad(gz, s.h, self._g(pre_o + '.dense.weight'))
         du = torch.empty(M, I, dtype=torch.bfloat16, device=dy.device)
-        L.gemm(gz, W2, du, M=M, N=I, K=H, b_major=1, epilogue=L.EPI_DGELU, aux=s.u)
+        L.gemm(gz, W2, du, M=M, N=I, K=H, b_major=1, epilogue=L.EPI_MUL, aux=s.dg)
         self._wgrad(du, s.a, self._g(pre_i + '.dense.weight'), self._g(pre_i + '.dense.bias'))
         da = torch.empty_like(dy)
         L.gemm(du, W1, da, M=M, N=H, K=I, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz)

@@ -53,9 +53,9 @@ int crct_device_check(void);
  * -------------------------------------------------------------------------------------------- */
 typedef enum {
     CRCT_EPI_BIAS = 0,      /* D = acc + bias                                    (bias may be NULL) */
-    CRCT_EPI_BIAS_GELU = 1, /* u = acc + bias; D2 = u (if D2); D = gelu_erf(u)    vilbert.py:111-117,454-457 */
+    CRCT_EPI_BIAS_GELU = 1, /* u = acc + bias; D = gelu_erf(u); D2 = gelu_erf'(u) (if D2)   vilbert.py:111-117,454-457 */
     CRCT_EPI_BIAS_RES = 2,  /* D = dropout(acc + bias) + aux                      vilbert.py:424-428,467-471,749-756 */
-    CRCT_EPI_DGELU = 3,     /* D = acc * gelu'(aux)                               backward of vilbert.py:456 */
+    CRCT_EPI_MUL = 3,       /* D = acc * aux   (aux = the D2 saved by BIAS_GELU)   backward of vilbert.py:456 */
     CRCT_EPI_F32 = 4        /* D (fp32) = acc, or D += acc when accumulate != 0 (wgrad, split-K) */
 } crct_epilogue_t;
 
@@ -65,7 +65,7 @@ typedef struct {
     void* D;            /* bf16 [M,N] (fp32 for CRCT_EPI_F32), row stride ldd */
     void* D2;           /* bf16 [M,N] row stride ldd, CRCT_EPI_BIAS_GELU only, may be NULL */
     const float* bias;  /* fp32 [N] or NULL */
-    const void* aux;    /* bf16 [M,N] row stride ldaux (residual / addend / pre-activation) or NULL */
+    const void* aux;    /* bf16 [M,N] row stride ldaux (residual / addend / saved activation derivative) or NULL */
     int32_t M, N, K;
     int32_t lda, ldb, ldd, ldaux; /* in elements */
     int32_t a_major, b_major;

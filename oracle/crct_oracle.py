@@ -270,7 +270,7 @@ def ffn_fwd(w, a, pre_i, pre_o):
     h = _q(gelu(u))
     z = _q(tlin(h, w[pre_o + 'dense.weight'], w[pre_o + 'dense.bias']) + a)
     y, mean, rstd = ln_fwd(z, w[pre_o + 'LayerNorm.weight'], w[pre_o + 'LayerNorm.bias'])
-    return _q(y), dict(a=a, u=_q(u), h=h, z=z, mean=mean, rstd=rstd)
+    return _q(y), dict(a=a, u=u, h=h, z=z, mean=mean, rstd=rstd)
 
 
 def ffn_bwd(w, g, dy, c, pre_i, pre_o):
@@ -281,7 +281,7 @@ def ffn_bwd(w, g, dy, c, pre_i, pre_o):
     dz = _q(dz)
     dh, dW, _ = tlin_bwd(dz, c['h'], w[pre_o + 'dense.weight'])
     g.add(pre_o + 'dense.weight', dW)
-    du = _q(dh * gelu_grad(c['u']))
+    du = _q(dh * _q(gelu_grad(c['u'])))      # the CUDA path stores gelu'(u) in bf16 from the forward epilogue
     da, dW, dbias = tlin_bwd(du, c['a'], w[pre_i + 'dense.weight'])
     g.add(pre_i + 'dense.weight', dW)
     g.add(pre_i + 'dense.bias', dbias)

@@ -30,7 +30,7 @@ for a, b, M, N, K, am, bm, ep in ev:
     k = (M, N, K, am, bm, ep); agg[k][0] += 1; agg[k][1] += a.elapsed_time(b) * 1e3
 tot = sum(v for c, v in agg.values())
 print(f'{len(ev)} GEMMs, {tot/1e3:.2f} ms')
-names = {0: 'bias', 1: 'gelu', 2: 'res', 3: 'dgelu', 4: 'f32'}
+names = {0: 'bias', 1: 'gelu', 2: 'res', 3: 'mul', 4: 'f32'}
 for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
     M, N, K, am, bm, ep = k
     print(f'{v:8.0f} us n={c:3d} avg={v/c:7.1f} us {2*M*N*K*c/v/1e6:7.0f} TFLOP/s  M={M} N={N} K={K} a_mn={am} b_mn={bm} {names[ep]}')
