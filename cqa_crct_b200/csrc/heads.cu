@@ -23,6 +23,7 @@ struct LinParams {
     int act;                                  // 0 none, 1 relu, 2 leaky(0.01), 3 tanh
     float slope;
     int accumulate;
+    int ksplit;                               // CTAs of the cluster that share one output tile along K (1, 2, 4, 8)
 };
 
 // 64x64 output tile per CLUSTER, 4x4 per thread.  These problems are weight-streaming (M = batch, every weight used
@@ -31,6 +32,7 @@ struct LinParams {
 // thread-block cluster (grid.z = cluster size S <= 8): every CTA loads its K chunk (at most two 64-deep slabs, all
 // loads in flight at once), the partial tiles meet through distributed shared memory, and CTA r finishes rows
 // [64 r / S, 64 (r+1) / S) of the tile (bias, activation, mask, store) — deterministic, no workspace, no atomics.
+// (barrier.cluster only waits for non-exited threads, so groups of a cluster whose tile is out of range just leave.)
 constexpr int MAX_BATCH = 12;
 struct LinBatch {
     LinParams p[MAX_BATCH];
@@ -43,9 +45,10 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinBatch 
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const LinParams& p = batch.p[blockIdx.y / batch.gy];
-    const int m0 = (int)(blockIdx.y % batch.gy) * BM, n0 = blockIdx.x * BN;
-    if (m0 >= p.M || n0 >= p.N) return;                 // the whole cluster shares (x, y): it leaves together
-    const int S = gridDim.z, r = blockIdx.z;
+    // a problem with a short K uses ksplit < cluster size: the cluster then covers (cluster size / ksplit) N tiles
+    const int S = p.ksplit, groups = (int)gridDim.z / S, grp = (int)blockIdx.z / S, r = (int)blockIdx.z % S;
+    const int m0 = (int)(blockIdx.y % batch.gy) * BM, n0 = ((int)blockIdx.x * groups + grp) * BN;
+    if (m0 >= p.M || n0 >= p.N) return;                 // a K-split group shares (m0, n0): it leaves together
     __shared__ float smem[2 * BK * (BM + 4)];
     float (*As)[BM + 4] = reinterpret_cast<float (*)[BM + 4]>(smem);
     float (*Bs)[BN + 4] = reinterpret_cast<float (*)[BN + 4]>(smem + BK * (BM + 4));
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinBatch 
         const int m = m0 + ml, n = n0 + nl;
         if (m >= p.M || n >= p.N) continue;
         float v = 0.f;
-        for (int s2 = 0; s2 < S; ++s2) v += cluster.map_shared_rank(smem, s2)[ml * (BN + 1) + nl];
+        for (int s2 = 0; s2 < S; ++s2) v += cluster.map_shared_rank(smem, grp * S + s2)[ml * (BN + 1) + nl];
         if (p.bias) v += p.bias[n];
         if (p.act == 1) v = fmaxf(v, 0.f);
         else if (p.act == 2) v = v > 0.f ? v : 0.01f * v;
@@ -283,19 +286,27 @@ extern "C" CRCT_API int crct_linear_f32_batched(const crct_linear_t* problems, i
     if (!problems || count < 1 || count > MAX_BATCH) CRCT_FAIL(CRCT_ERR_ARG, "crct_linear_f32_batched: 1..%d problems", MAX_BATCH);
     LinBatch b;
     memset(&b, 0, sizeof(b));
-    int gx = 0, gy = 0, n = 0, kmax = 0;
+    int gy = 0, n = 0, S = 1;
+    auto ksplit = [](int K) {                            // at most two 64-deep slabs per CTA, up to 8 CTAs
+        int sp = 1;
+        while (sp < 8 && sp * 2 * BK < K) sp *= 2;
+        return sp;
+    };
     for (int i = 0; i < count; ++i) {
         if (problems[i].M <= 0 || problems[i].N <= 0 || problems[i].K <= 0) continue;
         if (int rc = fill_lin(b.p[n], &problems[i])) return rc;
-        gx = max(gx, (problems[i].N + BN - 1) / BN);
+        b.p[n].ksplit = ksplit(problems[i].K);
+        S = max(S, b.p[n].ksplit);
         gy = max(gy, (problems[i].M + BM - 1) / BM);
-        kmax = max(kmax, problems[i].K);
         ++n;
     }
     if (n == 0) return CRCT_OK;
+    int gx = 0;
+    for (int i = 0; i < n; ++i) {
+        const int groups = S / b.p[i].ksplit, tiles = (b.p[i].N + BN - 1) / BN;
+        gx = max(gx, (tiles + groups - 1) / groups);
+    }
     b.gy = gy;
-    int S = 1;                                           // K split = cluster size: at most two 64-deep slabs per CTA
-    while (S < 8 && S * 2 * BK < kmax) S *= 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(gx, gy * n, S);

@@ -94,8 +94,35 @@ layernorm_fwd_kernel(const bf16* __restrict__ z, const float* __restrict__ gamma
 // dz = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)), dxh = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dbias += sum_rows dzm (optional)
 // dy may carry an input dropout mask (seed_in), dzm = dz * keep(seed_out) * scale (optional second output).
-// The three column sums are accumulated in per-warp shared-memory rows (registers hold only the current row), so two
-// CTAs fit per SM; they meet in one atomic per column per CTA at the end.
+// One warp per row.  The three column sums are accumulated in per-warp shared-memory rows, so registers hold only row
+// data: the current row stays PACKED (bf16, as loaded) and is unpacked again for the second pass, which leaves room
+// to fetch the NEXT row before the current one is processed — the kernel is latency-bound (two CTAs per SM, a
+// dependent load -> reduce -> store chain per row), so that prefetch is what keeps HBM busy.
+template <int NCH>
+struct PackedRow {
+    uint4 dy[NCH], z[NCH];
+    float mean, rstd;
+};
+template <int NCH>
+__device__ __forceinline__ void load_packed_row(PackedRow<NCH>& r, const bf16* __restrict__ dy, const bf16* __restrict__ z,
+                                                const float* __restrict__ mean, const float* __restrict__ rstd, int row, int H,
+                                                int lane, int nchunks) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunks) {
+            r.dy[c] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * H + ch * 8));
+            r.z[c] = __ldg(reinterpret_cast<const uint4*>(z + (size_t)row * H + ch * 8));
+        }
+    }
+    r.mean = __ldg(mean + row);
+    r.rstd = __ldg(rstd + row);
+}
+__device__ __forceinline__ void unpack8f(const uint4& v, float (&f)[8]) {
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS, 2)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ mean_in,
@@ -103,8 +130,8 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
                      bf16* __restrict__ dzm, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                      int rows, int H, uint32_t thr_in, float scale_in, uint64_t seed_in, uint32_t thr_out, float scale_out,
                      uint64_t seed_out, const unsigned long long* __restrict__ salt) {
-    extern __shared__ __align__(16) float acc_s[];
-    if (salt != nullptr) { const unsigned long long sv = __ldg(salt); seed_in ^= sv; seed_out ^= sv; }       // [3][8 warps][H]
+    extern __shared__ __align__(16) float acc_s[];       // [3][8 warps][H]
+    if (salt != nullptr) { const unsigned long long sv = __ldg(salt); seed_in ^= sv; seed_out ^= sv; }
     constexpr int NW = ROW_THREADS / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = H >> 3;
@@ -114,38 +141,33 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
     for (int i = lane; i < H; i += 32) { my_g[i] = 0.f; my_b[i] = 0.f; my_d[i] = 0.f; }
     __syncwarp();
     const float invH = 1.0f / (float)H;
-    for (int row = blockIdx.x * NW + warp; row < rows; row += gridDim.x * NW) {
-        const float mean = mean_in[row], rstd = rstd_in[row];
-        float g[NCH][8], x[NCH][8];                      // g: dy then dxh ; x: z then xhat
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {                  // all loads of the row first (memory-level parallelism)
-            const int ch = lane + 32 * c;
-            if (ch < nchunks) {
-                load8_bf16(dy + (size_t)row * H + ch * 8, g[c]);
-                load8_bf16(z + (size_t)row * H + ch * 8, x[c]);
-            }
-        }
+    const int stride = gridDim.x * NW;
+    int row = blockIdx.x * NW + warp;
+    PackedRow<NCH> cur, nxt;
+    if (row < rows) load_packed_row<NCH>(cur, dy, z, mean_in, rstd_in, row, H, lane, nchunks);
+    for (; row < rows; row += stride) {
+        if (row + stride < rows) load_packed_row<NCH>(nxt, dy, z, mean_in, rstd_in, row + stride, H, lane, nchunks);
+        const float rstd = cur.rstd, nmr = -cur.mean * cur.rstd;     // xhat = z * rstd + nmr
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int ch = lane + 32 * c;
             if (ch < nchunks) {
-                float gm[8], pg[8], pb[8];
+                float d[8], x[8], gm[8], pg[8], pb[8];
+                unpack8f(cur.dy[c], d);
+                unpack8f(cur.z[c], x);
                 load8_f32(gamma + ch * 8, gm);
                 load8_f32(my_g + ch * 8, pg);
                 load8_f32(my_b + ch * 8, pb);
-                if (thr_in != 0u) dropout8(g[c], seed_in, (uint64_t)row * H + ch * 8, thr_in, scale_in);
+                if (thr_in != 0u) dropout8(d, seed_in, (uint64_t)row * H + ch * 8, thr_in, scale_in);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float d = g[c][j];
-                    const float xh = (x[c][j] - mean) * rstd;
-                    pg[j] = fmaf(d, xh, pg[j]);
-                    pb[j] += d;
-                    const float dxh = d * gm[j];
+                    const float xh = fmaf(x[j], rstd, nmr);
+                    pg[j] = fmaf(d[j], xh, pg[j]);
+                    pb[j] += d[j];
+                    const float dxh = d[j] * gm[j];
                     s1 += dxh;
                     s2 = fmaf(dxh, xh, s2);
-                    g[c][j] = dxh;
-                    x[c][j] = xh;
                 }
                 *reinterpret_cast<float4*>(my_g + ch * 8) = make_float4(pg[0], pg[1], pg[2], pg[3]);
                 *reinterpret_cast<float4*>(my_g + ch * 8 + 4) = make_float4(pg[4], pg[5], pg[6], pg[7]);
@@ -153,14 +175,22 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
                 *reinterpret_cast<float4*>(my_b + ch * 8 + 4) = make_float4(pb[4], pb[5], pb[6], pb[7]);
             }
         }
-        const float m1 = warp_sum(s1) * invH, m2 = warp_sum(s2) * invH;
+        // dz = rstd * (dxh - m1 - xhat * m2) = dxh * rstd - (m1 rstd) - xhat * (m2 rstd)
+        const float m1r = warp_sum(s1) * invH * rstd, m2r = warp_sum(s2) * invH * rstd;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int ch = lane + 32 * c;
             if (ch < nchunks) {
-                float o[8];
+                float d[8], x[8], gm[8], o[8];
+                unpack8f(cur.dy[c], d);
+                unpack8f(cur.z[c], x);
+                load8_f32(gamma + ch * 8, gm);
+                if (thr_in != 0u) dropout8(d, seed_in, (uint64_t)row * H + ch * 8, thr_in, scale_in);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] - m1 - x[c][j] * m2);
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = fmaf(x[j], rstd, nmr);
+                    o[j] = fmaf(-xh, m2r, fmaf(d[j] * gm[j], rstd, -m1r));
+                }
                 store8_bf16(dz + (size_t)row * H + ch * 8, o);
                 if (dzm != nullptr) {
                     dropout8(o, seed_out, (uint64_t)row * H + ch * 8, thr_out, scale_out);
@@ -174,6 +204,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
                 }
             }
         }
+        cur = nxt;
     }
     __syncthreads();
     for (int col = threadIdx.x; col < H; col += ROW_THREADS) {
