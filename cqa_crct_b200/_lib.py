@@ -90,7 +90,7 @@ class AdamWArgs(C.Structure):
 
 # every symbol include/crct_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf16', 'crct_cast_f32_to_bf16',
-           'crct_additive_mask', 'crct_layernorm_fwd', 'crct_layernorm_bwd', 'crct_colsum_bf16', 'crct_softmax_rows',
+           'crct_additive_mask', 'crct_layernorm_fwd', 'crct_layernorm_bwd', 'crct_layernorm_bwd_params', 'crct_colsum_bf16', 'crct_softmax_rows',
            'crct_embed_text_fwd', 'crct_embed_text_bwd', 'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd',
            'crct_attn_bwd', 'crct_linear_f32', 'crct_linear_f32_batched', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
            'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_bump_salt', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw']
@@ -123,7 +123,7 @@ def lib():
         _lib.crct_pool_mul_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
         _lib.crct_pool_mul_bwd.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
         _lib.crct_bump_salt.argtypes = [vp, vp]
-        for name in ('crct_gemm_bf16', 'crct_layernorm_bwd', 'crct_embed_text_fwd', 'crct_embed_text_bwd',
+        for name in ('crct_gemm_bf16', 'crct_layernorm_bwd', 'crct_layernorm_bwd_params', 'crct_embed_text_fwd', 'crct_embed_text_bwd',
                      'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd', 'crct_attn_bwd', 'crct_linear_f32',
                      'crct_hybrid_loss', 'crct_adamw'):
             getattr(_lib, name).argtypes = [vp, vp]
@@ -205,8 +205,7 @@ def layernorm_fwd(z, gamma, beta, y, mean=None, rstd=None):
     check(lib().crct_layernorm_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, H, stream_ptr()))
 
 
-def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0,
-                  seed_out=0):
+def _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out):
     _bf16(dy, 'dy'); _bf16(z, 'z'); _bf16(dz, 'dz'); _bf16(dzm, 'dzm')
     a = LnBwdArgs()
     a.dy, a.z, a.mean, a.rstd, a.gamma, a.dz, a.dzm = ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma), ptr(dz), ptr(dzm)
@@ -214,7 +213,20 @@ def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias=None, dzm=N
     a.rows, a.H = z.shape
     a.p_in, a.seed_in, a.p_out, a.seed_out = p_in, seed_in, p_out, seed_out
     a.salt = ptr(SALT)
+    return a
+
+
+def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dgamma=None, dbeta=None, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0,
+                  seed_out=0):
+    """dgamma = dbeta = dbias = None: input gradient only (see layernorm_bwd_params)."""
+    a = _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out)
     check(lib().crct_layernorm_bwd(C.byref(a), stream_ptr()))
+
+
+def layernorm_bwd_params(dy, z, mean, rstd, dz, dgamma, dbeta, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0):
+    """Column sums of the split LayerNorm backward: dgamma, dbeta and (from dzm, or dz when p_out == 0) dbias."""
+    a = _ln_bwd_args(dy, z, mean, rstd, None, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, 0)
+    check(lib().crct_layernorm_bwd_params(C.byref(a), stream_ptr()))
 
 
 def colsum_bf16(x, out, rows=None, N=None, ld=None):

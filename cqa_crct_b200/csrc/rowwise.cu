@@ -221,6 +221,136 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
     }
 }
 
+// ---- LayerNorm backward, split form (what the training step uses): the input gradient is on the backward's critical
+// path, the three column sums (dgamma, dbeta, dense-bias gradient) are weight gradients nothing waits for.
+//   ln_bwd_dz_kernel     : one warp per row, no accumulators -> few registers, many rows in flight; 61 MB at H = 768.
+//   ln_bwd_params_kernel : a lane owns 8 columns, accumulates the three sums in registers over a strided set of rows
+//                          (4 rows in flight), CTA reduce through smem, one atomic per column per CTA; re-reads dy, z and
+//                          dzm, which the dz kernel has just left in L2.
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_bwd_dz_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ mean_in,
+                 const float* __restrict__ rstd_in, const float* __restrict__ gamma, bf16* __restrict__ dz, bf16* __restrict__ dzm,
+                 int rows, int H, uint32_t thr_in, float scale_in, uint64_t seed_in, uint32_t thr_out, float scale_out,
+                 uint64_t seed_out, const unsigned long long* __restrict__ salt) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
+    if (row >= rows) return;
+    if (salt != nullptr) { const unsigned long long sv = __ldg(salt); seed_in ^= sv; seed_out ^= sv; }
+    const int nchunks = H >> 3;
+    PackedRow<NCH> r;
+    load_packed_row<NCH>(r, dy, z, mean_in, rstd_in, row, H, lane, nchunks);
+    const float rstd = r.rstd, nmr = -r.mean * r.rstd;
+    float g[NCH][8], x[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunks) {
+            float gm[8];
+            unpack8f(r.dy[c], g[c]);
+            unpack8f(r.z[c], x[c]);
+            load8_f32(gamma + ch * 8, gm);
+            if (thr_in != 0u) dropout8(g[c], seed_in, (uint64_t)row * H + ch * 8, thr_in, scale_in);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                x[c][j] = fmaf(x[c][j], rstd, nmr);
+                g[c][j] *= gm[j];
+                s1 += g[c][j];
+                s2 = fmaf(g[c][j], x[c][j], s2);
+            }
+        }
+    }
+    const float invH = 1.0f / (float)H;
+    const float m1r = warp_sum(s1) * invH * rstd, m2r = warp_sum(s2) * invH * rstd;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunks) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(-x[c][j], m2r, fmaf(g[c][j], rstd, -m1r));
+            store8_bf16(dz + (size_t)row * H + ch * 8, o);
+            if (dzm != nullptr) {
+                dropout8(o, seed_out, (uint64_t)row * H + ch * 8, thr_out, scale_out);
+                store8_bf16(dzm + (size_t)row * H + ch * 8, o);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_bwd_params_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const bf16* __restrict__ dzm,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int H, uint32_t thr_in, float scale_in,
+                     uint64_t seed_in, const unsigned long long* __restrict__ salt) {
+    constexpr int NW = ROW_THREADS / 32;
+    __shared__ float red[NW][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 256 + lane * 8;
+    if (salt != nullptr) seed_in ^= __ldg(salt);
+    float ag[8], ab[8], ad[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; ad[j] = 0.f; }
+    if (col < H) {
+        const int stride = gridDim.y * NW;
+        constexpr int U = 4;
+        for (int row0 = blockIdx.y * NW + warp; row0 < rows; row0 += U * stride) {
+            uint4 pd[U], pz[U], pm[U];
+            float mean[U], rstd[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                  // all loads of U rows first
+                const int row = row0 + u * stride;
+                if (row < rows) {
+                    pd[u] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * H + col));
+                    pz[u] = __ldg(reinterpret_cast<const uint4*>(z + (size_t)row * H + col));
+                    if (dbias != nullptr) pm[u] = __ldg(reinterpret_cast<const uint4*>(dzm + (size_t)row * H + col));
+                    mean[u] = __ldg(mean_in + row);
+                    rstd[u] = __ldg(rstd_in + row);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int row = row0 + u * stride;
+                if (row < rows) {
+                    float d[8], x[8];
+                    unpack8f(pd[u], d);
+                    unpack8f(pz[u], x);
+                    if (thr_in != 0u) dropout8(d, seed_in, (uint64_t)row * H + col, thr_in, scale_in);
+                    const float nmr = -mean[u] * rstd[u];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        ag[j] = fmaf(d[j], fmaf(x[j], rstd[u], nmr), ag[j]);
+                        ab[j] += d[j];
+                    }
+                    if (dbias != nullptr) {
+                        float m[8];
+                        unpack8f(pm[u], m);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) ad[j] += m[j];
+                    }
+                }
+            }
+        }
+    }
+    float* outs[3] = {dgamma, dbeta, dbias};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (outs[k] == nullptr) continue;                  // uniform across the CTA
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = k == 0 ? ag[j] : (k == 1 ? ab[j] : ad[j]);
+        __syncthreads();
+        const int c = blockIdx.x * 256 + threadIdx.x;
+        if (c < H) {
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) sum += red[w][threadIdx.x];
+            atomicAdd(outs[k] + c, sum);
+        }
+    }
+}
+
 // out[n] += sum_rows x[row, n]
 __global__ void __launch_bounds__(ROW_THREADS)
 colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows, int N, int ld) {
@@ -374,6 +504,11 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_text_fwd_kernel(const TextE
 }
 
 // backward scatter of dz (bf16, already through the LayerNorm backward) into the embedding tables
+__device__ __forceinline__ void add8_global(float* dst, const float (&d)[8]) {
+    ptx::red_add_f32x4(dst, d[0], d[1], d[2], d[3]);
+    ptx::red_add_f32x4(dst + 4, d[4], d[5], d[6], d[7]);
+}
+
 struct TextEmbBwdArgs {
     const long long* ids; const long long* types; const float* loc; const bf16* dz;
     float* g_word; float* g_pos; float* g_type; float* g_wloc; float* g_bloc;
@@ -407,11 +542,11 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_text_bwd_kernel(const TextE
             if (ch < nchunks) {
                 float d[8];
                 load8_bf16(a.dz + (size_t)row * H + ch * 8, d);
+                add8_global(a.g_word + (size_t)id * H + ch * 8, d);         // 128-bit reductions: 4x fewer L2 atomic ops
+                if (qa) add8_global(a.g_pos + (size_t)(t - first) * H + ch * 8, d);
+                if (ty != 0) add8_global(a.g_type + (size_t)ty_idx * H + ch * 8, d);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    atomicAdd(a.g_word + (size_t)id * H + ch * 8 + j, d[j]);
-                    if (qa) atomicAdd(a.g_pos + (size_t)(t - first) * H + ch * 8 + j, d[j]);
-                    if (ty != 0) atomicAdd(a.g_type + (size_t)ty_idx * H + ch * 8 + j, d[j]);
                     if (loc_on) {
                         acc[0].v[c][j] += d[j];
                         acc[1].v[c][j] += d[j] * bx.x; acc[2].v[c][j] += d[j] * bx.y;
@@ -511,9 +646,9 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_vis_bwd_kernel(const VisEmb
             if (ch < nchunks) {
                 float d[8];
                 load8_bf16(a.dz + (size_t)row * H + ch * 8, d);
+                add8_global(a.g_color + (size_t)cls * H + ch * 8, d);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    atomicAdd(a.g_color + (size_t)cls * H + ch * 8 + j, d[j]);
                     acc[0].v[c][j] += d[j] * bx.x; acc[1].v[c][j] += d[j] * bx.y;
                     acc[2].v[c][j] += d[j] * bx.z; acc[3].v[c][j] += d[j] * bx.w;
                 }
@@ -597,11 +732,29 @@ extern "C" CRCT_API int crct_layernorm_bwd(const crct_ln_bwd_t* a, crct_stream_t
     if (!a || !a->dy || !a->z || !a->mean || !a->rstd || !a->gamma || !a->dz) CRCT_FAIL(CRCT_ERR_ARG, "crct_layernorm_bwd: null pointer");
     if (int rc = check_row_width(a->H, "crct_layernorm_bwd")) return rc;
     if (a->rows <= 0) return CRCT_OK;
+    const bool dzm = a->dzm != nullptr && a->p_out > 0.f;
+    const int nch = (a->H / 8 + 31) / 32;
+    const float sc_in = a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, sc_out = a->p_out > 0.f ? 1.f / (1.f - a->p_out) : 1.f;
+    if (!a->dgamma && !a->dbeta && !a->dbias) {          // input gradient only (crct_layernorm_bwd_params does the sums)
+        auto launch = [&](auto kern) {
+            kern<<<row_grid(a->rows), ROW_THREADS, 0, as_stream(s)>>>(
+                reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), a->mean, a->rstd, a->gamma,
+                reinterpret_cast<bf16*>(a->dz), dzm ? reinterpret_cast<bf16*>(a->dzm) : nullptr, a->rows, a->H,
+                crct_drop_threshold(a->p_in), sc_in, a->seed_in, crct_drop_threshold(a->p_out), sc_out, a->seed_out,
+                reinterpret_cast<const unsigned long long*>(a->salt));
+        };
+        switch (nch) {
+            case 1: launch(ln_bwd_dz_kernel<1>); break;
+            case 2: launch(ln_bwd_dz_kernel<2>); break;
+            case 3: launch(ln_bwd_dz_kernel<3>); break;
+            default: launch(ln_bwd_dz_kernel<4>); break;
+        }
+        CRCT_LAUNCH_CHECK();
+        return CRCT_OK;
+    }
     int grid = 2 * crct_num_sms();
     if (grid > row_grid(a->rows)) grid = row_grid(a->rows);
     const size_t smem = (size_t)3 * (ROW_THREADS / 32) * a->H * sizeof(float);
-    const bool dzm = a->dzm != nullptr && a->p_out > 0.f;
-    const int nch = (a->H / 8 + 31) / 32;
     auto launch = [&](auto kern) {
         static bool configured[MAXC + 1] = {};    // all instantiations share one pointer type: track per chunk count
         if (!configured[nch]) {
@@ -611,8 +764,7 @@ extern "C" CRCT_API int crct_layernorm_bwd(const crct_ln_bwd_t* a, crct_stream_t
         kern<<<grid, ROW_THREADS, smem, as_stream(s)>>>(
             reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), a->mean, a->rstd, a->gamma,
             reinterpret_cast<bf16*>(a->dz), dzm ? reinterpret_cast<bf16*>(a->dzm) : nullptr, a->dgamma, a->dbeta, a->dbias,
-            a->rows, a->H, crct_drop_threshold(a->p_in), a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, a->seed_in,
-            crct_drop_threshold(a->p_out), a->p_out > 0.f ? 1.f / (1.f - a->p_out) : 1.f, a->seed_out,
+            a->rows, a->H, crct_drop_threshold(a->p_in), sc_in, a->seed_in, crct_drop_threshold(a->p_out), sc_out, a->seed_out,
             reinterpret_cast<const unsigned long long*>(a->salt));
     };
     switch (nch) {
@@ -621,6 +773,25 @@ extern "C" CRCT_API int crct_layernorm_bwd(const crct_ln_bwd_t* a, crct_stream_t
         case 3: launch(layernorm_bwd_kernel<3>); break;
         default: launch(layernorm_bwd_kernel<4>); break;
     }
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_layernorm_bwd_params(const crct_ln_bwd_t* a, crct_stream_t s) {
+    if (!a || !a->dy || !a->z || !a->mean || !a->rstd) CRCT_FAIL(CRCT_ERR_ARG, "crct_layernorm_bwd_params: null pointer");
+    if (int rc = check_row_width(a->H, "crct_layernorm_bwd_params")) return rc;
+    if (a->rows <= 0 || (!a->dgamma && !a->dbeta && !a->dbias)) return CRCT_OK;
+    const void* dzm = (a->dzm != nullptr && a->p_out > 0.f) ? a->dzm : a->dz;
+    if (a->dbias && !dzm) CRCT_FAIL(CRCT_ERR_ARG, "crct_layernorm_bwd_params: dbias needs dzm (or dz)");
+    const int gx = (a->H + 255) / 256;
+    int gy = (2 * crct_num_sms() + gx - 1) / gx;
+    const int max_gy = (a->rows + 63) / 64;
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    ln_bwd_params_kernel<<<dim3(gx, gy), ROW_THREADS, 0, as_stream(s)>>>(
+        reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), reinterpret_cast<const bf16*>(dzm), a->mean, a->rstd,
+        a->dgamma, a->dbeta, a->dbias, a->rows, a->H, crct_drop_threshold(a->p_in), a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, a->seed_in,
+        reinterpret_cast<const unsigned long long*>(a->salt));
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }

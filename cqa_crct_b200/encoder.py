@@ -286,8 +286,7 @@ class VisualDialogEncoder(nn.Module):
         M, H = dy.shape
         dz = torch.empty_like(dy)
         dzm = torch.empty_like(dy) if s.p > 0 else None
-        L.layernorm_bwd(dy, s.z, s.mean, s.rstd, self._p(pre_o + '.LayerNorm.weight'), dz, self._g(pre_o + '.LayerNorm.weight'),
-                        self._g(pre_o + '.LayerNorm.bias'), dbias=self._g(pre_o + '.dense.bias'), dzm=dzm, p_out=s.p, seed_out=s.seed)
+        self._ln_bwd(dy, s.z, s.mean, s.rstd, pre_o + '.LayerNorm', dz, self._g(pre_o + '.dense.bias'), dzm, p_out=s.p, seed_out=s.seed)
         gz = dzm if dzm is not None else dz
         W1, W2 = self._w(pre_i + '.dense.weight'), self._w(pre_o + '.dense.weight')
         I = W1.shape[0]
@@ -299,23 +298,26 @@ class VisualDialogEncoder(nn.Module):
         L.gemm(du, W1, da, M=M, N=H, K=I, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz)
         return da
 
+    def _wg(self, *tensors):
+        """Context: what runs inside is a weight gradient — nothing in the backward chain waits for it — so it goes to a
+        second stream, ordered after everything enqueued so far on the current one: its CTAs take the SMs that the
+        chain's kernels (partial last waves, small grids) leave idle.  `tensors` are its operands: they stay referenced
+        until `_wgrad_join` (called before a gradient range is reported finished) has made the chain wait for it."""
+        if not self.overlap_streams:
+            return _NullCtx()
+        dev = tensors[0].device
+        cur = torch.cuda.current_stream(dev)
+        if self._wg_stream is None or self._wg_stream.device != dev:
+            self._wg_stream = torch.cuda.Stream(device=dev)
+        self._wg_stream.wait_stream(cur)
+        self._wg_hold.append((tensors, cur))
+        return torch.cuda.stream(self._wg_stream)
+
     def _wgrad(self, dy, x, gW, gb=None):
-        """gW[out,in] += dy^T x  (fp32 accumulate, split-K) and, when `gb` is given, gb += colsum(dy).
-        Nothing in the backward chain waits for weight gradients, so they are issued on a second stream: their CTAs take
-        the SMs that the chain's kernels (partial last waves, small grids) leave idle.  `_wgrad_join` (called before a
-        gradient range is reported finished) makes the chain's stream wait for them and releases the operands."""
+        """gW[out,in] += dy^T x  (fp32 accumulate, split-K) and, when `gb` is given, gb += colsum(dy)."""
         rows, No = dy.shape
         Ki = x.shape[1]
-        dev = dy.device
-        ws = None
-        if self.overlap_streams:
-            cur = torch.cuda.current_stream(dev)
-            if self._wg_stream is None or self._wg_stream.device != dev:
-                self._wg_stream = torch.cuda.Stream(device=dev)
-            ws = self._wg_stream
-            ws.wait_stream(cur)
-            self._wg_hold.append((dy, x, cur))
-        with torch.cuda.stream(ws) if ws is not None else _NullCtx():
+        with self._wg(dy, x):
             if gb is not None:
                 L.colsum_bf16(dy, gb)
             L.gemm(dy, x, gW, M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, lda=dy.stride(0),
@@ -323,9 +325,18 @@ class VisualDialogEncoder(nn.Module):
 
     def _wgrad_join(self):
         if self._wg_hold:
-            for cur in {id(c): c for _, _, c in self._wg_hold}.values():
+            for cur in {id(c): c for _, c in self._wg_hold}.values():
                 cur.wait_stream(self._wg_stream)
             self._wg_hold.clear()
+
+    def _ln_bwd(self, dy, z, mean, rstd, pre_ln, dz, g_dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0):
+        """LayerNorm backward in its split form: dz (and the dropout-masked dzm) on the chain's stream, the three column
+        sums (dgamma, dbeta, dense-bias gradient) with the weight gradients."""
+        L.layernorm_bwd(dy, z, mean, rstd, self._p(pre_ln + '.weight'), dz, dzm=dzm, p_in=p_in, seed_in=seed_in, p_out=p_out,
+                        seed_out=seed_out)
+        with self._wg(dy, z, dz, dzm):
+            L.layernorm_bwd_params(dy, z, mean, rstd, dz, self._g(pre_ln + '.weight'), self._g(pre_ln + '.bias'), dbias=g_dbias,
+                                   dzm=dzm, p_in=p_in, seed_in=seed_in, p_out=p_out)
 
     def _attn_out_fwd(self, ctx, x, pre_dense, pre_ln, p_drop, seed, keep):
         """dense + dropout + residual + LayerNorm (vilbert.py:424-428 / 555-559 / 749-756)."""
@@ -343,8 +354,7 @@ class VisualDialogEncoder(nn.Module):
         M, H = da.shape
         dz = torch.empty_like(da)
         dzm = torch.empty_like(da) if s.p > 0 else None
-        L.layernorm_bwd(da, s.z, s.mean, s.rstd, self._p(pre_ln + '.weight'), dz, self._g(pre_ln + '.weight'), self._g(pre_ln + '.bias'),
-                        dbias=self._g(pre_dense + '.bias'), dzm=dzm, p_out=s.p, seed_out=s.seed)
+        self._ln_bwd(da, s.z, s.mean, s.rstd, pre_ln, dz, self._g(pre_dense + '.bias'), dzm, p_out=s.p, seed_out=s.seed)
         gz = dzm if dzm is not None else dz
         W = self._w(pre_dense + '.weight')
         self._wgrad(gz, s.ctx, self._g(pre_dense + '.weight'))
@@ -702,9 +712,8 @@ class VisualDialogEncoder(nn.Module):
             e = 'bert.v_embeddings'
             with lanes.vis():
                 dzv = torch.empty_like(dv)
-                L.layernorm_bwd(dv, sv.zv, sv.mv, sv.rv, self._p(e + '.LayerNorm.weight'), dzv, self._g(e + '.LayerNorm.weight'),
-                                self._g(e + '.LayerNorm.bias'), dbias=self._g(e + '.new_image_embeddings.bias'), p_in=sv.p_ev,
-                                seed_in=sv.s_ev)
+                self._ln_bwd(dv, sv.zv, sv.mv, sv.rv, e + '.LayerNorm', dzv, self._g(e + '.new_image_embeddings.bias'), p_in=sv.p_ev,
+                             seed_in=sv.s_ev)
                 self._wgrad(dzv, sv.probs, self._g(e + '.new_image_embeddings.weight'), self._g(e + '.new_loc_emb.bias'))
                 L.embed_vis_bwd(dzv, sv.box2, sv.cls2, self._g(e + '.color_emb.weight'), self._g(e + '.new_loc_emb.weight'))
 
@@ -732,8 +741,7 @@ class VisualDialogEncoder(nn.Module):
             vis_embeddings_bwd(dv)
         e = 'bert.embeddings'
         dzt = torch.empty_like(dt)
-        L.layernorm_bwd(dt, sv.zt, sv.mt, sv.rt, self._p(e + '.LayerNorm.weight'), dzt, self._g(e + '.LayerNorm.weight'),
-                        self._g(e + '.LayerNorm.bias'), p_in=sv.p_et, seed_in=sv.s_et)
+        self._ln_bwd(dt, sv.zt, sv.mt, sv.rt, e + '.LayerNorm', dzt, p_in=sv.p_et, seed_in=sv.s_et)
         L.embed_text_bwd(sv.ids, sv.types, sv.loc, dzt, self._g(e + '.word_embeddings.weight'), self._g(e + '.position_embeddings.weight'),
                          self._g(e + '.plotqa_type_embeddings.weight'), self._g(e + '.txt_location_embeddings.weight'),
                          self._g(e + '.txt_location_embeddings.bias'))

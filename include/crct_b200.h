@@ -114,6 +114,10 @@ typedef struct {
     const uint64_t* salt; /* optional device word XOR-ed into both seeds */
 } crct_ln_bwd_t;
 int crct_layernorm_bwd(const crct_ln_bwd_t* args, crct_stream_t stream);
+/* Split form: crct_layernorm_bwd with dgamma = dbeta = dbias = NULL computes only dz / dzm (the part the backward
+ * chain waits for); this call then accumulates the three column sums from dy, z and the dzm (dz when p_out == 0)
+ * that call wrote.  Same struct; gamma is not read. */
+int crct_layernorm_bwd_params(const crct_ln_bwd_t* args, crct_stream_t stream);
 /* out[n] += sum_rows x[row,n]   (bias gradients).  x bf16 [rows,N], row stride ld. */
 int crct_colsum_bf16(const void* x, float* out, int rows, int N, int ld, crct_stream_t stream);
 /* softmax over the RoI feature axis, fp32 in -> bf16 GEMM operand (vilbert.py:1476). */

@@ -140,6 +140,18 @@ def test_layernorm_fwd_bwd(rows, H):
     assert abs(float(kept.float().mean()) - 0.9) < 0.02
     assert relmax(dzm.float()[kept], (dz.float() / 0.9)[kept]) < 1e-2
     assert relmax(dbias, dzm.float().sum(0)) < 3e-3            # reference built from bf16-rounded dzm
+    # split form (what the training step runs): dz/dzm alone, then the three column sums as a second launch
+    dz2, dzm2 = torch.empty_like(z), torch.empty_like(z)
+    dg2, db2, dbias2 = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    L.layernorm_bwd(dy, z, mean, rstd, gamma, dz2, dzm=dzm2, p_out=0.1, seed_out=5)
+    L.layernorm_bwd_params(dy, z, mean, rstd, dz2, dg2, db2, dbias=dbias2, dzm=dzm2, p_out=0.1)
+    assert torch.equal(dz2, dz) and torch.equal(dzm2, dzm)
+    assert relmax(dg2, dgr) < 2e-4 and relmax(db2, dbr) < 2e-4
+    assert relmax(dbias2, dzm.float().sum(0)) < 2e-4
+    dbias2.zero_()
+    L.layernorm_bwd(dy, z, mean, rstd, gamma, dz2)            # no dropout: the dense-bias gradient sums dz itself
+    L.layernorm_bwd_params(dy, z, mean, rstd, dz2, None, None, dbias=dbias2)
+    assert relmax(dbias2, dz2.float().sum(0)) < 2e-4
 
 
 def test_layernorm_bwd_mask_matches_gemm_epilogue_mask():
