@@ -42,6 +42,8 @@ class FusedAdamW:
             o = arena.offsets[p.name]
             group[o // 64:(o + p.numel + 63) // 64] = gid
         dev = arena.w32.device
+        self._lang = lang
+        self._group_host = group
         self.group = group.to(dev)
         self.m = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.n, dtype=torch.float32, device=dev)
@@ -53,6 +55,13 @@ class FusedAdamW:
 
     def current_lrs(self):
         return [max(b * self.lr_factor, self.min_lr) if b * self.lr_factor > self.min_lr else self.min_lr for b in self.base_lr]
+
+    def base_lr_per_param(self):
+        return [self.base_lr[self.group_of(p) if p.live else 0] for _, _, p in self._named()]
+
+    def lr_per_param(self):
+        lrs = self.current_lrs()
+        return [lrs[self.group_of(p) if p.live else 0] for _, _, p in self._named()]
 
     def zero_grad(self, set_to_none: bool = False):
         self.enc.zero_grad()
@@ -88,13 +97,79 @@ class FusedAdamW:
                 self.betas[0], self.betas[1], self.eps, 1, grad_scale, dyn=self.dyn)
         arena.mark_bf16_fresh()
 
+    # ---- checkpoint layout (f4): what `torch.optim.AdamW(...).state_dict()` gives for `get_optimizer`'s grouping
+    def _named(self):
+        """[(index, reference parameter name, spec entry)] in `named_parameters()` order = the reference's param-group
+        order (CRCT/utils.py:236-247: one group per tensor; the tied decoder weight appears once)."""
+        return [(i, 'bert_pretrained.' + p.name, p) for i, p in enumerate(self.enc.arena.spec)]
+
+    def group_of(self, p):
+        o = self.enc.arena.offsets[p.name]
+        return int(self._group_host[o // 64])
+
     def state_dict(self):
-        return {'step': self.step_count, 'exp_avg': self.m, 'exp_avg_sq': self.v, 'lr_factor': self.lr_factor, 'min_lr': self.min_lr}
+        """torch.optim.AdamW layout: `param_groups` = one group per parameter (lr / weight_decay / betas / eps /
+        initial_lr, `params: [index]`), `state[index] = {step, exp_avg, exp_avg_sq}` for every tensor that has received
+        a gradient.  The reference's 36 never-used tensors have no state entry there either (their .grad stays None
+        under `find_unused_parameters=True`, CRCT/train.py:141).  The moment tensors are VIEWS of the flat arenas —
+        `torch.save` writes them without a copy through Python."""
+        arena = self.enc.arena
+        lrs = self.current_lrs()
+        groups, state = [], {}
+        for i, _, p in self._named():
+            gid = self.group_of(p) if p.live else (2 if 'bert_pretrained.' + p.name not in self._lang else 0) + \
+                (1 if any(nd in 'bert_pretrained.' + p.name for nd in _NO_DECAY) else 0)
+            groups.append({'lr': lrs[gid], 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': self.wd[gid], 'amsgrad': False,
+                           'initial_lr': self.base_lr[gid], 'params': [i]})
+            if p.live and self.step_count > 0:
+                o = arena.offsets[p.name]
+                state[i] = {'step': torch.tensor(float(self.step_count)), 'exp_avg': self.m[o:o + p.numel].view(p.shape),
+                            'exp_avg_sq': self.v[o:o + p.numel].view(p.shape)}
+        return {'state': state, 'param_groups': groups}
 
     def load_state_dict(self, sd):
-        self.step_count, self.lr_factor, self.min_lr = sd['step'], sd['lr_factor'], sd['min_lr']
-        self.m.copy_(sd['exp_avg'])
-        self.v.copy_(sd['exp_avg_sq'])
+        """Accepts the layout above — i.e. also the `optimizer_state_dict` of a reference checkpoint
+        (CRCT/train.py:110-119) — and the flat layout of `flat_state_dict()`."""
+        if 'exp_avg' in sd:                              # flat
+            self.step_count, self.lr_factor, self.min_lr = int(sd['step']), sd['lr_factor'], sd['min_lr']
+            self.m.copy_(sd['exp_avg'])
+            self.v.copy_(sd['exp_avg_sq'])
+            return
+        arena = self.enc.arena
+        named = self._named()
+        groups = sd['param_groups']
+        index_of = {}                                    # saved parameter index -> position in named_parameters() order
+        pos = 0
+        for g in groups:
+            for idx in g['params']:
+                index_of[idx] = pos
+                pos += 1
+        if pos != len(named):
+            raise ValueError(f'optimizer state has {pos} parameters, the model has {len(named)}')
+        steps = set()
+        self.m.zero_()
+        self.v.zero_()
+        for idx, st in sd['state'].items():
+            _, _, p = named[index_of[int(idx)]]
+            if not p.live:
+                continue
+            if tuple(st['exp_avg'].shape) != tuple(p.shape):
+                raise ValueError(f'optimizer state of {p.name}: shape {tuple(st["exp_avg"].shape)} != {tuple(p.shape)}')
+            o = arena.offsets[p.name]
+            self.m[o:o + p.numel].copy_(st['exp_avg'].reshape(-1))
+            self.v[o:o + p.numel].copy_(st['exp_avg_sq'].reshape(-1))
+            steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise ValueError(f'per-parameter step counts differ ({sorted(steps)}): one fused step count is kept')
+        self.step_count = steps.pop() if steps else 0
+        base = [None] * 4
+        for g, (_, _, p) in zip(groups, named):          # base learning rates per group, from initial_lr when present
+            if p.live:
+                base[self.group_of(p)] = float(g.get('initial_lr', g['lr']))
+        self.base_lr = [b if b is not None else old for b, old in zip(base, self.base_lr)]
+
+    def flat_state_dict(self):
+        return {'step': self.step_count, 'exp_avg': self.m, 'exp_avg_sq': self.v, 'lr_factor': self.lr_factor, 'min_lr': self.min_lr}
 
 
 class WarmupLinearScheduleNonZero:
@@ -120,8 +195,16 @@ class WarmupLinearScheduleNonZero:
         return self.opt.current_lrs()
 
     def state_dict(self):
-        return {'last_epoch': self.last_epoch, 'warmup_steps': self.warmup_steps, 't_total': self.t_total}
+        """`_LRScheduler.state_dict()` layout (every attribute but the optimizer), so the `scheduler_state_dict` of a
+        reference checkpoint (CRCT/train.py:287) and ours are interchangeable."""
+        return {'warmup_steps': self.warmup_steps, 't_total': self.t_total, 'min_lr': self.opt.min_lr,
+                'base_lrs': list(self.opt.base_lr_per_param()), 'last_epoch': self.last_epoch, '_step_count': self.last_epoch + 1,
+                'verbose': False, '_get_lr_called_within_step': False, '_last_lr': list(self.opt.lr_per_param())}
 
     def load_state_dict(self, sd):
-        self.last_epoch = sd['last_epoch']
+        self.last_epoch = int(sd['last_epoch'])
+        self.warmup_steps = sd.get('warmup_steps', self.warmup_steps)
+        self.t_total = sd.get('t_total', self.t_total)
+        if 'min_lr' in sd:
+            self.opt.min_lr = sd['min_lr']
         self.opt.lr_factor = self.factor(self.last_epoch)
