@@ -175,10 +175,24 @@ def main():
         sched = WarmupLinearScheduleNonZero(opt, warmup_steps=3000, t_total=200000, min_lr=1.3e-5)
     else:
         enc.eval()
-    host = [make_batch(B, T, R, 1024, seed=1234 + 17 * rank + i) for i in range(4)]
-    pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
-    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items() if k != 'needs_reg')
+    if train:
+        host = [make_batch(B, T, R, 1024, seed=1234 + 17 * rank + i) for i in range(4)]
+        pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+        resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+        h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items() if k != 'needs_reg')
+        d2h_bytes = 4
+    else:
+        # evaluation batches are QUESTIONS with their candidate answers (CRCT/evaluation.py:231-317): B candidate sequences
+        # = 16 questions x 32 candidates; visual tensors once per question (cqa_crct_b200.evaluate, f3)
+        from cqa_crct_b200.evaluate import evaluate_batch, to_device
+        from cqa_crct_b200.synthetic import make_question_batch
+        NQ = 16
+        host = [make_question_batch(NQ, T, R, 1024, seed=1234 + 17 * rank + i, total=B) for i in range(4)]
+        pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+        resident = [to_device(b, dev) for b in host]
+        h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items()) + (B + NQ + 1) * 8
+        d2h_bytes = NQ * 8 + NQ * 4
+        config['questions_per_batch'] = NQ
 
     gstep = None
     captured_launches = 0
@@ -198,12 +212,9 @@ def main():
             opt.step()
             sched.step()
             return float(loss) if read_loss else None
-        with torch.no_grad():
-            out = glue_forward(model, batch, params, evaluation=True)
-        scores, reg = out[4], out[5]
-        if read_loss:
-            pick = torch.softmax(scores, 1)[:, 0].argmax()           # evaluation.py:254-258,287-296 on one candidate group
-            return float(reg[0][pick])
+        out = evaluate_batch(model, batch, params, eval_batch_size=B)       # host batch: copied to the device in here
+        if read_loss:                                                        # per-question answers + regression values to the host
+            return out['answers'].cpu(), out['reg_output'].cpu()
         return None
 
     def barrier():
@@ -263,7 +274,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         ms2, _, _ = timed(pinned, True)
-        e2e = {'value': B * world / (ms2 / args.steps / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+        e2e = {'value': B * world / (ms2 / args.steps / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
                'ms_per_step': ms2 / args.steps}
 
     # ---- roofline of the dominant kernel: every GEMM launch of ONE more step, timed with CUDA events on the launch stream
@@ -294,8 +305,7 @@ def main():
                 enc.zero_grad()
                 glue_forward(enc, resident[0], params)[0].backward()
             else:
-                with torch.no_grad():
-                    glue_forward(enc, resident[0], params, evaluation=True)
+                evaluate_batch(enc, resident[0], params, eval_batch_size=B)
             torch.cuda.synchronize()
         finally:
             L.gemm = orig

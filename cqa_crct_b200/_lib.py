@@ -88,12 +88,23 @@ class AdamWArgs(C.Structure):
                 ('grad_scale', f32), ('dyn', vp)]
 
 
+class SelectArgs(C.Structure):
+    _fields_ = [('logits', vp), ('reg_pred', vp), ('reg_dist', vp), ('reg_l1', vp), ('offsets', vp), ('forced', vp), ('answer', vp),
+                ('prob', vp), ('sel_pred', vp), ('sel_dist', vp), ('sel_l1', vp), ('Q', i32)]
+
+
+class ScoreArgs(C.Structure):
+    _fields_ = [('answer', vp), ('gt_id', vp), ('needs_reg', vp), ('sel_dist', vp), ('sel_l1', vp), ('tolerance', vp), ('flags', vp),
+                ('total', vp), ('Q', i32)]
+
+
 # every symbol include/crct_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf16', 'crct_cast_f32_to_bf16',
            'crct_additive_mask', 'crct_layernorm_fwd', 'crct_layernorm_bwd', 'crct_layernorm_bwd_params', 'crct_colsum_bf16', 'crct_softmax_rows',
            'crct_embed_text_fwd', 'crct_embed_text_bwd', 'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd',
            'crct_attn_bwd', 'crct_linear_f32', 'crct_linear_f32_batched', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
-           'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_bump_salt', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw']
+           'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_bump_salt', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw',
+           'crct_expand_blocks', 'crct_select_answers', 'crct_score_answers']
 
 _lib = None
 SALT = None         # device int64[1] tensor XOR-ed into every dropout seed on the device (set by the encoder); None = off
@@ -118,6 +129,7 @@ def lib():
         _lib.crct_gather_first.argtypes = [vp, C.c_longlong, vp, C.c_int, C.c_int, vp]
         _lib.crct_scatter_first.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, vp]
         _lib.crct_colsum_f32.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, vp]
+        _lib.crct_expand_blocks.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, vp]
         _lib.crct_linear_f32_batched.argtypes = [vp, C.c_int, vp]
         _lib.crct_scale_rows.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp]
         _lib.crct_pool_mul_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
@@ -125,7 +137,7 @@ def lib():
         _lib.crct_bump_salt.argtypes = [vp, vp]
         for name in ('crct_gemm_bf16', 'crct_layernorm_bwd', 'crct_layernorm_bwd_params', 'crct_embed_text_fwd', 'crct_embed_text_bwd',
                      'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd', 'crct_attn_bwd', 'crct_linear_f32',
-                     'crct_hybrid_loss', 'crct_adamw'):
+                     'crct_hybrid_loss', 'crct_adamw', 'crct_select_answers', 'crct_score_answers'):
             getattr(_lib, name).argtypes = [vp, vp]
     return _lib
 
@@ -373,3 +385,28 @@ def adamw(w, g, m, v, w_bf16, group, n, lr4, wd4, beta1, beta2, eps, step, grad_
         a.lr[i], a.weight_decay[i] = lr4[i], wd4[i]
     a.beta1, a.beta2, a.eps, a.step, a.grad_scale, a.dyn = beta1, beta2, eps, step, grad_scale, ptr(dyn)
     check(lib().crct_adamw(C.byref(a), stream_ptr()))
+
+
+def expand_blocks(src, group, dst):
+    """dst[n] = src[group[n]] over the leading dimension (include/crct_b200.h: crct_expand_blocks)."""
+    n = group.numel()
+    if n == 0:
+        return
+    per = dst.numel() // max(n, 1) * dst.element_size()
+    assert src.dtype == dst.dtype and group.dtype == torch.int64 and src.is_contiguous() and dst.is_contiguous()
+    check(lib().crct_expand_blocks(ptr(src), ptr(group), ptr(dst), n, per, stream_ptr()))
+
+
+def select_answers(logits, reg_pred, reg_dist, reg_l1, offsets, answer, sel_pred, sel_dist, sel_l1, prob=None, forced=None):
+    a = SelectArgs()
+    a.logits, a.reg_pred, a.reg_dist, a.reg_l1 = ptr(logits), ptr(reg_pred), ptr(reg_dist), ptr(reg_l1)
+    a.offsets, a.forced, a.answer, a.prob = ptr(offsets), ptr(forced), ptr(answer), ptr(prob)
+    a.sel_pred, a.sel_dist, a.sel_l1, a.Q = ptr(sel_pred), ptr(sel_dist), ptr(sel_l1), answer.numel()
+    check(lib().crct_select_answers(C.byref(a), stream_ptr()))
+
+
+def score_answers(answer, gt_id, needs_reg, sel_dist, sel_l1, tolerance, total, flags=None):
+    a = ScoreArgs()
+    a.answer, a.gt_id, a.needs_reg, a.sel_dist, a.sel_l1 = ptr(answer), ptr(gt_id), ptr(needs_reg), ptr(sel_dist), ptr(sel_l1)
+    a.tolerance, a.flags, a.total, a.Q = ptr(tolerance), ptr(flags), ptr(total), answer.numel()
+    check(lib().crct_score_answers(C.byref(a), stream_ptr()))

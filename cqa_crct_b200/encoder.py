@@ -599,24 +599,31 @@ class VisualDialogEncoder(nn.Module):
         return dt, dv
 
     # ------------------------------------------------------------------ whole model
-    def _run_forward(self, ids, types, loc, feat, box, cls, amask, imask, labels, Rt, kind, keep):
+    def _run_forward(self, ids, types, loc, feat, box, cls, amask, imask, labels, Rt, kind, keep, group=None):
         cfg, arena = self.cfg, self.arena
         L.device_check()
         self._bind_grads()
         arena.refresh_bf16()
         dev = ids.device
         B, T = ids.shape
-        R, F = feat.shape[1], feat.shape[2]
+        Bv, R, F = feat.shape          # Bv = B, or the number of questions when `group` maps candidates to questions (f3)
         H, Hv = cfg.hidden_size, cfg.v_hidden_size
+        if group is None and Bv != B:
+            raise ValueError(f'{B} text rows but {Bv} visual rows (pass image_group to share visual inputs between candidates)')
+        if group is not None and (keep or group.shape != (B,)):
+            raise ValueError('image_group [B] is an inference-only input (one question index per candidate sequence)')
         if F != cfg.v_feature_size:
             raise ValueError(f'image_feat has {F} features, config says {cfg.v_feature_size}')
         if box.shape[-1] != 4:
             raise ValueError('image_loc must be [B,R,4] (CRCT/fig_dataloader.py:346 strips the 5th column)')
         step = self._step
         t_mask = torch.empty(B, T, dtype=torch.float32, device=dev)
-        v_mask = torch.empty(B, R, dtype=torch.float32, device=dev)
+        v_mask = torch.empty(Bv, R, dtype=torch.float32, device=dev)
         L.additive_mask(amask, t_mask)
         L.additive_mask(imask, v_mask)
+        if group is not None:              # per-candidate copy of the per-question mask (read by both lanes: allocated here)
+            m_q, v_mask = v_mask, torch.empty(B, R, dtype=torch.float32, device=dev)
+            L.expand_blocks(m_q, group, v_mask)
         sv = _Saved() if keep else None
         # --- embeddings (vilbert.py:1412-1413); from here to the heads the visual lane runs on its own stream
         lanes = self._lanes(dev)
@@ -632,20 +639,27 @@ class VisualDialogEncoder(nn.Module):
                          self._p(e + '.txt_location_embeddings.bias'), self._p(e + '.LayerNorm.weight'), self._p(e + '.LayerNorm.bias'),
                          t, zt, mt, rt, dropout_p=p_et, seed=s_et)
         e = 'bert.v_embeddings'
-        feat2 = feat.reshape(B * R, F)
-        box2, cls2 = box.reshape(B * R, 4), cls.reshape(B * R)
+        feat2 = feat.reshape(Bv * R, F)
+        box2, cls2 = box.reshape(Bv * R, 4), cls.reshape(Bv * R)
         p_ev, s_ev = self._drop(cfg.hidden_dropout_prob), _seed(step, 'emb_v')      # nn.Dropout(config.hidden_dropout_prob), vilbert.py:1470
         with lanes.vis():
-            probs = torch.empty(B * R, F, dtype=torch.bfloat16, device=dev)
+            probs = torch.empty(Bv * R, F, dtype=torch.bfloat16, device=dev)
             L.softmax_rows(feat2, probs)
-            gimg = self._linear(probs, self._w(e + '.new_image_embeddings.weight'), self._p(e + '.new_image_embeddings.bias'), B * R)
-            v = torch.empty(B * R, Hv, dtype=torch.bfloat16, device=dev)
+            gimg = self._linear(probs, self._w(e + '.new_image_embeddings.weight'), self._p(e + '.new_image_embeddings.bias'), Bv * R)
+            v = torch.empty(Bv * R, Hv, dtype=torch.bfloat16, device=dev)
             zv = torch.empty_like(v) if keep else None
-            mv = torch.empty(B * R, dtype=torch.float32, device=dev) if keep else None
-            rv = torch.empty(B * R, dtype=torch.float32, device=dev) if keep else None
+            mv = torch.empty(Bv * R, dtype=torch.float32, device=dev) if keep else None
+            rv = torch.empty(Bv * R, dtype=torch.float32, device=dev) if keep else None
             L.embed_vis_fwd(gimg, box2, cls2, self._p(e + '.new_loc_emb.weight'), self._p(e + '.new_loc_emb.bias'),
                             self._p(e + '.color_emb.weight'), self._p(e + '.LayerNorm.weight'), self._p(e + '.LayerNorm.bias'),
                             v, zv, mv, rv, dropout_p=p_ev, seed=s_ev)
+            if group is not None:
+                # f3: the visual embedding depends on the image only — computed once per question above, fanned out to the
+                # question's candidate sequences here (the reference replicates the fp32 inputs on the host instead,
+                # fig_dataloader.py:690-693); from the first co-attention on the visual stream is per candidate
+                v_q = v
+                v = torch.empty(B * R, Hv, dtype=torch.bfloat16, device=dev)
+                L.expand_blocks(v_q.view(Bv, R * Hv), group, v.view(B, R * Hv))
         # --- encoder (vilbert.py:852-939): text layers on the text lane, visual layers on the visual lane (v_layer[k-1]
         # and layer[5+k] are independent, vilbert.py:868-886; the 3520-row visual kernels fill the SMs the text kernels'
         # partial waves leave idle); the lanes meet inside every connection layer.
@@ -789,8 +803,10 @@ class VisualDialogEncoder(nn.Module):
     def forward(self, input_ids, txt_loc, image_feat, image_loc, sep_indices=None, sep_len=None, token_type_ids=None,
                 attention_mask=None, masked_lm_labels=None, next_sentence_label=None, head_mask=None, random_round_indices=None,
                 output_nsp_scores=False, output_lm_scores=False, image_attention_mask=None, image_label=None, image_target=None,
-                gt_reg=None, areas=None, legend_pred=None):
-        """Same signature and return tuple as encoder_decorator.py:19-54.  `sep_indices`, `sep_len`, `masked_lm_labels`
+                gt_reg=None, areas=None, legend_pred=None, image_group=None):
+        """Same signature and return tuple as encoder_decorator.py:19-54, plus one optional inference-only argument:
+        `image_group [B] int64` — when given, `image_feat / image_loc / image_attention_mask / image_target` hold one row per
+        QUESTION and `image_group[b]` names the row candidate sequence b belongs to (f3, `cqa_crct_b200.evaluate`).  `sep_indices`, `sep_len`, `masked_lm_labels`
         (presence only), `image_label`, `head_mask`, `random_round_indices`, `legend_pred` take no part in the arithmetic
         (SURVEY.md §8b); `areas` is FigureQA/DVQA-only."""
         dev = self.arena.w32.device
@@ -813,7 +829,7 @@ class VisualDialogEncoder(nn.Module):
             raise ValueError('image_target (RoI class ids for color_emb, vilbert.py:1479) is required')
         cls = cvt(image_target, torch.int64)
         amask = cvt(attention_mask) if attention_mask is not None else torch.ones(B, T, dtype=torch.int64, device=dev)   # :1366-1367
-        imask = cvt(image_attention_mask) if image_attention_mask is not None else torch.ones(B, R, dtype=torch.int64, device=dev)
+        imask = cvt(image_attention_mask) if image_attention_mask is not None else torch.ones(feat.shape[0], R, dtype=torch.int64, device=dev)
         if amask.dtype not in (torch.bool, torch.uint8, torch.int64, torch.float32):
             amask = amask.to(torch.int64)
         if imask.dtype not in (torch.bool, torch.uint8, torch.int64, torch.float32):
@@ -827,7 +843,10 @@ class VisualDialogEncoder(nn.Module):
         L.SALT = self._salt
         if self.training:
             L.bump_salt(self._salt)          # fresh dropout masks for this step (also on CUDA-graph replay)
-        logits, outs, scalars, seq_t, sv = self._run_forward(ids, types, loc, feat, box, cls, amask, imask, labels, Rt, kind, keep)
+        group = cvt(image_group, torch.int64)
+        if group is not None and train_branch:
+            raise ValueError('image_group is an inference-only input')
+        logits, outs, scalars, seq_t, sv = self._run_forward(ids, types, loc, feat, box, cls, amask, imask, labels, Rt, kind, keep, group)
         reg_pred, reg_loss, reg_l1, reg_dist = outs
         nsp_loss = scalars[1:2]
         if keep:

@@ -116,3 +116,41 @@ def default_params(model_config: str, device: str = 'cpu', **over) -> dict:
     }
     p.update(over)
     return p
+
+
+def make_question_batch(Q: int, T: int = 124, R: int = 44, feat_dim: int = 1024, seed: int = 1234, vocab_size: int = 30522,
+                        min_ans: int = 2, max_ans: int = 48, total: int = None) -> Dict[str, torch.Tensor]:
+    """One EVALUATION batch in the de-duplicated layout of `cqa_crct_b200.evaluate` (f3): Q questions, question q with
+    `num_ans[q]` candidate answers (reference: one dataset item per question with all its candidates,
+    CRCT/fig_dataloader.py:584-587,648,690-693; up to EVAL_PADDED_SIZE = 120 candidates, fixed vocabulary alone = 35).
+    Text tensors hold one row per candidate (N = sum(num_ans)), visual tensors and R one row per question.
+    `total` forces N (the last question absorbs the difference)."""
+    g = torch.Generator().manual_seed(seed ^ 0x5EED)
+    num_ans = torch.randint(min_ans, max_ans + 1, (Q,), generator=g)
+    if total is not None:
+        base = max(min_ans, total // Q)
+        num_ans = torch.full((Q,), base, dtype=torch.int64)
+        num_ans[-1] = total - base * (Q - 1)
+        assert int(num_ans[-1]) >= 1
+    N = int(num_ans.sum())
+    txt = make_batch(N, T, R=1, feat_dim=8, seed=seed + 1, vocab_size=vocab_size)
+    vis = make_batch(Q, T=8, R=R, feat_dim=feat_dim, seed=seed + 2, vocab_size=vocab_size)
+    # candidates of one question share everything but the answer tokens: copy the first candidate's row, then re-draw the
+    # answer span (type 1) of the others
+    off = 0
+    for q in range(Q):
+        n = int(num_ans[q])
+        for k in ('tokens', 'loc', 'segments', 'sep_indices', 'hist_len'):
+            txt[k][off + 1:off + n] = txt[k][off]
+        ans = (txt['segments'][off] == 1).nonzero().view(-1)
+        if ans.numel() > 1:
+            span = ans[:-1]                                                     # keep the closing [SEP]
+            txt['tokens'][off + 1:off + n, span] = torch.randint(1000, vocab_size, (n - 1, span.numel()), generator=g)
+        off += n
+    gt_id = (torch.rand(Q, generator=g) * num_ans).long()
+    gt_id[torch.rand(Q, generator=g) < 0.05] = -1                               # ground truth not among the candidates (fig_dataloader.py:590-599)
+    out = {k: txt[k] for k in ('tokens', 'loc', 'segments', 'mask', 'sep_indices', 'hist_len', 'next_sentence_labels')}
+    out.update({k: vis[k] for k in ('image_feat', 'image_loc', 'image_mask', 'image_target', 'image_label', 'R')})
+    out.update({'num_ans': num_ans, 'gt_id': gt_id, 'needs_reg': vis['needs_reg'], 'tolerance_margin': vis['R'][:, 2].clone(),
+                'id': torch.arange(Q)})
+    return out

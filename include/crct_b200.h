@@ -283,6 +283,42 @@ typedef struct {
 } crct_adamw_t;
 int crct_adamw(const crct_adamw_t* args, crct_stream_t stream);
 
+/* f3  evaluation: candidate expansion and per-question answer selection on the device.
+ * crct_expand_blocks: dst[n] = src[group[n]] for n_blocks blocks of bytes_per_block bytes (multiple of 4; 16-byte vectors
+ * when sizes and pointers allow).  Fans the per-QUESTION visual embedding [Q, R*Hv] (and additive mask [Q, R]) out to the
+ * per-CANDIDATE rows the encoder works on — replaces the host-side replication of CRCT/fig_dataloader.py:690-693,697-703. */
+int crct_expand_blocks(const void* src, const int64_t* group, void* dst, long long n_blocks, long long bytes_per_block,
+                       crct_stream_t stream);
+/* Per question q with candidates offsets[q] .. offsets[q+1]-1: prob = softmax(logits)[:,0] (CRCT/evaluation.py:254-258),
+ * answer[q] = first argmax of prob within the question (evaluation.py:291) or forced[q] when `forced` is given (the
+ * '_REGS' branch, evaluation.py:289); sel_* = the regression columns of that candidate (evaluation.py:293-295). */
+typedef struct {
+    const float* logits;      /* [N,2] */
+    const float* reg_pred;    /* [N] regression[0] */
+    const float* reg_dist;    /* [N] regression[4] (relative distance, the 5 % measure) */
+    const float* reg_l1;      /* [N] regression[2] */
+    const int64_t* offsets;   /* [Q+1] exclusive prefix sum of num_ans */
+    const int64_t* forced;    /* [Q] or NULL */
+    int64_t* answer;          /* [Q] index within the question */
+    float* prob;              /* [N] or NULL */
+    float* sel_pred; float* sel_dist; float* sel_l1;   /* [Q] each */
+    int32_t Q;
+} crct_select_t;
+int crct_select_answers(const crct_select_t* args, crct_stream_t stream);
+/* Correctness flags and the running 6x2 accuracy table of `reduce_total_acc` (CRCT/evaluation.py:306-313,494-525):
+ * flags[q] = {nsp_right, reg_right, reg_t_right, correct(+-5 %), correct(tolerance)}; total[row][0] += hits,
+ * total[row][1] += population, rows = {nsp, cls-on-regression, reg 5 %, reg tolerance, total 5 %, total tolerance}. */
+typedef struct {
+    const int64_t* answer; const int64_t* gt_id;   /* [Q] */
+    const uint8_t* needs_reg;                      /* [Q] */
+    const float* sel_dist; const float* sel_l1;    /* [Q] */
+    const float* tolerance;                        /* [Q] batch['tolerance_margin'] */
+    uint8_t* flags;                                /* [Q,5] or NULL */
+    double* total;                                 /* [6,2], accumulated */
+    int32_t Q;
+} crct_score_t;
+int crct_score_answers(const crct_score_t* args, crct_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

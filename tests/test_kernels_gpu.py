@@ -137,7 +137,7 @@ def test_layernorm_fwd_bwd(rows, H):
     dbias.zero_(); dg.zero_(); db.zero_()
     L.layernorm_bwd(dy, z, mean, rstd, gamma, dz, dg, db, dbias=dbias, dzm=dzm, p_out=0.1, seed_out=5)
     kept = dzm.float() != 0
-    assert abs(float(kept.float().mean()) - 0.9) < 0.02
+    assert abs(float(kept.float().mean()) - 0.9) < max(0.02, 4.5 * (0.09 / kept.numel()) ** 0.5)      # 4.5 sigma of the keep-rate estimate
     assert relmax(dzm.float()[kept], (dz.float() / 0.9)[kept]) < 1e-2
     assert relmax(dbias, dzm.float().sum(0)) < 3e-3            # reference built from bf16-rounded dzm
     # split form (what the training step runs): dz/dzm alone, then the three column sums as a second launch

@@ -48,3 +48,49 @@ def test_param_spec_is_the_reference_named_parameters():
         assert ref == mine
         dead = {p.name for p in param_spec(ModelConfig(cfg_path)) if not p.live}
         assert len(dead) == (36 if f == 'vilbert.json' else 20)
+
+
+def _reference_eval_lines(lo, hi):
+    """Source lines [lo, hi] (1-based) of the reference's evaluation.py, de-indented — executed where they lie, not copied:
+    the module itself cannot be imported offline (fig_dataloader -> pytorch_transformers, matplotlib)."""
+    import textwrap
+    path = os.path.join(ref_shim.REFERENCE_ROOT, 'CRCT', 'evaluation.py')
+    src = open(path).read().splitlines()
+    return textwrap.dedent('\n'.join(src[lo - 1:hi]))
+
+
+@pytest.mark.parametrize('seed,force', [(0, False), (1, False), (2, True)])
+def test_eval_oracle_against_the_reference_selection_lines(seed, force, monkeypatch):
+    """oracle/eval_oracle.py vs the reference's own answer-selection block (evaluation.py:274-312) and
+    `reduce_total_acc` (:494-525) run on the same arrays."""
+    import numpy as np
+    from oracle.eval_oracle import select_and_score
+    from cqa_crct_b200.synthetic import make_question_batch
+    qb = make_question_batch(23, 16, 4, 8, seed=seed, vocab_size=2048, max_ans=40)
+    if force:
+        qb['gt_id'] = qb['gt_id'].clamp(min=0)
+    N = int(qb['num_ans'].sum())
+    g = torch.Generator().manual_seed(seed)
+    scores = torch.randn(N, 2, generator=g) * 3
+    scores[5] = scores[4]                                     # an exact tie inside a question: first maximum wins
+    reg_pred, reg_dist, reg_l1 = torch.randn(N, generator=g), torch.rand(N, generator=g) * 0.1, torch.rand(N, generator=g) * 0.02
+    mine = select_and_score(scores, reg_pred, reg_dist, reg_l1, qb['num_ans'], qb['gt_id'], qb['needs_reg'], qb['tolerance_margin'],
+                            force_gt=force)
+    ns = {'torch': torch, 'np': np, 'params': {'binary_answers': False, 'qa_file': 'qa_pairs_REGS.json' if force else 'qa_pairs.json'},
+          'batch': {'num_ans': qb['num_ans'], 'gt_id': qb['gt_id'].view(-1, 1), 'tokens': qb['tokens'], 'id': qb['id'].view(-1, 1),
+                    'needs_reg': qb['needs_reg'].view(-1, 1), 'tolerance_margin': qb['tolerance_margin'].view(-1, 1),
+                    'next_sentence_labels': qb['next_sentence_labels']},
+          'output': torch.softmax(scores, 1)[:, 0], 'reg_output': reg_pred, 'reg_loss_lst': reg_dist, 'reg_t_loss_lst': reg_l1}
+    exec(_reference_eval_lines(274, 312), ns)
+    assert torch.equal(ns['answers'], mine['answers'])
+    assert torch.equal(ns['reg_answers_output'], mine['reg_output'])
+    assert torch.equal(ns['reg_answers_loss'], mine['reg_loss']) and torch.equal(ns['reg_answers_t_loss'], mine['reg_t_loss'])
+    flags = torch.stack([ns['nsp_right'], ns['reg_right'], ns['reg_t_right'], ns['correct_answers'], ns['correct_answers_t_loss']], 1)
+    assert torch.equal(flags.to(torch.uint8), mine['flags'])
+    # reduce_total_acc allocates with .cuda() and all-reduces: identity / no-op on this CPU-only check
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    fn_ns = {'torch': torch, 'dist': type('D', (), {'all_reduce': staticmethod(lambda *a, **k: None)})}
+    exec(_reference_eval_lines(494, 525), fn_ns)
+    total = fn_ns['reduce_total_acc'](torch.zeros(6, 2).double(), ns['needs_regression'], ns['nsp_right'], ns['reg_right'],
+                                      ns['reg_t_right'], None)
+    assert torch.equal(total, mine['total_correct'])
