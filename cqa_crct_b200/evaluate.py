@@ -81,13 +81,15 @@ def to_device(qb: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
 
 
 def evaluate_batch(model, qb: Dict[str, torch.Tensor], params: dict, eval_batch_size: int = 512,
-                   total_correct: Optional[torch.Tensor] = None, dist_group=None, force_gt: bool = False) -> Dict[str, torch.Tensor]:
+                   total_correct: Optional[torch.Tensor] = None, dist_group=None, force_gt: bool = False,
+                   reduce: bool = True) -> Dict[str, torch.Tensor]:
     """CRCT/evaluation.py:231-317 for one dataloader batch.  Returns device tensors:
     `answers [Q]` (index within the question), `prob [N]` (softmax(nsp)[:,0] per candidate), `reg_output / reg_loss /
     reg_t_loss [Q]` (the selected candidate's regression[0] / [4] / [2]), `flags [Q,5]` uint8 = (nsp_right, reg_right,
     reg_t_right, correct +-5 %, correct within tolerance) and `total_correct [6,2]` float64 (the table of
     `reduce_total_acc`, summed over ranks when a process group is initialised), accumulated into the tensor passed in.
-    `force_gt` is the '_REGS' branch of evaluation.py:288-289 (answer = gt_id)."""
+    `force_gt` is the '_REGS' branch of evaluation.py:288-289 (answer = gt_id); `reduce=False` leaves the cross-rank sum to
+    the caller (one all-reduce of the final table instead of one per batch)."""
     enc = getattr(model, 'module', model)
     dev = enc.arena.w32.device
     if dev.type != 'cuda':
@@ -120,7 +122,7 @@ def evaluate_batch(model, qb: Dict[str, torch.Tensor], params: dict, eval_batch_
     needs = qb['needs_reg'].view(-1).to(torch.uint8).contiguous()
     L.score_answers(answers, qb['gt_id'].view(-1).to(torch.int64).contiguous(), needs, sel[1], sel[2],
                     qb['tolerance_margin'].view(-1).float().contiguous(), batch_total, flags=flags)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(dist_group) > 1:
+    if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(dist_group) > 1:
         dist.all_reduce(batch_total, op=dist.ReduceOp.SUM, group=dist_group)      # evaluation.py:519-521
     if total_correct is None:
         total_correct = torch.zeros(6, 2, dtype=torch.float64, device=dev)
