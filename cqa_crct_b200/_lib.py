@@ -104,7 +104,10 @@ EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf
            'crct_embed_text_fwd', 'crct_embed_text_bwd', 'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd',
            'crct_attn_bwd', 'crct_linear_f32', 'crct_linear_f32_batched', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
            'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_bump_salt', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw',
-           'crct_expand_blocks', 'crct_select_answers', 'crct_score_answers']
+           'crct_expand_blocks', 'crct_select_answers', 'crct_score_answers',
+           'crct_f32_gemm', 'crct_f32_layernorm_fwd', 'crct_f32_layernorm_bwd', 'crct_f32_layernorm_bwd_params', 'crct_f32_attn_fwd',
+           'crct_f32_attn_bwd', 'crct_f32_embed_text_fwd', 'crct_f32_embed_text_bwd', 'crct_f32_embed_vis_fwd', 'crct_f32_embed_vis_bwd',
+           'crct_f32_softmax_rows', 'crct_f32_gather_first', 'crct_f32_scatter_first']
 
 _lib = None
 SALT = None         # device int64[1] tensor XOR-ed into every dropout seed on the device (set by the encoder); None = off
@@ -130,6 +133,10 @@ def lib():
         _lib.crct_scatter_first.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, vp]
         _lib.crct_colsum_f32.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, vp]
         _lib.crct_expand_blocks.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, vp]
+        _lib.crct_f32_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        _lib.crct_f32_softmax_rows.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        _lib.crct_f32_gather_first.argtypes = [vp, C.c_longlong, vp, C.c_int, C.c_int, vp]
+        _lib.crct_f32_scatter_first.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, vp]
         _lib.crct_linear_f32_batched.argtypes = [vp, C.c_int, vp]
         _lib.crct_scale_rows.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp]
         _lib.crct_pool_mul_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
@@ -137,7 +144,9 @@ def lib():
         _lib.crct_bump_salt.argtypes = [vp, vp]
         for name in ('crct_gemm_bf16', 'crct_layernorm_bwd', 'crct_layernorm_bwd_params', 'crct_embed_text_fwd', 'crct_embed_text_bwd',
                      'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd', 'crct_attn_bwd', 'crct_linear_f32',
-                     'crct_hybrid_loss', 'crct_adamw', 'crct_select_answers', 'crct_score_answers'):
+                     'crct_hybrid_loss', 'crct_adamw', 'crct_select_answers', 'crct_score_answers', 'crct_f32_gemm', 'crct_f32_layernorm_bwd',
+                     'crct_f32_layernorm_bwd_params', 'crct_f32_attn_fwd', 'crct_f32_attn_bwd', 'crct_f32_embed_text_fwd',
+                     'crct_f32_embed_text_bwd', 'crct_f32_embed_vis_fwd', 'crct_f32_embed_vis_bwd'):
             getattr(_lib, name).argtypes = [vp, vp]
     return _lib
 
@@ -163,6 +172,10 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _is32(t):
+    return t is not None and t.dtype == torch.float32
+
+
 def _bf16(t, what):
     if t is not None and t.dtype != torch.bfloat16:
         raise CrctError(f'{what} must be bfloat16, got {t.dtype}')
@@ -176,12 +189,17 @@ def _f32(t, what):
 def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None, aux=None, D2=None,
          lda=None, ldb=None, ldd=None, ldaux=None, accumulate=0, split_k=0, block_n=0, dropout_p=0.0, seed=0,
          max_ctas=0, dbg=None, cta_group=0):
-    """D[M,N] = epilogue(A·Bᵀ) — see include/crct_b200.h for operand majors."""
-    _bf16(A, 'A'); _bf16(B, 'B'); _bf16(aux, 'aux'); _bf16(D2, 'D2'); _f32(bias, 'bias')
-    if epilogue == EPI_F32:
-        _f32(D, 'D')
+    """D[M,N] = epilogue(A·Bᵀ) — see include/crct_b200.h for operand majors.  fp32 operands select the check-mode kernel."""
+    f32 = _is32(A)
+    if f32:
+        for t, w in ((B, 'B'), (aux, 'aux'), (D2, 'D2'), (bias, 'bias'), (D, 'D')):
+            _f32(t, w)
     else:
-        _bf16(D, 'D')
+        _bf16(A, 'A'); _bf16(B, 'B'); _bf16(aux, 'aux'); _bf16(D2, 'D2'); _f32(bias, 'bias')
+        if epilogue == EPI_F32:
+            _f32(D, 'D')
+        else:
+            _bf16(D, 'D')
     a = GemmArgs()
     a.A, a.B, a.D, a.D2, a.bias, a.aux = ptr(A), ptr(B), ptr(D), ptr(D2), ptr(bias), ptr(aux)
     a.M, a.N, a.K = M, N, K
@@ -196,7 +214,7 @@ def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None
     if dbg is not None:
         for i, v in enumerate(dbg):
             a.dbg[i] = v
-    check(lib().crct_gemm_bf16(C.byref(a), stream_ptr()))
+    check((lib().crct_f32_gemm if f32 else lib().crct_gemm_bf16)(C.byref(a), stream_ptr()))
 
 
 def cast_f32_to_bf16(src, dst):
@@ -212,13 +230,17 @@ def additive_mask(mask, out):
 
 
 def layernorm_fwd(z, gamma, beta, y, mean=None, rstd=None):
-    _bf16(z, 'z'); _bf16(y, 'y'); _f32(gamma, 'gamma')
     rows, H = z.shape
+    if _is32(z):
+        _f32(y, 'y'); _f32(gamma, 'gamma')
+        return check(lib().crct_f32_layernorm_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, H, stream_ptr()))
+    _bf16(z, 'z'); _bf16(y, 'y'); _f32(gamma, 'gamma')
     check(lib().crct_layernorm_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, H, stream_ptr()))
 
 
 def _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out):
-    _bf16(dy, 'dy'); _bf16(z, 'z'); _bf16(dz, 'dz'); _bf16(dzm, 'dzm')
+    chk = _f32 if _is32(dy) else _bf16
+    chk(dy, 'dy'); chk(z, 'z'); chk(dz, 'dz'); chk(dzm, 'dzm')
     a = LnBwdArgs()
     a.dy, a.z, a.mean, a.rstd, a.gamma, a.dz, a.dzm = ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma), ptr(dz), ptr(dzm)
     a.dgamma, a.dbeta, a.dbias = ptr(dgamma), ptr(dbeta), ptr(dbias)
@@ -232,25 +254,29 @@ def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dgamma=None, dbeta=None, dbias=N
                   seed_out=0):
     """dgamma = dbeta = dbias = None: input gradient only (see layernorm_bwd_params)."""
     a = _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out)
-    check(lib().crct_layernorm_bwd(C.byref(a), stream_ptr()))
+    check((lib().crct_f32_layernorm_bwd if _is32(dy) else lib().crct_layernorm_bwd)(C.byref(a), stream_ptr()))
 
 
 def layernorm_bwd_params(dy, z, mean, rstd, dz, dgamma, dbeta, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0):
     """Column sums of the split LayerNorm backward: dgamma, dbeta and (from dzm, or dz when p_out == 0) dbias."""
     a = _ln_bwd_args(dy, z, mean, rstd, None, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, 0)
-    check(lib().crct_layernorm_bwd_params(C.byref(a), stream_ptr()))
+    check((lib().crct_f32_layernorm_bwd_params if _is32(dy) else lib().crct_layernorm_bwd_params)(C.byref(a), stream_ptr()))
 
 
 def colsum_bf16(x, out, rows=None, N=None, ld=None):
-    _bf16(x, 'x'); _f32(out, 'out')
     rows = x.shape[0] if rows is None else rows
     N = x.shape[1] if N is None else N
+    if _is32(x):
+        return colsum_f32(x, out, rows, N, x.stride(0) if ld is None else ld)
+    _bf16(x, 'x'); _f32(out, 'out')
     check(lib().crct_colsum_bf16(ptr(x), ptr(out), rows, N, x.stride(0) if ld is None else ld, stream_ptr()))
 
 
 def softmax_rows(x, out):
-    _f32(x, 'x'); _bf16(out, 'out')
     rows, F = x.shape
+    if _is32(out):
+        return check(lib().crct_f32_softmax_rows(ptr(x), ptr(out), rows, F, stream_ptr()))
+    _f32(x, 'x'); _bf16(out, 'out')
     check(lib().crct_softmax_rows(ptr(x), ptr(out), rows, F, stream_ptr()))
 
 
@@ -264,7 +290,7 @@ def embed_text_fwd(ids, types, loc, word, pos, type_, w_loc, b_loc, gamma, beta,
     a.B, a.T = ids.shape
     a.H, a.max_pos = word.shape[1], pos.shape[0]
     a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
-    check(lib().crct_embed_text_fwd(C.byref(a), stream_ptr()))
+    check((lib().crct_f32_embed_text_fwd if _is32(y) else lib().crct_embed_text_fwd)(C.byref(a), stream_ptr()))
 
 
 def embed_text_bwd(ids, types, loc, dz, g_word, g_pos, g_type, g_wloc, g_bloc):
@@ -273,7 +299,7 @@ def embed_text_bwd(ids, types, loc, dz, g_word, g_pos, g_type, g_wloc, g_bloc):
     a.g_word, a.g_pos, a.g_type, a.g_wloc, a.g_bloc = ptr(g_word), ptr(g_pos), ptr(g_type), ptr(g_wloc), ptr(g_bloc)
     a.B, a.T = ids.shape
     a.H = dz.shape[-1]
-    check(lib().crct_embed_text_bwd(C.byref(a), stream_ptr()))
+    check((lib().crct_f32_embed_text_bwd if _is32(dz) else lib().crct_embed_text_bwd)(C.byref(a), stream_ptr()))
 
 
 def embed_vis_fwd(g, box, cls, w_loc, b_loc, color, gamma, beta, y, z=None, mean=None, rstd=None, dropout_p=0.0, seed=0):
@@ -283,14 +309,14 @@ def embed_vis_fwd(g, box, cls, w_loc, b_loc, color, gamma, beta, y, z=None, mean
     a.y, a.z, a.mean, a.rstd = ptr(y), ptr(z), ptr(mean), ptr(rstd)
     a.rows, a.H = g.shape
     a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
-    check(lib().crct_embed_vis_fwd(C.byref(a), stream_ptr()))
+    check((lib().crct_f32_embed_vis_fwd if _is32(y) else lib().crct_embed_vis_fwd)(C.byref(a), stream_ptr()))
 
 
 def embed_vis_bwd(dz, box, cls, g_color, g_wloc):
     a = EmbedVisBwdArgs()
     a.dz, a.box, a.cls, a.g_color, a.g_wloc = ptr(dz), ptr(box), ptr(cls), ptr(g_color), ptr(g_wloc)
     a.rows, a.H = dz.shape
-    check(lib().crct_embed_vis_bwd(C.byref(a), stream_ptr()))
+    check((lib().crct_f32_embed_vis_bwd if _is32(dz) else lib().crct_embed_vis_bwd)(C.byref(a), stream_ptr()))
 
 
 def attn_fwd(q, k, v, mask_add, out, lse, *, B, nh, dh, Lq, Lk, ldq, ldk, ldv, ldo, dropout_p=0.0, seed=0):
@@ -299,7 +325,7 @@ def attn_fwd(q, k, v, mask_add, out, lse, *, B, nh, dh, Lq, Lk, ldq, ldk, ldv, l
     a.ldq, a.ldk, a.ldv, a.ldo = ldq, ldk, ldv, ldo
     a.B, a.nh, a.dh, a.Lq, a.Lk = B, nh, dh, Lq, Lk
     a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
-    check(lib().crct_attn_fwd(C.byref(a), stream_ptr()))
+    check((lib().crct_f32_attn_fwd if _is32(q) else lib().crct_attn_fwd)(C.byref(a), stream_ptr()))
 
 
 def attn_bwd(q, k, v, mask_add, out, dout, lse, dq, dk, dv, *, B, nh, dh, Lq, Lk, ldq, ldk, ldv, ldo, lddo, lddq, lddk,
@@ -310,7 +336,7 @@ def attn_bwd(q, k, v, mask_add, out, dout, lse, dq, dk, dv, *, B, nh, dh, Lq, Lk
     a.ldq, a.ldk, a.ldv, a.ldo, a.lddo, a.lddq, a.lddk, a.lddv = ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv
     a.B, a.nh, a.dh, a.Lq, a.Lk = B, nh, dh, Lq, Lk
     a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
-    check(lib().crct_attn_bwd(C.byref(a), stream_ptr()))
+    check((lib().crct_f32_attn_bwd if _is32(q) else lib().crct_attn_bwd)(C.byref(a), stream_ptr()))
 
 
 def linear_f32(A, sa_m, sa_k, B, sb_k, sb_n, Cout, ldc, M, N, K, bias=None, act=ACT_NONE, dmask=None, ldm=0, slope=0.0,
@@ -338,12 +364,12 @@ def linear_f32_batched(problems):
 
 def gather_first(src, row_stride, out):
     B, H = out.shape
-    check(lib().crct_gather_first(ptr(src), row_stride, ptr(out), B, H, stream_ptr()))
+    check((lib().crct_f32_gather_first if _is32(src) else lib().crct_gather_first)(ptr(src), row_stride, ptr(out), B, H, stream_ptr()))
 
 
 def scatter_first(g, dst, row_stride):
     B, H = g.shape
-    check(lib().crct_scatter_first(ptr(g), ptr(dst), row_stride, B, H, stream_ptr()))
+    check((lib().crct_f32_scatter_first if _is32(dst) else lib().crct_scatter_first)(ptr(g), ptr(dst), row_stride, B, H, stream_ptr()))
 
 
 def colsum_f32(x, out, M, N, ld):

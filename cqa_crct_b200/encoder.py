@@ -155,8 +155,16 @@ class _CrctFunction(torch.autograd.Function):
 class VisualDialogEncoder(nn.Module):
     """Drop-in for CRCT/backbone/encoder_decorator.py:9 `VisualDialogEncoder(params)`."""
 
-    def __init__(self, params: dict):
+    def __init__(self, params: dict, precision: Optional[str] = None):
+        """`precision`: 'bf16' (default; production kernels) or 'fp32' — the CHECK MODE of csrc/check_f32.cu: same schedule,
+        same dropout streams, fp32 activations and plain fp32 arithmetic (slow; for parity work, not for training runs).
+        Also read from params['precision']."""
         super().__init__()
+        precision = precision or params.get('precision', 'bf16')
+        if precision not in ('bf16', 'fp32'):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.fp32 = precision == 'fp32'
+        self.act = torch.float32 if self.fp32 else torch.bfloat16
         config_path = params['model_config']
         assert os.path.exists(config_path), "model_config file not found"      # encoder_decorator.py:13
         self.params = params
@@ -231,8 +239,11 @@ class VisualDialogEncoder(nn.Module):
         return self.arena.w32, self.arena.g32, self.arena.w16
 
     # ------------------------------------------------------------------ small helpers
-    def _w(self, name):      # bf16 operand view
-        return self.arena.view(self.arena.w16, name)
+    def _wflat(self):        # GEMM operand arena: the bf16 copy, or the fp32 masters themselves in check mode
+        return self.arena.w32 if self.fp32 else self.arena.w16
+
+    def _w(self, name):      # GEMM operand view
+        return self.arena.view(self._wflat(), name)
 
     def _p(self, name):      # fp32 master view
         return self.arena.view(self.arena.w32, name)
@@ -254,7 +265,7 @@ class VisualDialogEncoder(nn.Module):
     # ------------------------------------------------------------------ building blocks (forward)
     def _linear(self, x, W, bias, M, epilogue=L.EPI_BIAS, aux=None, D2=None, p=0.0, seed=0):
         N, K = W.shape
-        D = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
+        D = torch.empty(M, N, dtype=self.act, device=x.device)
         L.gemm(x, W, D, M=M, N=N, K=K, bias=bias, epilogue=epilogue, aux=aux, D2=D2, dropout_p=p, seed=seed)
         return D
 
@@ -272,7 +283,7 @@ class VisualDialogEncoder(nn.Module):
         """intermediate + output blocks (vilbert.py:454-457,467-471 / 585-588,598-602)."""
         M = a.shape[0]
         W1, W2 = self._w(pre_i + '.dense.weight'), self._w(pre_o + '.dense.weight')
-        dg = torch.empty(M, W1.shape[0], dtype=torch.bfloat16, device=a.device) if keep else None      # gelu'(u), for the backward
+        dg = torch.empty(M, W1.shape[0], dtype=self.act, device=a.device) if keep else None      # gelu'(u), for the backward
         h = self._linear(a, W1, self._p(pre_i + '.dense.bias'), M, L.EPI_BIAS_GELU, D2=dg)
         z = self._linear(h, W2, self._p(pre_o + '.dense.bias'), M, L.EPI_BIAS_RES, aux=a, p=p_drop, seed=seed)
         y, mean, rstd = self._ln(z, pre_o + '.LayerNorm', keep)
@@ -291,7 +302,7 @@ class VisualDialogEncoder(nn.Module):
         W1, W2 = self._w(pre_i + '.dense.weight'), self._w(pre_o + '.dense.weight')
         I = W1.shape[0]
         self._wgrad(gz, s.h, self._g(pre_o + '.dense.weight'))
-        du = torch.empty(M, I, dtype=torch.bfloat16, device=dy.device)
+        du = torch.empty(M, I, dtype=self.act, device=dy.device)
         L.gemm(gz, W2, du, M=M, N=I, K=H, b_major=1, epilogue=L.EPI_MUL, aux=s.dg)
         self._wgrad(du, s.a, self._g(pre_i + '.dense.weight'), self._g(pre_i + '.dense.bias'))
         da = torch.empty_like(dy)
@@ -358,7 +369,7 @@ class VisualDialogEncoder(nn.Module):
         gz = dzm if dzm is not None else dz
         W = self._w(pre_dense + '.weight')
         self._wgrad(gz, s.ctx, self._g(pre_dense + '.weight'))
-        dctx = torch.empty(M, W.shape[1], dtype=torch.bfloat16, device=da.device)
+        dctx = torch.empty(M, W.shape[1], dtype=self.act, device=da.device)
         L.gemm(gz, W, dctx, M=M, N=W.shape[1], K=H, b_major=1)
         return dz, dctx
 
@@ -367,10 +378,10 @@ class VisualDialogEncoder(nn.Module):
         M, H = x.shape
         dh = H // nh
         step = self._step
-        Wqkv = self.arena.fused(self.arena.w16, [pre + '.attention.self.' + n for n in names], '.weight')
+        Wqkv = self.arena.fused(self._wflat(), [pre + '.attention.self.' + n for n in names], '.weight')
         bqkv = self.arena.fused(self.arena.w32, [pre + '.attention.self.' + n for n in names], '.bias')
         qkv = self._linear(x, Wqkv, bqkv, M)
-        ctx = torch.empty(M, H, dtype=torch.bfloat16, device=x.device)
+        ctx = torch.empty(M, H, dtype=self.act, device=x.device)
         lse = torch.empty(B, nh, Lseq, dtype=torch.float32, device=x.device) if keep else None
         p_att, s_att = self._drop(drops[0]), _seed(step, 'attn', layer)
         L.attn_fwd(qkv, qkv[:, H:], qkv[:, 2 * H:], mask_add, ctx, lse, B=B, nh=nh, dh=dh, Lq=Lseq, Lk=Lseq, ldq=3 * H, ldk=3 * H,
@@ -396,7 +407,7 @@ class VisualDialogEncoder(nn.Module):
                    lddv=3 * H, dropout_p=s.p_att, seed=s.s_att)
         mods = [pre + '.attention.self.' + n for n in names]
         self._wgrad(dqkv, s.x, self.arena.fused(self.arena.g32, mods, '.weight'), self.arena.fused(self.arena.g32, mods, '.bias'))
-        Wqkv = self.arena.fused(self.arena.w16, mods, '.weight')
+        Wqkv = self.arena.fused(self._wflat(), mods, '.weight')
         dx = torch.empty_like(dy)
         L.gemm(dqkv, Wqkv, dx, M=M, N=H, K=3 * H, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz1)
         return dx
@@ -413,15 +424,15 @@ class VisualDialogEncoder(nn.Module):
         m1 = [pre + '.biattention.' + n for n in ('query1', 'key1', 'value1')]
         m2 = [pre + '.biattention.' + n for n in ('query2', 'key2', 'value2')]
         with lanes.vis():
-            qkv1 = self._linear(v, self.arena.fused(self.arena.w16, m1, '.weight'), self.arena.fused(self.arena.w32, m1, '.bias'), Mv)
-        qkv2 = self._linear(t, self.arena.fused(self.arena.w16, m2, '.weight'), self.arena.fused(self.arena.w32, m2, '.bias'), Mt)
+            qkv1 = self._linear(v, self.arena.fused(self._wflat(), m1, '.weight'), self.arena.fused(self.arena.w32, m1, '.bias'), Mv)
+        qkv2 = self._linear(t, self.arena.fused(self._wflat(), m2, '.weight'), self.arena.fused(self.arena.w32, m2, '.bias'), Mt)
         lanes.meet()
         self._x_hold = (qkv1, qkv2)        # replaces the previous layer's pair: both lanes are past its readers now
         p1, s1 = self._drop(cfg.v_attention_probs_dropout_prob), _seed(step, 'co_attn1', layer)      # dropout1, vilbert.py:642,696
         p2, s2 = self._drop(cfg.attention_probs_dropout_prob), _seed(step, 'co_attn2', layer)        # dropout2, vilbert.py:649,718
         # biOutput is called with crossed arguments (vilbert.py:780): visual <- ctx2 via dense1/LayerNorm1, text <- ctx1 via dense2/LayerNorm2
         with lanes.vis():                  # visual queries over text keys/values
-            ctx2 = torch.empty(Mv, Hb, dtype=torch.bfloat16, device=t.device)
+            ctx2 = torch.empty(Mv, Hb, dtype=self.act, device=t.device)
             lse2 = torch.empty(B, nh, R, dtype=torch.float32, device=t.device) if keep else None
             L.attn_fwd(qkv1, qkv2[:, Hb:], qkv2[:, 2 * Hb:], t_mask, ctx2, lse2, B=B, nh=nh, dh=dh, Lq=R, Lk=T, ldq=ld, ldk=ld, ldv=ld,
                        ldo=Hb, dropout_p=p2, seed=s2)
@@ -429,7 +440,7 @@ class VisualDialogEncoder(nn.Module):
                                           self._drop(cfg.v_hidden_dropout_prob), _seed(step, 'co_out_v', layer), keep)
             yv, sf_v = self._ffn_fwd(av, pre + '.v_intermediate', pre + '.v_output', self._drop(cfg.v_hidden_dropout_prob),
                                      _seed(step, 'co_ffn_v', layer), keep)
-        ctx1 = torch.empty(Mt, Hb, dtype=torch.bfloat16, device=t.device)          # text queries over visual keys/values
+        ctx1 = torch.empty(Mt, Hb, dtype=self.act, device=t.device)          # text queries over visual keys/values
         lse1 = torch.empty(B, nh, T, dtype=torch.float32, device=t.device) if keep else None
         L.attn_fwd(qkv2, qkv1[:, Hb:], qkv1[:, 2 * Hb:], v_mask, ctx1, lse1, B=B, nh=nh, dh=dh, Lq=T, Lk=R, ldq=ld, ldk=ld, ldv=ld,
                    ldo=Hb, dropout_p=p1, seed=s1)
@@ -477,10 +488,10 @@ class VisualDialogEncoder(nn.Module):
         with lanes.vis():
             self._wgrad(dqkv1, s.v, self.arena.fused(self.arena.g32, m1, '.weight'), self.arena.fused(self.arena.g32, m1, '.bias'))
             dv = torch.empty_like(dyv)
-            L.gemm(dqkv1, self.arena.fused(self.arena.w16, m1, '.weight'), dv, M=Mv, N=Hv, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzv)
+            L.gemm(dqkv1, self.arena.fused(self._wflat(), m1, '.weight'), dv, M=Mv, N=Hv, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzv)
         self._wgrad(dqkv2, s.t, self.arena.fused(self.arena.g32, m2, '.weight'), self.arena.fused(self.arena.g32, m2, '.bias'))
         dt = torch.empty_like(dyt)
-        L.gemm(dqkv2, self.arena.fused(self.arena.w16, m2, '.weight'), dt, M=Mt, N=H, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzt)
+        L.gemm(dqkv2, self.arena.fused(self._wflat(), m2, '.weight'), dt, M=Mt, N=H, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzt)
         return dv, dt
 
     # ------------------------------------------------------------------ heads (fp32, CUDA cores)
@@ -592,8 +603,8 @@ class VisualDialogEncoder(nn.Module):
                 pt_, nt = self._bwd_problems(dt_, ldt, xt, f'regressor.txt_pipe.{idx}', dx=dhw0, accumulate_dx=1)
             L.linear_f32_batched(pv_ + pt_)
             dv_, dt_, ldv, ldt = nv, nt, nv.stride(0), nt.stride(0)
-        dt = torch.zeros(B * T, H, dtype=torch.bfloat16, device=dev)
-        dv = torch.zeros(B * R, Hv, dtype=torch.bfloat16, device=dev)
+        dt = torch.zeros(B * T, H, dtype=self.act, device=dev)
+        dv = torch.zeros(B * R, Hv, dtype=self.act, device=dev)
         L.scatter_first(dhw0, dt, T * H)
         L.scatter_first(dhv0, dv, R * Hv)
         return dt, dv
@@ -629,7 +640,7 @@ class VisualDialogEncoder(nn.Module):
         lanes = self._lanes(dev)
         lanes.v_wait_t()
         e = 'bert.embeddings'
-        t = torch.empty(B * T, H, dtype=torch.bfloat16, device=dev)
+        t = torch.empty(B * T, H, dtype=self.act, device=dev)
         zt = torch.empty_like(t) if keep else None
         mt = torch.empty(B * T, dtype=torch.float32, device=dev) if keep else None
         rt = torch.empty(B * T, dtype=torch.float32, device=dev) if keep else None
@@ -643,10 +654,10 @@ class VisualDialogEncoder(nn.Module):
         box2, cls2 = box.reshape(Bv * R, 4), cls.reshape(Bv * R)
         p_ev, s_ev = self._drop(cfg.hidden_dropout_prob), _seed(step, 'emb_v')      # nn.Dropout(config.hidden_dropout_prob), vilbert.py:1470
         with lanes.vis():
-            probs = torch.empty(Bv * R, F, dtype=torch.bfloat16, device=dev)
+            probs = torch.empty(Bv * R, F, dtype=self.act, device=dev)
             L.softmax_rows(feat2, probs)
             gimg = self._linear(probs, self._w(e + '.new_image_embeddings.weight'), self._p(e + '.new_image_embeddings.bias'), Bv * R)
-            v = torch.empty(Bv * R, Hv, dtype=torch.bfloat16, device=dev)
+            v = torch.empty(Bv * R, Hv, dtype=self.act, device=dev)
             zv = torch.empty_like(v) if keep else None
             mv = torch.empty(Bv * R, dtype=torch.float32, device=dev) if keep else None
             rv = torch.empty(Bv * R, dtype=torch.float32, device=dev) if keep else None
@@ -658,7 +669,7 @@ class VisualDialogEncoder(nn.Module):
                 # question's candidate sequences here (the reference replicates the fp32 inputs on the host instead,
                 # fig_dataloader.py:690-693); from the first co-attention on the visual stream is per candidate
                 v_q = v
-                v = torch.empty(B * R, Hv, dtype=torch.bfloat16, device=dev)
+                v = torch.empty(B * R, Hv, dtype=self.act, device=dev)
                 L.expand_blocks(v_q.view(Bv, R * Hv), group, v.view(B, R * Hv))
         # --- encoder (vilbert.py:852-939): text layers on the text lane, visual layers on the visual lane (v_layer[k-1]
         # and layer[5+k] are independent, vilbert.py:868-886; the 3520-row visual kernels fill the SMs the text kernels'

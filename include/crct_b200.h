@@ -319,6 +319,29 @@ typedef struct {
 } crct_score_t;
 int crct_score_answers(const crct_score_t* args, crct_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * fp32 CHECK MODE (csrc/check_f32.cu): the operators above with fp32 activation storage and plain fp32 CUDA-core
+ * arithmetic (exact erf, IEEE division, no tensor cores).  Same argument structs and the same dropout streams as the
+ * production entry points; every pointer documented as bf16 above is fp32 here.  `VisualDialogEncoder(params,
+ * precision='fp32')` runs the whole forward/backward schedule through these: <= 1e-4 against the fp64 oracle, and an
+ * on-device yardstick for the bf16 path at sizes the CPU oracle cannot reach.  dk/dv of crct_f32_attn_bwd are
+ * overwritten (deterministic two-pass backward, no atomics).
+ * -------------------------------------------------------------------------------------------- */
+int crct_f32_gemm(const crct_gemm_t* args, crct_stream_t stream);
+int crct_f32_layernorm_fwd(const float* z, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                           int rows, int H, crct_stream_t stream);
+int crct_f32_layernorm_bwd(const crct_ln_bwd_t* args, crct_stream_t stream);
+int crct_f32_layernorm_bwd_params(const crct_ln_bwd_t* args, crct_stream_t stream);
+int crct_f32_attn_fwd(const crct_attn_fwd_t* args, crct_stream_t stream);
+int crct_f32_attn_bwd(const crct_attn_bwd_t* args, crct_stream_t stream);
+int crct_f32_embed_text_fwd(const crct_embed_text_t* args, crct_stream_t stream);
+int crct_f32_embed_text_bwd(const crct_embed_text_bwd_t* args, crct_stream_t stream);
+int crct_f32_embed_vis_fwd(const crct_embed_vis_t* args, crct_stream_t stream);
+int crct_f32_embed_vis_bwd(const crct_embed_vis_bwd_t* args, crct_stream_t stream);
+int crct_f32_softmax_rows(const float* x, float* out, int rows, int F, crct_stream_t stream);
+int crct_f32_gather_first(const float* src, long long row_stride, float* out, int B, int H, crct_stream_t stream);
+int crct_f32_scatter_first(const float* g, float* dst, long long row_stride, int B, int H, crct_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
