@@ -281,7 +281,7 @@ def main():
     roof = None
     if rank == 0:
         sustained, burst, hbm, src = load_peaks()
-        events, flops = [], []
+        events, flops, gbytes = [], [], []
         orig = L.gemm
 
         def timed_gemm(A, Bm, D, **kw):
@@ -291,6 +291,9 @@ def main():
             b.record()
             events.append((a, b))
             flops.append(2.0 * kw['M'] * kw['N'] * kw['K'])
+            mn = kw['M'] * kw['N']            # operands once + output (+ residual / multiplier read, + GELU' write)
+            gbytes.append(2.0 * (kw['M'] * kw['K'] + kw['N'] * kw['K']) + mn * (4.0 if kw.get('epilogue') == L.EPI_F32 else 2.0)
+                          + (2.0 * mn if kw.get('aux') is not None else 0.0) + (2.0 * mn if kw.get('D2') is not None else 0.0))
 
         L.gemm = timed_gemm
         import cqa_crct_b200.encoder as E
@@ -324,8 +327,15 @@ def main():
         raw_ms = sum(a.elapsed_time(b) for a, b in events)
         gemm_ms = max(raw_ms - overhead_ms * len(events), 0.5 * raw_ms)
         achieved = sum(flops) / (gemm_ms / 1e3) / 1e12
+        traffic = None                        # DRAM bytes per GEMM launch from the committed ncu capture of this workload
+        tp = os.path.join(ROOT, 'profiles', 'r01_gemm_dram_traffic.json')
+        if os.path.exists(tp):
+            td = json.load(open(tp))
+            if td.get('workload') == args.workload and td.get('gemm_launches_per_step') == len(events):
+                traffic = td['dram_bytes_per_launch']
         roof = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel', 'achieved': achieved, 'peak': sustained, 'unit': 'TFLOP/s',
-                'frac': achieved / sustained, 'traffic': None, 'peak_source': f'{src} (bf16_tflops_sustained; burst {burst})',
+                'frac': achieved / sustained, 'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu, profiles/r01_gemm_dram_traffic.json)',
+                'algorithmic_bytes_per_launch': sum(gbytes) / max(1, len(gbytes)), 'peak_source': f'{src} (bf16_tflops_sustained; burst {burst})',
                 'launches_per_step': len(events), 'timing': 'CUDA events around every GEMM launch of one extra step run on ONE stream '
                 '(the timed steps overlap the text lane, the visual lane and the weight gradients on three streams)', 'gemm_ms_per_step': gemm_ms, 'gemm_ms_per_step_raw': raw_ms,
                 'event_pair_overhead_us': overhead_ms * 1e3, 'gemm_share_of_step': gemm_ms / ms_step,

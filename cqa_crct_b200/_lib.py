@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcrct_b200.so')
+LIB_PATH = os.environ.get('CRCT_B200_LIB') or os.path.join(_HERE, 'libcrct_b200.so')      # override: A/B runs of two builds
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL, EPI_F32 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3

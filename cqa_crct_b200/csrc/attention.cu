@@ -98,7 +98,8 @@ struct FwdParams {
 };
 
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const FwdParams p) {
+// occupancy is what hides the load-then-compute structure of a CTA: 5 CTAs per SM where registers allow (dh <= 48)
+__global__ void __launch_bounds__(ATT_THREADS, DH <= 48 ? 5 : 4) attn_fwd_kernel(const FwdParams p) {
     constexpr int LD = Smem<DH>::LD;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int LQP = (p.Lq + 15) & ~15, LKP = (p.Lk + KB - 1) & ~(KB - 1);
@@ -231,7 +232,8 @@ struct BwdParams {
 };
 
 template <int DH, int PASS>     // PASS 0: this warp owns 16 keys -> dK, dV ; PASS 1: this warp owns 16 queries -> dQ
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const BwdParams p) {
+// 3 CTAs per SM (<= 168 registers; pass A of dh = 64 would spill 170 B and stays at 2)
+__global__ void __launch_bounds__(ATT_THREADS, (DH == 64 && PASS == 0) ? 2 : 3) attn_bwd_kernel(const BwdParams p) {
     constexpr int LD = Smem<DH>::LD;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int LQP = (p.Lq + KB - 1) & ~(KB - 1), LKP = (p.Lk + KB - 1) & ~(KB - 1);
