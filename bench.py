@@ -127,6 +127,7 @@ def main():
     ap.add_argument('--workload', default='train', choices=list(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--opt-overlap', action='store_true', help='run AdamW under the backward instead of after it (A/B; measured slower)')
     ap.add_argument('--no-graph', action='store_true', help='enqueue every launch from Python instead of replaying the captured step')
     args = ap.parse_args()
     B, T, R, train = WORKLOADS[args.workload]
@@ -164,7 +165,7 @@ def main():
     from cqa_crct_b200.synthetic import default_params, make_batch
     L.device_check()
     dev = torch.device('cuda', local_rank)
-    params = default_params(CFG, device=str(dev), max_seq_len=T, max_vis_features=R, L1=True)
+    params = default_params(CFG, device=str(dev), max_seq_len=T, max_vis_features=R, L1=True, overlap_optimizer=args.opt_overlap)
     torch.manual_seed(0)
     enc = VisualDialogEncoder(params).to(dev)
     model = DistributedDataParallel(enc) if world > 1 else enc

@@ -189,6 +189,8 @@ class VisualDialogEncoder(nn.Module):
         self.grad_ready_hook = None          # set by cqa_crct_b200.parallel.DistributedDataParallel
         self.overlap_streams = True          # visual lane / text lane on two streams, weight gradients on a third
         self.segment_ranges = False          # set by graph.GraphedTrainStep when it cuts the step at bucket boundaries
+        self.async_range_hook = None         # f(lo, hi, streams): gradients of [lo, hi) are final once `streams` reach this point
+                                             # (no stream is joined; used to run the optimizer under the rest of the backward)
         self._x_hold = None                  # tensors read across lanes, kept until the lanes have met again
         self._side_stream = None
         self._wg_stream = None
@@ -719,9 +721,12 @@ class VisualDialogEncoder(nn.Module):
         # Finished ranges are only reported one by one when somebody consumes them (the data-parallel hook, or a graph
         # cut into per-bucket segments): reporting a range makes the caller's stream wait for both other streams.
         fine = self.grad_ready_hook is not None or self.segment_ranges
+        ahook = None if fine else self.async_range_hook
         lanes = self._lanes(dev)
         if fine:
             yield arena.offsets['bert.t_pooler.dense.weight'], arena.live_end
+        elif ahook:
+            ahook(arena.offsets['bert.t_pooler.dense.weight'], arena.live_end, [torch.cuda.current_stream(dev)])
         lanes.v_wait_t()
         dv_heads = dv                      # allocated on the text lane, read on the visual lane: keep it until the end
         pending = []                       # finished layers whose range has not been reported yet
@@ -762,6 +767,11 @@ class VisualDialogEncoder(nn.Module):
                 for r in report():
                     yield r
                 lanes.v_wait_t()           # a graph cut may follow a report: the visual lane re-forks from the text lane
+            elif ahook and (kind_ == 'c' or k > last_c):
+                streams = [torch.cuda.current_stream(dev)] + ([self._wg_stream] if (self.overlap_streams and self._wg_stream is not None) else []) + \
+                    ([lanes.v] if lanes.split else [])
+                ahook(min(r[0] for r in pending), max(r[1] for r in pending), streams)
+                pending.clear()
         if last_c < 0:
             vis_embeddings_bwd(dv)
         e = 'bert.embeddings'
@@ -778,6 +788,8 @@ class VisualDialogEncoder(nn.Module):
                 yield r
             yield 0, self._block_range('bert.v_embeddings')[1]
         else:
+            if ahook:                      # what is left: both embedding blocks (everything is joined into this stream by now)
+                ahook(0, self._block_range('bert.v_embeddings')[1], [torch.cuda.current_stream(dev)])
             yield 0, arena.live_end
 
     def train_step_stages(self, batch, nsp_coeff: float = 1.0, reg_coeff: float = 1.0):

@@ -50,6 +50,13 @@ class GraphedTrainStep:
         self._loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
         self._loss_slot = 0
         self.launches_per_step = 0
+        # optional (single GPU): run the optimizer range by range on its own stream under the rest of the backward.  Measured on
+        # B200 (profiles/r01_ab_overlap_prio_s7.txt): 0.10-0.25 ms per step SLOWER than AdamW after the backward — the HBM-bound
+        # update takes bandwidth and SM slots from cold-operand GEMMs that are themselves latency-sensitive — so it is off by
+        # default; stream priorities (chain above fillers) measured neutral to slightly negative and were removed.
+        self.overlap_optimizer = self.world == 1 and bool(params.get('overlap_optimizer', False))
+        self._opt_stream = torch.cuda.Stream(device=dev) if self.overlap_optimizer else None
+        self._opt_pending = None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -67,15 +74,51 @@ class GraphedTrainStep:
                 scheduler.step()
 
     # -- one step, eagerly (warm-up): same calls as the captured version, exchange through the wrapper's hook logic
+    OPT_CHUNK = 24 << 20                  # elements per optimizer launch (~0.13 ms of HBM time each)
+
+    def _opt_hook(self, lo, hi, streams):
+        """`VisualDialogEncoder.async_range_hook`: gradients of [lo, hi) are final once `streams` reach this point.  Ranges arrive
+        from the arena's tail; they are merged to >= OPT_CHUNK and updated on the optimizer stream, which waits for exactly
+        those streams — nothing waits for the optimizer until the end of the step."""
+        if self._opt_pending is None:
+            self._opt_pending = [lo, hi, list(streams)]
+        else:
+            self._opt_pending[0] = lo
+            self._opt_pending[2] += [s for s in streams if s not in self._opt_pending[2]]
+        if self._opt_pending[1] - self._opt_pending[0] >= self.OPT_CHUNK or lo == 0:
+            plo, phi, pstreams = self._opt_pending
+            self._opt_pending = None
+            for s in pstreams:
+                self._opt_stream.wait_stream(s)
+            with torch.cuda.stream(self._opt_stream):
+                self.opt.step_range_captured(plo, phi)
+
+    def _stages(self):
+        """One forward + backward; with `overlap_optimizer` the optimizer is launched from inside it (and joined here)."""
+        if not self.overlap_optimizer:
+            yield from self.enc.train_step_stages(self.static, self.nsp_coeff, self.reg_coeff)
+            return
+        self.enc.async_range_hook = self._opt_hook
+        try:
+            yield from self.enc.train_step_stages(self.static, self.nsp_coeff, self.reg_coeff)
+        finally:
+            self.enc.async_range_hook = None
+        torch.cuda.current_stream().wait_stream(self._opt_stream)
+        self.enc.arena.mark_bf16_fresh()
+
+    def _optimizer_tail(self):
+        if not self.overlap_optimizer:
+            self.opt.step_captured()
+
     def _eager_step(self):
         self.opt.zero_grad()
         works = []
-        for lo, hi in self._buckets(self.enc.train_step_stages(self.static, self.nsp_coeff, self.reg_coeff)):
+        for lo, hi in self._buckets(self._stages()):
             if self.world > 1:
                 works.append(dist.all_reduce(self.enc.arena.g32[lo:hi], op=dist.ReduceOp.AVG, group=self.ddp.pg, async_op=True))
         for w in works:
             w.wait()
-        self.opt.step_captured()
+        self._optimizer_tail()
 
     def _buckets(self, stages):
         """Merge the finished ranges (descending, contiguous) into buckets of >= the wrapper's bucket size."""
@@ -101,12 +144,12 @@ class GraphedTrainStep:
 
         g = begin()
         self.opt.zero_grad()
-        for lo, hi in self._buckets(self.enc.train_step_stages(self.static, self.nsp_coeff, self.reg_coeff)):
+        for lo, hi in self._buckets(self._stages()):
             if self.world > 1:                   # cut here: the bucket [lo, hi) is final once this segment has run
                 g.capture_end()
                 self.segments.append((g, (lo, hi)))
                 g = begin()
-        self.opt.step_captured()
+        self._optimizer_tail()
         g.capture_end()
         self.segments.append((g, None))
         self.loss = self.enc.last_scalars[0:1]

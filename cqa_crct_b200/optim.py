@@ -97,6 +97,17 @@ class FusedAdamW:
                 self.betas[0], self.betas[1], self.eps, 1, grad_scale, dyn=self.dyn)
         arena.mark_bf16_fresh()
 
+    def step_range_captured(self, lo: int, hi: int, grad_scale: float = 1.0):
+        """The same update restricted to arena elements [lo, hi) (multiples of 64), scalars from `self.dyn`: lets the step
+        run the optimizer for the part of the arena whose gradients are final while the backward is still producing the
+        rest (AdamW is HBM-bound, the backward's GEMMs are tensor-bound)."""
+        arena = self.enc.arena
+        hi = min(hi, self.n)
+        if lo % 64 or hi % 64 or hi <= lo:
+            raise ValueError(f'optimizer range [{lo}, {hi}) must be a non-empty multiple of 64 elements')
+        L.adamw(arena.w32[lo:hi], arena.g32[lo:hi], self.m[lo:hi], self.v[lo:hi], arena.w16[lo:hi], self.group[lo // 64:hi // 64], hi - lo,
+                self.base_lr, self.wd, self.betas[0], self.betas[1], self.eps, 1, grad_scale, dyn=self.dyn)
+
     # ---- checkpoint layout (f4): what `torch.optim.AdamW(...).state_dict()` gives for `get_optimizer`'s grouping
     def _named(self):
         """[(index, reference parameter name, spec entry)] in `named_parameters()` order = the reference's param-group

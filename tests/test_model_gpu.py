@@ -180,14 +180,17 @@ def test_stress_shape_forward_backward_runs():
     assert torch.isfinite(loss) and torch.isfinite(m.arena.g32).all()
 
 
-def test_graphed_train_step_matches_eager_and_redraws_dropout():
+@pytest.mark.parametrize('overlap_optimizer', [False, True])
+def test_graphed_train_step_matches_eager_and_redraws_dropout(overlap_optimizer):
     """cqa_crct_b200.graph.GraphedTrainStep: the captured step updates the weights exactly like the eager calls
-    (dropout off), and with dropout on every replay draws new masks (device salt) — losses differ between replays."""
+    (dropout off), and with dropout on every replay draws new masks (device salt) — losses differ between replays.
+    `overlap_optimizer`: AdamW launched range by range under the backward instead of after it — same result."""
     from cqa_crct_b200.graph import GraphedTrainStep
     from cqa_crct_b200.optim import FusedAdamW
     rec = load_golden('tiny_train_l1')
     m1, params, cfg, sd, batch, gb = build(rec)
     m2, *_ = build(rec)
+    params = dict(params, overlap_optimizer=overlap_optimizer)
     o1, o2 = FusedAdamW(m1, lr=2e-5, image_lr=2e-5), FusedAdamW(m2, lr=2e-5, image_lr=2e-5)      # the reference's lr (options.py:21)
     g = GraphedTrainStep(m2, o2, params, gb, warmup_steps=1)          # 1 eager warm-up step applied; capture itself runs nothing
     o1.zero_grad()
