@@ -57,6 +57,7 @@ class GraphedTrainStep:
         self.overlap_optimizer = self.world == 1 and bool(params.get('overlap_optimizer', False))
         self._opt_stream = torch.cuda.Stream(device=dev) if self.overlap_optimizer else None
         self._opt_pending = None
+        self.opt_chunk = int(params.get('optimizer_chunk', 24 << 20))      # elements per optimizer launch (~0.13 ms of HBM time)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -74,18 +75,16 @@ class GraphedTrainStep:
                 scheduler.step()
 
     # -- one step, eagerly (warm-up): same calls as the captured version, exchange through the wrapper's hook logic
-    OPT_CHUNK = 24 << 20                  # elements per optimizer launch (~0.13 ms of HBM time each)
-
     def _opt_hook(self, lo, hi, streams):
         """`VisualDialogEncoder.async_range_hook`: gradients of [lo, hi) are final once `streams` reach this point.  Ranges arrive
-        from the arena's tail; they are merged to >= OPT_CHUNK and updated on the optimizer stream, which waits for exactly
+        from the arena's tail; they are merged to >= `opt_chunk` and updated on the optimizer stream, which waits for exactly
         those streams — nothing waits for the optimizer until the end of the step."""
         if self._opt_pending is None:
             self._opt_pending = [lo, hi, list(streams)]
         else:
             self._opt_pending[0] = lo
             self._opt_pending[2] += [s for s in streams if s not in self._opt_pending[2]]
-        if self._opt_pending[1] - self._opt_pending[0] >= self.OPT_CHUNK or lo == 0:
+        if self._opt_pending[1] - self._opt_pending[0] >= self.opt_chunk or lo == 0:
             plo, phi, pstreams = self._opt_pending
             self._opt_pending = None
             for s in pstreams:

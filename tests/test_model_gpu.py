@@ -190,7 +190,7 @@ def test_graphed_train_step_matches_eager_and_redraws_dropout(overlap_optimizer)
     rec = load_golden('tiny_train_l1')
     m1, params, cfg, sd, batch, gb = build(rec)
     m2, *_ = build(rec)
-    params = dict(params, overlap_optimizer=overlap_optimizer)
+    params = dict(params, overlap_optimizer=overlap_optimizer, optimizer_chunk=1 << 16)     # several optimizer launches on the tiny model
     o1, o2 = FusedAdamW(m1, lr=2e-5, image_lr=2e-5), FusedAdamW(m2, lr=2e-5, image_lr=2e-5)      # the reference's lr (options.py:21)
     g = GraphedTrainStep(m2, o2, params, gb, warmup_steps=1)          # 1 eager warm-up step applied; capture itself runs nothing
     o1.zero_grad()
