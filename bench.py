@@ -28,6 +28,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+    os.environ['NCCL_DEBUG'] = 'WARN'          # NCCL's version banner goes to stdout: keep stdout to the one JSON line
 import torch                      # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
@@ -128,6 +130,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--opt-overlap', action='store_true', help='run AdamW under the backward instead of after it (A/B; measured slower)')
+    ap.add_argument('--bucket-mb', type=float, default=25.0, help='gradient all-reduce bucket size (fp32 MB)')
     ap.add_argument('--no-graph', action='store_true', help='enqueue every launch from Python instead of replaying the captured step')
     args = ap.parse_args()
     B, T, R, train = WORKLOADS[args.workload]
@@ -168,7 +171,7 @@ def main():
     params = default_params(CFG, device=str(dev), max_seq_len=T, max_vis_features=R, L1=True, overlap_optimizer=args.opt_overlap)
     torch.manual_seed(0)
     enc = VisualDialogEncoder(params).to(dev)
-    model = DistributedDataParallel(enc) if world > 1 else enc
+    model = DistributedDataParallel(enc, bucket_cap_mb=args.bucket_mb) if world > 1 else enc
     opt = sched = None
     if train:
         enc.train()

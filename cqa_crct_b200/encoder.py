@@ -189,6 +189,7 @@ class VisualDialogEncoder(nn.Module):
         self.grad_ready_hook = None          # set by cqa_crct_b200.parallel.DistributedDataParallel
         self.overlap_streams = True          # visual lane / text lane on two streams, weight gradients on a third
         self.segment_ranges = False          # set by graph.GraphedTrainStep when it cuts the step at bucket boundaries
+        self.report_min_elems = 0            # fine mode: report (= join the lanes) only once this many gradient elements are final
         self.async_range_hook = None         # f(lo, hi, streams): gradients of [lo, hi) are final once `streams` reach this point
                                              # (no stream is joined; used to run the optimizer under the rest of the backward)
         self._x_hold = None                  # tensors read across lanes, kept until the lanes have met again
@@ -763,8 +764,8 @@ class VisualDialogEncoder(nn.Module):
             pending.append(self._block_range(pre))
             if k == last_c:
                 vis_embeddings_bwd(dv)     # nothing visual is left but the embeddings: next to the remaining text layers
-            if fine and (kind_ == 'c' or k > last_c):
-                for r in report():
+            if fine and (kind_ == 'c' or k > last_c) and sum(hi - lo for lo, hi in pending) >= self.report_min_elems:
+                for r in report():         # every report joins the three streams: one per exchange bucket, not per block
                     yield r
                 lanes.v_wait_t()           # a graph cut may follow a report: the visual lane re-forks from the text lane
             elif ahook and (kind_ == 'c' or k > last_c):

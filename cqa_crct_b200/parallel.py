@@ -29,6 +29,7 @@ class DistributedDataParallel(nn.Module):
         self.require_sync = True
         self.buckets_last_step = []
         module.grad_ready_hook = self._on_ready
+        module.report_min_elems = self.bucket_elems          # the backward joins its streams once per bucket
         if broadcast_parameters and self.world > 1:
             dist.broadcast(module.arena.w32, src=0, group=self.pg)        # DDP construction semantics: rank 0's weights win
 
