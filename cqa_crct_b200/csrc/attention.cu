@@ -13,6 +13,7 @@
 // Backward = two register-resident passes over the recomputed probabilities (no atomics, no cross-warp
 // reduction): pass A owns 16 keys per warp -> dK, dV;  pass B owns 16 queries per warp -> dQ.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -232,8 +233,12 @@ struct BwdParams {
 };
 
 template <int DH, int PASS>     // PASS 0: this warp owns 16 keys -> dK, dV ; PASS 1: this warp owns 16 queries -> dQ
-// 3 CTAs per SM (<= 168 registers; pass A of dh = 64 would spill 170 B and stays at 2)
-__global__ void __launch_bounds__(ATT_THREADS, (DH == 64 && PASS == 0) ? 2 : 3) attn_bwd_kernel(const BwdParams p) {
+// PASS 0: dK, dV (warp owns 16 keys).  PASS 1: dQ (warp owns 16 queries; recomputes S and dP).  PASS 2: both in one kernel —
+// pass A also parks dS^T (bf16, exactly the operand of its dK contraction) in shared memory and, after one barrier, a third
+// phase contracts it with K: 5 contractions and one operand load instead of 7 and two.  Needs LKP x (LQP + 8) x 2 more
+// bytes of shared memory (35 KB at 124 x 124), so 2 CTAs per SM; shapes whose dS^T does not fit use passes 0 + 1.
+// 3 CTAs per SM for the split passes (<= 168 registers; pass A of dh = 64 would spill 170 B and stays at 2)
+__global__ void __launch_bounds__(ATT_THREADS, (PASS == 2 || (DH == 64 && PASS == 0)) ? 2 : 3) attn_bwd_kernel(const BwdParams p) {
     constexpr int LD = Smem<DH>::LD;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int LQP = (p.Lq + KB - 1) & ~(KB - 1), LKP = (p.Lk + KB - 1) & ~(KB - 1);
@@ -244,6 +249,8 @@ __global__ void __launch_bounds__(ATT_THREADS, (DH == 64 && PASS == 0) ? 2 : 3) 
     float* mask_s = reinterpret_cast<float*>(Vs + LKP * LD);
     float* lse_s = mask_s + LKP;
     float* D_s = lse_s + LQP;
+    const int LDS = LQP + 8;                                       // dS^T[key][query] row stride: conflict-free 32-bit stores
+    bf16* dSs = reinterpret_cast<bf16*>(D_s + LQP);                // PASS 2 only
 
     const int b = blockIdx.x / p.nh, h = blockIdx.x % p.nh;
     load_tile<DH>(Qs, p.q + (size_t)b * p.Lq * p.ldq + h * DH, p.ldq, p.Lq, LQP);
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (DH == 64 && PASS == 0) ? 2 : 3) 
     const float scale2 = p.scale * LOG2E;
 
     // ---------------- pass A: this warp owns 16 keys -> dK, dV ----------------
-    if constexpr (PASS == 0)
+    if constexpr (PASS == 0 || PASS == 2)
     for (int k0 = warp * 16; k0 < LKP && k0 < ((p.Lk + 15) & ~15); k0 += NWARPS * 16) {
         uint32_t ak[DH / 16][4], av[DH / 16][4];
 #pragma unroll
@@ -322,6 +329,10 @@ __global__ void __launch_bounds__(ATT_THREADS, (DH == 64 && PASS == 0) ? 2 : 3) 
                     st[j][c] = pr * fac;
                     dpt[j][c] = pr * (dpt[j][c] * fac - ((c & 1) ? dd.y : dd.x)) * p.scale;
                 }
+                if constexpr (PASS == 2) {                           // rows = keys k0+g / k0+g+8, columns = queries qi0, qi0+1
+                    *reinterpret_cast<uint32_t*>(dSs + (k0 + g) * LDS + qi0) = pack_bf16x2(dpt[j][0], dpt[j][1]);
+                    *reinterpret_cast<uint32_t*>(dSs + (k0 + g + 8) * LDS + qi0) = pack_bf16x2(dpt[j][2], dpt[j][3]);
+                }
             }
 #pragma unroll
             for (int kk = 0; kk < KB / 16; ++kk) {
@@ -353,6 +364,38 @@ __global__ void __launch_bounds__(ATT_THREADS, (DH == 64 && PASS == 0) ? 2 : 3) 
             if (r1 < p.Lk) {
                 *reinterpret_cast<uint32_t*>(p.dk + ((size_t)b * p.Lk + r1) * p.lddk + col) = pack_bf16x2(dk[j][2], dk[j][3]);
                 *reinterpret_cast<uint32_t*>(p.dv + ((size_t)b * p.Lk + r1) * p.lddv + col) = pack_bf16x2(dv[j][2], dv[j][3]);
+            }
+        }
+    }
+
+    // ---------------- phase C (fused variant): dQ = dS K from the parked dS^T; this warp owns 16 queries ----------------
+    if constexpr (PASS == 2) {
+        __syncthreads();
+        const int LK16 = (p.Lk + 15) & ~15;
+        for (int q0 = warp * 16; q0 < ((p.Lq + 15) & ~15); q0 += NWARPS * 16) {
+            float dq[DH / 8][4];
+#pragma unroll
+            for (int j = 0; j < DH / 8; ++j) { dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f; }
+            for (int k0 = 0; k0 < LK16; k0 += 16) {
+                // A fragment dS[q0 .. q0+15][k0 .. k0+15] out of dS^T[key][query]: four transposed 8x8 blocks
+                // (queries +0 / +8 within keys +0, then within keys +8)
+                uint32_t ads[4];
+                const int m = lane >> 3, rr = lane & 7;
+                ldmatrix_x4_trans(ads, ptx::smem_u32(dSs + (k0 + rr + (m >> 1) * 8) * LDS + q0 + (m & 1) * 8));
+#pragma unroll
+                for (int nt = 0; nt < DH / 16; ++nt) {
+                    uint32_t r[4];
+                    load_b_frag_trans<LD>(r, Ks, k0, nt * 16, lane);              // dQ += dS K
+                    mma16816(dq[2 * nt], ads, r[0], r[1]);
+                    mma16816(dq[2 * nt + 1], ads, r[2], r[3]);
+                }
+            }
+            const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+            for (int j = 0; j < DH / 8; ++j) {
+                const int col = h * DH + j * 8 + 2 * t;
+                if (r0 < p.Lq) *reinterpret_cast<uint32_t*>(p.dq + ((size_t)b * p.Lq + r0) * p.lddq + col) = pack_bf16x2(dq[j][0], dq[j][1]);
+                if (r1 < p.Lq) *reinterpret_cast<uint32_t*>(p.dq + ((size_t)b * p.Lq + r1) * p.lddq + col) = pack_bf16x2(dq[j][2], dq[j][3]);
             }
         }
     }
@@ -447,6 +490,19 @@ int launch_bwd(const BwdParams& p, cudaStream_t st) {
     const int LQP = (p.Lq + KB - 1) & ~(KB - 1), LKP = (p.Lk + KB - 1) & ~(KB - 1);
     const size_t smem = (size_t)(2 * LQP + 2 * LKP) * LD * 2 + (size_t)(LKP + 2 * LQP) * 4;
     if (smem > 200 * 1024) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_bwd: Lq=%d Lk=%d do not fit in shared memory", p.Lq, p.Lk);
+    // fused single kernel when dS^T fits next to the operand tiles with two CTAs per SM
+    const size_t smem_fused = smem + (size_t)LKP * (LQP + 8) * 2;
+    static const bool split_only = getenv("CRCT_ATTN_BWD_SPLIT") != nullptr;       // A/B switch
+    if (smem_fused <= 110 * 1024 && !split_only) {
+        static size_t configured_fused = 0;
+        if (smem_fused > configured_fused) {
+            CRCT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
+            configured_fused = smem_fused;
+        }
+        attn_bwd_kernel<DH, 2><<<p.B * p.nh, ATT_THREADS, smem_fused, st>>>(p);      // dK, dV, dQ
+        CRCT_LAUNCH_CHECK();
+        return CRCT_OK;
+    }
     static size_t configured = 0;
     if (smem > configured) {
         CRCT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
