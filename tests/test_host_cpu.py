@@ -125,3 +125,47 @@ def test_dropout_hash_reference_values_and_rate():
     thr = int(0.5 * 65536 + 0.5)
     both = sum(keep(7, 2 * i, thr) and keep(7, 2 * i + 1, thr) for i in range(20000)) / 20000
     assert abs(both - 0.25) < 0.02
+
+
+def test_question_batch_layout_and_expansion():
+    """f3 host logic: one row per candidate for the text keys, one row per question for the visual keys; the expanded batch
+    is the reference's layout after cut_batch_padding (CRCT/fig_dataloader.py:690-703)."""
+    from cqa_crct_b200.evaluate import candidate_groups, expand_question_batch, TEXT_KEYS, VIS_KEYS
+    from cqa_crct_b200.synthetic import make_question_batch
+    qb = make_question_batch(7, 32, 12, 64, seed=9, vocab_size=2048, max_ans=11)
+    N, Q = int(qb['num_ans'].sum()), 7
+    for k in TEXT_KEYS:
+        assert qb[k].shape[0] == N, k
+    for k in VIS_KEYS:
+        assert qb[k].shape[0] == Q, k
+    grp = candidate_groups(qb['num_ans'])
+    assert grp.shape == (N,) and torch.equal(torch.bincount(grp, minlength=Q), qb['num_ans'])
+    assert torch.equal(grp, torch.sort(grp).values)                      # candidates of a question are contiguous
+    full = expand_question_batch(qb)
+    for k in VIS_KEYS:
+        assert full[k].shape[0] == N and torch.equal(full[k], qb[k][grp]), k
+    # candidates of one question share the chart text and the question, differ in the answer span only
+    off = 0
+    for n in qb['num_ans'].tolist():
+        seg = qb['segments'][off]
+        same = seg != 1
+        assert all(torch.equal(qb['tokens'][off + i][same], qb['tokens'][off][same]) for i in range(n))
+        off += n
+    assert ((qb['gt_id'] >= -1) & (qb['gt_id'] < qb['num_ans'])).all()
+    qb512 = make_question_batch(16, 124, 44, 32, seed=1, total=512)
+    assert int(qb512['num_ans'].sum()) == 512 and qb512['tokens'].shape == (512, 124)
+
+
+def test_optimizer_range_and_bucket_bookkeeping():
+    """Ranges reported by the backward are 64-element aligned and tile the live arena from its tail; the per-bucket report
+    threshold only merges neighbours (cqa_crct_b200/encoder.py `_backward_stages`, parallel.py)."""
+    from cqa_crct_b200.encoder import VisualDialogEncoder
+    m = VisualDialogEncoder(default_params(os.path.join(CONFIG_DIR, 'vilbert.json')))
+    a = m.arena
+    blocks = [m._block_range(p) for p in ['bert.embeddings', 'bert.v_embeddings'] +
+              [{'t': f'bert.encoder.layer.{i}', 'v': f'bert.encoder.v_layer.{i}', 'c': f'bert.encoder.c_layer.{i}'}[k] for k, i in m.cfg.schedule()]]
+    assert blocks[0][0] == 0
+    for (lo, hi), (lo2, hi2) in zip(blocks, blocks[1:]):
+        assert hi == lo2 and lo % 64 == 0 and hi % 64 == 0
+    assert blocks[-1][1] == a.offsets['bert.t_pooler.dense.weight'] and a.live_end % 64 == 0
+    assert a.live_end <= a.total and sum(p.numel for p in a.spec if p.live) <= a.live_end

@@ -94,3 +94,39 @@ def test_eval_oracle_against_the_reference_selection_lines(seed, force, monkeypa
     total = fn_ns['reduce_total_acc'](torch.zeros(6, 2).double(), ns['needs_regression'], ns['nsp_right'], ns['reg_right'],
                                       ns['reg_t_right'], None)
     assert torch.equal(total, mine['total_correct'])
+
+
+def test_train_flags_are_the_reference_flags_with_the_same_defaults():
+    """cqa_crct_b200.train.read_command_line vs CRCT/options.py:9-81: every flag kept from the reference has the reference's
+    type and default (so existing command lines keep their meaning); the only additions are the synthetic-data / launch
+    flags, and the only changed defaults are the ones the synthetic data replaces."""
+    import argparse
+    import re
+    from cqa_crct_b200 import train as T
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, 'CRCT', 'options.py')).read()
+    body = src[src.index('parser = argparse.ArgumentParser'):src.index('try:')]
+    ns = {'argparse': argparse, 'sys': __import__('sys')}
+    exec(re.sub(r'^    ', '', body, flags=re.M), ns)                    # the reference's own add_argument calls
+    ref = {a.dest: a for a in ns['parser']._actions if a.dest != 'help'}
+    captured = {}
+    orig = argparse.ArgumentParser.parse_args
+
+    def grab(self, args=None, namespace=None):
+        captured['actions'] = {a.dest: a for a in self._actions if a.dest != 'help'}
+        return orig(self, args, namespace)
+    argparse.ArgumentParser.parse_args = grab
+    try:
+        T.read_command_line([])
+    finally:
+        argparse.ArgumentParser.parse_args = orig
+    mine = captured['actions']
+    added = set(mine) - set(ref)
+    assert added == {'max_vis_features', 'iters_per_epoch', 'eval_questions', 'graph'}, added
+    changed = {}
+    for k, a in mine.items():
+        if k in ref:
+            assert type(a) is type(ref[k]), k                           # store / store_true
+            if a.default != ref[k].default:
+                changed[k] = (ref[k].default, a.default)
+    # dataset-dependent defaults: config path, sequence length of config/plotqa.json, candidate chunk, qa file, class count
+    assert set(changed) <= {'model_config', 'max_seq_len', 'eval_batch_size', 'qa_file', 'categories'}, changed
