@@ -1,6 +1,7 @@
 // Library-wide plumbing: error messages, device checks.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -23,6 +24,12 @@ int crct_num_sms() {
         }
     }
     return sms;
+}
+
+bool crct_pdl_enabled() {
+    // opt-in: measured 0.1-0.3 ms per step SLOWER on B200 (profiles/r01_ab_pdl_s14.txt) — see common.cuh
+    static const bool on = []() { const char* e = getenv("CRCT_PDL"); return e && e[0] == '1'; }();
+    return on;
 }
 
 extern "C" CRCT_API const char* crct_last_error(void) { return g_err; }

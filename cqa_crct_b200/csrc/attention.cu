@@ -103,6 +103,8 @@ template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS, DH <= 48 ? 5 : 4) attn_fwd_kernel(const FwdParams p) {
     constexpr int LD = Smem<DH>::LD;
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    pdl_launch_dependents();
+    pdl_wait();
     const int LQP = (p.Lq + 15) & ~15, LKP = (p.Lk + KB - 1) & ~(KB - 1);
     bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
     bf16* Ks = Qs + LQP * LD;
@@ -237,10 +239,13 @@ template <int DH, int PASS>     // PASS 0: this warp owns 16 keys -> dK, dV ; PA
 // pass A also parks dS^T (bf16, exactly the operand of its dK contraction) in shared memory and, after one barrier, a third
 // phase contracts it with K: 5 contractions and one operand load instead of 7 and two.  Needs LKP x (LQP + 8) x 2 more
 // bytes of shared memory (35 KB at 124 x 124), so 2 CTAs per SM; shapes whose dS^T does not fit use passes 0 + 1.
-// 3 CTAs per SM for the split passes (<= 168 registers; pass A of dh = 64 would spill 170 B and stays at 2)
-__global__ void __launch_bounds__(ATT_THREADS, (PASS == 2 || (DH == 64 && PASS == 0)) ? 2 : 3) attn_bwd_kernel(const BwdParams p) {
+// 3 CTAs per SM for the split passes and for the fused kernel at dh = 32 (co-attention: 49 KB of shared memory per CTA);
+// <= 168 registers; pass A of dh = 64 would spill 170 B and stays at 2
+__global__ void __launch_bounds__(ATT_THREADS, ((PASS == 2 && DH != 32) || (DH == 64 && PASS == 0)) ? 2 : 3) attn_bwd_kernel(const BwdParams p) {
     constexpr int LD = Smem<DH>::LD;
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    pdl_launch_dependents();
+    pdl_wait();
     const int LQP = (p.Lq + KB - 1) & ~(KB - 1), LKP = (p.Lk + KB - 1) & ~(KB - 1);
     bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
     bf16* dOs = Qs + LQP * LD;
@@ -479,8 +484,7 @@ int launch_fwd(const FwdParams& p, cudaStream_t st) {
         CRCT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    attn_fwd_kernel<DH><<<p.B * p.nh, ATT_THREADS, smem, st>>>(p);
-    CRCT_LAUNCH_CHECK();
+    CRCT_CUDA(crct_launch_pdl(attn_fwd_kernel<DH>, dim3(p.B * p.nh), dim3(ATT_THREADS), smem, st, p));
     return CRCT_OK;
 }
 
@@ -499,8 +503,7 @@ int launch_bwd(const BwdParams& p, cudaStream_t st) {
             CRCT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
             configured_fused = smem_fused;
         }
-        attn_bwd_kernel<DH, 2><<<p.B * p.nh, ATT_THREADS, smem_fused, st>>>(p);      // dK, dV, dQ
-        CRCT_LAUNCH_CHECK();
+        CRCT_CUDA(crct_launch_pdl(attn_bwd_kernel<DH, 2>, dim3(p.B * p.nh), dim3(ATT_THREADS), smem_fused, st, p));      // dK, dV, dQ
         return CRCT_OK;
     }
     static size_t configured = 0;
@@ -509,10 +512,8 @@ int launch_bwd(const BwdParams& p, cudaStream_t st) {
         CRCT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    attn_bwd_kernel<DH, 0><<<p.B * p.nh, ATT_THREADS, smem, st>>>(p);      // dK, dV
-    CRCT_LAUNCH_CHECK();
-    attn_bwd_kernel<DH, 1><<<p.B * p.nh, ATT_THREADS, smem, st>>>(p);      // dQ
-    CRCT_LAUNCH_CHECK();
+    CRCT_CUDA(crct_launch_pdl(attn_bwd_kernel<DH, 0>, dim3(p.B * p.nh), dim3(ATT_THREADS), smem, st, p));      // dK, dV
+    CRCT_CUDA(crct_launch_pdl(attn_bwd_kernel<DH, 1>, dim3(p.B * p.nh), dim3(ATT_THREADS), smem, st, p));      // dQ
     return CRCT_OK;
 }
 

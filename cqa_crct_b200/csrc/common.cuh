@@ -29,6 +29,37 @@ static inline cudaStream_t as_stream(crct_stream_t s) { return reinterpret_cast<
 int crct_num_sms();
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched through crct_launch_pdl may have its CTAs scheduled — and run
+// whatever precedes pdl_wait() — while the previous kernel of the stream is still draining its last wave; pdl_wait()
+// returns once that kernel has completed and its writes are visible.  The ~700 kernels of a step form long dependent
+// chains, so the launch latency and the prologue (barrier init, TMEM allocation, descriptor prefetch) of every hot kernel
+// otherwise sit on the critical path.  Rules: a kernel launched this way calls pdl_wait() before its first global-memory
+// access; pdl_launch_dependents() at its top lets ITS successor be scheduled early (the trigger fires only when every
+// CTA of the grid has started, so a successor never takes SM resources from unscheduled CTAs of its predecessor).
+// Captured into CUDA graphs as programmatic dependency edges.
+// MEASURED (B200, train step B=80, profiles/r01_ab_pdl_s14.txt): 17.40 / 17.22 ms with the attribute against 17.11 / 17.10 ms
+// without — the early-resident successors cost more than the launch gaps they hide when three streams already keep the SMs
+// busy — so the attribute is OFF unless CRCT_PDL=1; without it the two instructions are no-ops.
+// ---------------------------------------------------------------------------------------------
+bool crct_pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t crct_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = crct_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // counter-based dropout RNG, identical in forward and backward and never stored.
 // One 32-bit hash serves the element pair (2i, 2i+1): element idx keeps iff its 16-bit half >= threshold, with
 // threshold = round(p * 65536) (0 => keep everything); kept values are scaled by 1/(1-p)

@@ -284,6 +284,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();    // the next kernel of the stream may be scheduled behind this grid (see common.cuh)
 
     if (warp == 0 && lane == 0) {
         ptx::tma_prefetch_desc(&tmA);
@@ -308,6 +309,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                 // everything above touched only this CTA's shared / tensor memory
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -461,6 +463,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();    // see the single-CTA kernel
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1;
@@ -489,6 +492,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     ptx::cluster_sync();                                   // barriers of BOTH CTAs initialised before any remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                 // everything above touched only this CTA's shared / tensor memory
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
@@ -635,8 +639,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int
         CRCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
         configured = true;
     }
-    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
-    CRCT_LAUNCH_CHECK();
+    CRCT_CUDA(crct_launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), Cfg<BN>::SMEM_BYTES, st, tmA, tmB, p));
     return CRCT_OK;
 }
 
@@ -648,8 +651,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, in
         CRCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM_BYTES));
         configured = true;
     }
-    kern<<<grid, NUM_THREADS, Cfg2<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);     // __cluster_dims__(2,1,1): grid is even
-    CRCT_LAUNCH_CHECK();
+    CRCT_CUDA(crct_launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), Cfg2<BN>::SMEM_BYTES, st, tmA, tmB, p));     // __cluster_dims__(2,1,1): grid is even
     return CRCT_OK;
 }
 

@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(ROW_THREADS) additive_mask_kernel(const void* 
 __global__ void __launch_bounds__(ROW_THREADS)
 layernorm_fwd_kernel(const bf16* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
                      bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
     if (row >= rows) return;
@@ -233,6 +235,8 @@ ln_bwd_dz_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const 
                  const float* __restrict__ rstd_in, const float* __restrict__ gamma, bf16* __restrict__ dz, bf16* __restrict__ dzm,
                  int rows, int H, uint32_t thr_in, float scale_in, uint64_t seed_in, uint32_t thr_out, float scale_out,
                  uint64_t seed_out, const unsigned long long* __restrict__ salt) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
     if (row >= rows) return;
@@ -284,6 +288,8 @@ ln_bwd_params_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int H, uint32_t thr_in, float scale_in,
                      uint64_t seed_in, const unsigned long long* __restrict__ salt) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int NW = ROW_THREADS / 32;
     __shared__ float red[NW][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -354,6 +360,8 @@ ln_bwd_params_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
 // out[n] += sum_rows x[row, n]
 __global__ void __launch_bounds__(ROW_THREADS)
 colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows, int N, int ld) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[ROW_THREADS / 32][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int col = blockIdx.x * 256 + lane * 8;
@@ -722,9 +730,8 @@ extern "C" CRCT_API int crct_layernorm_fwd(const void* z, const float* gamma, co
     if (!z || !gamma || !beta || !y || (mean == nullptr) != (rstd == nullptr)) CRCT_FAIL(CRCT_ERR_ARG, "crct_layernorm_fwd: bad pointer");
     if (int rc = check_row_width(H, "crct_layernorm_fwd")) return rc;
     if (rows <= 0) return CRCT_OK;
-    layernorm_fwd_kernel<<<row_grid(rows), ROW_THREADS, 0, as_stream(s)>>>(reinterpret_cast<const bf16*>(z), gamma, beta,
-                                                                          reinterpret_cast<bf16*>(y), mean, rstd, rows, H);
-    CRCT_LAUNCH_CHECK();
+    CRCT_CUDA(crct_launch_pdl(layernorm_fwd_kernel, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, as_stream(s), reinterpret_cast<const bf16*>(z),
+                              gamma, beta, reinterpret_cast<bf16*>(y), mean, rstd, rows, H));
     return CRCT_OK;
 }
 
@@ -737,7 +744,7 @@ extern "C" CRCT_API int crct_layernorm_bwd(const crct_ln_bwd_t* a, crct_stream_t
     const float sc_in = a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, sc_out = a->p_out > 0.f ? 1.f / (1.f - a->p_out) : 1.f;
     if (!a->dgamma && !a->dbeta && !a->dbias) {          // input gradient only (crct_layernorm_bwd_params does the sums)
         auto launch = [&](auto kern) {
-            kern<<<row_grid(a->rows), ROW_THREADS, 0, as_stream(s)>>>(
+            crct_launch_pdl(kern, dim3(row_grid(a->rows)), dim3(ROW_THREADS), 0, as_stream(s),
                 reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), a->mean, a->rstd, a->gamma,
                 reinterpret_cast<bf16*>(a->dz), dzm ? reinterpret_cast<bf16*>(a->dzm) : nullptr, a->rows, a->H,
                 crct_drop_threshold(a->p_in), sc_in, a->seed_in, crct_drop_threshold(a->p_out), sc_out, a->seed_out,
@@ -788,7 +795,7 @@ extern "C" CRCT_API int crct_layernorm_bwd_params(const crct_ln_bwd_t* a, crct_s
     const int max_gy = (a->rows + 63) / 64;
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
-    ln_bwd_params_kernel<<<dim3(gx, gy), ROW_THREADS, 0, as_stream(s)>>>(
+    crct_launch_pdl(ln_bwd_params_kernel, dim3(gx, gy), dim3(ROW_THREADS), 0, as_stream(s),
         reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), reinterpret_cast<const bf16*>(dzm), a->mean, a->rstd,
         a->dgamma, a->dbeta, a->dbias, a->rows, a->H, crct_drop_threshold(a->p_in), a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, a->seed_in,
         reinterpret_cast<const unsigned long long*>(a->salt));
@@ -805,7 +812,7 @@ extern "C" CRCT_API int crct_colsum_bf16(const void* x, float* out, int rows, in
     const int max_gy = (rows + 63) / 64;
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
-    colsum_kernel<<<dim3(gx, gy), ROW_THREADS, 0, as_stream(s)>>>(reinterpret_cast<const bf16*>(x), out, rows, N, ld);
+    crct_launch_pdl(colsum_kernel, dim3(gx, gy), dim3(ROW_THREADS), 0, as_stream(s), reinterpret_cast<const bf16*>(x), out, rows, N, ld);
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }
