@@ -28,8 +28,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-    os.environ['NCCL_DEBUG'] = 'WARN'          # NCCL's version banner goes to stdout: keep stdout to the one JSON line
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # NCCL's banner / warnings off stdout: stdout is the one JSON line
 import torch                      # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
