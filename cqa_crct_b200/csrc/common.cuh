@@ -207,14 +207,24 @@ __device__ __forceinline__ void load8_f32(const float* p, float (&f)[8]) {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-// dropout on 8 consecutive elements (4 hashes when e0 is even)
-__device__ __forceinline__ void dropout8(float (&f)[8], uint64_t seed, uint64_t e0, uint32_t thr, float scale) {
+// dropout on 8 consecutive elements starting at element counter e0, e0 a MULTIPLE OF 8 (every caller: row * width + column
+// chunk, width % 8 == 0): four pair hashes with the index/seed high words mixed once — the same decisions as crct_keep
+// element by element, without its odd-index path and 64-bit arithmetic per pair.  (ncu on the RES epilogue: the hash was
+// ~11 of ~20 instructions per element of an issue-bound epilogue.)
+__host__ __device__ __forceinline__ void dropout8(float (&f)[8], uint64_t seed, uint64_t e0, uint32_t thr, float scale) {
+    const uint64_t pair = e0 >> 1;
+    const uint32_t lo = (uint32_t)pair;
+    const uint32_t mix = (uint32_t)(pair >> 32) * 0x85EBCA77u + (uint32_t)(seed >> 32) * 0x27D4EB2Fu;
+    const uint32_t thr_hi = thr << 16;                       // (h >> 16) >= thr  <=>  h >= thr << 16
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-        bool k0, k1;
-        crct_keep2(seed, e0 + j, thr, k0, k1);
-        f[j] = k0 ? f[j] * scale : 0.f;
-        f[j + 1] = k1 ? f[j + 1] * scale : 0.f;
+    for (int j = 0; j < 4; ++j) {
+        uint32_t h = (lo + (uint32_t)j) * 0x9E3779B1u + (uint32_t)seed;
+        h ^= mix;
+        h ^= h >> 15; h *= 0x85EBCA6Bu;
+        h ^= h >> 13; h *= 0xC2B2AE35u;
+        h ^= h >> 16;
+        f[2 * j] = (h & 0xFFFFu) >= thr ? f[2 * j] * scale : 0.f;
+        f[2 * j + 1] = h >= thr_hi ? f[2 * j + 1] * scale : 0.f;
     }
 }
 
