@@ -578,21 +578,32 @@ class VisualDialogEncoder(nn.Module):
         dlogits, dpre = torch.empty_like(s.dlogits), torch.empty_like(s.dpre)
         L.scale_rows(s.dlogits, d_nsp.reshape(-1)[:1].contiguous().float(), dlogits)
         L.scale_rows(s.dpre, d_reg.reshape(-1).contiguous().float(), dpre)
+        # Per layer: the input gradient (dgrad) is the serial chain everything after it waits for; the weight and bias gradients
+        # are not — they go to the weight-gradient stream like the transformer's (`_wg`), so the chain's launches stay small
+        # (16.95 -> 16.84 ms per step, profiles/r01_ab_heads_wgrad_s19.txt).
+        def run(*layers):          # layers: (problems [wgrad, bias-grad, dgrad], dy, x)
+            L.linear_f32_batched([pr[2] for pr, _, _ in layers])
+            with self._wg(*[t for _, dy_, x_ in layers for t in (dy_, x_)]):
+                L.linear_f32_batched([q for pr, _, _ in layers for q in pr[:2]])
+
         # classifier + last fusion layer
         pc, dpooled = self._bwd_problems(dlogits, 2, s.pooled, 'cls.bi_seq_relationship')
         pf, d = self._bwd_problems(dpre, 1, s.acts_f[3], 'regressor.fusion.6', dmask=s.acts_f[3], slope=0.01)
-        L.linear_f32_batched(pc + pf)
+        run((pc, dlogits, s.pooled), (pf, dpre, s.acts_f[3]))
         dut, duv = torch.empty_like(s.pt), torch.empty_like(s.pv)
         L.pool_mul_bwd(dpooled, s.pt, s.pv, dut, duv, s.p_cls, s.s_cls)
         # poolers + fusion.4
         pt_, dhw0 = self._bwd_problems(dut, dut.stride(0), s.hw0, 'bert.t_pooler.dense')
         pv_, dhv0 = self._bwd_problems(duv, duv.stride(0), s.hv0, 'bert.v_pooler.dense')
-        pf, d = self._bwd_problems(d, d.stride(0), s.acts_f[2], 'regressor.fusion.4', dmask=s.acts_f[2], slope=0.01)
-        L.linear_f32_batched(pt_ + pv_ + pf)
-        pf, d = self._bwd_problems(d, d.stride(0), s.acts_f[1], 'regressor.fusion.2', dmask=s.acts_f[1], slope=0.01)
-        L.linear_f32_batched(pf)
-        pf, dpref = self._bwd_problems(d, d.stride(0), s.acts_f[0], 'regressor.fusion.0')      # input = cat(pipe outputs): no activation
-        L.linear_f32_batched(pf)
+        d_in = d
+        pf, d = self._bwd_problems(d_in, d_in.stride(0), s.acts_f[2], 'regressor.fusion.4', dmask=s.acts_f[2], slope=0.01)
+        run((pt_, dut, s.hw0), (pv_, duv, s.hv0), (pf, d_in, s.acts_f[2]))
+        d_in = d
+        pf, d = self._bwd_problems(d_in, d_in.stride(0), s.acts_f[1], 'regressor.fusion.2', dmask=s.acts_f[1], slope=0.01)
+        run((pf, d_in, s.acts_f[1]))
+        d_in = d
+        pf, dpref = self._bwd_problems(d_in, d_in.stride(0), s.acts_f[0], 'regressor.fusion.0')      # input = cat(pipe outputs): no activation
+        run((pf, d_in, s.acts_f[0]))
         # the two pipes, layer by layer, side by side
         dv_, dt_ = dpref, dpref[:, 256:]
         ldv = ldt = 512
@@ -604,7 +615,7 @@ class VisualDialogEncoder(nn.Module):
             else:          # first layer: its input gradient joins the pooler's (first-token hidden state)
                 pv_, nv = self._bwd_problems(dv_, ldv, xv, f'regressor.vis_pipe.{idx}', dx=dhv0, accumulate_dx=1)
                 pt_, nt = self._bwd_problems(dt_, ldt, xt, f'regressor.txt_pipe.{idx}', dx=dhw0, accumulate_dx=1)
-            L.linear_f32_batched(pv_ + pt_)
+            run((pv_, dv_, xv), (pt_, dt_, xt))
             dv_, dt_, ldv, ldt = nv, nt, nv.stride(0), nt.stride(0)
         dt = torch.zeros(B * T, H, dtype=self.act, device=dev)
         dv = torch.zeros(B * R, Hv, dtype=self.act, device=dev)
@@ -725,9 +736,11 @@ class VisualDialogEncoder(nn.Module):
         ahook = None if fine else self.async_range_hook
         lanes = self._lanes(dev)
         if fine:
+            self._wgrad_join()             # the heads' weight gradients run on the weight-gradient stream
             yield arena.offsets['bert.t_pooler.dense.weight'], arena.live_end
         elif ahook:
-            ahook(arena.offsets['bert.t_pooler.dense.weight'], arena.live_end, [torch.cuda.current_stream(dev)])
+            ahook(arena.offsets['bert.t_pooler.dense.weight'], arena.live_end, [torch.cuda.current_stream(dev)] +
+                  ([self._wg_stream] if (self.overlap_streams and self._wg_stream is not None) else []))
         lanes.v_wait_t()
         dv_heads = dv                      # allocated on the text lane, read on the visual lane: keep it until the end
         pending = []                       # finished layers whose range has not been reported yet
