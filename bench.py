@@ -28,7 +28,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # NCCL's banner / warnings off stdout: stdout is the one JSON line
+# stdout carries exactly ONE line, the JSON result: everything else any library writes to file descriptor 1 (NCCL prints its
+# version banner there) is sent to stderr; the result line goes to the saved descriptor.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_RESULT_FD, (json.dumps(line) + '\n').encode())
+
+
 import torch                      # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
@@ -152,7 +161,7 @@ def main():
                 'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
                                  'sample': f'{bs} sequences per step of the same shape (T={T}, R={R}), {"fwd+bwd" if train else "fwd"}, fp32, torch CPU ops'},
                 'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     if not torch.cuda.is_available():
@@ -359,7 +368,7 @@ def main():
                 'data': 'synthetic', 'config': dict(config, launch='one CUDA graph per step (captured glue_forward + backward + AdamW)' if gstep is not None else 'per-kernel launches from Python'),
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
                 'gpu_launches_per_step': launches / args.steps, 'roofline': roof, 'cpu_baseline': cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
