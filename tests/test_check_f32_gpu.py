@@ -199,3 +199,35 @@ def _keep(seed, idx, thr):
     h ^= h >> 13; h = h * 0xC2B2AE35 & Mk
     h ^= h >> 16
     return ((h >> 16) if idx & 1 else (h & 0xFFFF)) >= thr
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_edge_case_batches(precision):
+    """The degenerate batches of tests/test_oracle_vs_reference.py::test_edge_case_batches_against_reference (B = 1, no row /
+    every row needing regression, only the <IMG> region visible, zero target) through the CUDA path, forward and backward,
+    against the fp64 oracle: check-mode bars for fp32, the bf16 floor for the production kernels."""
+    from tests.test_oracle_vs_reference import _edge_batches
+    cfg_path = os.path.join(CONFIG_DIR, 'tiny.json')
+    cfg = ModelConfig(cfg_path)
+    sd = synth_state_dict(cfg, 228, seed=5, style='trained')
+    params = default_params(cfg_path, device='cuda', max_seq_len=24, max_vis_features=9, L1=True)
+    m = VisualDialogEncoder(params, precision=precision)
+    m.load_state_dict({'bert_pretrained.' + k: v for k, v in sd.items()}, strict=True)
+    m.to(DEV).eval()
+    tol_logit, tol_loss, tol_grad = (2e-5, 1e-5, 2e-5) if precision == 'fp32' else (6e-2, 2e-2, 0.2)
+    for name, batch in _edge_batches(cfg).items():
+        gb = {k: v.to(DEV) for k, v in batch.items()}
+        m.zero_grad()
+        loss, _, _, _, scores, reg, _ = glue_forward(m, gb, params)
+        loss.backward()
+        torch.cuda.synchronize()
+        out, cache = O.forward(sd, O.Config(cfg.__dict__), batch, train=True, l1=True, dtype=torch.float64)
+        g = O.backward(cache)
+        assert scale_err(scores, out['logits']) < tol_logit, name
+        assert abs(float(loss) - float(out['loss'])) < tol_loss, name
+        assert (int(reg[3][0]), int(reg[3][1])) == tuple(out['reg_right']) or precision == 'bf16', name
+        named = dict(m.bert_pretrained.named_parameters())
+        num = sum(float((named[k].grad.double().cpu() - v).norm() ** 2) for k, v in g.items())
+        den = sum(float(v.norm() ** 2) for v in g.values())
+        assert (num / den) ** 0.5 < tol_grad, (name, (num / den) ** 0.5)
+        assert torch.isfinite(m.arena.g32).all(), name

@@ -130,3 +130,55 @@ def test_train_flags_are_the_reference_flags_with_the_same_defaults():
                 changed[k] = (ref[k].default, a.default)
     # dataset-dependent defaults: config path, sequence length of config/plotqa.json, candidate chunk, qa file, class count
     assert set(changed) <= {'model_config', 'max_seq_len', 'eval_batch_size', 'qa_file', 'categories'}, changed
+
+
+def _edge_batches(cfg):
+    from cqa_crct_b200.synthetic import make_batch
+    mk = lambda B, seed: make_batch(B, 24, 9, cfg.v_feature_size, seed=seed, vocab_size=cfg.vocab_size)
+    b1 = mk(1, 3)
+    none = mk(5, 4); none['R'][:, 1] = 0; none['needs_reg'][:] = False
+    allr = mk(5, 5); allr['R'][:, 1] = 1
+    img = mk(4, 6); img['image_mask'][:, 1:] = 0
+    zero = mk(4, 8); zero['R'][0] = torch.tensor([0.0, 1.0, 0.01, 1.0])
+    return {'single sequence': b1, 'no regression rows': none, 'all regression rows': allr, 'only the <IMG> region visible': img,
+            'zero regression target': zero}
+
+
+@pytest.mark.parametrize('l1', [True, False])
+def test_edge_case_batches_against_reference(l1):
+    """Degenerate batches the reference handles in its loss bookkeeping (vilbert.py:1586-1657): B = 1, no row / every row
+    needing regression (empty boolean gather, regressor.py:36-42 on [0, H]), a fully masked visual stream but the <IMG>
+    token, a zero target (the 0/0 rule of the relative distance, :1632-1636)."""
+    cfg_path = os.path.join(CONFIG_DIR, 'tiny.json')
+    cfg = ModelConfig(cfg_path)
+    sd = synth_state_dict(cfg, 228, seed=5, style='trained')
+    params = default_params(cfg_path, max_seq_len=24, max_vis_features=9, L1=l1)
+    enc = ref_shim.RefEncoder(cfg_path, params)
+    enc.module.bert_pretrained.load_state_dict(sd)
+    enc.module.eval()
+    for name, batch in _edge_batches(cfg).items():
+        loss, _, nsp, _, scores, reg, _ = enc.glue_forward(enc.module, batch, params)
+        out, _ = O.forward(sd, O.Config(cfg.__dict__), batch, train=True, l1=l1, dtype=torch.float64)
+        assert abs(float(loss) - float(out['loss'])) < 1e-6, name
+        assert rel_err(out['logits'], scores.detach()) < 1e-5, name
+        for k, i in (('reg_pred', 0), ('reg_loss', 1), ('reg_l1', 2), ('reg_dist', 4)):
+            assert float((out[k].float() - reg[i].detach()).abs().max()) < 2e-5 * max(1.0, float(reg[i].detach().abs().max())), (name, k)
+        assert (int(reg[3][0]), int(reg[3][1])) == tuple(out['reg_right']), name
+
+
+def test_all_labels_ignored_is_a_documented_deviation():
+    """CrossEntropyLoss(ignore_index=-1) over a batch whose labels are ALL -1 is 0/0 = NaN in the reference
+    (vilbert.py:1513,1655-1657); the data loader never produces that batch (labels are 0/1, fig_dataloader.py:53-54).
+    This implementation returns nsp_loss = 0 there (deviations) — pinned here so it stays a decision."""
+    cfg_path = os.path.join(CONFIG_DIR, 'tiny.json')
+    cfg = ModelConfig(cfg_path)
+    sd = synth_state_dict(cfg, 228, seed=5, style='trained')
+    params = default_params(cfg_path, max_seq_len=24, max_vis_features=9)
+    enc = ref_shim.RefEncoder(cfg_path, params)
+    enc.module.bert_pretrained.load_state_dict(sd)
+    enc.module.eval()
+    batch = make_batch(4, 24, 9, cfg.v_feature_size, seed=7, vocab_size=cfg.vocab_size)
+    batch['next_sentence_labels'][:] = -1
+    loss = enc.glue_forward(enc.module, batch, params)[0]
+    out, _ = O.forward(sd, O.Config(cfg.__dict__), batch, train=True, l1=True, dtype=torch.float64)
+    assert torch.isnan(loss) and float(out['nsp_loss']) == 0.0 and torch.isfinite(out['loss'])
