@@ -231,3 +231,48 @@ def test_edge_case_batches(precision):
         den = sum(float(v.norm() ** 2) for v in g.values())
         assert (num / den) ** 0.5 < tol_grad, (name, (num / den) ** 0.5)
         assert torch.isfinite(m.arena.g32).all(), name
+
+
+def test_full_size_b80_properties():
+    """BASELINE.json's full train size (B = 80, T = 124, R = 44, full model), where the CPU oracle is out of reach in seconds:
+    (1) batch independence — every sequence's class logits and regression output from the B = 80 eval forward equal those
+        of the same sequences run in chunks of 8 (each output element is produced by one CTA in a fixed K order, so the
+        result could only change where the tile policy picked another kernel for the smaller problem: measured exactly 0,
+        bar 1e-6 of scale);
+    (2) the bf16 train step (dropout ON) against the fp32 check mode with the same masks: loss, logits, all gradients
+        (measured: loss 0.77317 vs 0.77321, logits 2.0e-2, gradients 8.0e-2)."""
+    cfg_path = os.path.join(CONFIG_DIR, 'vilbert.json')
+    cfg = ModelConfig(cfg_path)
+    sd = synth_state_dict(cfg, 228, 2, 'mild')
+    batch = make_batch(80, 124, 44, cfg.v_feature_size, seed=1234)
+    gb = {k: v.to(DEV) for k, v in batch.items()}
+    res = {}
+    for precision in ('bf16', 'fp32'):
+        torch.manual_seed(5)
+        params = default_params(cfg_path, device='cuda', L1=True)
+        m = VisualDialogEncoder(params, precision=precision)
+        m.load_state_dict({'bert_pretrained.' + k: v for k, v in sd.items()}, strict=True)
+        m.to(DEV)
+        if precision == 'bf16':
+            m.eval()
+            with torch.no_grad():
+                full = glue_forward(m, gb, params, evaluation=True)
+                parts = [glue_forward(m, gb, params, evaluation=True, sample_ids=slice(i, i + 8)) for i in range(0, 80, 8)]
+            s_full, r_full = full[4], full[5][0]
+            s_part = torch.cat([p[4] for p in parts])
+            r_part = torch.cat([p[5][0] for p in parts])
+            d_s, d_r = scale_err(s_part, s_full), scale_err(r_part, r_full)
+            print(f'B=80 vs 10 x B=8: logits {d_s:.2e}, regression {d_r:.2e}')
+            assert d_s < 1e-6 and d_r < 1e-6
+        m.train()
+        m.zero_grad()
+        loss, _, _, _, scores, reg, _ = glue_forward(m, gb, params)
+        loss.backward()
+        torch.cuda.synchronize()
+        res[precision] = (float(loss), scores.detach().clone(), m.arena.g32[:m.arena.live_end].clone())
+        del m
+        torch.cuda.empty_cache()
+    (l16, s16, g16), (l32, s32, g32) = res['bf16'], res['fp32']
+    e_logit, e_grad = scale_err(s16, s32), float((g16 - g32).norm() / g32.norm())
+    print(f'B=80 train, dropout on, bf16 vs fp32 check: loss {l16:.5f} / {l32:.5f}, logits {e_logit:.2e}, gradients {e_grad:.2e}')
+    assert abs(l16 - l32) < 2e-2 and e_logit < 6e-2 and e_grad < 0.2
