@@ -276,3 +276,54 @@ def test_full_size_b80_properties():
     e_logit, e_grad = scale_err(s16, s32), float((g16 - g32).norm() / g32.norm())
     print(f'B=80 train, dropout on, bf16 vs fp32 check: loss {l16:.5f} / {l32:.5f}, logits {e_logit:.2e}, gradients {e_grad:.2e}')
     assert abs(l16 - l32) < 2e-2 and e_logit < 6e-2 and e_grad < 0.2
+
+
+def test_stress_shape_bf16_vs_check_mode():
+    """BASELINE config 5 (2x regions, 2x tokens: T = 248, R = 88), full model, B = 3, dropout on: the production path (split
+    two-pass attention backward — dS^T of a 248 x 248 head does not fit next to the operand tiles) against the check mode."""
+    cfg_path = os.path.join(CONFIG_DIR, 'vilbert.json')
+    cfg = ModelConfig(cfg_path)
+    sd = synth_state_dict(cfg, 228, 2, 'mild')
+    batch = make_batch(3, 248, 88, cfg.v_feature_size, seed=99)
+    gb = {k: v.to(DEV) for k, v in batch.items()}
+    res = {}
+    for precision in ('fp32', 'bf16'):
+        torch.manual_seed(9)
+        params = default_params(cfg_path, device='cuda', max_seq_len=248, max_vis_features=88, L1=False)
+        m = VisualDialogEncoder(params, precision=precision)
+        m.load_state_dict({'bert_pretrained.' + k: v for k, v in sd.items()}, strict=True)
+        m.to(DEV).train()
+        m.zero_grad()
+        loss, _, _, _, scores, reg, _ = glue_forward(m, gb, params)
+        loss.backward()
+        torch.cuda.synchronize()
+        res[precision] = (float(loss.detach()), scores.detach().clone(), m.arena.g32[:m.arena.live_end].clone())
+        del m
+        torch.cuda.empty_cache()
+    (l32, s32, g32), (l16, s16, g16) = res['fp32'], res['bf16']
+    e_logit, e_grad = scale_err(s16, s32), float((g16 - g32).norm() / g32.norm())
+    print(f'stress shape, bf16 vs fp32 check: loss {l16:.5f} / {l32:.5f}, logits {e_logit:.2e}, gradients {e_grad:.2e}')
+    assert abs(l16 - l32) < 2e-2 and e_logit < 6e-2 and e_grad < 0.2
+
+
+def test_question_batch_full_model_bit_identical_to_replicated_layout():
+    """f3 at the real model size: 6 questions / 96 candidate sequences; de-duplicated visual inputs (embedding once per
+    question, fanned out on the device) give the same logits bit for bit as the reference's replicated layout."""
+    from cqa_crct_b200.evaluate import evaluate_batch, expand_question_batch
+    from cqa_crct_b200.synthetic import make_question_batch
+    cfg_path = os.path.join(CONFIG_DIR, 'vilbert.json')
+    cfg = ModelConfig(cfg_path)
+    sd = synth_state_dict(cfg, 228, 2, 'mild')
+    params = default_params(cfg_path, device='cuda', L1=True)
+    m = VisualDialogEncoder(params)
+    m.load_state_dict({'bert_pretrained.' + k: v for k, v in sd.items()}, strict=True)
+    m.to(DEV).eval()
+    qb = make_question_batch(6, 124, 44, cfg.v_feature_size, seed=3, total=96)
+    out = evaluate_batch(m, qb, params, eval_batch_size=40)               # chunks cut through questions
+    full = {k: v.to(DEV) for k, v in expand_question_batch(qb).items()}
+    with torch.no_grad():
+        scores, reg = glue_forward(m, full, params, evaluation=True)[4:6]
+    assert torch.equal(scores, out['logits'])
+    sel = out['answers'].cpu()
+    off = torch.cumsum(qb['num_ans'], 0) - qb['num_ans']
+    assert torch.equal(out['reg_output'].cpu(), reg[0].cpu()[off + sel])
