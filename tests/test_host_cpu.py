@@ -169,3 +169,41 @@ def test_optimizer_range_and_bucket_bookkeeping():
         assert hi == lo2 and lo % 64 == 0 and hi % 64 == 0
     assert blocks[-1][1] == a.offsets['bert.t_pooler.dense.weight'] and a.live_end % 64 == 0
     assert a.live_end <= a.total and sum(p.numel for p in a.spec if p.live) <= a.live_end
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """Every argument struct of include/crct_b200.h against its ctypes mirror in cqa_crct_b200/_lib.py: same size, same field
+    offsets in order — compiled from the header with gcc, so a field added on one side only cannot pass silently."""
+    import subprocess
+    pairs = {'crct_gemm_t': L.GemmArgs, 'crct_ln_bwd_t': L.LnBwdArgs, 'crct_embed_text_t': L.EmbedTextArgs,
+             'crct_embed_text_bwd_t': L.EmbedTextBwdArgs, 'crct_embed_vis_t': L.EmbedVisArgs, 'crct_embed_vis_bwd_t': L.EmbedVisBwdArgs,
+             'crct_attn_fwd_t': L.AttnFwdArgs, 'crct_attn_bwd_t': L.AttnBwdArgs, 'crct_linear_t': L.LinearArgs, 'crct_loss_t': L.LossArgs,
+             'crct_adamw_t': L.AdamWArgs, 'crct_select_t': L.SelectArgs, 'crct_score_t': L.ScoreArgs}
+    hdr_path = os.path.join(ROOT, 'include', 'crct_b200.h')
+    text = re.sub(r'/\*.*?\*/', '', open(hdr_path).read(), flags=re.S)
+    structs = dict((name, body) for body, name in re.findall(r'typedef struct \{(.*?)\}\s*(\w+);', text, flags=re.S))
+    assert set(pairs) <= set(structs), set(pairs) - set(structs)
+    assert {n for n in structs if n.startswith('crct_')} == set(pairs), 'a header struct has no ctypes mirror in this test'
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{hdr_path}"', 'int main(void) {']
+    for name in pairs:
+        fields = []
+        for decl in structs[name].split(';'):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for d in decl.split(','):
+                fields.append(re.sub(r'\[.*?\]', '', d).replace('*', ' ').split()[-1])
+        lines.append(f'  printf("{name} %zu", sizeof({name}));')
+        lines += [f'  printf(" %zu", offsetof({name}, {f}));' for f in fields]
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-std=c11', '-o', str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for row in out.strip().splitlines():
+        name, size, *offs = row.split()
+        cls = pairs[name]
+        assert int(size) == __import__('ctypes').sizeof(cls), name
+        assert [int(o) for o in offs] == [getattr(cls, f).offset for f, _ in cls._fields_], name
