@@ -207,3 +207,28 @@ def test_ctypes_structures_match_the_header_layout(tmp_path):
         cls = pairs[name]
         assert int(size) == __import__('ctypes').sizeof(cls), name
         assert [int(o) for o in offs] == [getattr(cls, f).offset for f, _ in cls._fields_], name
+
+
+def test_library_is_callable_from_plain_c(tmp_path):
+    """The boundary is a C ABI, not a Python extension: a C program that includes include/crct_b200.h and links
+    libcrct_b200.so calls it without torch.  Without a GPU the device check must fail with a status and a message."""
+    import subprocess
+    src = tmp_path / 'use.c'
+    src.write_text('#include <stdio.h>\n#include "crct_b200.h"\n'
+                   'int main(void) {\n'
+                   '  int v = crct_version();\n'
+                   '  int rc = crct_device_check();\n'
+                   '  crct_gemm_t g = {0};\n'
+                   '  int rc2 = crct_gemm_bf16(&g, 0);\n'
+                   '  printf("%d|%d|%d|%s\\n", v, rc, rc2, crct_last_error());\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / 'use'
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.run(['gcc', '-std=c11', '-I', os.path.join(ROOT, 'include'), '-o', str(exe), str(src), '-L', libdir, '-l:libcrct_b200.so',
+                    f'-Wl,-rpath,{libdir}'], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip()
+    v, rc, rc2, msg = out.split('|', 3)
+    assert int(v) >= 100
+    assert int(rc2) != 0 and msg                      # null operands are rejected with a message, never dereferenced
+    if not torch.cuda.is_available():
+        assert int(rc) != 0
