@@ -232,3 +232,20 @@ def test_library_is_callable_from_plain_c(tmp_path):
     assert int(rc2) != 0 and msg                      # null operands are rejected with a message, never dereferenced
     if not torch.cuda.is_available():
         assert int(rc) != 0
+
+
+def test_dropout8_equals_elementwise_keep_native(tmp_path):
+    """csrc/common.cuh: `dropout8` (what the GEMM epilogue, LayerNorm and embedding kernels call on 8-element chunks) against
+    `crct_keep` (what the attention kernels and the fp32 check mode evaluate per element) — the forward/backward and the
+    bf16/fp32 mask agreement rests on these two being the same function.  Built and run on the host with nvcc."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    exe = tmp_path / 'dropout8_check'
+    subprocess.run([nvcc, '-std=c++17', '-O2', '--expt-relaxed-constexpr', '-gencode', 'arch=compute_100a,code=sm_100a',
+                    '-I', os.path.join(ROOT, 'cqa_crct_b200', 'csrc'), '-o', str(exe), os.path.join(ROOT, 'tests', 'native', 'dropout8_check.cu')],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith('0 mismatches'), out.stdout
