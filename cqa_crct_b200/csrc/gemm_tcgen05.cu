@@ -709,6 +709,7 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
         CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: leading dimensions must be multiples of 8 elements");
     if (((uintptr_t)a->A | (uintptr_t)a->B | (uintptr_t)a->D | (uintptr_t)a->D2 | (uintptr_t)a->aux | (uintptr_t)a->bias) & 15)
         CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: pointers must be 16-byte aligned");
+    if (a->epilogue < CRCT_EPI_BIAS || a->epilogue > CRCT_EPI_F32) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: unknown epilogue %d", a->epilogue);
     if ((a->epilogue == CRCT_EPI_MUL) && !a->aux) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: MUL epilogue needs aux");
     const bool f32 = a->epilogue == CRCT_EPI_F32;
     int split_k = a->split_k;

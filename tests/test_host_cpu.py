@@ -249,3 +249,42 @@ def test_dropout8_equals_elementwise_keep_native(tmp_path):
                    check=True, capture_output=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith('0 mismatches'), out.stdout
+
+
+def test_argument_validation_returns_status_and_message():
+    """Error behaviour of the boundary: bad arguments are rejected on the host with a negative crct_status_t and
+    a message in crct_last_error() before anything is launched — no exception, no crash, no fallback.  Runs without a GPU."""
+    import ctypes as C
+    lib = L.lib()
+    msg = lambda: lib.crct_last_error().decode()
+    buf = (C.c_char * 4096)()
+    p = (C.addressof(buf) + 255) & ~255
+    ARG, SHAPE = -1, -4
+    g = L.GemmArgs()
+    assert lib.crct_gemm_bf16(C.byref(g), None) == ARG and 'null pointer' in msg()
+    g.A = g.B = g.D = p
+    g.M, g.N, g.K, g.lda, g.ldb, g.ldd = 128, 100, 64, 64, 64, 104
+    assert lib.crct_gemm_bf16(C.byref(g), None) == SHAPE and 'multiple of 8' in msg()
+    g.N, g.ldd, g.epilogue = 128, 128, 9
+    assert lib.crct_gemm_bf16(C.byref(g), None) == ARG and 'unknown epilogue' in msg()
+    g.epilogue = L.EPI_MUL
+    assert lib.crct_gemm_bf16(C.byref(g), None) == ARG and 'needs aux' in msg()
+    g.epilogue, g.A = L.EPI_BIAS, p + 2
+    assert lib.crct_gemm_bf16(C.byref(g), None) == ARG and '16-byte aligned' in msg()
+    a = L.AttnFwdArgs()
+    a.q = a.k = a.v = a.mask_add = a.out = p
+    a.B, a.nh, a.dh, a.Lq, a.Lk = 1, 2, 40, 8, 8
+    a.ldq = a.ldk = a.ldv = a.ldo = 80
+    assert lib.crct_attn_fwd(C.byref(a), None) == SHAPE and 'head dim 40' in msg()
+    assert lib.crct_layernorm_fwd(p, p, p, p, None, None, 4, 2048, None) == SHAPE and 'row width 2048' in msg()
+    assert lib.crct_layernorm_fwd(p, p, p, p, p, None, 4, 768, None) == ARG
+    assert lib.crct_expand_blocks(p, p, p, 4, 6, None) == ARG
+    assert lib.crct_select_answers(C.byref(L.SelectArgs()), None) == ARG and 'null pointer' in msg()
+    lin = L.LinearArgs()
+    lin.A = lin.B = lin.C = p
+    lin.M = lin.N = lin.K = 4
+    lin.act = 7
+    assert lib.crct_linear_f32(C.byref(lin), None) == ARG and 'unknown activation' in msg()
+    assert lib.crct_linear_f32_batched(C.byref(lin), 13, None) == ARG
+    f = L.GemmArgs()
+    assert lib.crct_f32_gemm(C.byref(f), None) == ARG and 'crct_f32_gemm' in msg()
