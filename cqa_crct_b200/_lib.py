@@ -103,7 +103,7 @@ EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf
            'crct_additive_mask', 'crct_layernorm_fwd', 'crct_layernorm_bwd', 'crct_layernorm_bwd_params', 'crct_colsum_bf16', 'crct_softmax_rows',
            'crct_embed_text_fwd', 'crct_embed_text_bwd', 'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd',
            'crct_attn_bwd', 'crct_linear_f32', 'crct_linear_f32_batched', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
-           'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_bump_salt', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw',
+           'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_bump_salt', 'crct_bump_salt_to', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw',
            'crct_expand_blocks', 'crct_select_answers', 'crct_score_answers',
            'crct_f32_gemm', 'crct_f32_layernorm_fwd', 'crct_f32_layernorm_bwd', 'crct_f32_layernorm_bwd_params', 'crct_f32_attn_fwd',
            'crct_f32_attn_bwd', 'crct_f32_embed_text_fwd', 'crct_f32_embed_text_bwd', 'crct_f32_embed_vis_fwd', 'crct_f32_embed_vis_bwd',
@@ -142,6 +142,7 @@ def lib():
         _lib.crct_pool_mul_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
         _lib.crct_pool_mul_bwd.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
         _lib.crct_bump_salt.argtypes = [vp, vp]
+        _lib.crct_bump_salt_to.argtypes = [vp, vp, vp]
         for name in ('crct_gemm_bf16', 'crct_layernorm_bwd', 'crct_layernorm_bwd_params', 'crct_embed_text_fwd', 'crct_embed_text_bwd',
                      'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd', 'crct_attn_bwd', 'crct_linear_f32',
                      'crct_hybrid_loss', 'crct_adamw', 'crct_select_answers', 'crct_score_answers', 'crct_f32_gemm', 'crct_f32_layernorm_bwd',
@@ -400,8 +401,10 @@ def scale_rows(x, s, out):
     check(lib().crct_scale_rows(ptr(x), ptr(s), 1 if s.numel() == B else 0, ptr(out), B, n, stream_ptr()))
 
 
-def bump_salt(salt):
-    check(lib().crct_bump_salt(ptr(salt), stream_ptr()))
+def bump_salt(salt, snapshot=None):
+    if snapshot is None:
+        return check(lib().crct_bump_salt(ptr(salt), stream_ptr()))
+    check(lib().crct_bump_salt_to(ptr(salt), ptr(snapshot), stream_ptr()))
 
 
 def adamw(w, g, m, v, w_bf16, group, n, lr4, wd4, beta1, beta2, eps, step, grad_scale=1.0, dyn=None):

@@ -683,11 +683,13 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_vis_bwd_kernel(const VisEmb
     }
 }
 
-__global__ void bump_salt_kernel(unsigned long long* salt) {
+__global__ void bump_salt_kernel(unsigned long long* salt, unsigned long long* snapshot) {
     unsigned long long z = *salt + 0x9E3779B97F4A7C15ull;          // splitmix64 step
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    *salt = z ^ (z >> 31);
+    z ^= z >> 31;
+    *salt = z;
+    if (snapshot) *snapshot = z;
 }
 
 inline int check_row_width(int H, const char* what) {
@@ -700,7 +702,14 @@ inline int row_grid(int rows) { return (rows + ROW_THREADS / 32 - 1) / (ROW_THRE
 
 extern "C" CRCT_API int crct_bump_salt(uint64_t* salt, crct_stream_t s) {
     if (!salt) CRCT_FAIL(CRCT_ERR_ARG, "crct_bump_salt: null pointer");
-    bump_salt_kernel<<<1, 1, 0, as_stream(s)>>>(reinterpret_cast<unsigned long long*>(salt));
+    bump_salt_kernel<<<1, 1, 0, as_stream(s)>>>(reinterpret_cast<unsigned long long*>(salt), nullptr);
+    CRCT_LAUNCH_CHECK();
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_bump_salt_to(uint64_t* salt, uint64_t* snapshot, crct_stream_t s) {
+    if (!salt || !snapshot) CRCT_FAIL(CRCT_ERR_ARG, "crct_bump_salt_to: null pointer");
+    bump_salt_kernel<<<1, 1, 0, as_stream(s)>>>(reinterpret_cast<unsigned long long*>(salt), reinterpret_cast<unsigned long long*>(snapshot));
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }

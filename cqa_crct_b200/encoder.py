@@ -48,6 +48,7 @@ class ParamArena:
         self.g32: Optional[torch.Tensor] = None
         self.w16: Optional[torch.Tensor] = None
         self._w16_version = -1
+        self.param_views: List[torch.Tensor] = []      # the nn.Parameters viewing w32 (set by the encoder)
 
     def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
         p = self.by_name[name]
@@ -73,14 +74,25 @@ class ParamArena:
             self.w16 = torch.empty(self.total, dtype=torch.bfloat16, device=self.w32.device)
             self._w16_version = -1
 
+    def version(self):
+        """Changes whenever a master weight may have changed: in-place writes to the arena itself AND to any of the
+        nn.Parameter views (after `.to()` / `.cuda()` rebinds `prm.data`, a view no longer shares the arena's version counter:
+        load_state_dict, torch.optim optimizers and manual `copy_` bump only the parameter's own counter)."""
+        return self.w32._version + sum(p._version for p in self.param_views)
+
     def refresh_bf16(self):
         """Re-cast the operand copy if any master weight changed since the last cast."""
-        if self._w16_version != self.w32._version:
+        v = self.version()
+        if self._w16_version != v:
             L.cast_f32_to_bf16(self.w32, self.w16)
-            self._w16_version = self.w32._version
+            self._w16_version = v
 
     def mark_bf16_fresh(self):
-        self._w16_version = self.w32._version
+        self._w16_version = self.version()
+
+    def invalidate(self):
+        """Force the next forward to re-cast the bf16 operand copy (for writers that bypass torch's version counters)."""
+        self._w16_version = -1
 
 
 class _Node(nn.Module):
@@ -184,6 +196,7 @@ class VisualDialogEncoder(nn.Module):
         for alias, src in TIED.items():
             _attach(root, alias, self._params_by_name[src])
         self.bert_pretrained = root
+        self.arena.param_views = list(self._params_by_name.values())
         self._step = 0                       # site seeds are launch constants; per-step variation comes from the device salt
         self._salt = None                    # int64[1] on the device, advanced by crct_bump_salt once per training forward
         self.grad_ready_hook = None          # set by cqa_crct_b200.parallel.DistributedDataParallel
@@ -242,6 +255,28 @@ class VisualDialogEncoder(nn.Module):
         return self.arena.w32, self.arena.g32, self.arena.w16
 
     # ------------------------------------------------------------------ small helpers
+    def _pass_salt(self, dev):
+        """Dropout salt of one forward pass.  The live counter `self._salt` (one device word, seeded from torch's seed and the
+        data-parallel RANK — the reference never seeds, so its ranks draw independent masks, CRCT/train.py:55) is advanced
+        once per training forward; the pass and its backward read a per-pass SNAPSHOT of it, so two forwards before the
+        first backward each recompute their own masks."""
+        if self._salt is None or self._salt.device != dev:
+            rank = 0
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                rank = torch.distributed.get_rank()
+            z = (rank + 1) * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF          # splitmix64(rank)
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+            z ^= z >> 31
+            seed = ((torch.initial_seed() * 0x9E3779B97F4A7C15) ^ (z if rank else 0)) & 0x7FFFFFFFFFFFFFFF
+            self._salt = torch.full((1,), seed, dtype=torch.int64, device=dev)
+        snap = self._salt
+        if self.training:
+            snap = torch.empty(1, dtype=torch.int64, device=dev)
+            L.bump_salt(self._salt, snap)
+        L.SALT = snap
+        return snap
+
     def _wflat(self):        # GEMM operand arena: the bf16 copy, or the fp32 masters themselves in check mode
         return self.arena.w32 if self.fp32 else self.arena.w16
 
@@ -726,7 +761,7 @@ class VisualDialogEncoder(nn.Module):
         from the tail of the arena (heads) to its head (embeddings).  `graph.GraphedTrainStep` drives it directly to
         cut the captured step into segments between which the bucketed all-reduces are launched."""
         cfg, arena = self.cfg, self.arena
-        L.SALT = self._salt
+        L.SALT = sv.salt                   # the word THIS pass's forward drew its masks with (not the live counter)
         B, T, R = sv.B, sv.T, sv.R
         dt, dv = self._heads_bwd(sv.heads, d_nsp, d_reg, B, T, R)
         dev = dt.device
@@ -816,14 +851,11 @@ class VisualDialogEncoder(nn.Module):
         B, T = ids.shape
         seq_len = torch.gather(batch['sep_indices'], 1, batch['hist_len'].view(-1, 1)).squeeze(1) + 1       # encoder_decorator.py:118-119
         amask = torch.arange(T, device=dev).unsqueeze(0) < seq_len.unsqueeze(1)
-        if self._salt is None or self._salt.device != dev:
-            self._salt = torch.full((1,), (torch.initial_seed() * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF, dtype=torch.int64, device=dev)
-        L.SALT = self._salt
-        if self.training:
-            L.bump_salt(self._salt)
+        salt = self._pass_salt(dev)
         logits, outs, scalars, _, sv = self._run_forward(
             ids, batch['segments'], batch['loc'], batch['image_feat'], batch['image_loc'], batch['image_target'], amask,
             batch['image_mask'], batch['next_sentence_labels'].view(-1), batch['R'], 'L1_smooth', True)
+        sv.salt = salt
         self.last_scalars, self.last_logits, self.last_reg = scalars, logits, outs
         d_nsp = torch.full((1,), float(nsp_coeff), dtype=torch.float32, device=dev)
         d_reg = torch.full((B,), float(reg_coeff) / B, dtype=torch.float32, device=dev)      # d mean_B(reg_loss) / d reg_loss[b]
@@ -875,11 +907,7 @@ class VisualDialogEncoder(nn.Module):
         Rt = cvt(Rt, torch.float32)
         labels = cvt(next_sentence_label, torch.int64).view(-1) if train_branch else None
         keep = train_branch and torch.is_grad_enabled()
-        if self._salt is None or self._salt.device != dev:
-            self._salt = torch.full((1,), (torch.initial_seed() * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF, dtype=torch.int64, device=dev)
-        L.SALT = self._salt
-        if self.training:
-            L.bump_salt(self._salt)          # fresh dropout masks for this step (also on CUDA-graph replay)
+        salt = self._pass_salt(dev)         # fresh dropout masks for this pass (also on CUDA-graph replay)
         group = cvt(image_group, torch.int64)
         if group is not None and train_branch:
             raise ValueError('image_group is an inference-only input')
@@ -887,7 +915,7 @@ class VisualDialogEncoder(nn.Module):
         reg_pred, reg_loss, reg_l1, reg_dist = outs
         nsp_loss = scalars[1:2]
         if keep:
-            sv.nsp_loss, sv.reg_loss = nsp_loss, reg_loss
+            sv.nsp_loss, sv.reg_loss, sv.salt = nsp_loss, reg_loss, salt
             anchor = self._params_by_name['bert.embeddings.word_embeddings.weight']
             nsp_loss, reg_loss = _CrctFunction.apply(anchor, self, sv)
         reg = [reg_pred, reg_loss, reg_l1, (scalars[3], scalars[4]), reg_dist]          # vilbert.py:1590-1648 (counts stay on device)

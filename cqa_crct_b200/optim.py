@@ -20,6 +20,8 @@ _NO_DECAY = ('bias', 'LayerNorm.bias', 'LayerNorm.weight')          # CRCT/utils
 
 
 class FusedAdamW:
+    _DYN_SLOTS = 8
+
     def __init__(self, model, lr: float = 2e-5, image_lr: float = 2e-5, weight_decay: float = 0.01,
                  betas=(0.9, 0.999), eps: float = 1e-8, language_weights: Optional[str] = None):
         enc = getattr(model, 'module', model)
@@ -78,17 +80,28 @@ class FusedAdamW:
     def enable_device_scalars(self):
         dev = self.enc.arena.w32.device
         self.dyn = torch.zeros(6, dtype=torch.float32, device=dev)
-        self._dyn_host = torch.zeros(6, dtype=torch.float32).pin_memory()
+        # ring of pinned slots, one event each: the host never rewrites a slot whose host->device copy may still be queued
+        # (a loop that enqueues steps without synchronising would otherwise hand step n the scalars of step n + k)
+        self._dyn_host = torch.zeros(self._DYN_SLOTS, 6, dtype=torch.float32).pin_memory()
+        self._dyn_events = [None] * self._DYN_SLOTS
+        self._dyn_slot = 0
 
     def push_device_scalars(self):
         """Advance the step counter and upload {lr[4], bias corrections} (call right before replaying a captured step)."""
         self.step_count += 1
         lrs = self.current_lrs()
-        h = self._dyn_host
+        slot = self._dyn_slot
+        self._dyn_slot = (slot + 1) % self._DYN_SLOTS
+        if self._dyn_events[slot] is not None:
+            self._dyn_events[slot].synchronize()         # the copy issued _DYN_SLOTS pushes ago has left this slot
+        h = self._dyn_host[slot]
         h[0], h[1], h[2], h[3] = lrs
         h[4] = 1.0 - self.betas[0] ** self.step_count
         h[5] = (1.0 - self.betas[1] ** self.step_count) ** 0.5
         self.dyn.copy_(h, non_blocking=True)
+        ev = self._dyn_events[slot] or torch.cuda.Event()
+        ev.record()
+        self._dyn_events[slot] = ev
 
     def step_captured(self, grad_scale: float = 1.0):
         """The launch to put INSIDE a CUDA graph: identical kernel, scalars taken from `self.dyn`."""

@@ -194,8 +194,12 @@ def train(gpu: int, params: dict) -> dict:
                     optimizer.zero_grad()
                     scheduler.step()
                     num_step_iterations += 1
+            n_reg = float(batch['needs_reg'].sum())                    # host tensor: no device sync (train.py:170)
+            # train.py:174-179: the logged regression loss is the mean over the rows that NEED regression (0 when there are
+            # none); regression[1] is dense with zeros elsewhere, so mean_B * B / n_reg is that mean
+            vec[2] *= vec.new_tensor(batch['needs_reg'].numel() / max(n_reg, 1.0))
             stats[:5] += vec
-            stats[5] += batch['needs_reg'].sum().item()                # host tensor: no device sync
+            stats[5] += n_reg
             seen += 1
             if (iter_id + 1) % PRINT_EVERY == 0 or iter_id + 1 == len(dataloader):           # :226-279, read once per window
                 s = stats.clone()

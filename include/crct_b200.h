@@ -243,6 +243,10 @@ int crct_pool_mul_bwd(const float* dpooled, const float* pt, const float* pv, fl
  * launch constant; `salt` is one device word the training loop advances once per step with this kernel, so a step
  * captured in a CUDA graph draws fresh masks on every replay while forward and backward of one step still agree. */
 int crct_bump_salt(uint64_t* salt, crct_stream_t stream);
+/* Same step, and the new value is also written to `snapshot`: one word per forward pass, which that pass and ITS backward
+ * pass both read — a second forward before the first one's backward (l1 = model(a); l2 = model(b); (l1 + l2).backward(),
+ * allowed by the reference because autograd stores its masks) then still recomputes the masks of its own forward. */
+int crct_bump_salt_to(uint64_t* salt, uint64_t* snapshot, crct_stream_t stream);
 /* Hybrid loss, metrics and (when dlogits/dpre are given) the gradients of
  *   loss = nsp_coeff * CE(logits, labels; ignore -1) + reg_coeff * mean_B(reg_loss)
  * R[b] = (value, needs_regression, tolerance, scale).  labels NULL = inference (no CE).  Outputs are dense [B]
