@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('CRCT_B200_LIB') or os.path.join(_HERE, 'libcrct_b200.so')      # override: A/B runs of two builds
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL, EPI_F32 = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL, EPI_F32, EPI_BIAS_RES_F32 = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
 
 vp, i32, i64, f32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
@@ -27,47 +27,50 @@ class GemmArgs(C.Structure):
     _fields_ = [('A', vp), ('B', vp), ('D', vp), ('D2', vp), ('bias', vp), ('aux', vp),
                 ('M', i32), ('N', i32), ('K', i32), ('lda', i32), ('ldb', i32), ('ldd', i32), ('ldaux', i32),
                 ('a_major', i32), ('b_major', i32), ('epilogue', i32), ('accumulate', i32), ('split_k', i32),
-                ('block_n', i32), ('dropout_p', f32), ('seed', u64), ('max_ctas', i32), ('cta_group', i32), ('dbg', i32 * 7), ('salt', vp)]
+                ('block_n', i32), ('dropout_p', f32), ('seed', u64), ('max_ctas', i32), ('cta_group', i32), ('dbg', i32 * 7), ('salt', vp),
+                ('a_rows_dev', vp)]
 
 
 class LnBwdArgs(C.Structure):
     _fields_ = [('dy', vp), ('z', vp), ('mean', vp), ('rstd', vp), ('gamma', vp), ('dz', vp), ('dzm', vp),
                 ('dgamma', vp), ('dbeta', vp), ('dbias', vp), ('rows', i32), ('H', i32),
-                ('p_in', f32), ('seed_in', u64), ('p_out', f32), ('seed_out', u64), ('salt', vp)]
+                ('p_in', f32), ('seed_in', u64), ('p_out', f32), ('seed_out', u64), ('salt', vp), ('z_f32', i32), ('rows_dev', vp)]
 
 
 class EmbedTextArgs(C.Structure):
     _fields_ = [('ids', vp), ('types', vp), ('loc', vp), ('word', vp), ('pos', vp), ('type', vp), ('w_loc', vp),
                 ('b_loc', vp), ('gamma', vp), ('beta', vp), ('y', vp), ('z', vp), ('mean', vp), ('rstd', vp),
-                ('B', i32), ('T', i32), ('H', i32), ('max_pos', i32), ('dropout_p', f32), ('seed', u64), ('salt', vp)]
+                ('B', i32), ('T', i32), ('H', i32), ('max_pos', i32), ('dropout_p', f32), ('seed', u64), ('salt', vp),
+                ('z_f32', i32), ('src_row', vp), ('rows_dev', vp)]
 
 
 class EmbedTextBwdArgs(C.Structure):
     _fields_ = [('ids', vp), ('types', vp), ('loc', vp), ('dz', vp), ('g_word', vp), ('g_pos', vp), ('g_type', vp),
-                ('g_wloc', vp), ('g_bloc', vp), ('B', i32), ('T', i32), ('H', i32)]
+                ('g_wloc', vp), ('g_bloc', vp), ('B', i32), ('T', i32), ('H', i32), ('src_row', vp), ('rows_dev', vp)]
 
 
 class EmbedVisArgs(C.Structure):
     _fields_ = [('g', vp), ('box', vp), ('cls', vp), ('w_loc', vp), ('b_loc', vp), ('color', vp), ('gamma', vp),
                 ('beta', vp), ('y', vp), ('z', vp), ('mean', vp), ('rstd', vp), ('rows', i32), ('H', i32),
-                ('dropout_p', f32), ('seed', u64), ('salt', vp)]
+                ('dropout_p', f32), ('seed', u64), ('salt', vp), ('z_f32', i32), ('src_row', vp), ('rows_dev', vp)]
 
 
 class EmbedVisBwdArgs(C.Structure):
-    _fields_ = [('dz', vp), ('box', vp), ('cls', vp), ('g_color', vp), ('g_wloc', vp), ('rows', i32), ('H', i32)]
+    _fields_ = [('dz', vp), ('box', vp), ('cls', vp), ('g_color', vp), ('g_wloc', vp), ('rows', i32), ('H', i32), ('src_row', vp),
+                ('rows_dev', vp)]
 
 
 class AttnFwdArgs(C.Structure):
     _fields_ = [('q', vp), ('k', vp), ('v', vp), ('ldq', i32), ('ldk', i32), ('ldv', i32), ('mask_add', vp),
                 ('out', vp), ('ldo', i32), ('lse', vp), ('B', i32), ('nh', i32), ('dh', i32), ('Lq', i32), ('Lk', i32),
-                ('dropout_p', f32), ('seed', u64), ('salt', vp)]
+                ('dropout_p', f32), ('seed', u64), ('salt', vp), ('cu_q', vp), ('cu_k', vp)]
 
 
 class AttnBwdArgs(C.Structure):
     _fields_ = [('q', vp), ('k', vp), ('v', vp), ('ldq', i32), ('ldk', i32), ('ldv', i32), ('mask_add', vp),
                 ('out', vp), ('ldo', i32), ('dout', vp), ('lddo', i32), ('lse', vp), ('dq', vp), ('dk', vp), ('dv', vp),
                 ('lddq', i32), ('lddk', i32), ('lddv', i32), ('B', i32), ('nh', i32), ('dh', i32), ('Lq', i32),
-                ('Lk', i32), ('dropout_p', f32), ('seed', u64), ('salt', vp)]
+                ('Lk', i32), ('dropout_p', f32), ('seed', u64), ('salt', vp), ('cu_q', vp), ('cu_k', vp)]
 
 
 class LinearArgs(C.Structure):
@@ -105,6 +108,7 @@ EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf
            'crct_attn_bwd', 'crct_linear_f32', 'crct_linear_f32_batched', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
            'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_bump_salt', 'crct_bump_salt_to', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw',
            'crct_expand_blocks', 'crct_select_answers', 'crct_score_answers',
+           'crct_row_map', 'crct_group_map', 'crct_gather_rows', 'crct_gather_rows_f32', 'crct_scatter_rows_f32', 'crct_fill_zero',
            'crct_f32_gemm', 'crct_f32_layernorm_fwd', 'crct_f32_layernorm_bwd', 'crct_f32_layernorm_bwd_params', 'crct_f32_attn_fwd',
            'crct_f32_attn_bwd', 'crct_f32_embed_text_fwd', 'crct_f32_embed_text_bwd', 'crct_f32_embed_vis_fwd', 'crct_f32_embed_vis_bwd',
            'crct_f32_softmax_rows', 'crct_f32_gather_first', 'crct_f32_scatter_first']
@@ -126,9 +130,15 @@ def lib():
             getattr(_lib, name)          # fail loudly on a stale library
         _lib.crct_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]
         _lib.crct_additive_mask.argtypes = [vp, C.c_int, vp, C.c_int, vp]
-        _lib.crct_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
-        _lib.crct_colsum_bf16.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
-        _lib.crct_softmax_rows.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        _lib.crct_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+        _lib.crct_colsum_bf16.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+        _lib.crct_softmax_rows.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        _lib.crct_row_map.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+        _lib.crct_group_map.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+        _lib.crct_gather_rows.argtypes = [vp, vp, vp, C.c_int, C.c_longlong, vp, vp]
+        _lib.crct_gather_rows_f32.argtypes = [vp, C.c_longlong, vp, vp, C.c_int, C.c_int, vp]
+        _lib.crct_scatter_rows_f32.argtypes = [vp, vp, C.c_longlong, vp, C.c_int, C.c_int, vp]
+        _lib.crct_fill_zero.argtypes = [vp, C.c_size_t, vp]
         _lib.crct_gather_first.argtypes = [vp, C.c_longlong, vp, C.c_int, C.c_int, vp]
         _lib.crct_scatter_first.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, vp]
         _lib.crct_colsum_f32.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, vp]
@@ -189,7 +199,7 @@ def _f32(t, what):
 
 def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None, aux=None, D2=None,
          lda=None, ldb=None, ldd=None, ldaux=None, accumulate=0, split_k=0, block_n=0, dropout_p=0.0, seed=0,
-         max_ctas=0, dbg=None, cta_group=0):
+         max_ctas=0, dbg=None, cta_group=0, rows_dev=None):
     """D[M,N] = epilogue(A·Bᵀ) — see include/crct_b200.h for operand majors.  fp32 operands select the check-mode kernel."""
     f32 = _is32(A)
     if f32:
@@ -197,7 +207,7 @@ def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None
             _f32(t, w)
     else:
         _bf16(A, 'A'); _bf16(B, 'B'); _bf16(aux, 'aux'); _bf16(D2, 'D2'); _f32(bias, 'bias')
-        if epilogue == EPI_F32:
+        if epilogue in (EPI_F32, EPI_BIAS_RES_F32):
             _f32(D, 'D')
         else:
             _bf16(D, 'D')
@@ -212,6 +222,9 @@ def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None
     a.accumulate, a.split_k, a.block_n = accumulate, split_k, block_n
     a.dropout_p, a.seed, a.max_ctas, a.cta_group = dropout_p, seed, max_ctas, cta_group
     a.salt = ptr(SALT)
+    a.a_rows_dev = ptr(rows_dev)
+    if f32 and rows_dev is not None:
+        raise CrctError('the fp32 check mode runs the padded layout (no device-side row counts)')
     if dbg is not None:
         for i, v in enumerate(dbg):
             a.dbg[i] = v
@@ -230,59 +243,66 @@ def additive_mask(mask, out):
     check(lib().crct_additive_mask(ptr(mask), kind, ptr(out), mask.numel(), stream_ptr()))
 
 
-def layernorm_fwd(z, gamma, beta, y, mean=None, rstd=None):
+def layernorm_fwd(z, gamma, beta, y, mean=None, rstd=None, rows_dev=None):
+    """y bf16 <- LayerNorm(z), z bf16 or fp32 (production keeps the pre-LayerNorm sum in fp32); fp32 y selects the check mode."""
     rows, H = z.shape
-    if _is32(z):
-        _f32(y, 'y'); _f32(gamma, 'gamma')
+    if _is32(y):
+        _f32(z, 'z'); _f32(gamma, 'gamma')
         return check(lib().crct_f32_layernorm_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, H, stream_ptr()))
-    _bf16(z, 'z'); _bf16(y, 'y'); _f32(gamma, 'gamma')
-    check(lib().crct_layernorm_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, H, stream_ptr()))
+    _bf16(y, 'y'); _f32(gamma, 'gamma')
+    if not _is32(z):
+        _bf16(z, 'z')
+    check(lib().crct_layernorm_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, H, int(_is32(z)), ptr(rows_dev), stream_ptr()))
 
 
-def _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out):
+def _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out, rows_dev=None):
     chk = _f32 if _is32(dy) else _bf16
-    chk(dy, 'dy'); chk(z, 'z'); chk(dz, 'dz'); chk(dzm, 'dzm')
+    chk(dy, 'dy'); chk(dz, 'dz'); chk(dzm, 'dzm')
+    if not _is32(z):
+        chk(z, 'z')
     a = LnBwdArgs()
     a.dy, a.z, a.mean, a.rstd, a.gamma, a.dz, a.dzm = ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(gamma), ptr(dz), ptr(dzm)
     a.dgamma, a.dbeta, a.dbias = ptr(dgamma), ptr(dbeta), ptr(dbias)
     a.rows, a.H = z.shape
     a.p_in, a.seed_in, a.p_out, a.seed_out = p_in, seed_in, p_out, seed_out
     a.salt = ptr(SALT)
+    a.z_f32, a.rows_dev = int(_is32(z) and not _is32(dy)), ptr(rows_dev)
     return a
 
 
 def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dgamma=None, dbeta=None, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0,
-                  seed_out=0):
+                  seed_out=0, rows_dev=None):
     """dgamma = dbeta = dbias = None: input gradient only (see layernorm_bwd_params)."""
-    a = _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out)
+    a = _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out, rows_dev)
     check((lib().crct_f32_layernorm_bwd if _is32(dy) else lib().crct_layernorm_bwd)(C.byref(a), stream_ptr()))
 
 
-def layernorm_bwd_params(dy, z, mean, rstd, dz, dgamma, dbeta, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0):
+def layernorm_bwd_params(dy, z, mean, rstd, dz, dgamma, dbeta, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0, rows_dev=None):
     """Column sums of the split LayerNorm backward: dgamma, dbeta and (from dzm, or dz when p_out == 0) dbias."""
-    a = _ln_bwd_args(dy, z, mean, rstd, None, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, 0)
+    a = _ln_bwd_args(dy, z, mean, rstd, None, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, 0, rows_dev)
     check((lib().crct_f32_layernorm_bwd_params if _is32(dy) else lib().crct_layernorm_bwd_params)(C.byref(a), stream_ptr()))
 
 
-def colsum_bf16(x, out, rows=None, N=None, ld=None):
+def colsum_bf16(x, out, rows=None, N=None, ld=None, rows_dev=None):
     rows = x.shape[0] if rows is None else rows
     N = x.shape[1] if N is None else N
     if _is32(x):
         return colsum_f32(x, out, rows, N, x.stride(0) if ld is None else ld)
     _bf16(x, 'x'); _f32(out, 'out')
-    check(lib().crct_colsum_bf16(ptr(x), ptr(out), rows, N, x.stride(0) if ld is None else ld, stream_ptr()))
+    check(lib().crct_colsum_bf16(ptr(x), ptr(out), rows, N, x.stride(0) if ld is None else ld, ptr(rows_dev), stream_ptr()))
 
 
-def softmax_rows(x, out):
-    rows, F = x.shape
+def softmax_rows(x, out, src_row=None, rows_dev=None):
+    """out[r] = softmax(x[src_row[r]]) (src_row None: r); out may have fewer (packed) rows than x."""
+    rows, F = out.shape
     if _is32(out):
         return check(lib().crct_f32_softmax_rows(ptr(x), ptr(out), rows, F, stream_ptr()))
     _f32(x, 'x'); _bf16(out, 'out')
-    check(lib().crct_softmax_rows(ptr(x), ptr(out), rows, F, stream_ptr()))
+    check(lib().crct_softmax_rows(ptr(x), ptr(out), rows, F, ptr(src_row), ptr(rows_dev), stream_ptr()))
 
 
 def embed_text_fwd(ids, types, loc, word, pos, type_, w_loc, b_loc, gamma, beta, y, z=None, mean=None, rstd=None,
-                   dropout_p=0.0, seed=0):
+                   dropout_p=0.0, seed=0, src_row=None, rows_dev=None):
     a = EmbedTextArgs()
     a.ids, a.types, a.loc = ptr(ids), ptr(types), ptr(loc)
     a.word, a.pos, a.type, a.w_loc, a.b_loc, a.gamma, a.beta = (ptr(word), ptr(pos), ptr(type_), ptr(w_loc), ptr(b_loc),
@@ -291,52 +311,59 @@ def embed_text_fwd(ids, types, loc, word, pos, type_, w_loc, b_loc, gamma, beta,
     a.B, a.T = ids.shape
     a.H, a.max_pos = word.shape[1], pos.shape[0]
     a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
+    a.z_f32, a.src_row, a.rows_dev = int(_is32(z) and not _is32(y)), ptr(src_row), ptr(rows_dev)
     check((lib().crct_f32_embed_text_fwd if _is32(y) else lib().crct_embed_text_fwd)(C.byref(a), stream_ptr()))
 
 
-def embed_text_bwd(ids, types, loc, dz, g_word, g_pos, g_type, g_wloc, g_bloc):
+def embed_text_bwd(ids, types, loc, dz, g_word, g_pos, g_type, g_wloc, g_bloc, src_row=None, rows_dev=None):
     a = EmbedTextBwdArgs()
     a.ids, a.types, a.loc, a.dz = ptr(ids), ptr(types), ptr(loc), ptr(dz)
     a.g_word, a.g_pos, a.g_type, a.g_wloc, a.g_bloc = ptr(g_word), ptr(g_pos), ptr(g_type), ptr(g_wloc), ptr(g_bloc)
     a.B, a.T = ids.shape
     a.H = dz.shape[-1]
+    a.src_row, a.rows_dev = ptr(src_row), ptr(rows_dev)
     check((lib().crct_f32_embed_text_bwd if _is32(dz) else lib().crct_embed_text_bwd)(C.byref(a), stream_ptr()))
 
 
-def embed_vis_fwd(g, box, cls, w_loc, b_loc, color, gamma, beta, y, z=None, mean=None, rstd=None, dropout_p=0.0, seed=0):
+def embed_vis_fwd(g, box, cls, w_loc, b_loc, color, gamma, beta, y, z=None, mean=None, rstd=None, dropout_p=0.0, seed=0,
+                  src_row=None, rows_dev=None):
     a = EmbedVisArgs()
     a.g, a.box, a.cls, a.w_loc, a.b_loc, a.color, a.gamma, a.beta = (ptr(g), ptr(box), ptr(cls), ptr(w_loc), ptr(b_loc),
                                                                      ptr(color), ptr(gamma), ptr(beta))
     a.y, a.z, a.mean, a.rstd = ptr(y), ptr(z), ptr(mean), ptr(rstd)
     a.rows, a.H = g.shape
     a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
+    a.z_f32, a.src_row, a.rows_dev = int(_is32(z) and not _is32(y)), ptr(src_row), ptr(rows_dev)
     check((lib().crct_f32_embed_vis_fwd if _is32(y) else lib().crct_embed_vis_fwd)(C.byref(a), stream_ptr()))
 
 
-def embed_vis_bwd(dz, box, cls, g_color, g_wloc):
+def embed_vis_bwd(dz, box, cls, g_color, g_wloc, src_row=None, rows_dev=None):
     a = EmbedVisBwdArgs()
     a.dz, a.box, a.cls, a.g_color, a.g_wloc = ptr(dz), ptr(box), ptr(cls), ptr(g_color), ptr(g_wloc)
     a.rows, a.H = dz.shape
+    a.src_row, a.rows_dev = ptr(src_row), ptr(rows_dev)
     check((lib().crct_f32_embed_vis_bwd if _is32(dz) else lib().crct_embed_vis_bwd)(C.byref(a), stream_ptr()))
 
 
-def attn_fwd(q, k, v, mask_add, out, lse, *, B, nh, dh, Lq, Lk, ldq, ldk, ldv, ldo, dropout_p=0.0, seed=0):
+def attn_fwd(q, k, v, mask_add, out, lse, *, B, nh, dh, Lq, Lk, ldq, ldk, ldv, ldo, dropout_p=0.0, seed=0, cu_q=None, cu_k=None):
     a = AttnFwdArgs()
     a.q, a.k, a.v, a.mask_add, a.out, a.lse = ptr(q), ptr(k), ptr(v), ptr(mask_add), ptr(out), ptr(lse)
     a.ldq, a.ldk, a.ldv, a.ldo = ldq, ldk, ldv, ldo
     a.B, a.nh, a.dh, a.Lq, a.Lk = B, nh, dh, Lq, Lk
     a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
+    a.cu_q, a.cu_k = ptr(cu_q), ptr(cu_k)
     check((lib().crct_f32_attn_fwd if _is32(q) else lib().crct_attn_fwd)(C.byref(a), stream_ptr()))
 
 
 def attn_bwd(q, k, v, mask_add, out, dout, lse, dq, dk, dv, *, B, nh, dh, Lq, Lk, ldq, ldk, ldv, ldo, lddo, lddq, lddk,
-             lddv, dropout_p=0.0, seed=0):
+             lddv, dropout_p=0.0, seed=0, cu_q=None, cu_k=None):
     a = AttnBwdArgs()
     a.q, a.k, a.v, a.mask_add, a.out, a.dout, a.lse = ptr(q), ptr(k), ptr(v), ptr(mask_add), ptr(out), ptr(dout), ptr(lse)
     a.dq, a.dk, a.dv = ptr(dq), ptr(dk), ptr(dv)
     a.ldq, a.ldk, a.ldv, a.ldo, a.lddo, a.lddq, a.lddk, a.lddv = ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv
     a.B, a.nh, a.dh, a.Lq, a.Lk = B, nh, dh, Lq, Lk
     a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
+    a.cu_q, a.cu_k = ptr(cu_q), ptr(cu_k)
     check((lib().crct_f32_attn_bwd if _is32(q) else lib().crct_attn_bwd)(C.byref(a), stream_ptr()))
 
 
@@ -439,3 +466,43 @@ def score_answers(answer, gt_id, needs_reg, sel_dist, sel_l1, tolerance, total, 
     a.answer, a.gt_id, a.needs_reg, a.sel_dist, a.sel_l1 = ptr(answer), ptr(gt_id), ptr(needs_reg), ptr(sel_dist), ptr(sel_l1)
     a.tolerance, a.flags, a.total, a.Q = ptr(tolerance), ptr(flags), ptr(total), answer.numel()
     check(lib().crct_score_answers(C.byref(a), stream_ptr()))
+
+
+# ---- var-len ("packed") rows: include/crct_b200.h "Var-len rows"
+def row_map(mask, cu, src_row):
+    kind = {torch.bool: 0, torch.uint8: 0, torch.int64: 1, torch.float32: 2}.get(mask.dtype)
+    if kind is None:
+        raise CrctError(f'unsupported mask dtype {mask.dtype}')
+    B, Lm = mask.shape
+    assert cu.dtype == torch.int32 and src_row.dtype == torch.int32 and cu.numel() >= B + 1 and src_row.numel() >= B * Lm
+    check(lib().crct_row_map(ptr(mask), kind, B, Lm, ptr(cu), ptr(src_row), stream_ptr()))
+
+
+def group_map(src_cu, group, cu, src_row):
+    assert group.dtype == torch.int64 and cu.dtype == torch.int32 and src_row.dtype == torch.int32
+    check(lib().crct_group_map(ptr(src_cu), ptr(group), group.numel(), ptr(cu), ptr(src_row), stream_ptr()))
+
+
+def gather_rows(src, idx, dst, rows_dev=None):
+    """dst[r] = src[idx[r]] over the leading dimension (16-byte multiples per row)."""
+    assert src.dtype == dst.dtype and idx.dtype == torch.int32 and src.is_contiguous() and dst.is_contiguous()
+    rows = dst.shape[0]
+    per = dst.numel() // max(rows, 1) * dst.element_size()
+    check(lib().crct_gather_rows(ptr(src), ptr(idx), ptr(dst), rows, per, ptr(rows_dev), stream_ptr()))
+
+
+def gather_rows_f32(src, row_index, out):
+    B, H = out.shape
+    _bf16(src, 'src'); _f32(out, 'out')
+    check(lib().crct_gather_rows_f32(ptr(src), src.stride(0), ptr(row_index), ptr(out), B, H, stream_ptr()))
+
+
+def scatter_rows_f32(g, dst, row_index):
+    B, H = g.shape
+    _bf16(dst, 'dst'); _f32(g, 'g')
+    check(lib().crct_scatter_rows_f32(ptr(g), ptr(dst), dst.stride(0), ptr(row_index), B, H, stream_ptr()))
+
+
+def fill_zero(t):
+    assert t.is_contiguous()
+    check(lib().crct_fill_zero(ptr(t), t.numel() * t.element_size(), stream_ptr()))

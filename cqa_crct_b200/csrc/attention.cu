@@ -96,6 +96,7 @@ struct FwdParams {
     int B, nh, Lq, Lk;
     float scale;
     uint32_t thr; float dscale; uint64_t seed; const unsigned long long* salt;
+    const int* cu_q; const int* cu_k;       // packed rows: sample b owns rows [cu[b], cu[b+1]) (Lq / Lk are then the maxima)
 };
 
 template <int DH>
@@ -105,18 +106,25 @@ __global__ void __launch_bounds__(ATT_THREADS, DH <= 48 ? 5 : 4) attn_fwd_kernel
     extern __shared__ __align__(16) uint8_t smem_raw[];
     pdl_launch_dependents();
     pdl_wait();
-    const int LQP = (p.Lq + 15) & ~15, LKP = (p.Lk + KB - 1) & ~(KB - 1);
+    const int LQP_S = (p.Lq + 15) & ~15, LKP_S = (p.Lk + KB - 1) & ~(KB - 1);       // shared-memory layout: the maxima
     bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
-    bf16* Ks = Qs + LQP * LD;
-    bf16* Vs = Ks + LKP * LD;
-    float* mask_s = reinterpret_cast<float*>(Vs + LKP * LD);
+    bf16* Ks = Qs + LQP_S * LD;
+    bf16* Vs = Ks + LKP_S * LD;
+    float* mask_s = reinterpret_cast<float*>(Vs + LKP_S * LD);
 
     const int b = blockIdx.x / p.nh, h = blockIdx.x % p.nh;
-    load_tile<DH>(Qs, p.q + (size_t)b * p.Lq * p.ldq + h * DH, p.ldq, p.Lq, LQP);
-    load_tile<DH>(Ks, p.k + (size_t)b * p.Lk * p.ldk + h * DH, p.ldk, p.Lk, LKP);
-    load_tile<DH>(Vs, p.v + (size_t)b * p.Lk * p.ldv + h * DH, p.ldv, p.Lk, LKP);
+    // this sample's rows: padded layout b * L, or the packed range [cu[b], cu[b+1])
+    size_t qrow0 = (size_t)b * p.Lq, krow0 = (size_t)b * p.Lk;
+    int Lq = p.Lq, Lk = p.Lk;
+    if (p.cu_q != nullptr) { const int c0 = __ldg(p.cu_q + b); qrow0 = c0; Lq = min(p.Lq, __ldg(p.cu_q + b + 1) - c0); }
+    if (p.cu_k != nullptr) { const int c0 = __ldg(p.cu_k + b); krow0 = c0; Lk = min(p.Lk, __ldg(p.cu_k + b + 1) - c0); }
+    const int LQP = (Lq + 15) & ~15, LKP = (Lk + KB - 1) & ~(KB - 1);
+    load_tile<DH>(Qs, p.q + qrow0 * p.ldq + h * DH, p.ldq, Lq, LQP);
+    load_tile<DH>(Ks, p.k + krow0 * p.ldk + h * DH, p.ldk, Lk, LKP);
+    load_tile<DH>(Vs, p.v + krow0 * p.ldv + h * DH, p.ldv, Lk, LKP);
     // scores are kept in the log2 domain: s2 = s * scale * log2(e) + mask * log2(e), p = 2^(s2 - m2)  (one MUFU.EX2 per element)
-    for (int i = threadIdx.x; i < LKP; i += ATT_THREADS) mask_s[i] = i < p.Lk ? p.mask_add[(size_t)b * p.Lk + i] * LOG2E : -INFINITY;
+    for (int i = threadIdx.x; i < LKP; i += ATT_THREADS)
+        mask_s[i] = i < Lk ? (p.mask_add != nullptr ? p.mask_add[(size_t)b * p.Lk + i] * LOG2E : 0.f) : -INFINITY;
     cp_async_wait_all();
     __syncthreads();
 
@@ -210,12 +218,12 @@ __global__ void __launch_bounds__(ATT_THREADS, DH <= 48 ? 5 : 4) attn_fwd_kernel
 #pragma unroll
         for (int j = 0; j < DH / 8; ++j) {
             const int col = h * DH + j * 8 + 2 * t;
-            if (r0 < p.Lq) *reinterpret_cast<uint32_t*>(p.out + ((size_t)b * p.Lq + r0) * p.ldo + col) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
-            if (r1 < p.Lq) *reinterpret_cast<uint32_t*>(p.out + ((size_t)b * p.Lq + r1) * p.ldo + col) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+            if (r0 < Lq) *reinterpret_cast<uint32_t*>(p.out + (qrow0 + r0) * p.ldo + col) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
+            if (r1 < Lq) *reinterpret_cast<uint32_t*>(p.out + (qrow0 + r1) * p.ldo + col) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
         }
         if (p.lse != nullptr && t == 0) {
-            if (r0 < p.Lq) p.lse[(size_t)blockIdx.x * p.Lq + r0] = (m_run[0] + __log2f(l_run[0])) * LN2;
-            if (r1 < p.Lq) p.lse[(size_t)blockIdx.x * p.Lq + r1] = (m_run[1] + __log2f(l_run[1])) * LN2;
+            if (r0 < Lq) p.lse[(size_t)blockIdx.x * p.Lq + r0] = (m_run[0] + __log2f(l_run[0])) * LN2;
+            if (r1 < Lq) p.lse[(size_t)blockIdx.x * p.Lq + r1] = (m_run[1] + __log2f(l_run[1])) * LN2;
         }
     }
 }
@@ -232,6 +240,7 @@ struct BwdParams {
     int B, nh, Lq, Lk;
     float scale;
     uint32_t thr; float dscale; uint64_t seed; const unsigned long long* salt;
+    const int* cu_q; const int* cu_k;
 };
 
 template <int DH, int PASS>     // PASS 0: this warp owns 16 keys -> dK, dV ; PASS 1: this warp owns 16 queries -> dQ
@@ -246,29 +255,35 @@ __global__ void __launch_bounds__(ATT_THREADS, ((PASS == 2 && DH != 32) || (DH =
     extern __shared__ __align__(16) uint8_t smem_raw[];
     pdl_launch_dependents();
     pdl_wait();
-    const int LQP = (p.Lq + KB - 1) & ~(KB - 1), LKP = (p.Lk + KB - 1) & ~(KB - 1);
+    const int LQP_S = (p.Lq + KB - 1) & ~(KB - 1), LKP_S = (p.Lk + KB - 1) & ~(KB - 1);      // shared-memory layout: the maxima
     bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
-    bf16* dOs = Qs + LQP * LD;
-    bf16* Ks = dOs + LQP * LD;
-    bf16* Vs = Ks + LKP * LD;
-    float* mask_s = reinterpret_cast<float*>(Vs + LKP * LD);
-    float* lse_s = mask_s + LKP;
-    float* D_s = lse_s + LQP;
-    const int LDS = LQP + 8;                                       // dS^T[key][query] row stride: conflict-free 32-bit stores
-    bf16* dSs = reinterpret_cast<bf16*>(D_s + LQP);                // PASS 2 only
+    bf16* dOs = Qs + LQP_S * LD;
+    bf16* Ks = dOs + LQP_S * LD;
+    bf16* Vs = Ks + LKP_S * LD;
+    float* mask_s = reinterpret_cast<float*>(Vs + LKP_S * LD);
+    float* lse_s = mask_s + LKP_S;
+    float* D_s = lse_s + LQP_S;
+    const int LDS = LQP_S + 8;                                     // dS^T[key][query] row stride: conflict-free 32-bit stores
+    bf16* dSs = reinterpret_cast<bf16*>(D_s + LQP_S);              // PASS 2 only
 
     const int b = blockIdx.x / p.nh, h = blockIdx.x % p.nh;
-    load_tile<DH>(Qs, p.q + (size_t)b * p.Lq * p.ldq + h * DH, p.ldq, p.Lq, LQP);
-    load_tile<DH>(dOs, p.dout + (size_t)b * p.Lq * p.lddo + h * DH, p.lddo, p.Lq, LQP);
-    load_tile<DH>(Ks, p.k + (size_t)b * p.Lk * p.ldk + h * DH, p.ldk, p.Lk, LKP);
-    load_tile<DH>(Vs, p.v + (size_t)b * p.Lk * p.ldv + h * DH, p.ldv, p.Lk, LKP);
-    for (int i = threadIdx.x; i < LKP; i += ATT_THREADS) mask_s[i] = i < p.Lk ? p.mask_add[(size_t)b * p.Lk + i] * LOG2E : -INFINITY;
+    size_t qrow0 = (size_t)b * p.Lq, krow0 = (size_t)b * p.Lk;     // padded layout, or the packed range [cu[b], cu[b+1])
+    int Lq = p.Lq, Lk = p.Lk;
+    if (p.cu_q != nullptr) { const int c0 = __ldg(p.cu_q + b); qrow0 = c0; Lq = min(p.Lq, __ldg(p.cu_q + b + 1) - c0); }
+    if (p.cu_k != nullptr) { const int c0 = __ldg(p.cu_k + b); krow0 = c0; Lk = min(p.Lk, __ldg(p.cu_k + b + 1) - c0); }
+    const int LQP = (Lq + KB - 1) & ~(KB - 1), LKP = (Lk + KB - 1) & ~(KB - 1);
+    load_tile<DH>(Qs, p.q + qrow0 * p.ldq + h * DH, p.ldq, Lq, LQP);
+    load_tile<DH>(dOs, p.dout + qrow0 * p.lddo + h * DH, p.lddo, Lq, LQP);
+    load_tile<DH>(Ks, p.k + krow0 * p.ldk + h * DH, p.ldk, Lk, LKP);
+    load_tile<DH>(Vs, p.v + krow0 * p.ldv + h * DH, p.ldv, Lk, LKP);
+    for (int i = threadIdx.x; i < LKP; i += ATT_THREADS)
+        mask_s[i] = i < Lk ? (p.mask_add != nullptr ? p.mask_add[(size_t)b * p.Lk + i] * LOG2E : 0.f) : -INFINITY;
     // D[q] = sum_d dO[q,d] * O[q,d]; padded queries get lse = +inf so their probabilities vanish
     for (int i = threadIdx.x; i < LQP; i += ATT_THREADS) {
         float d = 0.f, l = INFINITY;
-        if (i < p.Lq) {
-            const bf16* o = p.out + ((size_t)b * p.Lq + i) * p.ldo + h * DH;
-            const bf16* dd = p.dout + ((size_t)b * p.Lq + i) * p.lddo + h * DH;
+        if (i < Lq) {
+            const bf16* o = p.out + (qrow0 + i) * p.ldo + h * DH;
+            const bf16* dd = p.dout + (qrow0 + i) * p.lddo + h * DH;
 #pragma unroll
             for (int c = 0; c < DH / 8; ++c) {
                 float fo[8], fd[8];
@@ -292,7 +307,7 @@ __global__ void __launch_bounds__(ATT_THREADS, ((PASS == 2 && DH != 32) || (DH =
 
     // ---------------- pass A: this warp owns 16 keys -> dK, dV ----------------
     if constexpr (PASS == 0 || PASS == 2)
-    for (int k0 = warp * 16; k0 < LKP && k0 < ((p.Lk + 15) & ~15); k0 += NWARPS * 16) {
+    for (int k0 = warp * 16; k0 < LKP && k0 < ((Lk + 15) & ~15); k0 += NWARPS * 16) {
         uint32_t ak[DH / 16][4], av[DH / 16][4];
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) {
@@ -362,13 +377,13 @@ __global__ void __launch_bounds__(ATT_THREADS, ((PASS == 2 && DH != 32) || (DH =
 #pragma unroll
         for (int j = 0; j < DH / 8; ++j) {
             const int col = h * DH + j * 8 + 2 * t;
-            if (r0 < p.Lk) {
-                *reinterpret_cast<uint32_t*>(p.dk + ((size_t)b * p.Lk + r0) * p.lddk + col) = pack_bf16x2(dk[j][0], dk[j][1]);
-                *reinterpret_cast<uint32_t*>(p.dv + ((size_t)b * p.Lk + r0) * p.lddv + col) = pack_bf16x2(dv[j][0], dv[j][1]);
+            if (r0 < Lk) {
+                *reinterpret_cast<uint32_t*>(p.dk + (krow0 + r0) * p.lddk + col) = pack_bf16x2(dk[j][0], dk[j][1]);
+                *reinterpret_cast<uint32_t*>(p.dv + (krow0 + r0) * p.lddv + col) = pack_bf16x2(dv[j][0], dv[j][1]);
             }
-            if (r1 < p.Lk) {
-                *reinterpret_cast<uint32_t*>(p.dk + ((size_t)b * p.Lk + r1) * p.lddk + col) = pack_bf16x2(dk[j][2], dk[j][3]);
-                *reinterpret_cast<uint32_t*>(p.dv + ((size_t)b * p.Lk + r1) * p.lddv + col) = pack_bf16x2(dv[j][2], dv[j][3]);
+            if (r1 < Lk) {
+                *reinterpret_cast<uint32_t*>(p.dk + (krow0 + r1) * p.lddk + col) = pack_bf16x2(dk[j][2], dk[j][3]);
+                *reinterpret_cast<uint32_t*>(p.dv + (krow0 + r1) * p.lddv + col) = pack_bf16x2(dv[j][2], dv[j][3]);
             }
         }
     }
@@ -376,8 +391,8 @@ __global__ void __launch_bounds__(ATT_THREADS, ((PASS == 2 && DH != 32) || (DH =
     // ---------------- phase C (fused variant): dQ = dS K from the parked dS^T; this warp owns 16 queries ----------------
     if constexpr (PASS == 2) {
         __syncthreads();
-        const int LK16 = (p.Lk + 15) & ~15;
-        for (int q0 = warp * 16; q0 < ((p.Lq + 15) & ~15); q0 += NWARPS * 16) {
+        const int LK16 = (Lk + 15) & ~15;
+        for (int q0 = warp * 16; q0 < ((Lq + 15) & ~15); q0 += NWARPS * 16) {
             float dq[DH / 8][4];
 #pragma unroll
             for (int j = 0; j < DH / 8; ++j) { dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f; }
@@ -399,15 +414,15 @@ __global__ void __launch_bounds__(ATT_THREADS, ((PASS == 2 && DH != 32) || (DH =
 #pragma unroll
             for (int j = 0; j < DH / 8; ++j) {
                 const int col = h * DH + j * 8 + 2 * t;
-                if (r0 < p.Lq) *reinterpret_cast<uint32_t*>(p.dq + ((size_t)b * p.Lq + r0) * p.lddq + col) = pack_bf16x2(dq[j][0], dq[j][1]);
-                if (r1 < p.Lq) *reinterpret_cast<uint32_t*>(p.dq + ((size_t)b * p.Lq + r1) * p.lddq + col) = pack_bf16x2(dq[j][2], dq[j][3]);
+                if (r0 < Lq) *reinterpret_cast<uint32_t*>(p.dq + (qrow0 + r0) * p.lddq + col) = pack_bf16x2(dq[j][0], dq[j][1]);
+                if (r1 < Lq) *reinterpret_cast<uint32_t*>(p.dq + (qrow0 + r1) * p.lddq + col) = pack_bf16x2(dq[j][2], dq[j][3]);
             }
         }
     }
 
     // ---------------- pass B: this warp owns 16 queries -> dQ ----------------
     if constexpr (PASS == 1)
-    for (int q0 = warp * 16; q0 < ((p.Lq + 15) & ~15); q0 += NWARPS * 16) {
+    for (int q0 = warp * 16; q0 < ((Lq + 15) & ~15); q0 += NWARPS * 16) {
         uint32_t aq[DH / 16][4], ado[DH / 16][4];
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) {
@@ -467,8 +482,8 @@ __global__ void __launch_bounds__(ATT_THREADS, ((PASS == 2 && DH != 32) || (DH =
 #pragma unroll
         for (int j = 0; j < DH / 8; ++j) {
             const int col = h * DH + j * 8 + 2 * t;
-            if (r0 < p.Lq) *reinterpret_cast<uint32_t*>(p.dq + ((size_t)b * p.Lq + r0) * p.lddq + col) = pack_bf16x2(dq[j][0], dq[j][1]);
-            if (r1 < p.Lq) *reinterpret_cast<uint32_t*>(p.dq + ((size_t)b * p.Lq + r1) * p.lddq + col) = pack_bf16x2(dq[j][2], dq[j][3]);
+            if (r0 < Lq) *reinterpret_cast<uint32_t*>(p.dq + (qrow0 + r0) * p.lddq + col) = pack_bf16x2(dq[j][0], dq[j][1]);
+            if (r1 < Lq) *reinterpret_cast<uint32_t*>(p.dq + (qrow0 + r1) * p.lddq + col) = pack_bf16x2(dq[j][2], dq[j][3]);
         }
     }
 }
@@ -522,7 +537,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace
 
 extern "C" CRCT_API int crct_attn_fwd(const crct_attn_fwd_t* a, crct_stream_t s) {
-    if (!a || !a->q || !a->k || !a->v || !a->mask_add || !a->out) CRCT_FAIL(CRCT_ERR_ARG, "crct_attn_fwd: null pointer");
+    if (!a || !a->q || !a->k || !a->v || (!a->mask_add && !a->cu_k) || !a->out) CRCT_FAIL(CRCT_ERR_ARG, "crct_attn_fwd: null pointer");
     if (a->B <= 0 || a->nh <= 0 || a->Lq <= 0 || a->Lk <= 0) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_fwd: empty problem");
     if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8) || !aligned16(a->q) || !aligned16(a->k) || !aligned16(a->v) || !aligned16(a->out))
         CRCT_FAIL(CRCT_ERR_ARG, "crct_attn_fwd: operands must be 16-byte aligned with leading dimensions multiple of 8");
@@ -535,6 +550,7 @@ extern "C" CRCT_API int crct_attn_fwd(const crct_attn_fwd_t* a, crct_stream_t s)
     p.scale = 1.0f / sqrtf((float)a->dh);
     p.thr = crct_drop_threshold(a->dropout_p); p.dscale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; p.seed = a->seed;
     p.salt = reinterpret_cast<const unsigned long long*>(a->salt);
+    p.cu_q = a->cu_q; p.cu_k = a->cu_k;
     switch (a->dh) {
         case 32: return launch_fwd<32>(p, as_stream(s));
         case 48: return launch_fwd<48>(p, as_stream(s));
@@ -544,7 +560,7 @@ extern "C" CRCT_API int crct_attn_fwd(const crct_attn_fwd_t* a, crct_stream_t s)
 }
 
 extern "C" CRCT_API int crct_attn_bwd(const crct_attn_bwd_t* a, crct_stream_t s) {
-    if (!a || !a->q || !a->k || !a->v || !a->mask_add || !a->out || !a->dout || !a->lse || !a->dq || !a->dk || !a->dv)
+    if (!a || !a->q || !a->k || !a->v || (!a->mask_add && !a->cu_k) || !a->out || !a->dout || !a->lse || !a->dq || !a->dk || !a->dv)
         CRCT_FAIL(CRCT_ERR_ARG, "crct_attn_bwd: null pointer");
     if (a->B <= 0 || a->nh <= 0 || a->Lq <= 0 || a->Lk <= 0) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_bwd: empty problem");
     if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8) || (a->lddo % 8) || (a->lddq % 2) || (a->lddk % 2) || (a->lddv % 2) ||
@@ -562,6 +578,7 @@ extern "C" CRCT_API int crct_attn_bwd(const crct_attn_bwd_t* a, crct_stream_t s)
     p.scale = 1.0f / sqrtf((float)a->dh);
     p.thr = crct_drop_threshold(a->dropout_p); p.dscale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; p.seed = a->seed;
     p.salt = reinterpret_cast<const unsigned long long*>(a->salt);
+    p.cu_q = a->cu_q; p.cu_k = a->cu_k;
     switch (a->dh) {
         case 32: return launch_bwd<32>(p, as_stream(s));
         case 48: return launch_bwd<48>(p, as_stream(s));

@@ -53,7 +53,46 @@ struct KParams {
     uint64_t seed;
     const unsigned long long* salt;
     uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;   // bytes
+    const int* a_rows_dev;   // device-side count of A's stored rows (var-len packing): M, or GEMM-K for the wgrad form
+    int tile_m;              // rows of one output tile (128, or 256 for the CTA pair)
+    int k_tail;              // wgrad with a_rows_dev: valid rows of the last k-block (0 = whole), filled in by the kernel
 };
+
+// Problem size as the kernel sees it: the launch constants, or — with a_rows_dev — recomputed from the device-side row
+// count.  Every role (producer, MMA issuer, epilogue) derives the same tile list from it.
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ KParams resolve_dynamic(const KParams& p) {
+    KParams q = p;
+    if (p.a_rows_dev != nullptr) {
+        const int r = __ldg(p.a_rows_dev);
+        if constexpr (A_MN && B_MN) {                       // wgrad: the reduction runs over the stored rows
+            const int K = max(1, min(r, p.K));
+            q.K = K;
+            q.kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+            q.kb_per_split = (q.kb_total + p.split_k - 1) / p.split_k;
+            q.k_tail = K % BLOCK_K;
+        } else {
+            const int M = max(1, min(r, p.M));
+            q.M = M;
+            q.num_tiles = ((M + p.tile_m - 1) / p.tile_m) * p.num_n_tiles * p.split_k;
+        }
+    }
+    return q;
+}
+
+// wgrad over a device-side row count: rows [k_tail, 64) of the LAST k-block lie past the valid rows and hold whatever the
+// buffers held before (possibly NaN bit patterns).  Both operands are MN-major there — one 128-byte shared-memory line
+// per k index inside every 64-wide atom — so the lines of the invalid k are simply cleared (the swizzle permutes 16-byte
+// chunks WITHIN a line) before the MMAs of that block are issued.  Called by all 32 lanes of the MMA warp.
+__device__ __forceinline__ void zero_k_tail(uint8_t* stage_ptr, int atoms, int k_tail, int lane) {
+    for (int a = 0; a < atoms; ++a) {
+        uint8_t* atom = stage_ptr + (size_t)a * (BLOCK_K * 128);
+        for (int off = k_tail * 128 + lane * 16; off < BLOCK_K * 128; off += 32 * 16)
+            *reinterpret_cast<uint4*>(atom + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    ptx::fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
+    __syncwarp();
+}
 
 // UMMA shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
@@ -70,7 +109,8 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-constexpr bool epi_uses_aux(int epi) { return epi == CRCT_EPI_BIAS_RES || epi == CRCT_EPI_MUL; }
+constexpr bool epi_uses_aux(int epi) { return epi == CRCT_EPI_BIAS_RES || epi == CRCT_EPI_MUL || epi == CRCT_EPI_BIAS_RES_F32; }
+constexpr bool epi_is_res(int epi) { return epi == CRCT_EPI_BIAS_RES || epi == CRCT_EPI_BIAS_RES_F32; }
 
 // ---------------------------------------------------------------------------------------------
 // Epilogue.  A lane owns one accumulator row; per step it handles EPI_COLS = 16 consecutive columns = 32 bytes of
@@ -171,7 +211,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row, int co
                     for (int j = 0; j < 8; ++j) f[j] = gelu_f(f[j]);
                 }
             }
-            if constexpr (EPI == CRCT_EPI_BIAS_RES) {
+            if constexpr (epi_is_res(EPI)) {
                 if (p.drop_thr != 0u)
                     dropout8(f, seed, (uint64_t)row * (uint64_t)p.N + (uint64_t)(col0 + g * 8), p.drop_thr, p.drop_scale);
             }
@@ -188,9 +228,17 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row, int co
                     }
                 }
             }
+            if constexpr (EPI == CRCT_EPI_BIAS_RES_F32) {          // fp32 pre-LayerNorm sum: 8 floats = one 32-byte sector
+                if (col0 + g * 8 < p.N) {
+                    float* d = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0 + g * 8;
+                    *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[g * 4 + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
         }
+        if constexpr (EPI == CRCT_EPI_BIAS_RES_F32) return;
         const size_t off = (size_t)row * p.ldd + col0;
         if constexpr (EPI == CRCT_EPI_BIAS_GELU) {
             if (p.D2 != nullptr) st_row32(reinterpret_cast<bf16*>(p.D2) + off, p.wide != 0, p.N - col0, o2);
@@ -242,7 +290,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
     const int lane_grp = warp & 3;                          // TMEM lanes [32*lane_grp, +32) are this warp's
     const int col_q = (warp - EPI_WARP0) >> 2;              // column quarter
     uint64_t seed = p.seed;
-    if constexpr (EPI == CRCT_EPI_BIAS_RES) {
+    if constexpr (epi_is_res(EPI)) {
         if (p.drop_thr != 0u && p.salt != nullptr) seed ^= __ldg(p.salt);
     }
     const int row = m0 + lane_grp * 32 + lane;
@@ -266,7 +314,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p_launch) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -310,6 +358,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_wait();                 // everything above touched only this CTA's shared / tensor memory
+    const KParams p = resolve_dynamic<A_MN, B_MN>(p_launch);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -322,7 +371,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int m0 = (mn / p.num_n_tiles) * BLOCK_M;
                 const int n0 = (mn % p.num_n_tiles) * BN;
                 const int kb0 = ks * p.kb_per_split;
-                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);      // kb0 >= kb1: an empty split (device-side K), skipped by every role
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                     ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
@@ -347,33 +396,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // one lane issues; with a partial last k-block (k_tail, device-side K of a wgrad) the whole warp walks the loop so
+        // that all 32 lanes can clear the invalid k lines of that block before its MMAs
+        const bool tail = (A_MN && B_MN) && p.k_tail != 0;
+        if (lane == 0 || tail) {
             constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int ks = tile % p.split_k;
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                if (kb0 >= kb1) continue;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                ++it;
                 ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(full_bar(stage), phase);
                     ptx::tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t adesc = make_smem_desc(smem_a(stage) + k * p.a_kstep, p.a_lbo, p.a_sbo);
-                        const uint64_t bdesc = make_smem_desc(smem_b(stage) + k * p.b_kstep, p.b_lbo, p.b_sbo);
-                        ptx::tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    if constexpr (A_MN && B_MN) {
+                        if (tail && kb == p.kb_total - 1) {
+                            zero_k_tail(gbase + (size_t)stage * C::STAGE_BYTES, BLOCK_M / 64, p.k_tail, lane);
+                            zero_k_tail(gbase + (size_t)stage * C::STAGE_BYTES + C::A_BYTES, BN / 64, p.k_tail, lane);
+                        }
                     }
-                    ptx::tc_commit(empty_bar(stage));          // smem slot reusable once these MMAs retire
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t adesc = make_smem_desc(smem_a(stage) + k * p.a_kstep, p.a_lbo, p.a_sbo);
+                            const uint64_t bdesc = make_smem_desc(smem_b(stage) + k * p.b_kstep, p.b_lbo, p.b_sbo);
+                            ptx::tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        ptx::tc_commit(empty_bar(stage));          // smem slot reusable once these MMAs retire
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
-                ptx::tc_commit(tfull_bar(acc));                 // accumulator complete -> epilogue
+                if (lane == 0) ptx::tc_commit(tfull_bar(acc));      // accumulator complete -> epilogue
             }
         }
     } else if (warp >= EPI_WARP0) {
@@ -391,13 +453,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             origin(blockIdx.x, m0, n0);
             aux_load_tile<BN, EPI>(p, m0, n0, warp, lane, aux);
         }
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            {
+                const int kb0 = (tile % p.split_k) * p.kb_per_split;
+                if (kb0 >= min(p.kb_total, kb0 + p.kb_per_split)) continue;          // empty split (device-side K)
+            }
             int m0, n0, m0n = 0, n0n = 0;
             origin(tile, m0, n0);
             const bool has_next = tile + (int)gridDim.x < p.num_tiles;
             if (has_next) origin(tile + (int)gridDim.x, m0n, n0n);
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            ++it;
             epilogue_prepare<BN, EPI>(p, n0, warp, lane, bias_s + acc * 256);
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
@@ -661,6 +728,7 @@ int dispatch2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtenso
         if (epi == CRCT_EPI_BIAS) return launch2<BN, false, false, CRCT_EPI_BIAS>(tmA, tmB, p, grid, st);
         if (epi == CRCT_EPI_BIAS_GELU) return launch2<BN, false, false, CRCT_EPI_BIAS_GELU>(tmA, tmB, p, grid, st);
         if (epi == CRCT_EPI_BIAS_RES) return launch2<BN, false, false, CRCT_EPI_BIAS_RES>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_BIAS_RES_F32) return launch2<BN, false, false, CRCT_EPI_BIAS_RES_F32>(tmA, tmB, p, grid, st);
     } else if (!a_mn && b_mn) {
         if (epi == CRCT_EPI_BIAS) return launch2<BN, false, true, CRCT_EPI_BIAS>(tmA, tmB, p, grid, st);
         if (epi == CRCT_EPI_BIAS_RES) return launch2<BN, false, true, CRCT_EPI_BIAS_RES>(tmA, tmB, p, grid, st);
@@ -677,6 +745,7 @@ int dispatch(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensor
         if (epi == CRCT_EPI_BIAS) return launch<BN, false, false, CRCT_EPI_BIAS>(tmA, tmB, p, grid, st);
         if (epi == CRCT_EPI_BIAS_GELU) return launch<BN, false, false, CRCT_EPI_BIAS_GELU>(tmA, tmB, p, grid, st);
         if (epi == CRCT_EPI_BIAS_RES) return launch<BN, false, false, CRCT_EPI_BIAS_RES>(tmA, tmB, p, grid, st);
+        if (epi == CRCT_EPI_BIAS_RES_F32) return launch<BN, false, false, CRCT_EPI_BIAS_RES_F32>(tmA, tmB, p, grid, st);
     } else if (!a_mn && b_mn) {
         if (epi == CRCT_EPI_BIAS) return launch<BN, false, true, CRCT_EPI_BIAS>(tmA, tmB, p, grid, st);
         if (epi == CRCT_EPI_BIAS_RES) return launch<BN, false, true, CRCT_EPI_BIAS_RES>(tmA, tmB, p, grid, st);
@@ -709,7 +778,9 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
         CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: leading dimensions must be multiples of 8 elements");
     if (((uintptr_t)a->A | (uintptr_t)a->B | (uintptr_t)a->D | (uintptr_t)a->D2 | (uintptr_t)a->aux | (uintptr_t)a->bias) & 15)
         CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: pointers must be 16-byte aligned");
-    if (a->epilogue < CRCT_EPI_BIAS || a->epilogue > CRCT_EPI_F32) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: unknown epilogue %d", a->epilogue);
+    if (a->epilogue < CRCT_EPI_BIAS || a->epilogue > CRCT_EPI_BIAS_RES_F32) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: unknown epilogue %d", a->epilogue);
+    if (a->a_rows_dev && a->cta_group == 2) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: a_rows_dev is not supported by the CTA-pair kernel");
+    if (a->a_rows_dev && a->a_major && !a->b_major) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: a_rows_dev needs a_major = 0 (rows = M) or the wgrad form a_major = b_major = 1 (rows = K)");
     if ((a->epilogue == CRCT_EPI_MUL) && !a->aux) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: MUL epilogue needs aux");
     const bool f32 = a->epilogue == CRCT_EPI_F32;
     int split_k = a->split_k;
@@ -717,7 +788,7 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     const int sms = a->max_ctas > 0 ? a->max_ctas : crct_num_sms();
     if (sms <= 0) return CRCT_ERR_CUDA;
 
-    const bool pair = a->cta_group == 2 || (a->cta_group == 0 && crct_gemm_auto_pair(a));
+    const bool pair = a->cta_group == 2 || (a->cta_group == 0 && !a->a_rows_dev && crct_gemm_auto_pair(a));
     const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
     int bn = a->block_n;
     if (bn == 0) {
@@ -762,13 +833,17 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     p.ldd = a->ldd; p.ldaux = a->ldaux;
     {
         auto ok32 = [](const void* q, int ld) { return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 31u) == 0 && ld % 16 == 0); };
-        p.wide = (!f32 && a->N % 16 == 0 && ok32(a->D, a->ldd) && ok32(a->D2, a->ldd) && ok32(a->aux, a->ldaux)) ? 1 : 0;
+        const bool d32 = a->epilogue == CRCT_EPI_BIAS_RES_F32;        // fp32 D: only the aux rows go through the 32-byte path
+        p.wide = (!f32 && a->N % 16 == 0 && (d32 || ok32(a->D, a->ldd)) && ok32(a->D2, a->ldd) && ok32(a->aux, a->ldaux)) ? 1 : 0;
     }
     p.accumulate = a->accumulate;
     p.drop_thr = crct_drop_threshold(a->dropout_p);
     p.drop_scale = a->dropout_p > 0.f ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
     p.seed = a->seed;
     p.salt = reinterpret_cast<const unsigned long long*>(a->salt);
+    p.a_rows_dev = a->a_rows_dev;
+    p.tile_m = tile_m;
+    p.k_tail = 0;
     // K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO); LBO unused; +32 B per UMMA_K step.
     // MN-major, SWIZZLE_128B: one TMA box = 64 (MN) x BLOCK_K (K) -> K-groups of 8 rows 1024 B apart (SBO),
     //                         64-wide MN atoms BLOCK_K*128 B apart (LBO); +16 rows * 128 B per UMMA_K step.

@@ -36,6 +36,23 @@ __device__ __forceinline__ void row_stats(const Row& r, int nchunks, int lane, i
     rstd = rsqrtf(warp_sum(q) / (float)H + LN_EPS);
 }
 
+// Row counts may live on the device (var-len packing: the number of valid rows of a batch is only known there, and the
+// captured step must not depend on it): `rows_dev` non-NULL overrides `rows`, which then only sized the grid.
+__device__ __forceinline__ int dyn_rows(int rows, const int* __restrict__ rows_dev) {
+    return rows_dev != nullptr ? min(rows, __ldg(rows_dev)) : rows;
+}
+// 8 consecutive values of a pre-LayerNorm row: fp32 (production: z is kept in fp32 between the GEMM epilogue and the
+// LayerNorm — rounding it to bf16 was the largest single contributor to the end-to-end error) or bf16
+template <bool F32>
+__device__ __forceinline__ void load8_z(const void* base, size_t off, float (&f)[8]) {
+    if constexpr (F32) load8_f32(reinterpret_cast<const float*>(base) + off, f);
+    else load8_bf16(reinterpret_cast<const bf16*>(base) + off, f);
+}
+__device__ __forceinline__ void store8_f32(float* p, const float (&f)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
 // y = (z - mean) * rstd * gamma + beta, optional dropout on y; writes y (bf16)
 __device__ __forceinline__ void ln_write(const Row& z, int nchunks, int lane, float mean, float rstd, const float* gamma,
                                          const float* beta, bf16* y_row, uint64_t row_idx0, uint32_t thr, float scale, uint64_t seed) {
@@ -74,19 +91,21 @@ __global__ void __launch_bounds__(ROW_THREADS) additive_mask_kernel(const void* 
 }
 
 // ------------------------------------------------------------------------------------------------
+template <bool ZF32>
 __global__ void __launch_bounds__(ROW_THREADS)
-layernorm_fwd_kernel(const bf16* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H) {
+layernorm_fwd_kernel(const void* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
+                     const int* __restrict__ rows_dev) {
     pdl_launch_dependents();
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
-    if (row >= rows) return;
+    if (row >= dyn_rows(rows, rows_dev)) return;
     const int nchunks = H >> 3;
     Row r;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
-        if (lane + 32 * c < nchunks) load8_bf16(z + (size_t)row * H + (lane + 32 * c) * 8, r.v[c]);
+        if (lane + 32 * c < nchunks) load8_z<ZF32>(z, (size_t)row * H + (lane + 32 * c) * 8, r.v[c]);
     float mean, rstd;
     row_stats(r, nchunks, lane, H, mean, rstd);
     ln_write(r, nchunks, lane, mean, rstd, gamma, beta, y + (size_t)row * H, 0, 0u, 1.f, 0);
@@ -229,31 +248,35 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
 //   ln_bwd_params_kernel : a lane owns 8 columns, accumulates the three sums in registers over a strided set of rows
 //                          (4 rows in flight), CTA reduce through smem, one atomic per column per CTA; re-reads dy, z and
 //                          dzm, which the dz kernel has just left in L2.
-template <int NCH>
+template <int NCH, bool ZF32>
 __global__ void __launch_bounds__(ROW_THREADS)
-ln_bwd_dz_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ mean_in,
+ln_bwd_dz_kernel(const bf16* __restrict__ dy, const void* __restrict__ z, const float* __restrict__ mean_in,
                  const float* __restrict__ rstd_in, const float* __restrict__ gamma, bf16* __restrict__ dz, bf16* __restrict__ dzm,
                  int rows, int H, uint32_t thr_in, float scale_in, uint64_t seed_in, uint32_t thr_out, float scale_out,
-                 uint64_t seed_out, const unsigned long long* __restrict__ salt) {
+                 uint64_t seed_out, const unsigned long long* __restrict__ salt, const int* __restrict__ rows_dev) {
     pdl_launch_dependents();
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
-    if (row >= rows) return;
+    if (row >= dyn_rows(rows, rows_dev)) return;
     if (salt != nullptr) { const unsigned long long sv = __ldg(salt); seed_in ^= sv; seed_out ^= sv; }
     const int nchunks = H >> 3;
-    PackedRow<NCH> r;
-    load_packed_row<NCH>(r, dy, z, mean_in, rstd_in, row, H, lane, nchunks);
-    const float rstd = r.rstd, nmr = -r.mean * r.rstd;
     float g[NCH][8], x[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {                     // all loads of the row first
+        const int ch = lane + 32 * c;
+        if (ch < nchunks) {
+            load8_bf16(dy + (size_t)row * H + ch * 8, g[c]);
+            load8_z<ZF32>(z, (size_t)row * H + ch * 8, x[c]);
+        }
+    }
+    const float rstd = __ldg(rstd_in + row), nmr = -__ldg(mean_in + row) * rstd;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int ch = lane + 32 * c;
         if (ch < nchunks) {
             float gm[8];
-            unpack8f(r.dy[c], g[c]);
-            unpack8f(r.z[c], x[c]);
             load8_f32(gamma + ch * 8, gm);
             if (thr_in != 0u) dropout8(g[c], seed_in, (uint64_t)row * H + ch * 8, thr_in, scale_in);
 #pragma unroll
@@ -283,13 +306,15 @@ ln_bwd_dz_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const 
     }
 }
 
+template <bool ZF32>
 __global__ void __launch_bounds__(ROW_THREADS)
-ln_bwd_params_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const bf16* __restrict__ dzm,
+ln_bwd_params_kernel(const bf16* __restrict__ dy, const void* __restrict__ z, const bf16* __restrict__ dzm,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int H, uint32_t thr_in, float scale_in,
-                     uint64_t seed_in, const unsigned long long* __restrict__ salt) {
+                     uint64_t seed_in, const unsigned long long* __restrict__ salt, const int* __restrict__ rows_dev) {
     pdl_launch_dependents();
     pdl_wait();
+    rows = dyn_rows(rows, rows_dev);
     constexpr int NW = ROW_THREADS / 32;
     __shared__ float red[NW][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -302,14 +327,19 @@ ln_bwd_params_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
         const int stride = gridDim.y * NW;
         constexpr int U = 4;
         for (int row0 = blockIdx.y * NW + warp; row0 < rows; row0 += U * stride) {
-            uint4 pd[U], pz[U], pm[U];
+            uint4 pd[U], pz[U], pz2[U], pm[U];
             float mean[U], rstd[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {                  // all loads of U rows first
                 const int row = row0 + u * stride;
                 if (row < rows) {
                     pd[u] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)row * H + col));
-                    pz[u] = __ldg(reinterpret_cast<const uint4*>(z + (size_t)row * H + col));
+                    if constexpr (ZF32) {
+                        pz[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(z) + (size_t)row * H + col));
+                        pz2[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(z) + (size_t)row * H + col + 4));
+                    } else {
+                        pz[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(z) + (size_t)row * H + col));
+                    }
                     if (dbias != nullptr) pm[u] = __ldg(reinterpret_cast<const uint4*>(dzm + (size_t)row * H + col));
                     mean[u] = __ldg(mean_in + row);
                     rstd[u] = __ldg(rstd_in + row);
@@ -321,7 +351,12 @@ ln_bwd_params_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
                 if (row < rows) {
                     float d[8], x[8];
                     unpack8f(pd[u], d);
-                    unpack8f(pz[u], x);
+                    if constexpr (ZF32) {
+                        x[0] = __uint_as_float(pz[u].x); x[1] = __uint_as_float(pz[u].y); x[2] = __uint_as_float(pz[u].z); x[3] = __uint_as_float(pz[u].w);
+                        x[4] = __uint_as_float(pz2[u].x); x[5] = __uint_as_float(pz2[u].y); x[6] = __uint_as_float(pz2[u].z); x[7] = __uint_as_float(pz2[u].w);
+                    } else {
+                        unpack8f(pz[u], x);
+                    }
                     if (thr_in != 0u) dropout8(d, seed_in, (uint64_t)row * H + col, thr_in, scale_in);
                     const float nmr = -mean[u] * rstd[u];
 #pragma unroll
@@ -359,9 +394,10 @@ ln_bwd_params_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, co
 
 // out[n] += sum_rows x[row, n]
 __global__ void __launch_bounds__(ROW_THREADS)
-colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows, int N, int ld) {
+colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows, int N, int ld, const int* __restrict__ rows_dev) {
     pdl_launch_dependents();
     pdl_wait();
+    rows = dyn_rows(rows, rows_dev);
     __shared__ float red[ROW_THREADS / 32][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int col = blockIdx.x * 256 + lane * 8;
@@ -399,17 +435,19 @@ colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int rows, int
 
 // softmax over the F RoI features of one region, fp32 in -> bf16 GEMM operand (vilbert.py:1476)
 __global__ void __launch_bounds__(ROW_THREADS)
-softmax_rows_kernel(const float* __restrict__ x, bf16* __restrict__ out, int rows, int F) {
+softmax_rows_kernel(const float* __restrict__ x, bf16* __restrict__ out, int rows, int F, const int* __restrict__ src_row,
+                    const int* __restrict__ rows_dev) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
-    if (row >= rows) return;
+    if (row >= dyn_rows(rows, rows_dev)) return;
+    const int src = src_row != nullptr ? __ldg(src_row + row) : row;      // packed output row <- padded input row
     const int nchunks = F >> 3;
     Row r;
     float mx = -INFINITY;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
         if (lane + 32 * c < nchunks) {
-            load8_f32(x + (size_t)row * F + (lane + 32 * c) * 8, r.v[c]);
+            load8_f32(x + (size_t)src * F + (lane + 32 * c) * 8, r.v[c]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) mx = fmaxf(mx, r.v[c][j]);
         }
@@ -438,9 +476,10 @@ struct TextEmbArgs {
     const long long* ids; const long long* types; const float* loc;
     const float* word; const float* pos; const float* type; const float* w_loc; const float* b_loc;
     const float* gamma; const float* beta;
-    bf16* y; bf16* z; float* mean; float* rstd;
+    bf16* y; void* z; float* mean; float* rstd;
     int B, T, H;
     uint32_t thr; float scale; uint64_t seed; const unsigned long long* salt;
+    int z_f32; const int* src_row; const int* rows_dev;
 };
 
 __device__ __forceinline__ int first_qa_index(const long long* types_row, int T, int lane) {
@@ -454,17 +493,19 @@ __device__ __forceinline__ int first_qa_index(const long long* types_row, int T,
     return first;
 }
 
+// `row` = output row (packed when src_row is given), `src` = its token position b*T + t in the padded inputs
 __global__ void __launch_bounds__(ROW_THREADS) embed_text_fwd_kernel(const TextEmbArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
-    if (row >= a.B * a.T) return;
-    const int b = row / a.T, t = row % a.T;
+    if (row >= dyn_rows(a.B * a.T, a.rows_dev)) return;
+    const int src = a.src_row != nullptr ? __ldg(a.src_row + row) : row;
+    const int b = src / a.T, t = src % a.T;
     const int H = a.H, nchunks = H >> 3;
     const int first = first_qa_index(a.types + (size_t)b * a.T, a.T, lane);
-    const long long ty = a.types[row];
+    const long long ty = a.types[src];
     const bool qa = (ty == -1 || ty == 1);
-    const long long id = a.ids[row];
-    const float4 bx = *reinterpret_cast<const float4*>(a.loc + (size_t)row * 4);
+    const long long id = a.ids[src];
+    const float4 bx = *reinterpret_cast<const float4*>(a.loc + (size_t)src * 4);
     const bool loc_on = (fabsf(bx.x) + fabsf(bx.y) + fabsf(bx.z) + fabsf(bx.w)) != 0.f;
     const long long ty_idx = ty == -1 ? 0 : ty;
     Row r;
@@ -492,12 +533,15 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_text_fwd_kernel(const TextE
                     r.v[c][j] += tmp[j] + w.x * bx.x + w.y * bx.y + w.z * bx.z + w.w * bx.w;
                 }
             }
-            if (a.z) store8_bf16(a.z + (size_t)row * H + ch * 8, r.v[c]);
+            if (a.z) {
+                if (a.z_f32) store8_f32(reinterpret_cast<float*>(a.z) + (size_t)row * H + ch * 8, r.v[c]);
+                else store8_bf16(reinterpret_cast<bf16*>(a.z) + (size_t)row * H + ch * 8, r.v[c]);
+            }
         }
     }
-    // LayerNorm statistics are taken on the bf16-rounded z when z is materialised, so that the backward
+    // LayerNorm statistics are taken on the bf16-rounded z when z is materialised in bf16, so that the backward
     // (which re-reads z) sees exactly the normalised values of the forward
-    if (a.z) {
+    if (a.z && !a.z_f32) {
 #pragma unroll
         for (int c = 0; c < MAXC; ++c)
             if (lane + 32 * c < nchunks) {
@@ -521,6 +565,7 @@ struct TextEmbBwdArgs {
     const long long* ids; const long long* types; const float* loc; const bf16* dz;
     float* g_word; float* g_pos; float* g_type; float* g_wloc; float* g_bloc;
     int B, T, H;
+    const int* src_row; const int* rows_dev;
 };
 
 __global__ void __launch_bounds__(ROW_THREADS) embed_text_bwd_kernel(const TextEmbBwdArgs a) {
@@ -534,14 +579,15 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_text_bwd_kernel(const TextE
         for (int c = 0; c < MAXC; ++c)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[k].v[c][j] = 0.f;
-    const int rows = a.B * a.T;
+    const int rows = dyn_rows(a.B * a.T, a.rows_dev);
     for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < rows; row += gridDim.x * (ROW_THREADS / 32)) {
-        const int b = row / a.T, t = row % a.T;
+        const int src = a.src_row != nullptr ? __ldg(a.src_row + row) : row;
+        const int b = src / a.T, t = src % a.T;
         const int first = first_qa_index(a.types + (size_t)b * a.T, a.T, lane);
-        const long long ty = a.types[row];
+        const long long ty = a.types[src];
         const bool qa = (ty == -1 || ty == 1);
-        const long long id = a.ids[row];
-        const float4 bx = *reinterpret_cast<const float4*>(a.loc + (size_t)row * 4);
+        const long long id = a.ids[src];
+        const float4 bx = *reinterpret_cast<const float4*>(a.loc + (size_t)src * 4);
         const bool loc_on = (fabsf(bx.x) + fabsf(bx.y) + fabsf(bx.z) + fabsf(bx.w)) != 0.f;
         const long long ty_idx = ty == -1 ? 0 : ty;
 #pragma unroll
@@ -589,18 +635,20 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_text_bwd_kernel(const TextE
 struct VisEmbArgs {
     const bf16* g; const float* box; const long long* cls;
     const float* w_loc; const float* b_loc; const float* color; const float* gamma; const float* beta;
-    bf16* y; bf16* z; float* mean; float* rstd;
+    bf16* y; void* z; float* mean; float* rstd;
     int rows, H;
     uint32_t thr; float scale; uint64_t seed; const unsigned long long* salt;
+    int z_f32; const int* src_row; const int* rows_dev;
 };
 
 __global__ void __launch_bounds__(ROW_THREADS) embed_vis_fwd_kernel(const VisEmbArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
-    if (row >= a.rows) return;
+    if (row >= dyn_rows(a.rows, a.rows_dev)) return;
+    const int src = a.src_row != nullptr ? __ldg(a.src_row + row) : row;     // g / y / z rows are packed, box / cls padded
     const int H = a.H, nchunks = H >> 3;
-    const float4 bx = *reinterpret_cast<const float4*>(a.box + (size_t)row * 4);
-    const long long cls = a.cls[row];
+    const float4 bx = *reinterpret_cast<const float4*>(a.box + (size_t)src * 4);
+    const long long cls = a.cls[src];
     Row r;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
@@ -616,9 +664,13 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_vis_fwd_kernel(const VisEmb
                 r.v[c][j] += tmp[j] + bl[j] + w.x * bx.x + w.y * bx.y + w.z * bx.z + w.w * bx.w;
             }
             if (a.z) {
-                store8_bf16(a.z + (size_t)row * H + ch * 8, r.v[c]);
+                if (a.z_f32) {
+                    store8_f32(reinterpret_cast<float*>(a.z) + (size_t)row * H + ch * 8, r.v[c]);
+                } else {
+                    store8_bf16(reinterpret_cast<bf16*>(a.z) + (size_t)row * H + ch * 8, r.v[c]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) r.v[c][j] = __bfloat162float(__float2bfloat16(r.v[c][j]));
+                    for (int j = 0; j < 8; ++j) r.v[c][j] = __bfloat162float(__float2bfloat16(r.v[c][j]));
+                }
             }
         }
     }
@@ -632,6 +684,7 @@ struct VisEmbBwdArgs {
     const bf16* dz; const float* box; const long long* cls;
     float* g_color; float* g_wloc;
     int rows, H;
+    const int* src_row; const int* rows_dev;
 };
 
 __global__ void __launch_bounds__(ROW_THREADS) embed_vis_bwd_kernel(const VisEmbBwdArgs a) {
@@ -645,9 +698,11 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_vis_bwd_kernel(const VisEmb
         for (int c = 0; c < MAXC; ++c)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[k].v[c][j] = 0.f;
-    for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < a.rows; row += gridDim.x * (ROW_THREADS / 32)) {
-        const float4 bx = *reinterpret_cast<const float4*>(a.box + (size_t)row * 4);
-        const long long cls = a.cls[row];
+    const int rows = dyn_rows(a.rows, a.rows_dev);
+    for (int row = blockIdx.x * (ROW_THREADS / 32) + warp; row < rows; row += gridDim.x * (ROW_THREADS / 32)) {
+        const int src = a.src_row != nullptr ? __ldg(a.src_row + row) : row;
+        const float4 bx = *reinterpret_cast<const float4*>(a.box + (size_t)src * 4);
+        const long long cls = a.cls[src];
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
             const int ch = lane + 32 * c;
@@ -735,12 +790,16 @@ extern "C" CRCT_API int crct_additive_mask(const void* mask, int kind, float* ou
 }
 
 extern "C" CRCT_API int crct_layernorm_fwd(const void* z, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                                  int rows, int H, crct_stream_t s) {
+                                  int rows, int H, int z_f32, const int32_t* rows_dev, crct_stream_t s) {
     if (!z || !gamma || !beta || !y || (mean == nullptr) != (rstd == nullptr)) CRCT_FAIL(CRCT_ERR_ARG, "crct_layernorm_fwd: bad pointer");
     if (int rc = check_row_width(H, "crct_layernorm_fwd")) return rc;
     if (rows <= 0) return CRCT_OK;
-    CRCT_CUDA(crct_launch_pdl(layernorm_fwd_kernel, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, as_stream(s), reinterpret_cast<const bf16*>(z),
-                              gamma, beta, reinterpret_cast<bf16*>(y), mean, rstd, rows, H));
+    if (z_f32)
+        CRCT_CUDA(crct_launch_pdl(layernorm_fwd_kernel<true>, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, as_stream(s), z,
+                                  gamma, beta, reinterpret_cast<bf16*>(y), mean, rstd, rows, H, rows_dev));
+    else
+        CRCT_CUDA(crct_launch_pdl(layernorm_fwd_kernel<false>, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, as_stream(s), z,
+                                  gamma, beta, reinterpret_cast<bf16*>(y), mean, rstd, rows, H, rows_dev));
     return CRCT_OK;
 }
 
@@ -751,21 +810,32 @@ extern "C" CRCT_API int crct_layernorm_bwd(const crct_ln_bwd_t* a, crct_stream_t
     const bool dzm = a->dzm != nullptr && a->p_out > 0.f;
     const int nch = (a->H / 8 + 31) / 32;
     const float sc_in = a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, sc_out = a->p_out > 0.f ? 1.f / (1.f - a->p_out) : 1.f;
-    if (!a->dgamma && !a->dbeta && !a->dbias) {          // input gradient only (crct_layernorm_bwd_params does the sums)
+    const bool sums = a->dgamma || a->dbeta || a->dbias;
+    if (!sums || a->z_f32 || a->rows_dev) {              // input gradient only (crct_layernorm_bwd_params does the sums)
         auto launch = [&](auto kern) {
             crct_launch_pdl(kern, dim3(row_grid(a->rows)), dim3(ROW_THREADS), 0, as_stream(s),
-                reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), a->mean, a->rstd, a->gamma,
+                reinterpret_cast<const bf16*>(a->dy), a->z, a->mean, a->rstd, a->gamma,
                 reinterpret_cast<bf16*>(a->dz), dzm ? reinterpret_cast<bf16*>(a->dzm) : nullptr, a->rows, a->H,
                 crct_drop_threshold(a->p_in), sc_in, a->seed_in, crct_drop_threshold(a->p_out), sc_out, a->seed_out,
-                reinterpret_cast<const unsigned long long*>(a->salt));
+                reinterpret_cast<const unsigned long long*>(a->salt), a->rows_dev);
         };
-        switch (nch) {
-            case 1: launch(ln_bwd_dz_kernel<1>); break;
-            case 2: launch(ln_bwd_dz_kernel<2>); break;
-            case 3: launch(ln_bwd_dz_kernel<3>); break;
-            default: launch(ln_bwd_dz_kernel<4>); break;
+        if (a->z_f32) {
+            switch (nch) {
+                case 1: launch(ln_bwd_dz_kernel<1, true>); break;
+                case 2: launch(ln_bwd_dz_kernel<2, true>); break;
+                case 3: launch(ln_bwd_dz_kernel<3, true>); break;
+                default: launch(ln_bwd_dz_kernel<4, true>); break;
+            }
+        } else {
+            switch (nch) {
+                case 1: launch(ln_bwd_dz_kernel<1, false>); break;
+                case 2: launch(ln_bwd_dz_kernel<2, false>); break;
+                case 3: launch(ln_bwd_dz_kernel<3, false>); break;
+                default: launch(ln_bwd_dz_kernel<4, false>); break;
+            }
         }
         CRCT_LAUNCH_CHECK();
+        if (sums) return crct_layernorm_bwd_params(a, s);      // fp32 z / device row counts: the split form serves both calls
         return CRCT_OK;
     }
     int grid = 2 * crct_num_sms();
@@ -804,15 +874,19 @@ extern "C" CRCT_API int crct_layernorm_bwd_params(const crct_ln_bwd_t* a, crct_s
     const int max_gy = (a->rows + 63) / 64;
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
-    crct_launch_pdl(ln_bwd_params_kernel, dim3(gx, gy), dim3(ROW_THREADS), 0, as_stream(s),
-        reinterpret_cast<const bf16*>(a->dy), reinterpret_cast<const bf16*>(a->z), reinterpret_cast<const bf16*>(dzm), a->mean, a->rstd,
-        a->dgamma, a->dbeta, a->dbias, a->rows, a->H, crct_drop_threshold(a->p_in), a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, a->seed_in,
-        reinterpret_cast<const unsigned long long*>(a->salt));
+    auto launch = [&](auto kern) {
+        crct_launch_pdl(kern, dim3(gx, gy), dim3(ROW_THREADS), 0, as_stream(s),
+            reinterpret_cast<const bf16*>(a->dy), a->z, reinterpret_cast<const bf16*>(dzm), a->mean, a->rstd,
+            a->dgamma, a->dbeta, a->dbias, a->rows, a->H, crct_drop_threshold(a->p_in), a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, a->seed_in,
+            reinterpret_cast<const unsigned long long*>(a->salt), a->rows_dev);
+    };
+    if (a->z_f32) launch(ln_bwd_params_kernel<true>);
+    else launch(ln_bwd_params_kernel<false>);
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }
 
-extern "C" CRCT_API int crct_colsum_bf16(const void* x, float* out, int rows, int N, int ld, crct_stream_t s) {
+extern "C" CRCT_API int crct_colsum_bf16(const void* x, float* out, int rows, int N, int ld, const int32_t* rows_dev, crct_stream_t s) {
     if (!x || !out) CRCT_FAIL(CRCT_ERR_ARG, "crct_colsum_bf16: null pointer");
     if ((N % 8) || (ld % 8)) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_colsum_bf16: N and ld must be multiples of 8");
     if (rows <= 0 || N <= 0) return CRCT_OK;
@@ -821,16 +895,17 @@ extern "C" CRCT_API int crct_colsum_bf16(const void* x, float* out, int rows, in
     const int max_gy = (rows + 63) / 64;
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
-    crct_launch_pdl(colsum_kernel, dim3(gx, gy), dim3(ROW_THREADS), 0, as_stream(s), reinterpret_cast<const bf16*>(x), out, rows, N, ld);
+    crct_launch_pdl(colsum_kernel, dim3(gx, gy), dim3(ROW_THREADS), 0, as_stream(s), reinterpret_cast<const bf16*>(x), out, rows, N, ld, rows_dev);
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }
 
-extern "C" CRCT_API int crct_softmax_rows(const float* x, void* out, int rows, int F, crct_stream_t s) {
+extern "C" CRCT_API int crct_softmax_rows(const float* x, void* out, int rows, int F, const int32_t* src_row, const int32_t* rows_dev,
+                                          crct_stream_t s) {
     if (!x || !out) CRCT_FAIL(CRCT_ERR_ARG, "crct_softmax_rows: null pointer");
     if (int rc = check_row_width(F, "crct_softmax_rows")) return rc;
     if (rows <= 0) return CRCT_OK;
-    softmax_rows_kernel<<<row_grid(rows), ROW_THREADS, 0, as_stream(s)>>>(x, reinterpret_cast<bf16*>(out), rows, F);
+    softmax_rows_kernel<<<row_grid(rows), ROW_THREADS, 0, as_stream(s)>>>(x, reinterpret_cast<bf16*>(out), rows, F, src_row, rows_dev);
     CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }
@@ -844,8 +919,9 @@ extern "C" CRCT_API int crct_embed_text_fwd(const crct_embed_text_t* a, crct_str
     TextEmbArgs k;
     k.ids = reinterpret_cast<const long long*>(a->ids); k.types = reinterpret_cast<const long long*>(a->types); k.loc = a->loc;
     k.word = a->word; k.pos = a->pos; k.type = a->type; k.w_loc = a->w_loc; k.b_loc = a->b_loc; k.gamma = a->gamma; k.beta = a->beta;
-    k.y = reinterpret_cast<bf16*>(a->y); k.z = reinterpret_cast<bf16*>(a->z); k.mean = a->mean; k.rstd = a->rstd;
+    k.y = reinterpret_cast<bf16*>(a->y); k.z = a->z; k.mean = a->mean; k.rstd = a->rstd;
     k.B = a->B; k.T = a->T; k.H = a->H;
+    k.z_f32 = a->z_f32; k.src_row = a->src_row; k.rows_dev = a->rows_dev;
     k.thr = crct_drop_threshold(a->dropout_p); k.scale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; k.seed = a->seed;
     k.salt = reinterpret_cast<const unsigned long long*>(a->salt);
     if (a->B * a->T <= 0) return CRCT_OK;
@@ -863,6 +939,7 @@ extern "C" CRCT_API int crct_embed_text_bwd(const crct_embed_text_bwd_t* a, crct
     k.dz = reinterpret_cast<const bf16*>(a->dz);
     k.g_word = a->g_word; k.g_pos = a->g_pos; k.g_type = a->g_type; k.g_wloc = a->g_wloc; k.g_bloc = a->g_bloc;
     k.B = a->B; k.T = a->T; k.H = a->H;
+    k.src_row = a->src_row; k.rows_dev = a->rows_dev;
     const int rows = a->B * a->T;
     if (rows <= 0) return CRCT_OK;
     int grid = crct_num_sms();
@@ -879,8 +956,9 @@ extern "C" CRCT_API int crct_embed_vis_fwd(const crct_embed_vis_t* a, crct_strea
     VisEmbArgs k;
     k.g = reinterpret_cast<const bf16*>(a->g); k.box = a->box; k.cls = reinterpret_cast<const long long*>(a->cls);
     k.w_loc = a->w_loc; k.b_loc = a->b_loc; k.color = a->color; k.gamma = a->gamma; k.beta = a->beta;
-    k.y = reinterpret_cast<bf16*>(a->y); k.z = reinterpret_cast<bf16*>(a->z); k.mean = a->mean; k.rstd = a->rstd;
+    k.y = reinterpret_cast<bf16*>(a->y); k.z = a->z; k.mean = a->mean; k.rstd = a->rstd;
     k.rows = a->rows; k.H = a->H;
+    k.z_f32 = a->z_f32; k.src_row = a->src_row; k.rows_dev = a->rows_dev;
     k.thr = crct_drop_threshold(a->dropout_p); k.scale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; k.seed = a->seed;
     k.salt = reinterpret_cast<const unsigned long long*>(a->salt);
     if (a->rows <= 0) return CRCT_OK;
@@ -895,6 +973,7 @@ extern "C" CRCT_API int crct_embed_vis_bwd(const crct_embed_vis_bwd_t* a, crct_s
     VisEmbBwdArgs k;
     k.dz = reinterpret_cast<const bf16*>(a->dz); k.box = a->box; k.cls = reinterpret_cast<const long long*>(a->cls);
     k.g_color = a->g_color; k.g_wloc = a->g_wloc; k.rows = a->rows; k.H = a->H;
+    k.src_row = a->src_row; k.rows_dev = a->rows_dev;
     if (a->rows <= 0) return CRCT_OK;
     int grid = crct_num_sms();
     if (grid > row_grid(a->rows)) grid = row_grid(a->rows);

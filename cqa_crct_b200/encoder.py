@@ -147,6 +147,19 @@ class _Saved:
     pass
 
 
+class _Rows:
+    """Row layout of one stream (text tokens / image regions) for one pass.
+
+    Padded (the reference's layout, `cu is None`): sample b owns rows [b*L, (b+1)*L) and an additive key mask hides the padding.
+    Packed (`cu` = int32[B+1] on the device, csrc/varlen.cu): only the rows whose mask is 1 exist, sample b owns rows
+    [cu[b], cu[b+1]); `n` = the device word cu[B] every kernel reads its row count from (buffers are still allocated for B*L
+    rows — the host never learns the count, so one captured CUDA graph serves every batch), `src[r]` = padded position of row r."""
+
+    def __init__(self, B, L, cu=None, src=None, mask_add=None):
+        self.B, self.L, self.cu, self.src, self.mask_add = B, L, cu, src, mask_add
+        self.n = cu[B:B + 1] if cu is not None else None
+
+
 class _CrctFunction(torch.autograd.Function):
     """Ties the hand-written forward/backward into autograd: inputs = one anchor parameter, outputs =
     (nsp_loss[1], reg_loss[B]); backward runs the whole CUDA backward and accumulates into the gradient arena."""
@@ -177,6 +190,9 @@ class VisualDialogEncoder(nn.Module):
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         self.fp32 = precision == 'fp32'
         self.act = torch.float32 if self.fp32 else torch.bfloat16
+        # var-len ("packed") rows: only the tokens / regions whose mask is 1 go through the encoder (csrc/varlen.cu); exact —
+        # masked keys have probability 0 in the reference.  The fp32 check mode runs the reference's padded layout.
+        self.varlen = bool(params.get('varlen', True)) and not self.fp32
         config_path = params['model_config']
         assert os.path.exists(config_path), "model_config file not found"      # encoder_decorator.py:13
         self.params = params
@@ -301,50 +317,60 @@ class VisualDialogEncoder(nn.Module):
         return _Lanes(cur, self._side_stream)
 
     # ------------------------------------------------------------------ building blocks (forward)
-    def _linear(self, x, W, bias, M, epilogue=L.EPI_BIAS, aux=None, D2=None, p=0.0, seed=0):
+    def _linear(self, x, W, bias, M, epilogue=L.EPI_BIAS, aux=None, D2=None, p=0.0, seed=0, n=None):
         N, K = W.shape
         D = torch.empty(M, N, dtype=self.act, device=x.device)
-        L.gemm(x, W, D, M=M, N=N, K=K, bias=bias, epilogue=epilogue, aux=aux, D2=D2, dropout_p=p, seed=seed)
+        L.gemm(x, W, D, M=M, N=N, K=K, bias=bias, epilogue=epilogue, aux=aux, D2=D2, dropout_p=p, seed=seed, rows_dev=n)
         return D
 
-    def _ln(self, z, pre, keep):
+    def _linear_res(self, x, W, bias, M, aux, p, seed, n=None):
+        """z = dropout(x W^T + b) + aux, the pre-LayerNorm sum: kept in fp32 (CRCT_EPI_BIAS_RES_F32) — rounding z to bf16
+        before the LayerNorm was the largest single contributor to the end-to-end error (tools/parity_sensitivity.py)."""
+        N, K = W.shape
+        z = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        L.gemm(x, W, z, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES if self.fp32 else L.EPI_BIAS_RES_F32, aux=aux,
+               dropout_p=p, seed=seed, rows_dev=n)
+        return z
+
+    def _ln(self, z, pre, keep, n=None):
         rows, H = z.shape
-        y = torch.empty_like(z)
+        y = torch.empty(rows, H, dtype=self.act, device=z.device)
         mean = rstd = None
         if keep:
             mean = torch.empty(rows, dtype=torch.float32, device=z.device)
             rstd = torch.empty(rows, dtype=torch.float32, device=z.device)
-        L.layernorm_fwd(z, self._p(pre + '.weight'), self._p(pre + '.bias'), y, mean, rstd)
+        L.layernorm_fwd(z, self._p(pre + '.weight'), self._p(pre + '.bias'), y, mean, rstd, rows_dev=n)
         return y, mean, rstd
 
-    def _ffn_fwd(self, a, pre_i, pre_o, p_drop, seed, keep):
+    def _ffn_fwd(self, a, pre_i, pre_o, p_drop, seed, keep, n=None):
         """intermediate + output blocks (vilbert.py:454-457,467-471 / 585-588,598-602)."""
         M = a.shape[0]
         W1, W2 = self._w(pre_i + '.dense.weight'), self._w(pre_o + '.dense.weight')
         dg = torch.empty(M, W1.shape[0], dtype=self.act, device=a.device) if keep else None      # gelu'(u), for the backward
-        h = self._linear(a, W1, self._p(pre_i + '.dense.bias'), M, L.EPI_BIAS_GELU, D2=dg)
-        z = self._linear(h, W2, self._p(pre_o + '.dense.bias'), M, L.EPI_BIAS_RES, aux=a, p=p_drop, seed=seed)
-        y, mean, rstd = self._ln(z, pre_o + '.LayerNorm', keep)
+        h = self._linear(a, W1, self._p(pre_i + '.dense.bias'), M, L.EPI_BIAS_GELU, D2=dg, n=n)
+        z = self._linear_res(h, W2, self._p(pre_o + '.dense.bias'), M, a, p_drop, seed, n)
+        y, mean, rstd = self._ln(z, pre_o + '.LayerNorm', keep, n)
         s = None
         if keep:
             s = _Saved()
-            s.a, s.dg, s.h, s.z, s.mean, s.rstd, s.p, s.seed = a, dg, h, z, mean, rstd, p_drop, seed
+            s.a, s.dg, s.h, s.z, s.mean, s.rstd, s.p, s.seed, s.n = a, dg, h, z, mean, rstd, p_drop, seed, n
         return y, s
 
     def _ffn_bwd(self, dy, s, pre_i, pre_o):
         M, H = dy.shape
+        n = s.n
         dz = torch.empty_like(dy)
         dzm = torch.empty_like(dy) if s.p > 0 else None
-        self._ln_bwd(dy, s.z, s.mean, s.rstd, pre_o + '.LayerNorm', dz, self._g(pre_o + '.dense.bias'), dzm, p_out=s.p, seed_out=s.seed)
+        self._ln_bwd(dy, s.z, s.mean, s.rstd, pre_o + '.LayerNorm', dz, self._g(pre_o + '.dense.bias'), dzm, p_out=s.p, seed_out=s.seed, n=n)
         gz = dzm if dzm is not None else dz
         W1, W2 = self._w(pre_i + '.dense.weight'), self._w(pre_o + '.dense.weight')
         I = W1.shape[0]
-        self._wgrad(gz, s.h, self._g(pre_o + '.dense.weight'))
+        self._wgrad(gz, s.h, self._g(pre_o + '.dense.weight'), n=n)
         du = torch.empty(M, I, dtype=self.act, device=dy.device)
-        L.gemm(gz, W2, du, M=M, N=I, K=H, b_major=1, epilogue=L.EPI_MUL, aux=s.dg)
-        self._wgrad(du, s.a, self._g(pre_i + '.dense.weight'), self._g(pre_i + '.dense.bias'))
+        L.gemm(gz, W2, du, M=M, N=I, K=H, b_major=1, epilogue=L.EPI_MUL, aux=s.dg, rows_dev=n)
+        self._wgrad(du, s.a, self._g(pre_i + '.dense.weight'), self._g(pre_i + '.dense.bias'), n=n)
         da = torch.empty_like(dy)
-        L.gemm(du, W1, da, M=M, N=H, K=I, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz)
+        L.gemm(du, W1, da, M=M, N=H, K=I, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz, rows_dev=n)
         return da
 
     def _wg(self, *tensors):
@@ -362,15 +388,15 @@ class VisualDialogEncoder(nn.Module):
         self._wg_hold.append((tensors, cur))
         return torch.cuda.stream(self._wg_stream)
 
-    def _wgrad(self, dy, x, gW, gb=None):
-        """gW[out,in] += dy^T x  (fp32 accumulate, split-K) and, when `gb` is given, gb += colsum(dy)."""
+    def _wgrad(self, dy, x, gW, gb=None, n=None):
+        """gW[out,in] += dy^T x  (fp32 accumulate, split-K) and, when `gb` is given, gb += colsum(dy); `n`: device row count."""
         rows, No = dy.shape
         Ki = x.shape[1]
         with self._wg(dy, x):
             if gb is not None:
-                L.colsum_bf16(dy, gb)
+                L.colsum_bf16(dy, gb, rows_dev=n)
             L.gemm(dy, x, gW, M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, lda=dy.stride(0),
-                   ldb=x.stride(0), ldd=Ki)
+                   ldb=x.stride(0), ldd=Ki, rows_dev=n)
 
     def _wgrad_join(self):
         if self._wg_hold:
@@ -378,60 +404,62 @@ class VisualDialogEncoder(nn.Module):
                 cur.wait_stream(self._wg_stream)
             self._wg_hold.clear()
 
-    def _ln_bwd(self, dy, z, mean, rstd, pre_ln, dz, g_dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0):
+    def _ln_bwd(self, dy, z, mean, rstd, pre_ln, dz, g_dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0, n=None):
         """LayerNorm backward in its split form: dz (and the dropout-masked dzm) on the chain's stream, the three column
         sums (dgamma, dbeta, dense-bias gradient) with the weight gradients."""
         L.layernorm_bwd(dy, z, mean, rstd, self._p(pre_ln + '.weight'), dz, dzm=dzm, p_in=p_in, seed_in=seed_in, p_out=p_out,
-                        seed_out=seed_out)
+                        seed_out=seed_out, rows_dev=n)
         with self._wg(dy, z, dz, dzm):
             L.layernorm_bwd_params(dy, z, mean, rstd, dz, self._g(pre_ln + '.weight'), self._g(pre_ln + '.bias'), dbias=g_dbias,
-                                   dzm=dzm, p_in=p_in, seed_in=seed_in, p_out=p_out)
+                                   dzm=dzm, p_in=p_in, seed_in=seed_in, p_out=p_out, rows_dev=n)
 
-    def _attn_out_fwd(self, ctx, x, pre_dense, pre_ln, p_drop, seed, keep):
+    def _attn_out_fwd(self, ctx, x, pre_dense, pre_ln, p_drop, seed, keep, n=None):
         """dense + dropout + residual + LayerNorm (vilbert.py:424-428 / 555-559 / 749-756)."""
         M = x.shape[0]
-        z = self._linear(ctx, self._w(pre_dense + '.weight'), self._p(pre_dense + '.bias'), M, L.EPI_BIAS_RES, aux=x, p=p_drop, seed=seed)
-        a, mean, rstd = self._ln(z, pre_ln, keep)
+        z = self._linear_res(ctx, self._w(pre_dense + '.weight'), self._p(pre_dense + '.bias'), M, x, p_drop, seed, n)
+        a, mean, rstd = self._ln(z, pre_ln, keep, n)
         s = None
         if keep:
             s = _Saved()
-            s.ctx, s.z, s.mean, s.rstd, s.p, s.seed = ctx, z, mean, rstd, p_drop, seed
+            s.ctx, s.z, s.mean, s.rstd, s.p, s.seed, s.n = ctx, z, mean, rstd, p_drop, seed, n
         return a, s
 
     def _attn_out_bwd(self, da, s, pre_dense, pre_ln):
         """returns (dz for the residual path, dctx)."""
         M, H = da.shape
+        n = s.n
         dz = torch.empty_like(da)
         dzm = torch.empty_like(da) if s.p > 0 else None
-        self._ln_bwd(da, s.z, s.mean, s.rstd, pre_ln, dz, self._g(pre_dense + '.bias'), dzm, p_out=s.p, seed_out=s.seed)
+        self._ln_bwd(da, s.z, s.mean, s.rstd, pre_ln, dz, self._g(pre_dense + '.bias'), dzm, p_out=s.p, seed_out=s.seed, n=n)
         gz = dzm if dzm is not None else dz
         W = self._w(pre_dense + '.weight')
-        self._wgrad(gz, s.ctx, self._g(pre_dense + '.weight'))
+        self._wgrad(gz, s.ctx, self._g(pre_dense + '.weight'), n=n)
         dctx = torch.empty(M, W.shape[1], dtype=self.act, device=da.device)
-        L.gemm(gz, W, dctx, M=M, N=W.shape[1], K=H, b_major=1)
+        L.gemm(gz, W, dctx, M=M, N=W.shape[1], K=H, b_major=1, rows_dev=n)
         return dz, dctx
 
-    def _self_layer_fwd(self, x, mask_add, B, Lseq, nh, pre, names, drops, layer, keep):
-        """BertLayer / BertImageLayer (vilbert.py:474-485, 605-616)."""
+    def _self_layer_fwd(self, x, rw, nh, pre, names, drops, layer, keep):
+        """BertLayer / BertImageLayer (vilbert.py:474-485, 605-616).  `rw`: the stream's row layout (_Rows)."""
         M, H = x.shape
+        B, Lseq, n = rw.B, rw.L, rw.n
         dh = H // nh
         step = self._step
-        Wqkv = self.arena.fused(self._wflat(), [pre + '.attention.self.' + n for n in names], '.weight')
-        bqkv = self.arena.fused(self.arena.w32, [pre + '.attention.self.' + n for n in names], '.bias')
-        qkv = self._linear(x, Wqkv, bqkv, M)
+        Wqkv = self.arena.fused(self._wflat(), [pre + '.attention.self.' + nm for nm in names], '.weight')
+        bqkv = self.arena.fused(self.arena.w32, [pre + '.attention.self.' + nm for nm in names], '.bias')
+        qkv = self._linear(x, Wqkv, bqkv, M, n=n)
         ctx = torch.empty(M, H, dtype=self.act, device=x.device)
         lse = torch.empty(B, nh, Lseq, dtype=torch.float32, device=x.device) if keep else None
         p_att, s_att = self._drop(drops[0]), _seed(step, 'attn', layer)
-        L.attn_fwd(qkv, qkv[:, H:], qkv[:, 2 * H:], mask_add, ctx, lse, B=B, nh=nh, dh=dh, Lq=Lseq, Lk=Lseq, ldq=3 * H, ldk=3 * H,
-                   ldv=3 * H, ldo=H, dropout_p=p_att, seed=s_att)
+        L.attn_fwd(qkv, qkv[:, H:], qkv[:, 2 * H:], rw.mask_add, ctx, lse, B=B, nh=nh, dh=dh, Lq=Lseq, Lk=Lseq, ldq=3 * H, ldk=3 * H,
+                   ldv=3 * H, ldo=H, dropout_p=p_att, seed=s_att, cu_q=rw.cu, cu_k=rw.cu)
         a, s_out = self._attn_out_fwd(ctx, x, pre + '.attention.output.dense', pre + '.attention.output.LayerNorm',
-                                      self._drop(drops[1]), _seed(step, 'attn_out', layer), keep)
-        y, s_ffn = self._ffn_fwd(a, pre + '.intermediate', pre + '.output', self._drop(drops[1]), _seed(step, 'ffn_out', layer), keep)
+                                      self._drop(drops[1]), _seed(step, 'attn_out', layer), keep, n)
+        y, s_ffn = self._ffn_fwd(a, pre + '.intermediate', pre + '.output', self._drop(drops[1]), _seed(step, 'ffn_out', layer), keep, n)
         s = None
         if keep:
             s = _Saved()
             s.x, s.qkv, s.lse, s.out, s.ffn, s.p_att, s.s_att = x, qkv, lse, s_out, s_ffn, p_att, s_att
-            s.B, s.L, s.nh, s.mask = B, Lseq, nh, mask_add
+            s.rw, s.nh = rw, nh
         return y, s
 
     def _self_layer_bwd(self, dy, s, pre, names):
@@ -440,30 +468,32 @@ class VisualDialogEncoder(nn.Module):
         da = self._ffn_bwd(dy, s.ffn, pre + '.intermediate', pre + '.output')
         dz1, dctx = self._attn_out_bwd(da, s.out, pre + '.attention.output.dense', pre + '.attention.output.LayerNorm')
         dqkv = torch.empty_like(s.qkv)
-        L.attn_bwd(s.qkv, s.qkv[:, H:], s.qkv[:, 2 * H:], s.mask, s.out.ctx, dctx, s.lse, dqkv, dqkv[:, H:], dqkv[:, 2 * H:],
-                   B=s.B, nh=s.nh, dh=dh, Lq=s.L, Lk=s.L, ldq=3 * H, ldk=3 * H, ldv=3 * H, ldo=H, lddo=H, lddq=3 * H, lddk=3 * H,
-                   lddv=3 * H, dropout_p=s.p_att, seed=s.s_att)
-        mods = [pre + '.attention.self.' + n for n in names]
-        self._wgrad(dqkv, s.x, self.arena.fused(self.arena.g32, mods, '.weight'), self.arena.fused(self.arena.g32, mods, '.bias'))
+        rw = s.rw
+        L.attn_bwd(s.qkv, s.qkv[:, H:], s.qkv[:, 2 * H:], rw.mask_add, s.out.ctx, dctx, s.lse, dqkv, dqkv[:, H:], dqkv[:, 2 * H:],
+                   B=rw.B, nh=s.nh, dh=dh, Lq=rw.L, Lk=rw.L, ldq=3 * H, ldk=3 * H, ldv=3 * H, ldo=H, lddo=H, lddq=3 * H, lddk=3 * H,
+                   lddv=3 * H, dropout_p=s.p_att, seed=s.s_att, cu_q=rw.cu, cu_k=rw.cu)
+        mods = [pre + '.attention.self.' + nm for nm in names]
+        self._wgrad(dqkv, s.x, self.arena.fused(self.arena.g32, mods, '.weight'), self.arena.fused(self.arena.g32, mods, '.bias'), n=rw.n)
         Wqkv = self.arena.fused(self._wflat(), mods, '.weight')
         dx = torch.empty_like(dy)
-        L.gemm(dqkv, Wqkv, dx, M=M, N=H, K=3 * H, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz1)
+        L.gemm(dqkv, Wqkv, dx, M=M, N=H, K=3 * H, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz1, rows_dev=rw.n)
         return dx
 
-    def _co_layer_fwd(self, v, t, v_mask, t_mask, B, T, R, pre, layer, keep, lanes):
+    def _co_layer_fwd(self, v, t, rv, rt, pre, layer, keep, lanes):
         """BertConnectionLayer (vilbert.py:774-788); stream 1 = visual, stream 2 = text.  Each lane projects its own
         q/k/v, the lanes meet once (each attention reads the other lane's keys/values), then run apart again."""
         cfg, step = self.cfg, self._step
         Mv, Hv = v.shape
         Mt, H = t.shape
+        B, T, R = rt.B, rt.L, rv.L
         nh, Hb = cfg.bi_num_attention_heads, cfg.bi_hidden_size
         dh = Hb // nh
         ld = 3 * Hb
-        m1 = [pre + '.biattention.' + n for n in ('query1', 'key1', 'value1')]
-        m2 = [pre + '.biattention.' + n for n in ('query2', 'key2', 'value2')]
+        m1 = [pre + '.biattention.' + nm for nm in ('query1', 'key1', 'value1')]
+        m2 = [pre + '.biattention.' + nm for nm in ('query2', 'key2', 'value2')]
         with lanes.vis():
-            qkv1 = self._linear(v, self.arena.fused(self._wflat(), m1, '.weight'), self.arena.fused(self.arena.w32, m1, '.bias'), Mv)
-        qkv2 = self._linear(t, self.arena.fused(self._wflat(), m2, '.weight'), self.arena.fused(self.arena.w32, m2, '.bias'), Mt)
+            qkv1 = self._linear(v, self.arena.fused(self._wflat(), m1, '.weight'), self.arena.fused(self.arena.w32, m1, '.bias'), Mv, n=rv.n)
+        qkv2 = self._linear(t, self.arena.fused(self._wflat(), m2, '.weight'), self.arena.fused(self.arena.w32, m2, '.bias'), Mt, n=rt.n)
         lanes.meet()
         self._x_hold = (qkv1, qkv2)        # replaces the previous layer's pair: both lanes are past its readers now
         p1, s1 = self._drop(cfg.v_attention_probs_dropout_prob), _seed(step, 'co_attn1', layer)      # dropout1, vilbert.py:642,696
@@ -472,26 +502,26 @@ class VisualDialogEncoder(nn.Module):
         with lanes.vis():                  # visual queries over text keys/values
             ctx2 = torch.empty(Mv, Hb, dtype=self.act, device=t.device)
             lse2 = torch.empty(B, nh, R, dtype=torch.float32, device=t.device) if keep else None
-            L.attn_fwd(qkv1, qkv2[:, Hb:], qkv2[:, 2 * Hb:], t_mask, ctx2, lse2, B=B, nh=nh, dh=dh, Lq=R, Lk=T, ldq=ld, ldk=ld, ldv=ld,
-                       ldo=Hb, dropout_p=p2, seed=s2)
+            L.attn_fwd(qkv1, qkv2[:, Hb:], qkv2[:, 2 * Hb:], rt.mask_add, ctx2, lse2, B=B, nh=nh, dh=dh, Lq=R, Lk=T, ldq=ld, ldk=ld, ldv=ld,
+                       ldo=Hb, dropout_p=p2, seed=s2, cu_q=rv.cu, cu_k=rt.cu)
             av, so_v = self._attn_out_fwd(ctx2, v, pre + '.biOutput.dense1', pre + '.biOutput.LayerNorm1',
-                                          self._drop(cfg.v_hidden_dropout_prob), _seed(step, 'co_out_v', layer), keep)
+                                          self._drop(cfg.v_hidden_dropout_prob), _seed(step, 'co_out_v', layer), keep, rv.n)
             yv, sf_v = self._ffn_fwd(av, pre + '.v_intermediate', pre + '.v_output', self._drop(cfg.v_hidden_dropout_prob),
-                                     _seed(step, 'co_ffn_v', layer), keep)
+                                     _seed(step, 'co_ffn_v', layer), keep, rv.n)
         ctx1 = torch.empty(Mt, Hb, dtype=self.act, device=t.device)          # text queries over visual keys/values
         lse1 = torch.empty(B, nh, T, dtype=torch.float32, device=t.device) if keep else None
-        L.attn_fwd(qkv2, qkv1[:, Hb:], qkv1[:, 2 * Hb:], v_mask, ctx1, lse1, B=B, nh=nh, dh=dh, Lq=T, Lk=R, ldq=ld, ldk=ld, ldv=ld,
-                   ldo=Hb, dropout_p=p1, seed=s1)
+        L.attn_fwd(qkv2, qkv1[:, Hb:], qkv1[:, 2 * Hb:], rv.mask_add, ctx1, lse1, B=B, nh=nh, dh=dh, Lq=T, Lk=R, ldq=ld, ldk=ld, ldv=ld,
+                   ldo=Hb, dropout_p=p1, seed=s1, cu_q=rt.cu, cu_k=rv.cu)
         at, so_t = self._attn_out_fwd(ctx1, t, pre + '.biOutput.dense2', pre + '.biOutput.LayerNorm2',
-                                      self._drop(cfg.hidden_dropout_prob), _seed(step, 'co_out_t', layer), keep)
+                                      self._drop(cfg.hidden_dropout_prob), _seed(step, 'co_out_t', layer), keep, rt.n)
         yt, sf_t = self._ffn_fwd(at, pre + '.t_intermediate', pre + '.t_output', self._drop(cfg.hidden_dropout_prob),
-                                 _seed(step, 'co_ffn_t', layer), keep)
+                                 _seed(step, 'co_ffn_t', layer), keep, rt.n)
         s = None
         if keep:
             s = _Saved()
             s.v, s.t, s.qkv1, s.qkv2, s.lse1, s.lse2 = v, t, qkv1, qkv2, lse1, lse2
             s.so_v, s.so_t, s.sf_v, s.sf_t = so_v, so_t, sf_v, sf_t
-            s.p1, s.s1, s.p2, s.s2, s.v_mask, s.t_mask, s.B, s.T, s.R = p1, s1, p2, s2, v_mask, t_mask, B, T, R
+            s.p1, s.s1, s.p2, s.s2, s.rv, s.rt, s.B, s.T, s.R = p1, s1, p2, s2, rv, rt, B, T, R
         return yv, yt, s
 
     def _co_layer_bwd(self, dyv, dyt, s, pre, lanes):
@@ -502,8 +532,9 @@ class VisualDialogEncoder(nn.Module):
         Mt, H = dyt.shape
         nh, Hb = cfg.bi_num_attention_heads, cfg.bi_hidden_size
         dh, ld = Hb // nh, 3 * Hb
-        m1 = [pre + '.biattention.' + n for n in ('query1', 'key1', 'value1')]
-        m2 = [pre + '.biattention.' + n for n in ('query2', 'key2', 'value2')]
+        m1 = [pre + '.biattention.' + nm for nm in ('query1', 'key1', 'value1')]
+        m2 = [pre + '.biattention.' + nm for nm in ('query2', 'key2', 'value2')]
+        rv, rt = s.rv, s.rt
         with lanes.vis():
             dav = self._ffn_bwd(dyv, s.sf_v, pre + '.v_intermediate', pre + '.v_output')
             dzv, dctx2 = self._attn_out_bwd(dav, s.so_v, pre + '.biOutput.dense1', pre + '.biOutput.LayerNorm1')
@@ -513,23 +544,25 @@ class VisualDialogEncoder(nn.Module):
         dqkv2 = torch.empty_like(s.qkv2)
         lanes.meet()
         # direction 1: q = text (qkv2[:, :Hb]), k/v = visual  -> dq2, dk1, dv1
-        L.attn_bwd(s.qkv2, s.qkv1[:, Hb:], s.qkv1[:, 2 * Hb:], s.v_mask, s.so_t.ctx, dctx1, s.lse1, dqkv2, dqkv1[:, Hb:], dqkv1[:, 2 * Hb:],
+        L.attn_bwd(s.qkv2, s.qkv1[:, Hb:], s.qkv1[:, 2 * Hb:], rv.mask_add, s.so_t.ctx, dctx1, s.lse1, dqkv2, dqkv1[:, Hb:], dqkv1[:, 2 * Hb:],
                    B=s.B, nh=nh, dh=dh, Lq=s.T, Lk=s.R, ldq=ld, ldk=ld, ldv=ld, ldo=Hb, lddo=Hb, lddq=ld, lddk=ld, lddv=ld,
-                   dropout_p=s.p1, seed=s.s1)
+                   dropout_p=s.p1, seed=s.s1, cu_q=rt.cu, cu_k=rv.cu)
         with lanes.vis():
             # direction 2: q = visual (qkv1[:, :Hb]), k/v = text -> dq1, dk2, dv2
-            L.attn_bwd(s.qkv1, s.qkv2[:, Hb:], s.qkv2[:, 2 * Hb:], s.t_mask, s.so_v.ctx, dctx2, s.lse2, dqkv1, dqkv2[:, Hb:], dqkv2[:, 2 * Hb:],
+            L.attn_bwd(s.qkv1, s.qkv2[:, Hb:], s.qkv2[:, 2 * Hb:], rt.mask_add, s.so_v.ctx, dctx2, s.lse2, dqkv1, dqkv2[:, Hb:], dqkv2[:, 2 * Hb:],
                        B=s.B, nh=nh, dh=dh, Lq=s.R, Lk=s.T, ldq=ld, ldk=ld, ldv=ld, ldo=Hb, lddo=Hb, lddq=ld, lddk=ld, lddv=ld,
-                       dropout_p=s.p2, seed=s.s2)
+                       dropout_p=s.p2, seed=s.s2, cu_q=rv.cu, cu_k=rt.cu)
         lanes.meet()
         self._x_hold = (dqkv1, dqkv2, dctx1, dctx2)
         with lanes.vis():
-            self._wgrad(dqkv1, s.v, self.arena.fused(self.arena.g32, m1, '.weight'), self.arena.fused(self.arena.g32, m1, '.bias'))
+            self._wgrad(dqkv1, s.v, self.arena.fused(self.arena.g32, m1, '.weight'), self.arena.fused(self.arena.g32, m1, '.bias'), n=rv.n)
             dv = torch.empty_like(dyv)
-            L.gemm(dqkv1, self.arena.fused(self._wflat(), m1, '.weight'), dv, M=Mv, N=Hv, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzv)
-        self._wgrad(dqkv2, s.t, self.arena.fused(self.arena.g32, m2, '.weight'), self.arena.fused(self.arena.g32, m2, '.bias'))
+            L.gemm(dqkv1, self.arena.fused(self._wflat(), m1, '.weight'), dv, M=Mv, N=Hv, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzv,
+                   rows_dev=rv.n)
+        self._wgrad(dqkv2, s.t, self.arena.fused(self.arena.g32, m2, '.weight'), self.arena.fused(self.arena.g32, m2, '.bias'), n=rt.n)
         dt = torch.empty_like(dyt)
-        L.gemm(dqkv2, self.arena.fused(self._wflat(), m2, '.weight'), dt, M=Mt, N=H, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzt)
+        L.gemm(dqkv2, self.arena.fused(self._wflat(), m2, '.weight'), dt, M=Mt, N=H, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzt,
+               rows_dev=rt.n)
         return dv, dt
 
     # ------------------------------------------------------------------ heads (fp32, CUDA cores)
@@ -558,13 +591,18 @@ class VisualDialogEncoder(nn.Module):
                                    slope=slope, accumulate=accumulate_dx))
         return probs, dx
 
-    def _heads_fwd(self, t, v, B, T, R, labels, Rt, kind, keep):
+    def _heads_fwd(self, t, v, rt, rv, labels, Rt, kind, keep):
         cfg, dev = self.cfg, t.device
+        B, T, R = rt.B, rt.L, rv.L
         H, Hv, Hb = cfg.hidden_size, cfg.v_hidden_size, cfg.bi_hidden_size
         hw0 = torch.empty(B, H, dtype=torch.float32, device=dev)
         hv0 = torch.empty(B, Hv, dtype=torch.float32, device=dev)
-        L.gather_first(t, T * H, hw0)          # vilbert.py:958 / 1600
-        L.gather_first(v, R * Hv, hv0)         # vilbert.py:973 / 1599
+        if rt.cu is not None:                  # packed rows: sample b's first token / region is row cu[b]
+            L.gather_rows_f32(t, rt.cu, hw0)
+            L.gather_rows_f32(v, rv.cu, hv0)
+        else:
+            L.gather_first(t, T * H, hw0)          # vilbert.py:958 / 1600
+            L.gather_first(v, R * Hv, hv0)         # vilbert.py:973 / 1599
         prefusion = torch.empty(B, 512, dtype=torch.float32, device=dev)          # cat((hv, hw), -1), regressor.py:40
         p_t, pt = self._fwd_problem(hw0, 'bert.t_pooler.dense', L.ACT_RELU)
         p_v, pv = self._fwd_problem(hv0, 'bert.v_pooler.dense', L.ACT_RELU)
@@ -607,8 +645,9 @@ class VisualDialogEncoder(nn.Module):
             s.acts_v, s.acts_t, s.acts_f, s.prefusion, s.dlogits, s.dpre = acts_v, acts_t, acts_f, prefusion, dlogits, dpre
         return logits, outs, scalars, s
 
-    def _heads_bwd(self, s, d_nsp, d_reg, B, T, R):
+    def _heads_bwd(self, s, d_nsp, d_reg, rt, rv):
         cfg, dev = self.cfg, s.hw0.device
+        B, T, R = rt.B, rt.L, rv.L
         H, Hv = cfg.hidden_size, cfg.v_hidden_size
         dlogits, dpre = torch.empty_like(s.dlogits), torch.empty_like(s.dpre)
         L.scale_rows(s.dlogits, d_nsp.reshape(-1)[:1].contiguous().float(), dlogits)
@@ -652,10 +691,16 @@ class VisualDialogEncoder(nn.Module):
                 pt_, nt = self._bwd_problems(dt_, ldt, xt, f'regressor.txt_pipe.{idx}', dx=dhw0, accumulate_dx=1)
             run((pv_, dv_, xv), (pt_, dt_, xt))
             dv_, dt_, ldv, ldt = nv, nt, nv.stride(0), nt.stride(0)
-        dt = torch.zeros(B * T, H, dtype=self.act, device=dev)
-        dv = torch.zeros(B * R, Hv, dtype=self.act, device=dev)
-        L.scatter_first(dhw0, dt, T * H)
-        L.scatter_first(dhv0, dv, R * Hv)
+        dt = torch.empty(B * T, H, dtype=self.act, device=dev)
+        dv = torch.empty(B * R, Hv, dtype=self.act, device=dev)
+        L.fill_zero(dt)
+        L.fill_zero(dv)
+        if rt.cu is not None:
+            L.scatter_rows_f32(dhw0, dt, rt.cu)
+            L.scatter_rows_f32(dhv0, dv, rv.cu)
+        else:
+            L.scatter_first(dhw0, dt, T * H)
+            L.scatter_first(dhv0, dv, R * Hv)
         return dt, dv
 
     # ------------------------------------------------------------------ whole model
@@ -677,73 +722,91 @@ class VisualDialogEncoder(nn.Module):
         if box.shape[-1] != 4:
             raise ValueError('image_loc must be [B,R,4] (CRCT/fig_dataloader.py:346 strips the 5th column)')
         step = self._step
-        t_mask = torch.empty(B, T, dtype=torch.float32, device=dev)
-        v_mask = torch.empty(Bv, R, dtype=torch.float32, device=dev)
-        L.additive_mask(amask, t_mask)
-        L.additive_mask(imask, v_mask)
-        if group is not None:              # per-candidate copy of the per-question mask (read by both lanes: allocated here)
-            m_q, v_mask = v_mask, torch.empty(B, R, dtype=torch.float32, device=dev)
-            L.expand_blocks(m_q, group, v_mask)
+        i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
+        if self.varlen:
+            # packed rows (csrc/varlen.cu): compact the valid tokens / regions once; no additive masks from here on
+            rt = _Rows(B, T, i32(B + 1), i32(B * T))
+            L.row_map(amask, rt.cu, rt.src)
+            rvq = _Rows(Bv, R, i32(Bv + 1), i32(Bv * R))           # per question (f3) == per sequence without `group`
+            L.row_map(imask, rvq.cu, rvq.src)
+            rv = rvq
+            if group is not None:          # candidate n shares the packed region rows of question group[n]
+                rv = _Rows(B, R, i32(B + 1), i32(B * R))
+                L.group_map(rvq.cu, group, rv.cu, rv.src)
+        else:
+            t_mask = torch.empty(B, T, dtype=torch.float32, device=dev)
+            v_mask = torch.empty(Bv, R, dtype=torch.float32, device=dev)
+            L.additive_mask(amask, t_mask)
+            L.additive_mask(imask, v_mask)
+            if group is not None:          # per-candidate copy of the per-question mask (read by both lanes: allocated here)
+                m_q, v_mask = v_mask, torch.empty(B, R, dtype=torch.float32, device=dev)
+                L.expand_blocks(m_q, group, v_mask)
+            rt, rvq = _Rows(B, T, mask_add=t_mask), _Rows(Bv, R)
+            rv = _Rows(B, R, mask_add=v_mask)
         sv = _Saved() if keep else None
         # --- embeddings (vilbert.py:1412-1413); from here to the heads the visual lane runs on its own stream
         lanes = self._lanes(dev)
         lanes.v_wait_t()
         e = 'bert.embeddings'
         t = torch.empty(B * T, H, dtype=self.act, device=dev)
-        zt = torch.empty_like(t) if keep else None
+        zt = torch.empty(B * T, H, dtype=torch.float32, device=dev) if keep else None      # pre-LayerNorm sums stay fp32
         mt = torch.empty(B * T, dtype=torch.float32, device=dev) if keep else None
-        rt = torch.empty(B * T, dtype=torch.float32, device=dev) if keep else None
+        rt_ = torch.empty(B * T, dtype=torch.float32, device=dev) if keep else None
         p_et, s_et = self._drop(cfg.hidden_dropout_prob), _seed(step, 'emb_t')
         L.embed_text_fwd(ids, types, loc, self._p(e + '.word_embeddings.weight'), self._p(e + '.position_embeddings.weight'),
                          self._p(e + '.plotqa_type_embeddings.weight'), self._p(e + '.txt_location_embeddings.weight'),
                          self._p(e + '.txt_location_embeddings.bias'), self._p(e + '.LayerNorm.weight'), self._p(e + '.LayerNorm.bias'),
-                         t, zt, mt, rt, dropout_p=p_et, seed=s_et)
+                         t, zt, mt, rt_, dropout_p=p_et, seed=s_et, src_row=rt.src, rows_dev=rt.n)
         e = 'bert.v_embeddings'
         feat2 = feat.reshape(Bv * R, F)
         box2, cls2 = box.reshape(Bv * R, 4), cls.reshape(Bv * R)
         p_ev, s_ev = self._drop(cfg.hidden_dropout_prob), _seed(step, 'emb_v')      # nn.Dropout(config.hidden_dropout_prob), vilbert.py:1470
         with lanes.vis():
             probs = torch.empty(Bv * R, F, dtype=self.act, device=dev)
-            L.softmax_rows(feat2, probs)
-            gimg = self._linear(probs, self._w(e + '.new_image_embeddings.weight'), self._p(e + '.new_image_embeddings.bias'), Bv * R)
+            L.softmax_rows(feat2, probs, src_row=rvq.src, rows_dev=rvq.n)
+            gimg = self._linear(probs, self._w(e + '.new_image_embeddings.weight'), self._p(e + '.new_image_embeddings.bias'), Bv * R,
+                                n=rvq.n)
             v = torch.empty(Bv * R, Hv, dtype=self.act, device=dev)
-            zv = torch.empty_like(v) if keep else None
+            zv = torch.empty(Bv * R, Hv, dtype=torch.float32, device=dev) if keep else None
             mv = torch.empty(Bv * R, dtype=torch.float32, device=dev) if keep else None
-            rv = torch.empty(Bv * R, dtype=torch.float32, device=dev) if keep else None
+            rv_ = torch.empty(Bv * R, dtype=torch.float32, device=dev) if keep else None
             L.embed_vis_fwd(gimg, box2, cls2, self._p(e + '.new_loc_emb.weight'), self._p(e + '.new_loc_emb.bias'),
                             self._p(e + '.color_emb.weight'), self._p(e + '.LayerNorm.weight'), self._p(e + '.LayerNorm.bias'),
-                            v, zv, mv, rv, dropout_p=p_ev, seed=s_ev)
+                            v, zv, mv, rv_, dropout_p=p_ev, seed=s_ev, src_row=rvq.src, rows_dev=rvq.n)
             if group is not None:
                 # f3: the visual embedding depends on the image only — computed once per question above, fanned out to the
                 # question's candidate sequences here (the reference replicates the fp32 inputs on the host instead,
                 # fig_dataloader.py:690-693); from the first co-attention on the visual stream is per candidate
                 v_q = v
                 v = torch.empty(B * R, Hv, dtype=self.act, device=dev)
-                L.expand_blocks(v_q.view(Bv, R * Hv), group, v.view(B, R * Hv))
+                if self.varlen:
+                    L.gather_rows(v_q, rv.src, v, rows_dev=rv.n)
+                else:
+                    L.expand_blocks(v_q.view(Bv, R * Hv), group, v.view(B, R * Hv))
         # --- encoder (vilbert.py:852-939): text layers on the text lane, visual layers on the visual lane (v_layer[k-1]
         # and layer[5+k] are independent, vilbert.py:868-886; the 3520-row visual kernels fill the SMs the text kernels'
         # partial waves leave idle); the lanes meet inside every connection layer.
         layers = []
         for kind_, i in cfg.schedule():
             if kind_ == 't':
-                t, s = self._self_layer_fwd(t, t_mask, B, T, cfg.num_attention_heads, f'bert.encoder.layer.{i}', ('query', 'key', 'value'),
+                t, s = self._self_layer_fwd(t, rt, cfg.num_attention_heads, f'bert.encoder.layer.{i}', ('query', 'key', 'value'),
                                             (cfg.attention_probs_dropout_prob, cfg.hidden_dropout_prob), i, keep)
             elif kind_ == 'v':
                 with lanes.vis():
-                    v, s = self._self_layer_fwd(v, v_mask, B, R, cfg.v_num_attention_heads, f'bert.encoder.v_layer.{i}',
+                    v, s = self._self_layer_fwd(v, rv, cfg.v_num_attention_heads, f'bert.encoder.v_layer.{i}',
                                                 ('query', 'key', 'value'),
                                                 (cfg.v_attention_probs_dropout_prob, cfg.v_hidden_dropout_prob), 100 + i, keep)
             else:
-                v, t, s = self._co_layer_fwd(v, t, v_mask, t_mask, B, T, R, f'bert.encoder.c_layer.{i}', 200 + i, keep, lanes)
+                v, t, s = self._co_layer_fwd(v, t, rv, rt, f'bert.encoder.c_layer.{i}', 200 + i, keep, lanes)
             layers.append(s)
         lanes.t_wait_v()
         self._x_hold = None
-        logits, outs, scalars, s_heads = self._heads_fwd(t, v, B, T, R, labels, Rt, kind, keep)
+        logits, outs, scalars, s_heads = self._heads_fwd(t, v, rt, rv, labels, Rt, kind, keep)
         if keep:
-            sv.B, sv.T, sv.R = B, T, R
+            sv.B, sv.T, sv.R, sv.rows_t, sv.rows_v = B, T, R, rt, rv
             sv.ids, sv.types, sv.loc, sv.box2, sv.cls2, sv.probs = ids, types, loc, box2, cls2, probs
-            sv.zt, sv.mt, sv.rt, sv.p_et, sv.s_et = zt, mt, rt, p_et, s_et
-            sv.zv, sv.mv, sv.rv, sv.p_ev, sv.s_ev = zv, mv, rv, p_ev, s_ev
+            sv.zt, sv.mt, sv.rt, sv.p_et, sv.s_et = zt, mt, rt_, p_et, s_et
+            sv.zv, sv.mv, sv.rv, sv.p_ev, sv.s_ev = zv, mv, rv_, p_ev, s_ev
             sv.layers, sv.heads = layers, s_heads
         return logits, outs, scalars, t, sv
 
@@ -763,7 +826,8 @@ class VisualDialogEncoder(nn.Module):
         cfg, arena = self.cfg, self.arena
         L.SALT = sv.salt                   # the word THIS pass's forward drew its masks with (not the live counter)
         B, T, R = sv.B, sv.T, sv.R
-        dt, dv = self._heads_bwd(sv.heads, d_nsp, d_reg, B, T, R)
+        rows_t, rows_v = sv.rows_t, sv.rows_v
+        dt, dv = self._heads_bwd(sv.heads, d_nsp, d_reg, rows_t, rows_v)
         dev = dt.device
         # Finished ranges are only reported one by one when somebody consumes them (the data-parallel hook, or a graph
         # cut into per-bucket segments): reporting a range makes the caller's stream wait for both other streams.
@@ -792,9 +856,10 @@ class VisualDialogEncoder(nn.Module):
             with lanes.vis():
                 dzv = torch.empty_like(dv)
                 self._ln_bwd(dv, sv.zv, sv.mv, sv.rv, e + '.LayerNorm', dzv, self._g(e + '.new_image_embeddings.bias'), p_in=sv.p_ev,
-                             seed_in=sv.s_ev)
-                self._wgrad(dzv, sv.probs, self._g(e + '.new_image_embeddings.weight'), self._g(e + '.new_loc_emb.bias'))
-                L.embed_vis_bwd(dzv, sv.box2, sv.cls2, self._g(e + '.color_emb.weight'), self._g(e + '.new_loc_emb.weight'))
+                             seed_in=sv.s_ev, n=rows_v.n)
+                self._wgrad(dzv, sv.probs, self._g(e + '.new_image_embeddings.weight'), self._g(e + '.new_loc_emb.bias'), n=rows_v.n)
+                L.embed_vis_bwd(dzv, sv.box2, sv.cls2, self._g(e + '.color_emb.weight'), self._g(e + '.new_loc_emb.weight'),
+                                src_row=rows_v.src, rows_dev=rows_v.n)
 
         items = list(reversed(list(zip(cfg.schedule(), sv.layers))))
         last_c = max((k for k, ((kind_, _), _) in enumerate(items) if kind_ == 'c'), default=-1)
@@ -825,10 +890,10 @@ class VisualDialogEncoder(nn.Module):
             vis_embeddings_bwd(dv)
         e = 'bert.embeddings'
         dzt = torch.empty_like(dt)
-        self._ln_bwd(dt, sv.zt, sv.mt, sv.rt, e + '.LayerNorm', dzt, p_in=sv.p_et, seed_in=sv.s_et)
+        self._ln_bwd(dt, sv.zt, sv.mt, sv.rt, e + '.LayerNorm', dzt, p_in=sv.p_et, seed_in=sv.s_et, n=rows_t.n)
         L.embed_text_bwd(sv.ids, sv.types, sv.loc, dzt, self._g(e + '.word_embeddings.weight'), self._g(e + '.position_embeddings.weight'),
                          self._g(e + '.plotqa_type_embeddings.weight'), self._g(e + '.txt_location_embeddings.weight'),
-                         self._g(e + '.txt_location_embeddings.bias'))
+                         self._g(e + '.txt_location_embeddings.bias'), src_row=rows_t.src, rows_dev=rows_t.n)
         rest = report()
         self._x_hold = None
         del dv_heads

@@ -56,7 +56,8 @@ typedef enum {
     CRCT_EPI_BIAS_GELU = 1, /* u = acc + bias; D = gelu_erf(u); D2 = gelu_erf'(u) (if D2)   vilbert.py:111-117,454-457 */
     CRCT_EPI_BIAS_RES = 2,  /* D = dropout(acc + bias) + aux                      vilbert.py:424-428,467-471,749-756 */
     CRCT_EPI_MUL = 3,       /* D = acc * aux   (aux = the D2 saved by BIAS_GELU)   backward of vilbert.py:456 */
-    CRCT_EPI_F32 = 4        /* D (fp32) = acc, or D += acc when accumulate != 0 (wgrad, split-K) */
+    CRCT_EPI_F32 = 4,       /* D (fp32) = acc, or D += acc when accumulate != 0 (wgrad, split-K) */
+    CRCT_EPI_BIAS_RES_F32 = 5 /* CRCT_EPI_BIAS_RES with an fp32 D: the pre-LayerNorm sum z stays unrounded until the LayerNorm */
 } crct_epilogue_t;
 
 typedef struct {
@@ -79,6 +80,10 @@ typedef struct {
     int32_t cta_group;  /* 0 = choose; 1 = one CTA per 128 x BN tile; 2 = CTA pair (tcgen05 cta_group::2) per 256 x BN tile */
     int32_t dbg[7];     /* descriptor overrides for bring-up; must be 0 in production */
     const uint64_t* salt; /* optional DEVICE word XOR-ed into `seed` at run time (see crct_bump_salt), or NULL */
+    const int32_t* a_rows_dev; /* optional DEVICE word: the number of valid ROWS of A as stored (var-len packing, see crct_row_map)
+                                * — M for a_major = 0 (tiles past it are skipped, rows past it are not written), GEMM-K for the
+                                * wgrad form a_major = b_major = 1 (rows past it contribute nothing).  The M / K fields are then
+                                * the upper bounds the buffers were allocated for.  Not with cta_group = 2. */
 } crct_gemm_t;
 
 int crct_gemm_bf16(const crct_gemm_t* args, crct_stream_t stream);
@@ -90,10 +95,13 @@ int crct_gemm_bf16(const crct_gemm_t* args, crct_stream_t stream);
 int crct_cast_f32_to_bf16(const float* src, void* dst_bf16, size_t n, crct_stream_t stream);
 /* out[i] = (1 - mask[i]) * -10000  (vilbert.py:1380-1396).  kind: 0 = bool/uint8, 1 = int64, 2 = fp32. */
 int crct_additive_mask(const void* mask, int kind, float* out, int n, crct_stream_t stream);
-/* y = LayerNorm(z) with eps = 1e-12 inside the sqrt (vilbert.py:281-294).  z,y bf16 [rows,H]; mean/rstd fp32 [rows]
- * or both NULL (inference). */
+/* Row counts on the device.  Kernels that take `rows_dev` (a DEVICE int32, or NULL) process min(rows, *rows_dev) rows;
+ * `rows` then only sizes the grid.  This is how the var-len ("packed") layout runs inside a captured CUDA graph: the number
+ * of valid token / region rows of a batch (crct_row_map) is never read by the host. */
+/* y = LayerNorm(z) with eps = 1e-12 inside the sqrt (vilbert.py:281-294).  z bf16 (z_f32 = 0) or fp32 (z_f32 = 1)
+ * [rows,H], y bf16; mean/rstd fp32 [rows] or both NULL (inference). */
 int crct_layernorm_fwd(const void* z, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                       int rows, int H, crct_stream_t stream);
+                       int rows, int H, int z_f32, const int32_t* rows_dev, crct_stream_t stream);
 /* LayerNorm backward.  dy may carry the dropout that FOLLOWED the LayerNorm in the forward (embeddings:
  * p_in, seed_in); dzm is dz with the dropout that PRECEDED the residual add re-applied (p_out, seed_out; element
  * counter row*H+col — the same stream the CRCT_EPI_BIAS_RES epilogue used), i.e. the gradient of the dense output. */
@@ -112,6 +120,8 @@ typedef struct {
     float p_in;  uint64_t seed_in;
     float p_out; uint64_t seed_out;
     const uint64_t* salt; /* optional device word XOR-ed into both seeds */
+    int32_t z_f32;        /* 1: z is fp32 (what CRCT_EPI_BIAS_RES_F32 / the embeddings with z_f32 wrote) */
+    const int32_t* rows_dev;
 } crct_ln_bwd_t;
 int crct_layernorm_bwd(const crct_ln_bwd_t* args, crct_stream_t stream);
 /* Split form: crct_layernorm_bwd with dgamma = dbeta = dbias = NULL computes only dz / dzm (the part the backward
@@ -119,9 +129,11 @@ int crct_layernorm_bwd(const crct_ln_bwd_t* args, crct_stream_t stream);
  * that call wrote.  Same struct; gamma is not read. */
 int crct_layernorm_bwd_params(const crct_ln_bwd_t* args, crct_stream_t stream);
 /* out[n] += sum_rows x[row,n]   (bias gradients).  x bf16 [rows,N], row stride ld. */
-int crct_colsum_bf16(const void* x, float* out, int rows, int N, int ld, crct_stream_t stream);
-/* softmax over the RoI feature axis, fp32 in -> bf16 GEMM operand (vilbert.py:1476). */
-int crct_softmax_rows(const float* x, void* out_bf16, int rows, int F, crct_stream_t stream);
+int crct_colsum_bf16(const void* x, float* out, int rows, int N, int ld, const int32_t* rows_dev, crct_stream_t stream);
+/* softmax over the RoI feature axis, fp32 in -> bf16 GEMM operand (vilbert.py:1476).  src_row (or NULL): output row r is
+ * computed from input row src_row[r] (packed output from the padded [B*R,F] input). */
+int crct_softmax_rows(const float* x, void* out_bf16, int rows, int F, const int32_t* src_row, const int32_t* rows_dev,
+                      crct_stream_t stream);
 
 /* K5  text embedding (vilbert.py:320-358): word + position (question/answer tokens only, counted from the first
  * such token) + plotqa type (-1 -> 0, none for type 0) + Linear(4->H)(box) (none, bias included, for an all-zero
@@ -137,6 +149,9 @@ typedef struct {
     int32_t B, T, H, max_pos;
     float dropout_p; uint64_t seed;
     const uint64_t* salt;
+    int32_t z_f32;            /* 1: z is written in fp32 */
+    const int32_t* src_row;   /* packed layout: output row r is token src_row[r] = b*T + t (crct_row_map); NULL = all B*T rows */
+    const int32_t* rows_dev;
 } crct_embed_text_t;
 int crct_embed_text_fwd(const crct_embed_text_t* args, crct_stream_t stream);
 /* scatter of dz (after crct_layernorm_bwd) into the tables; all outputs += . */
@@ -145,6 +160,7 @@ typedef struct {
     const void* dz;        /* bf16 [B*T,H] */
     float* g_word; float* g_pos; float* g_type; float* g_wloc; float* g_bloc;
     int32_t B, T, H;
+    const int32_t* src_row; const int32_t* rows_dev;   /* as in crct_embed_text_t */
 } crct_embed_text_bwd_t;
 int crct_embed_text_bwd(const crct_embed_text_bwd_t* args, crct_stream_t stream);
 
@@ -159,12 +175,16 @@ typedef struct {
     int32_t rows, H;
     float dropout_p; uint64_t seed;
     const uint64_t* salt;
+    int32_t z_f32;
+    const int32_t* src_row;   /* packed layout: g / y / z row r belongs to region src_row[r] = b*R + i of box / cls */
+    const int32_t* rows_dev;
 } crct_embed_vis_t;
 int crct_embed_vis_fwd(const crct_embed_vis_t* args, crct_stream_t stream);
 typedef struct {
     const void* dz; const float* box; const int64_t* cls;
     float* g_color; float* g_wloc;   /* += ; the two bias gradients are crct_colsum_bf16(dz) */
     int32_t rows, H;
+    const int32_t* src_row; const int32_t* rows_dev;
 } crct_embed_vis_bwd_t;
 int crct_embed_vis_bwd(const crct_embed_vis_bwd_t* args, crct_stream_t stream);
 
@@ -185,6 +205,10 @@ typedef struct {
     float dropout_p;        /* on the probabilities; element counter ((b*nh+h)*Lq+i)*Lk+j */
     uint64_t seed;
     const uint64_t* salt;
+    /* packed (var-len) rows: when cu_q / cu_k (DEVICE int32 [B+1], crct_row_map) are given, sample b's queries are rows
+     * [cu_q[b], cu_q[b+1]) of q / out and its keys rows [cu_k[b], cu_k[b+1]) of k / v; Lq / Lk are then the maxima (lse and the
+     * dropout counters keep the [B,nh,Lq(,Lk)] indexing).  With cu_k, mask_add may be NULL: every packed key is valid. */
+    const int32_t* cu_q; const int32_t* cu_k;
 } crct_attn_fwd_t;
 int crct_attn_fwd(const crct_attn_fwd_t* args, crct_stream_t stream);
 
@@ -201,6 +225,7 @@ typedef struct {
     float dropout_p;
     uint64_t seed;
     const uint64_t* salt;
+    const int32_t* cu_q; const int32_t* cu_k;   /* as in crct_attn_fwd_t */
 } crct_attn_bwd_t;
 int crct_attn_bwd(const crct_attn_bwd_t* args, crct_stream_t stream);
 
@@ -243,6 +268,26 @@ int crct_pool_mul_bwd(const float* dpooled, const float* pt, const float* pv, fl
  * launch constant; `salt` is one device word the training loop advances once per step with this kernel, so a step
  * captured in a CUDA graph draws fresh masks on every replay while forward and backward of one step still agree. */
 int crct_bump_salt(uint64_t* salt, crct_stream_t stream);
+/* ------------------------------------------------------------------------------------------------
+ * Var-len ("packed") rows.  The reference pads to T tokens / R regions (CRCT/utils.py:152,178) and masks the padding
+ * additively (vilbert.py:1380-1396); masked keys get probability exactly 0, so padded rows influence nothing
+ * (SURVEY.md §2.3).  crct_row_map compacts the rows with mask != 0:
+ *   cu[b] = valid rows before sample b (cu[B] = total: pass `cu + B` as `rows_dev` / `a_rows_dev`),
+ *   src_row[r] = b*L + t of packed row r.   mask kinds as in crct_additive_mask; a sample without valid rows keeps row 0.
+ * crct_group_map: candidate n of an evaluation batch shares the packed region rows of question group[n] (f3):
+ *   cu[n], and src_row[r] = the question-level packed row that candidate-level packed row r copies.
+ * crct_gather_rows: dst[r,:] = src[idx[r],:] (rows of row_bytes, 16-byte multiples).
+ * crct_gather_rows_f32 / crct_scatter_rows_f32: the first-token rows the heads read (vilbert.py:958,973,1599-1600) at
+ *   arbitrary row indices (row_index = cu for the packed layout) — fp32 <-> bf16.
+ * crct_fill_zero: cudaMemsetAsync on the stream (gradient buffers that are only scattered into).
+ * -------------------------------------------------------------------------------------------- */
+int crct_row_map(const void* mask, int kind, int B, int L, int32_t* cu, int32_t* src_row, crct_stream_t stream);
+int crct_group_map(const int32_t* src_cu, const int64_t* group, int N, int32_t* cu, int32_t* src_row, crct_stream_t stream);
+int crct_gather_rows(const void* src, const int32_t* idx, void* dst, int rows, long long row_bytes, const int32_t* rows_dev,
+                     crct_stream_t stream);
+int crct_gather_rows_f32(const void* src_bf16, long long ld, const int32_t* row_index, float* out, int B, int H, crct_stream_t stream);
+int crct_scatter_rows_f32(const float* g, void* dst_bf16, long long ld, const int32_t* row_index, int B, int H, crct_stream_t stream);
+int crct_fill_zero(void* dst, size_t bytes, crct_stream_t stream);
 /* Same step, and the new value is also written to `snapshot`: one word per forward pass, which that pass and ITS backward
  * pass both read — a second forward before the first one's backward (l1 = model(a); l2 = model(b); (l1 + l2).backward(),
  * allowed by the reference because autograd stores its masks) then still recomputes the masks of its own forward. */
