@@ -28,13 +28,13 @@ class GemmArgs(C.Structure):
                 ('M', i32), ('N', i32), ('K', i32), ('lda', i32), ('ldb', i32), ('ldd', i32), ('ldaux', i32),
                 ('a_major', i32), ('b_major', i32), ('epilogue', i32), ('accumulate', i32), ('split_k', i32),
                 ('block_n', i32), ('dropout_p', f32), ('seed', u64), ('max_ctas', i32), ('cta_group', i32), ('dbg', i32 * 7), ('salt', vp),
-                ('a_rows_dev', vp)]
+                ('a_rows_dev', vp), ('drop_rows', vp)]
 
 
 class LnBwdArgs(C.Structure):
     _fields_ = [('dy', vp), ('z', vp), ('mean', vp), ('rstd', vp), ('gamma', vp), ('dz', vp), ('dzm', vp),
                 ('dgamma', vp), ('dbeta', vp), ('dbias', vp), ('rows', i32), ('H', i32),
-                ('p_in', f32), ('seed_in', u64), ('p_out', f32), ('seed_out', u64), ('salt', vp), ('z_f32', i32), ('rows_dev', vp)]
+                ('p_in', f32), ('seed_in', u64), ('p_out', f32), ('seed_out', u64), ('salt', vp), ('z_f32', i32), ('rows_dev', vp), ('drop_rows', vp)]
 
 
 class EmbedTextArgs(C.Structure):
@@ -199,7 +199,7 @@ def _f32(t, what):
 
 def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None, aux=None, D2=None,
          lda=None, ldb=None, ldd=None, ldaux=None, accumulate=0, split_k=0, block_n=0, dropout_p=0.0, seed=0,
-         max_ctas=0, dbg=None, cta_group=0, rows_dev=None):
+         max_ctas=0, dbg=None, cta_group=0, rows_dev=None, drop_rows=None):
     """D[M,N] = epilogue(A·Bᵀ) — see include/crct_b200.h for operand majors.  fp32 operands select the check-mode kernel."""
     f32 = _is32(A)
     if f32:
@@ -222,7 +222,7 @@ def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None
     a.accumulate, a.split_k, a.block_n = accumulate, split_k, block_n
     a.dropout_p, a.seed, a.max_ctas, a.cta_group = dropout_p, seed, max_ctas, cta_group
     a.salt = ptr(SALT)
-    a.a_rows_dev = ptr(rows_dev)
+    a.a_rows_dev, a.drop_rows = ptr(rows_dev), ptr(drop_rows)
     if f32 and rows_dev is not None:
         raise CrctError('the fp32 check mode runs the padded layout (no device-side row counts)')
     if dbg is not None:
@@ -255,7 +255,7 @@ def layernorm_fwd(z, gamma, beta, y, mean=None, rstd=None, rows_dev=None):
     check(lib().crct_layernorm_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, H, int(_is32(z)), ptr(rows_dev), stream_ptr()))
 
 
-def _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out, rows_dev=None):
+def _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out, rows_dev=None, drop_rows=None):
     chk = _f32 if _is32(dy) else _bf16
     chk(dy, 'dy'); chk(dz, 'dz'); chk(dzm, 'dzm')
     if not _is32(z):
@@ -266,20 +266,21 @@ def _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, 
     a.rows, a.H = z.shape
     a.p_in, a.seed_in, a.p_out, a.seed_out = p_in, seed_in, p_out, seed_out
     a.salt = ptr(SALT)
-    a.z_f32, a.rows_dev = int(_is32(z) and not _is32(dy)), ptr(rows_dev)
+    a.z_f32, a.rows_dev, a.drop_rows = int(_is32(z) and not _is32(dy)), ptr(rows_dev), ptr(drop_rows)
     return a
 
 
 def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dgamma=None, dbeta=None, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0,
-                  seed_out=0, rows_dev=None):
+                  seed_out=0, rows_dev=None, drop_rows=None):
     """dgamma = dbeta = dbias = None: input gradient only (see layernorm_bwd_params)."""
-    a = _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out, rows_dev)
+    a = _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out, rows_dev, drop_rows)
     check((lib().crct_f32_layernorm_bwd if _is32(dy) else lib().crct_layernorm_bwd)(C.byref(a), stream_ptr()))
 
 
-def layernorm_bwd_params(dy, z, mean, rstd, dz, dgamma, dbeta, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0, rows_dev=None):
+def layernorm_bwd_params(dy, z, mean, rstd, dz, dgamma, dbeta, dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0, rows_dev=None,
+                         drop_rows=None):
     """Column sums of the split LayerNorm backward: dgamma, dbeta and (from dzm, or dz when p_out == 0) dbias."""
-    a = _ln_bwd_args(dy, z, mean, rstd, None, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, 0, rows_dev)
+    a = _ln_bwd_args(dy, z, mean, rstd, None, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, 0, rows_dev, drop_rows)
     check((lib().crct_f32_layernorm_bwd_params if _is32(dy) else lib().crct_layernorm_bwd_params)(C.byref(a), stream_ptr()))
 
 

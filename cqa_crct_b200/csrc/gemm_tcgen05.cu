@@ -56,6 +56,7 @@ struct KParams {
     const int* a_rows_dev;   // device-side count of A's stored rows (var-len packing): M, or GEMM-K for the wgrad form
     int tile_m;              // rows of one output tile (128, or 256 for the CTA pair)
     int k_tail;              // wgrad with a_rows_dev: valid rows of the last k-block (0 = whole), filled in by the kernel
+    const int* drop_rows;    // dropout counters use drop_rows[row] instead of row (packed rows keep their padded positions' masks)
 };
 
 // Problem size as the kernel sees it: the launch constants, or — with a_rows_dev — recomputed from the device-side row
@@ -160,7 +161,7 @@ __device__ __forceinline__ void prefetch_aux(const KParams& p, int row, int col,
 // one accumulator row x EPI_COLS columns: bias (smem copy) / GELU (+ GELU') / dropout + residual / multiply -> global
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row, int col0, const uint32_t (&v)[EPI_COLS],
-                                               const float* bias_s, const AuxRegs& aux, uint64_t seed) {
+                                               const float* bias_s, const AuxRegs& aux, uint64_t seed, int drow) {
     if (row >= p.M) return;
     if constexpr (EPI == CRCT_EPI_F32) {
 #pragma unroll
@@ -213,7 +214,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row, int co
             }
             if constexpr (epi_is_res(EPI)) {
                 if (p.drop_thr != 0u)
-                    dropout8(f, seed, (uint64_t)row * (uint64_t)p.N + (uint64_t)(col0 + g * 8), p.drop_thr, p.drop_scale);
+                    dropout8(f, seed, (uint64_t)drow * (uint64_t)p.N + (uint64_t)(col0 + g * 8), p.drop_thr, p.drop_scale);
             }
             if constexpr (epi_uses_aux(EPI)) {
                 if (p.aux != nullptr) {
@@ -295,6 +296,10 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
     }
     const int row = m0 + lane_grp * 32 + lane;
     const int rown = m0n + lane_grp * 32 + lane;
+    int drow = row;
+    if constexpr (epi_is_res(EPI)) {
+        if (p.drop_thr != 0u && p.drop_rows != nullptr && row < p.M) drow = __ldg(p.drop_rows + row);
+    }
     const int cbase = col_q * (BN / 4);
     const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cbase;
     uint32_t v[2][EPI_COLS];
@@ -305,7 +310,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
         ptx::tc_wait_ld();
         reg_fence16(v[c & 1]);              // the loaded values exist from here on (tcgen05.ld is asynchronous)
         if (c + 1 < STEPS) ptx::tc_ld_32x16(taddr + (uint32_t)((c + 1) * EPI_COLS), v[(c + 1) & 1]);
-        if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row, n0 + cc, v[c & 1], bias_s + cc, aux[c], seed);     // warp-uniform
+        if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row, n0 + cc, v[c & 1], bias_s + cc, aux[c], seed, drow);     // warp-uniform
         if constexpr (epi_uses_aux(EPI)) {
             if (has_next) prefetch_aux<EPI>(p, rown, n0n + cc, aux[c]);
         }
@@ -842,6 +847,7 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     p.seed = a->seed;
     p.salt = reinterpret_cast<const unsigned long long*>(a->salt);
     p.a_rows_dev = a->a_rows_dev;
+    p.drop_rows = a->drop_rows;
     p.tile_m = tile_m;
     p.k_tail = 0;
     // K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO); LBO unused; +32 B per UMMA_K step.

@@ -253,13 +253,15 @@ __global__ void __launch_bounds__(ROW_THREADS)
 ln_bwd_dz_kernel(const bf16* __restrict__ dy, const void* __restrict__ z, const float* __restrict__ mean_in,
                  const float* __restrict__ rstd_in, const float* __restrict__ gamma, bf16* __restrict__ dz, bf16* __restrict__ dzm,
                  int rows, int H, uint32_t thr_in, float scale_in, uint64_t seed_in, uint32_t thr_out, float scale_out,
-                 uint64_t seed_out, const unsigned long long* __restrict__ salt, const int* __restrict__ rows_dev) {
+                 uint64_t seed_out, const unsigned long long* __restrict__ salt, const int* __restrict__ rows_dev,
+                 const int* __restrict__ drop_rows) {
     pdl_launch_dependents();
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (ROW_THREADS / 32) + warp;
     if (row >= dyn_rows(rows, rows_dev)) return;
     if (salt != nullptr) { const unsigned long long sv = __ldg(salt); seed_in ^= sv; seed_out ^= sv; }
+    const uint64_t drow = drop_rows != nullptr ? (uint64_t)__ldg(drop_rows + row) : (uint64_t)row;     // dropout counters: padded position
     const int nchunks = H >> 3;
     float g[NCH][8], x[NCH][8];
 #pragma unroll
@@ -278,7 +280,7 @@ ln_bwd_dz_kernel(const bf16* __restrict__ dy, const void* __restrict__ z, const 
         if (ch < nchunks) {
             float gm[8];
             load8_f32(gamma + ch * 8, gm);
-            if (thr_in != 0u) dropout8(g[c], seed_in, (uint64_t)row * H + ch * 8, thr_in, scale_in);
+            if (thr_in != 0u) dropout8(g[c], seed_in, drow * H + ch * 8, thr_in, scale_in);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 x[c][j] = fmaf(x[c][j], rstd, nmr);
@@ -299,7 +301,7 @@ ln_bwd_dz_kernel(const bf16* __restrict__ dy, const void* __restrict__ z, const 
             for (int j = 0; j < 8; ++j) o[j] = fmaf(-x[c][j], m2r, fmaf(g[c][j], rstd, -m1r));
             store8_bf16(dz + (size_t)row * H + ch * 8, o);
             if (dzm != nullptr) {
-                dropout8(o, seed_out, (uint64_t)row * H + ch * 8, thr_out, scale_out);
+                dropout8(o, seed_out, drow * H + ch * 8, thr_out, scale_out);
                 store8_bf16(dzm + (size_t)row * H + ch * 8, o);
             }
         }
@@ -311,7 +313,8 @@ __global__ void __launch_bounds__(ROW_THREADS)
 ln_bwd_params_kernel(const bf16* __restrict__ dy, const void* __restrict__ z, const bf16* __restrict__ dzm,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int H, uint32_t thr_in, float scale_in,
-                     uint64_t seed_in, const unsigned long long* __restrict__ salt, const int* __restrict__ rows_dev) {
+                     uint64_t seed_in, const unsigned long long* __restrict__ salt, const int* __restrict__ rows_dev,
+                     const int* __restrict__ drop_rows) {
     pdl_launch_dependents();
     pdl_wait();
     rows = dyn_rows(rows, rows_dev);
@@ -357,7 +360,8 @@ ln_bwd_params_kernel(const bf16* __restrict__ dy, const void* __restrict__ z, co
                     } else {
                         unpack8f(pz[u], x);
                     }
-                    if (thr_in != 0u) dropout8(d, seed_in, (uint64_t)row * H + col, thr_in, scale_in);
+                    if (thr_in != 0u)
+                        dropout8(d, seed_in, (drop_rows != nullptr ? (uint64_t)__ldg(drop_rows + row) : (uint64_t)row) * H + col, thr_in, scale_in);
                     const float nmr = -mean[u] * rstd[u];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_text_fwd_kernel(const TextE
     }
     float mean, rstd;
     row_stats(r, nchunks, lane, H, mean, rstd);
-    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)row * H, a.thr, a.scale, a.salt ? (a.seed ^ __ldg(a.salt)) : a.seed);
+    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)src * H, a.thr, a.scale, a.salt ? (a.seed ^ __ldg(a.salt)) : a.seed);
     if (lane == 0 && a.mean) { a.mean[row] = mean; a.rstd[row] = rstd; }
 }
 
@@ -676,7 +680,7 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_vis_fwd_kernel(const VisEmb
     }
     float mean, rstd;
     row_stats(r, nchunks, lane, H, mean, rstd);
-    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)row * H, a.thr, a.scale, a.salt ? (a.seed ^ __ldg(a.salt)) : a.seed);
+    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)src * H, a.thr, a.scale, a.salt ? (a.seed ^ __ldg(a.salt)) : a.seed);
     if (lane == 0 && a.mean) { a.mean[row] = mean; a.rstd[row] = rstd; }
 }
 
@@ -811,13 +815,13 @@ extern "C" CRCT_API int crct_layernorm_bwd(const crct_ln_bwd_t* a, crct_stream_t
     const int nch = (a->H / 8 + 31) / 32;
     const float sc_in = a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, sc_out = a->p_out > 0.f ? 1.f / (1.f - a->p_out) : 1.f;
     const bool sums = a->dgamma || a->dbeta || a->dbias;
-    if (!sums || a->z_f32 || a->rows_dev) {              // input gradient only (crct_layernorm_bwd_params does the sums)
+    if (!sums || a->z_f32 || a->rows_dev || a->drop_rows) {              // input gradient only (crct_layernorm_bwd_params does the sums)
         auto launch = [&](auto kern) {
             crct_launch_pdl(kern, dim3(row_grid(a->rows)), dim3(ROW_THREADS), 0, as_stream(s),
                 reinterpret_cast<const bf16*>(a->dy), a->z, a->mean, a->rstd, a->gamma,
                 reinterpret_cast<bf16*>(a->dz), dzm ? reinterpret_cast<bf16*>(a->dzm) : nullptr, a->rows, a->H,
                 crct_drop_threshold(a->p_in), sc_in, a->seed_in, crct_drop_threshold(a->p_out), sc_out, a->seed_out,
-                reinterpret_cast<const unsigned long long*>(a->salt), a->rows_dev);
+                reinterpret_cast<const unsigned long long*>(a->salt), a->rows_dev, a->drop_rows);
         };
         if (a->z_f32) {
             switch (nch) {
@@ -878,7 +882,7 @@ extern "C" CRCT_API int crct_layernorm_bwd_params(const crct_ln_bwd_t* a, crct_s
         crct_launch_pdl(kern, dim3(gx, gy), dim3(ROW_THREADS), 0, as_stream(s),
             reinterpret_cast<const bf16*>(a->dy), a->z, reinterpret_cast<const bf16*>(dzm), a->mean, a->rstd,
             a->dgamma, a->dbeta, a->dbias, a->rows, a->H, crct_drop_threshold(a->p_in), a->p_in > 0.f ? 1.f / (1.f - a->p_in) : 1.f, a->seed_in,
-            reinterpret_cast<const unsigned long long*>(a->salt), a->rows_dev);
+            reinterpret_cast<const unsigned long long*>(a->salt), a->rows_dev, a->drop_rows);
     };
     if (a->z_f32) launch(ln_bwd_params_kernel<true>);
     else launch(ln_bwd_params_kernel<false>);

@@ -323,13 +323,13 @@ class VisualDialogEncoder(nn.Module):
         L.gemm(x, W, D, M=M, N=N, K=K, bias=bias, epilogue=epilogue, aux=aux, D2=D2, dropout_p=p, seed=seed, rows_dev=n)
         return D
 
-    def _linear_res(self, x, W, bias, M, aux, p, seed, n=None):
+    def _linear_res(self, x, W, bias, M, aux, p, seed, n=None, src=None):
         """z = dropout(x W^T + b) + aux, the pre-LayerNorm sum: kept in fp32 (CRCT_EPI_BIAS_RES_F32) — rounding z to bf16
         before the LayerNorm was the largest single contributor to the end-to-end error (tools/parity_sensitivity.py)."""
         N, K = W.shape
         z = torch.empty(M, N, dtype=torch.float32, device=x.device)
         L.gemm(x, W, z, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES if self.fp32 else L.EPI_BIAS_RES_F32, aux=aux,
-               dropout_p=p, seed=seed, rows_dev=n)
+               dropout_p=p, seed=seed, rows_dev=n, drop_rows=src)
         return z
 
     def _ln(self, z, pre, keep, n=None):
@@ -342,18 +342,19 @@ class VisualDialogEncoder(nn.Module):
         L.layernorm_fwd(z, self._p(pre + '.weight'), self._p(pre + '.bias'), y, mean, rstd, rows_dev=n)
         return y, mean, rstd
 
-    def _ffn_fwd(self, a, pre_i, pre_o, p_drop, seed, keep, n=None):
+    def _ffn_fwd(self, a, pre_i, pre_o, p_drop, seed, keep, rw=None):
         """intermediate + output blocks (vilbert.py:454-457,467-471 / 585-588,598-602)."""
         M = a.shape[0]
         W1, W2 = self._w(pre_i + '.dense.weight'), self._w(pre_o + '.dense.weight')
         dg = torch.empty(M, W1.shape[0], dtype=self.act, device=a.device) if keep else None      # gelu'(u), for the backward
+        n, src = (rw.n, rw.src) if rw is not None else (None, None)
         h = self._linear(a, W1, self._p(pre_i + '.dense.bias'), M, L.EPI_BIAS_GELU, D2=dg, n=n)
-        z = self._linear_res(h, W2, self._p(pre_o + '.dense.bias'), M, a, p_drop, seed, n)
+        z = self._linear_res(h, W2, self._p(pre_o + '.dense.bias'), M, a, p_drop, seed, n, src)
         y, mean, rstd = self._ln(z, pre_o + '.LayerNorm', keep, n)
         s = None
         if keep:
             s = _Saved()
-            s.a, s.dg, s.h, s.z, s.mean, s.rstd, s.p, s.seed, s.n = a, dg, h, z, mean, rstd, p_drop, seed, n
+            s.a, s.dg, s.h, s.z, s.mean, s.rstd, s.p, s.seed, s.n, s.src = a, dg, h, z, mean, rstd, p_drop, seed, n, src
         return y, s
 
     def _ffn_bwd(self, dy, s, pre_i, pre_o):
@@ -361,7 +362,8 @@ class VisualDialogEncoder(nn.Module):
         n = s.n
         dz = torch.empty_like(dy)
         dzm = torch.empty_like(dy) if s.p > 0 else None
-        self._ln_bwd(dy, s.z, s.mean, s.rstd, pre_o + '.LayerNorm', dz, self._g(pre_o + '.dense.bias'), dzm, p_out=s.p, seed_out=s.seed, n=n)
+        self._ln_bwd(dy, s.z, s.mean, s.rstd, pre_o + '.LayerNorm', dz, self._g(pre_o + '.dense.bias'), dzm, p_out=s.p, seed_out=s.seed, n=n,
+                     src=s.src)
         gz = dzm if dzm is not None else dz
         W1, W2 = self._w(pre_i + '.dense.weight'), self._w(pre_o + '.dense.weight')
         I = W1.shape[0]
@@ -404,24 +406,25 @@ class VisualDialogEncoder(nn.Module):
                 cur.wait_stream(self._wg_stream)
             self._wg_hold.clear()
 
-    def _ln_bwd(self, dy, z, mean, rstd, pre_ln, dz, g_dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0, n=None):
+    def _ln_bwd(self, dy, z, mean, rstd, pre_ln, dz, g_dbias=None, dzm=None, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0, n=None, src=None):
         """LayerNorm backward in its split form: dz (and the dropout-masked dzm) on the chain's stream, the three column
         sums (dgamma, dbeta, dense-bias gradient) with the weight gradients."""
         L.layernorm_bwd(dy, z, mean, rstd, self._p(pre_ln + '.weight'), dz, dzm=dzm, p_in=p_in, seed_in=seed_in, p_out=p_out,
-                        seed_out=seed_out, rows_dev=n)
+                        seed_out=seed_out, rows_dev=n, drop_rows=src)
         with self._wg(dy, z, dz, dzm):
             L.layernorm_bwd_params(dy, z, mean, rstd, dz, self._g(pre_ln + '.weight'), self._g(pre_ln + '.bias'), dbias=g_dbias,
-                                   dzm=dzm, p_in=p_in, seed_in=seed_in, p_out=p_out, rows_dev=n)
+                                   dzm=dzm, p_in=p_in, seed_in=seed_in, p_out=p_out, rows_dev=n, drop_rows=src)
 
-    def _attn_out_fwd(self, ctx, x, pre_dense, pre_ln, p_drop, seed, keep, n=None):
+    def _attn_out_fwd(self, ctx, x, pre_dense, pre_ln, p_drop, seed, keep, rw=None):
         """dense + dropout + residual + LayerNorm (vilbert.py:424-428 / 555-559 / 749-756)."""
         M = x.shape[0]
-        z = self._linear_res(ctx, self._w(pre_dense + '.weight'), self._p(pre_dense + '.bias'), M, x, p_drop, seed, n)
+        n, src = (rw.n, rw.src) if rw is not None else (None, None)
+        z = self._linear_res(ctx, self._w(pre_dense + '.weight'), self._p(pre_dense + '.bias'), M, x, p_drop, seed, n, src)
         a, mean, rstd = self._ln(z, pre_ln, keep, n)
         s = None
         if keep:
             s = _Saved()
-            s.ctx, s.z, s.mean, s.rstd, s.p, s.seed, s.n = ctx, z, mean, rstd, p_drop, seed, n
+            s.ctx, s.z, s.mean, s.rstd, s.p, s.seed, s.n, s.src = ctx, z, mean, rstd, p_drop, seed, n, src
         return a, s
 
     def _attn_out_bwd(self, da, s, pre_dense, pre_ln):
@@ -430,7 +433,7 @@ class VisualDialogEncoder(nn.Module):
         n = s.n
         dz = torch.empty_like(da)
         dzm = torch.empty_like(da) if s.p > 0 else None
-        self._ln_bwd(da, s.z, s.mean, s.rstd, pre_ln, dz, self._g(pre_dense + '.bias'), dzm, p_out=s.p, seed_out=s.seed, n=n)
+        self._ln_bwd(da, s.z, s.mean, s.rstd, pre_ln, dz, self._g(pre_dense + '.bias'), dzm, p_out=s.p, seed_out=s.seed, n=n, src=s.src)
         gz = dzm if dzm is not None else dz
         W = self._w(pre_dense + '.weight')
         self._wgrad(gz, s.ctx, self._g(pre_dense + '.weight'), n=n)
@@ -453,8 +456,8 @@ class VisualDialogEncoder(nn.Module):
         L.attn_fwd(qkv, qkv[:, H:], qkv[:, 2 * H:], rw.mask_add, ctx, lse, B=B, nh=nh, dh=dh, Lq=Lseq, Lk=Lseq, ldq=3 * H, ldk=3 * H,
                    ldv=3 * H, ldo=H, dropout_p=p_att, seed=s_att, cu_q=rw.cu, cu_k=rw.cu)
         a, s_out = self._attn_out_fwd(ctx, x, pre + '.attention.output.dense', pre + '.attention.output.LayerNorm',
-                                      self._drop(drops[1]), _seed(step, 'attn_out', layer), keep, n)
-        y, s_ffn = self._ffn_fwd(a, pre + '.intermediate', pre + '.output', self._drop(drops[1]), _seed(step, 'ffn_out', layer), keep, n)
+                                      self._drop(drops[1]), _seed(step, 'attn_out', layer), keep, rw)
+        y, s_ffn = self._ffn_fwd(a, pre + '.intermediate', pre + '.output', self._drop(drops[1]), _seed(step, 'ffn_out', layer), keep, rw)
         s = None
         if keep:
             s = _Saved()
@@ -505,17 +508,17 @@ class VisualDialogEncoder(nn.Module):
             L.attn_fwd(qkv1, qkv2[:, Hb:], qkv2[:, 2 * Hb:], rt.mask_add, ctx2, lse2, B=B, nh=nh, dh=dh, Lq=R, Lk=T, ldq=ld, ldk=ld, ldv=ld,
                        ldo=Hb, dropout_p=p2, seed=s2, cu_q=rv.cu, cu_k=rt.cu)
             av, so_v = self._attn_out_fwd(ctx2, v, pre + '.biOutput.dense1', pre + '.biOutput.LayerNorm1',
-                                          self._drop(cfg.v_hidden_dropout_prob), _seed(step, 'co_out_v', layer), keep, rv.n)
+                                          self._drop(cfg.v_hidden_dropout_prob), _seed(step, 'co_out_v', layer), keep, rv)
             yv, sf_v = self._ffn_fwd(av, pre + '.v_intermediate', pre + '.v_output', self._drop(cfg.v_hidden_dropout_prob),
-                                     _seed(step, 'co_ffn_v', layer), keep, rv.n)
+                                     _seed(step, 'co_ffn_v', layer), keep, rv)
         ctx1 = torch.empty(Mt, Hb, dtype=self.act, device=t.device)          # text queries over visual keys/values
         lse1 = torch.empty(B, nh, T, dtype=torch.float32, device=t.device) if keep else None
         L.attn_fwd(qkv2, qkv1[:, Hb:], qkv1[:, 2 * Hb:], rv.mask_add, ctx1, lse1, B=B, nh=nh, dh=dh, Lq=T, Lk=R, ldq=ld, ldk=ld, ldv=ld,
                    ldo=Hb, dropout_p=p1, seed=s1, cu_q=rt.cu, cu_k=rv.cu)
         at, so_t = self._attn_out_fwd(ctx1, t, pre + '.biOutput.dense2', pre + '.biOutput.LayerNorm2',
-                                      self._drop(cfg.hidden_dropout_prob), _seed(step, 'co_out_t', layer), keep, rt.n)
+                                      self._drop(cfg.hidden_dropout_prob), _seed(step, 'co_out_t', layer), keep, rt)
         yt, sf_t = self._ffn_fwd(at, pre + '.t_intermediate', pre + '.t_output', self._drop(cfg.hidden_dropout_prob),
-                                 _seed(step, 'co_ffn_t', layer), keep, rt.n)
+                                 _seed(step, 'co_ffn_t', layer), keep, rt)
         s = None
         if keep:
             s = _Saved()
@@ -856,7 +859,7 @@ class VisualDialogEncoder(nn.Module):
             with lanes.vis():
                 dzv = torch.empty_like(dv)
                 self._ln_bwd(dv, sv.zv, sv.mv, sv.rv, e + '.LayerNorm', dzv, self._g(e + '.new_image_embeddings.bias'), p_in=sv.p_ev,
-                             seed_in=sv.s_ev, n=rows_v.n)
+                             seed_in=sv.s_ev, n=rows_v.n, src=rows_v.src)
                 self._wgrad(dzv, sv.probs, self._g(e + '.new_image_embeddings.weight'), self._g(e + '.new_loc_emb.bias'), n=rows_v.n)
                 L.embed_vis_bwd(dzv, sv.box2, sv.cls2, self._g(e + '.color_emb.weight'), self._g(e + '.new_loc_emb.weight'),
                                 src_row=rows_v.src, rows_dev=rows_v.n)
@@ -890,7 +893,7 @@ class VisualDialogEncoder(nn.Module):
             vis_embeddings_bwd(dv)
         e = 'bert.embeddings'
         dzt = torch.empty_like(dt)
-        self._ln_bwd(dt, sv.zt, sv.mt, sv.rt, e + '.LayerNorm', dzt, p_in=sv.p_et, seed_in=sv.s_et, n=rows_t.n)
+        self._ln_bwd(dt, sv.zt, sv.mt, sv.rt, e + '.LayerNorm', dzt, p_in=sv.p_et, seed_in=sv.s_et, n=rows_t.n, src=rows_t.src)
         L.embed_text_bwd(sv.ids, sv.types, sv.loc, dzt, self._g(e + '.word_embeddings.weight'), self._g(e + '.position_embeddings.weight'),
                          self._g(e + '.plotqa_type_embeddings.weight'), self._g(e + '.txt_location_embeddings.weight'),
                          self._g(e + '.txt_location_embeddings.bias'), src_row=rows_t.src, rows_dev=rows_t.n)

@@ -84,6 +84,8 @@ typedef struct {
                                 * — M for a_major = 0 (tiles past it are skipped, rows past it are not written), GEMM-K for the
                                 * wgrad form a_major = b_major = 1 (rows past it contribute nothing).  The M / K fields are then
                                 * the upper bounds the buffers were allocated for.  Not with cta_group = 2. */
+    const int32_t* drop_rows;  /* optional DEVICE int32 [M]: the dropout element counter of output row m is drop_rows[m] * N + n
+                                * instead of m * N + n (packed rows draw the masks of their padded positions: crct_row_map's src_row) */
 } crct_gemm_t;
 
 int crct_gemm_bf16(const crct_gemm_t* args, crct_stream_t stream);
@@ -122,6 +124,7 @@ typedef struct {
     const uint64_t* salt; /* optional device word XOR-ed into both seeds */
     int32_t z_f32;        /* 1: z is fp32 (what CRCT_EPI_BIAS_RES_F32 / the embeddings with z_f32 wrote) */
     const int32_t* rows_dev;
+    const int32_t* drop_rows; /* as in crct_gemm_t: row index used by both dropout counters */
 } crct_ln_bwd_t;
 int crct_layernorm_bwd(const crct_ln_bwd_t* args, crct_stream_t stream);
 /* Split form: crct_layernorm_bwd with dgamma = dbeta = dbias = NULL computes only dz / dzm (the part the backward
