@@ -302,9 +302,16 @@ def main():
             orig(A, Bm, D, **kw)
             b.record()
             events.append((a, b))
-            flops.append(2.0 * kw['M'] * kw['N'] * kw['K'])
-            mn = kw['M'] * kw['N']            # operands once + output (+ residual / multiplier read, + GELU' write)
-            gbytes.append(2.0 * (kw['M'] * kw['K'] + kw['N'] * kw['K']) + mn * (4.0 if kw.get('epilogue') == L.EPI_F32 else 2.0)
+            M_, K_ = kw['M'], kw['K']
+            if kw.get('rows_dev') is not None:        # packed rows: the kernel runs the device-side count, not the allocation
+                r = int(kw['rows_dev'])
+                if kw.get('a_major'):
+                    K_ = min(K_, r)
+                else:
+                    M_ = min(M_, r)
+            flops.append(2.0 * M_ * kw['N'] * K_)
+            mn = M_ * kw['N']                 # operands once + output (+ residual / multiplier read, + GELU' write)
+            gbytes.append(2.0 * (M_ * K_ + kw['N'] * K_) + mn * (4.0 if kw.get('epilogue') in (L.EPI_F32, L.EPI_BIAS_RES_F32) else 2.0)
                           + (2.0 * mn if kw.get('aux') is not None else 0.0) + (2.0 * mn if kw.get('D2') is not None else 0.0))
 
         L.gemm = timed_gemm

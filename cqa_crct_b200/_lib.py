@@ -41,7 +41,7 @@ class EmbedTextArgs(C.Structure):
     _fields_ = [('ids', vp), ('types', vp), ('loc', vp), ('word', vp), ('pos', vp), ('type', vp), ('w_loc', vp),
                 ('b_loc', vp), ('gamma', vp), ('beta', vp), ('y', vp), ('z', vp), ('mean', vp), ('rstd', vp),
                 ('B', i32), ('T', i32), ('H', i32), ('max_pos', i32), ('dropout_p', f32), ('seed', u64), ('salt', vp),
-                ('z_f32', i32), ('src_row', vp), ('rows_dev', vp)]
+                ('z_f32', i32), ('src_row', vp), ('rows_dev', vp), ('y32', vp)]
 
 
 class EmbedTextBwdArgs(C.Structure):
@@ -52,7 +52,7 @@ class EmbedTextBwdArgs(C.Structure):
 class EmbedVisArgs(C.Structure):
     _fields_ = [('g', vp), ('box', vp), ('cls', vp), ('w_loc', vp), ('b_loc', vp), ('color', vp), ('gamma', vp),
                 ('beta', vp), ('y', vp), ('z', vp), ('mean', vp), ('rstd', vp), ('rows', i32), ('H', i32),
-                ('dropout_p', f32), ('seed', u64), ('salt', vp), ('z_f32', i32), ('src_row', vp), ('rows_dev', vp)]
+                ('dropout_p', f32), ('seed', u64), ('salt', vp), ('z_f32', i32), ('src_row', vp), ('rows_dev', vp), ('y32', vp)]
 
 
 class EmbedVisBwdArgs(C.Structure):
@@ -108,7 +108,7 @@ EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf
            'crct_attn_bwd', 'crct_linear_f32', 'crct_linear_f32_batched', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
            'crct_pool_mul_fwd', 'crct_pool_mul_bwd', 'crct_bump_salt', 'crct_bump_salt_to', 'crct_hybrid_loss', 'crct_scale_rows', 'crct_adamw',
            'crct_expand_blocks', 'crct_select_answers', 'crct_score_answers',
-           'crct_row_map', 'crct_group_map', 'crct_gather_rows', 'crct_gather_rows_f32', 'crct_scatter_rows_f32', 'crct_fill_zero',
+           'crct_layernorm_rows_f32', 'crct_row_map', 'crct_group_map', 'crct_gather_rows', 'crct_gather_rows_f32', 'crct_scatter_rows_f32', 'crct_fill_zero',
            'crct_f32_gemm', 'crct_f32_layernorm_fwd', 'crct_f32_layernorm_bwd', 'crct_f32_layernorm_bwd_params', 'crct_f32_attn_fwd',
            'crct_f32_attn_bwd', 'crct_f32_embed_text_fwd', 'crct_f32_embed_text_bwd', 'crct_f32_embed_vis_fwd', 'crct_f32_embed_vis_bwd',
            'crct_f32_softmax_rows', 'crct_f32_gather_first', 'crct_f32_scatter_first']
@@ -130,9 +130,10 @@ def lib():
             getattr(_lib, name)          # fail loudly on a stale library
         _lib.crct_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]
         _lib.crct_additive_mask.argtypes = [vp, C.c_int, vp, C.c_int, vp]
-        _lib.crct_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+        _lib.crct_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
         _lib.crct_colsum_bf16.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
         _lib.crct_softmax_rows.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        _lib.crct_layernorm_rows_f32.argtypes = [vp, vp, vp, vp, C.c_longlong, vp, C.c_int, C.c_int, vp]
         _lib.crct_row_map.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         _lib.crct_group_map.argtypes = [vp, vp, C.c_int, vp, vp, vp]
         _lib.crct_gather_rows.argtypes = [vp, vp, vp, C.c_int, C.c_longlong, vp, vp]
@@ -206,7 +207,8 @@ def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None
         for t, w in ((B, 'B'), (aux, 'aux'), (D2, 'D2'), (bias, 'bias'), (D, 'D')):
             _f32(t, w)
     else:
-        _bf16(A, 'A'); _bf16(B, 'B'); _bf16(aux, 'aux'); _bf16(D2, 'D2'); _f32(bias, 'bias')
+        _bf16(A, 'A'); _bf16(B, 'B'); _bf16(D2, 'D2'); _f32(bias, 'bias')
+        (_f32 if epilogue == EPI_BIAS_RES_F32 else _bf16)(aux, 'aux')
         if epilogue in (EPI_F32, EPI_BIAS_RES_F32):
             _f32(D, 'D')
         else:
@@ -243,7 +245,7 @@ def additive_mask(mask, out):
     check(lib().crct_additive_mask(ptr(mask), kind, ptr(out), mask.numel(), stream_ptr()))
 
 
-def layernorm_fwd(z, gamma, beta, y, mean=None, rstd=None, rows_dev=None):
+def layernorm_fwd(z, gamma, beta, y, mean=None, rstd=None, rows_dev=None, y32=None):
     """y bf16 <- LayerNorm(z), z bf16 or fp32 (production keeps the pre-LayerNorm sum in fp32); fp32 y selects the check mode."""
     rows, H = z.shape
     if _is32(y):
@@ -252,7 +254,9 @@ def layernorm_fwd(z, gamma, beta, y, mean=None, rstd=None, rows_dev=None):
     _bf16(y, 'y'); _f32(gamma, 'gamma')
     if not _is32(z):
         _bf16(z, 'z')
-    check(lib().crct_layernorm_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, H, int(_is32(z)), ptr(rows_dev), stream_ptr()))
+    _f32(y32, 'y32')
+    check(lib().crct_layernorm_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(y), ptr(y32), ptr(mean), ptr(rstd), rows, H, int(_is32(z)), ptr(rows_dev),
+                                   stream_ptr()))
 
 
 def _ln_bwd_args(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dbias, dzm, p_in, seed_in, p_out, seed_out, rows_dev=None, drop_rows=None):
@@ -303,7 +307,7 @@ def softmax_rows(x, out, src_row=None, rows_dev=None):
 
 
 def embed_text_fwd(ids, types, loc, word, pos, type_, w_loc, b_loc, gamma, beta, y, z=None, mean=None, rstd=None,
-                   dropout_p=0.0, seed=0, src_row=None, rows_dev=None):
+                   dropout_p=0.0, seed=0, src_row=None, rows_dev=None, y32=None):
     a = EmbedTextArgs()
     a.ids, a.types, a.loc = ptr(ids), ptr(types), ptr(loc)
     a.word, a.pos, a.type, a.w_loc, a.b_loc, a.gamma, a.beta = (ptr(word), ptr(pos), ptr(type_), ptr(w_loc), ptr(b_loc),
@@ -312,7 +316,7 @@ def embed_text_fwd(ids, types, loc, word, pos, type_, w_loc, b_loc, gamma, beta,
     a.B, a.T = ids.shape
     a.H, a.max_pos = word.shape[1], pos.shape[0]
     a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
-    a.z_f32, a.src_row, a.rows_dev = int(_is32(z) and not _is32(y)), ptr(src_row), ptr(rows_dev)
+    a.z_f32, a.src_row, a.rows_dev, a.y32 = int(_is32(z) and not _is32(y)), ptr(src_row), ptr(rows_dev), ptr(y32)
     check((lib().crct_f32_embed_text_fwd if _is32(y) else lib().crct_embed_text_fwd)(C.byref(a), stream_ptr()))
 
 
@@ -327,14 +331,14 @@ def embed_text_bwd(ids, types, loc, dz, g_word, g_pos, g_type, g_wloc, g_bloc, s
 
 
 def embed_vis_fwd(g, box, cls, w_loc, b_loc, color, gamma, beta, y, z=None, mean=None, rstd=None, dropout_p=0.0, seed=0,
-                  src_row=None, rows_dev=None):
+                  src_row=None, rows_dev=None, y32=None):
     a = EmbedVisArgs()
     a.g, a.box, a.cls, a.w_loc, a.b_loc, a.color, a.gamma, a.beta = (ptr(g), ptr(box), ptr(cls), ptr(w_loc), ptr(b_loc),
                                                                      ptr(color), ptr(gamma), ptr(beta))
     a.y, a.z, a.mean, a.rstd = ptr(y), ptr(z), ptr(mean), ptr(rstd)
     a.rows, a.H = g.shape
     a.dropout_p, a.seed, a.salt = dropout_p, seed, ptr(SALT)
-    a.z_f32, a.src_row, a.rows_dev = int(_is32(z) and not _is32(y)), ptr(src_row), ptr(rows_dev)
+    a.z_f32, a.src_row, a.rows_dev, a.y32 = int(_is32(z) and not _is32(y)), ptr(src_row), ptr(rows_dev), ptr(y32)
     check((lib().crct_f32_embed_vis_fwd if _is32(y) else lib().crct_embed_vis_fwd)(C.byref(a), stream_ptr()))
 
 
@@ -507,3 +511,10 @@ def scatter_rows_f32(g, dst, row_index):
 def fill_zero(t):
     assert t.is_contiguous()
     check(lib().crct_fill_zero(ptr(t), t.numel() * t.element_size(), stream_ptr()))
+
+
+def layernorm_rows_f32(z, gamma, beta, out, row_index=None, row_step=0):
+    """out[b] = LayerNorm(z[row_index[b]]) (or z[b * row_step]) in fp32 — the heads' inputs."""
+    B, H = out.shape
+    _f32(z, 'z'); _f32(out, 'out')
+    check(lib().crct_layernorm_rows_f32(ptr(z), ptr(gamma), ptr(beta), ptr(row_index), row_step, ptr(out), B, H, stream_ptr()))

@@ -110,7 +110,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-constexpr bool epi_uses_aux(int epi) { return epi == CRCT_EPI_BIAS_RES || epi == CRCT_EPI_MUL || epi == CRCT_EPI_BIAS_RES_F32; }
+constexpr bool epi_uses_aux(int epi) { return epi == CRCT_EPI_BIAS_RES || epi == CRCT_EPI_MUL; }      // bf16 aux, fetched a tile ahead
 constexpr bool epi_is_res(int epi) { return epi == CRCT_EPI_BIAS_RES || epi == CRCT_EPI_BIAS_RES_F32; }
 
 // ---------------------------------------------------------------------------------------------
@@ -229,22 +229,61 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row, int co
                     }
                 }
             }
-            if constexpr (EPI == CRCT_EPI_BIAS_RES_F32) {          // fp32 pre-LayerNorm sum: 8 floats = one 32-byte sector
-                if (col0 + g * 8 < p.N) {
-                    float* d = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0 + g * 8;
-                    *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
-                    *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                }
-            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[g * 4 + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
         }
-        if constexpr (EPI == CRCT_EPI_BIAS_RES_F32) return;
         const size_t off = (size_t)row * p.ldd + col0;
         if constexpr (EPI == CRCT_EPI_BIAS_GELU) {
             if (p.D2 != nullptr) st_row32(reinterpret_cast<bf16*>(p.D2) + off, p.wide != 0, p.N - col0, o2);
         }
         st_row32(reinterpret_cast<bf16*>(p.D) + off, p.wide != 0, p.N - col0, o);
+    }
+}
+
+// ---- CRCT_EPI_BIAS_RES_F32: z (fp32) = dropout(acc + bias) + aux (fp32).  The residual stream stays fp32 end to end: the
+// LayerNorm writes its output twice (bf16 = the next GEMM's operand, fp32 = the next residual), and this epilogue adds the
+// fp32 copy.  16 fp32 columns per lane and step = 64 bytes: held one STEP ahead inside a tile and — step 0 only — one TILE
+// ahead (the tile-ahead scheme of the bf16 aux would need 64 registers per lane at BN = 256).
+__device__ __forceinline__ void aux32_load(const KParams& p, int row, int col, float (&f)[EPI_COLS]) {
+#pragma unroll
+    for (int i = 0; i < EPI_COLS; ++i) f[i] = 0.f;
+    if (row < p.M) {
+        const float* src = reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ldaux + col;
+#pragma unroll
+        for (int h = 0; h < EPI_COLS / 8; ++h) {
+            if (col + h * 8 < p.N) {
+                uint32_t v[8];
+                asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(src + h * 8));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[h * 8 + j] = __uint_as_float(v[j]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void epilogue_chunk_res32(const KParams& p, int row, int col0, const uint32_t (&v)[EPI_COLS],
+                                                     const float* bias_s, const float (&ax)[EPI_COLS], uint64_t seed, int drow) {
+    if (row >= p.M) return;
+#pragma unroll
+    for (int g = 0; g < EPI_COLS / 8; ++g) {
+        if (col0 + g * 8 >= p.N) break;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+        if (p.bias != nullptr) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + g * 8 + 4);
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        }
+        if (p.drop_thr != 0u) dropout8(f, seed, (uint64_t)drow * (uint64_t)p.N + (uint64_t)(col0 + g * 8), p.drop_thr, p.drop_scale);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += ax[g * 8 + j];
+        float* d = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0 + g * 8;
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :: "l"(d), "r"(__float_as_uint(f[0])), "r"(__float_as_uint(f[1])), "r"(__float_as_uint(f[2])), "r"(__float_as_uint(f[3])),
+                        "r"(__float_as_uint(f[4])), "r"(__float_as_uint(f[5])), "r"(__float_as_uint(f[6])), "r"(__float_as_uint(f[7])) : "memory");
     }
 }
 
@@ -257,16 +296,29 @@ template <int BN>
 struct EpiGeom {
     static constexpr int STEPS = (BN / 4) / EPI_COLS;
 };
+// what a lane keeps of the aux operand across tiles: its row's BN/4 bf16 columns of the next tile, or (fp32 aux) step 0 only
+template <int BN, int EPI>
+struct AuxTile {
+    AuxRegs r[EpiGeom<BN>::STEPS];
+};
+template <int BN>
+struct AuxTile<BN, CRCT_EPI_BIAS_RES_F32> {
+    float f[EPI_COLS];
+};
 
 // aux (residual / multiplier) is fetched ONE TILE AHEAD: a lane keeps its row's BN/4 columns of the current tile in
 // registers (STEPS x 32 B); as soon as a step's 32 bytes are consumed, the same registers receive the next tile's
 // bytes, so every load has a whole tile time to arrive even when the epilogue is the critical path.
 template <int BN, int EPI>
-__device__ __forceinline__ void aux_load_tile(const KParams& p, int m0, int n0, int warp, int lane, AuxRegs (&aux)[EpiGeom<BN>::STEPS]) {
+__device__ __forceinline__ void aux_load_tile(const KParams& p, int m0, int n0, int warp, int lane, AuxTile<BN, EPI>& aux) {
     const int row = m0 + (warp & 3) * 32 + lane;
     const int cbase = n0 + ((warp - EPI_WARP0) >> 2) * (BN / 4);
+    if constexpr (EPI == CRCT_EPI_BIAS_RES_F32) {
+        aux32_load(p, row, cbase, aux.f);
+    } else {
 #pragma unroll
-    for (int c = 0; c < EpiGeom<BN>::STEPS; ++c) prefetch_aux<EPI>(p, row, cbase + c * EPI_COLS, aux[c]);
+        for (int c = 0; c < EpiGeom<BN>::STEPS; ++c) prefetch_aux<EPI>(p, row, cbase + c * EPI_COLS, aux.r[c]);
+    }
 }
 
 // Stage the tile's bias slice in smem (named barrier 1 among the epilogue warps); runs before the accumulator is ready.
@@ -286,7 +338,7 @@ __device__ __forceinline__ void epilogue_prepare(const KParams& p, int n0, int w
 // tile (m0n, n0n; has_next = 0 on the CTA's last tile).
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_acc, int m0, int n0, int warp, int lane,
-                                              const float* bias_s, AuxRegs (&aux)[EpiGeom<BN>::STEPS], bool has_next, int m0n, int n0n) {
+                                              const float* bias_s, AuxTile<BN, EPI>& aux, bool has_next, int m0n, int n0n) {
     constexpr int STEPS = EpiGeom<BN>::STEPS;
     const int lane_grp = warp & 3;                          // TMEM lanes [32*lane_grp, +32) are this warp's
     const int col_q = (warp - EPI_WARP0) >> 2;              // column quarter
@@ -304,15 +356,31 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
     const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cbase;
     uint32_t v[2][EPI_COLS];
     ptx::tc_ld_32x16(taddr, v[0]);
+    if constexpr (EPI == CRCT_EPI_BIAS_RES_F32) {
+        float ax[2][EPI_COLS];
 #pragma unroll
-    for (int c = 0; c < STEPS; ++c) {
-        const int cc = cbase + c * EPI_COLS;
-        ptx::tc_wait_ld();
-        reg_fence16(v[c & 1]);              // the loaded values exist from here on (tcgen05.ld is asynchronous)
-        if (c + 1 < STEPS) ptx::tc_ld_32x16(taddr + (uint32_t)((c + 1) * EPI_COLS), v[(c + 1) & 1]);
-        if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row, n0 + cc, v[c & 1], bias_s + cc, aux[c], seed, drow);     // warp-uniform
-        if constexpr (epi_uses_aux(EPI)) {
-            if (has_next) prefetch_aux<EPI>(p, rown, n0n + cc, aux[c]);
+        for (int i = 0; i < EPI_COLS; ++i) ax[0][i] = aux.f[i];
+#pragma unroll
+        for (int c = 0; c < STEPS; ++c) {
+            const int cc = cbase + c * EPI_COLS;
+            if (c + 1 < STEPS) aux32_load(p, row, n0 + cc + EPI_COLS, ax[(c + 1) & 1]);        // one step ahead
+            ptx::tc_wait_ld();
+            reg_fence16(v[c & 1]);
+            if (c + 1 < STEPS) ptx::tc_ld_32x16(taddr + (uint32_t)((c + 1) * EPI_COLS), v[(c + 1) & 1]);
+            if (n0 + cc < p.N) epilogue_chunk_res32(p, row, n0 + cc, v[c & 1], bias_s + cc, ax[c & 1], seed, drow);
+        }
+        if (has_next) aux32_load(p, rown, n0n + cbase, aux.f);                                 // step 0 of the next tile
+    } else {
+#pragma unroll
+        for (int c = 0; c < STEPS; ++c) {
+            const int cc = cbase + c * EPI_COLS;
+            ptx::tc_wait_ld();
+            reg_fence16(v[c & 1]);              // the loaded values exist from here on (tcgen05.ld is asynchronous)
+            if (c + 1 < STEPS) ptx::tc_ld_32x16(taddr + (uint32_t)((c + 1) * EPI_COLS), v[(c + 1) & 1]);
+            if (n0 + cc < p.N) epilogue_chunk<EPI>(p, row, n0 + cc, v[c & 1], bias_s + cc, aux.r[c], seed, drow);     // warp-uniform
+            if constexpr (epi_uses_aux(EPI)) {
+                if (has_next) prefetch_aux<EPI>(p, rown, n0n + cc, aux.r[c]);
+            }
         }
     }
 }
@@ -452,7 +520,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             m0 = (mn / p.num_n_tiles) * BLOCK_M;
             n0 = (mn % p.num_n_tiles) * BN;
         };
-        AuxRegs aux[EpiGeom<BN>::STEPS];
+        AuxTile<BN, EPI> aux;
         if (blockIdx.x < p.num_tiles) {
             int m0, n0;
             origin(blockIdx.x, m0, n0);
@@ -640,7 +708,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             m0 = (mn / p.num_n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
             n0 = (mn % p.num_n_tiles) * BN;
         };
-        AuxRegs aux[EpiGeom<BN>::STEPS];
+        AuxTile<BN, EPI> aux;
         if (cluster_id < p.num_tiles) {
             int m0, n0;
             origin(cluster_id, m0, n0);
@@ -787,6 +855,8 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     if (a->a_rows_dev && a->cta_group == 2) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: a_rows_dev is not supported by the CTA-pair kernel");
     if (a->a_rows_dev && a->a_major && !a->b_major) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: a_rows_dev needs a_major = 0 (rows = M) or the wgrad form a_major = b_major = 1 (rows = K)");
     if ((a->epilogue == CRCT_EPI_MUL) && !a->aux) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: MUL epilogue needs aux");
+    if (a->epilogue == CRCT_EPI_BIAS_RES_F32 && (!a->aux || ((uintptr_t)a->aux & 31) || ((uintptr_t)a->D & 31)))
+        CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: RES_F32 epilogue needs a 32-byte aligned fp32 aux and D");
     const bool f32 = a->epilogue == CRCT_EPI_F32;
     int split_k = a->split_k;
     const int kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
@@ -838,8 +908,8 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     p.ldd = a->ldd; p.ldaux = a->ldaux;
     {
         auto ok32 = [](const void* q, int ld) { return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 31u) == 0 && ld % 16 == 0); };
-        const bool d32 = a->epilogue == CRCT_EPI_BIAS_RES_F32;        // fp32 D: only the aux rows go through the 32-byte path
-        p.wide = (!f32 && a->N % 16 == 0 && (d32 || ok32(a->D, a->ldd)) && ok32(a->D2, a->ldd) && ok32(a->aux, a->ldaux)) ? 1 : 0;
+        const bool d32 = a->epilogue == CRCT_EPI_BIAS_RES_F32;        // fp32 D and aux: their own 32-byte path
+        p.wide = (!f32 && !d32 && a->N % 16 == 0 && ok32(a->D, a->ldd) && ok32(a->D2, a->ldd) && ok32(a->aux, a->ldaux)) ? 1 : 0;
     }
     p.accumulate = a->accumulate;
     p.drop_thr = crct_drop_threshold(a->dropout_p);

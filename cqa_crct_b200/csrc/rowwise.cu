@@ -54,8 +54,10 @@ __device__ __forceinline__ void store8_f32(float* p, const float (&f)[8]) {
 }
 
 // y = (z - mean) * rstd * gamma + beta, optional dropout on y; writes y (bf16)
+// (and, when y32_row is given, the same values unrounded: the fp32 copy the next residual add reads)
 __device__ __forceinline__ void ln_write(const Row& z, int nchunks, int lane, float mean, float rstd, const float* gamma,
-                                         const float* beta, bf16* y_row, uint64_t row_idx0, uint32_t thr, float scale, uint64_t seed) {
+                                         const float* beta, bf16* y_row, float* y32_row, uint64_t row_idx0, uint32_t thr, float scale,
+                                         uint64_t seed) {
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
         const int ch = lane + 32 * c;
@@ -67,6 +69,7 @@ __device__ __forceinline__ void ln_write(const Row& z, int nchunks, int lane, fl
             for (int j = 0; j < 8; ++j) o[j] = (z.v[c][j] - mean) * rstd * g[j] + b[j];
             if (thr != 0u) dropout8(o, seed, row_idx0 + ch * 8, thr, scale);
             store8_bf16(y_row + ch * 8, o);
+            if (y32_row != nullptr) store8_f32(y32_row + ch * 8, o);
         }
     }
 }
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(ROW_THREADS) additive_mask_kernel(const void* 
 template <bool ZF32>
 __global__ void __launch_bounds__(ROW_THREADS)
 layernorm_fwd_kernel(const void* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
+                     bf16* __restrict__ y, float* __restrict__ y32, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
                      const int* __restrict__ rows_dev) {
     pdl_launch_dependents();
     pdl_wait();
@@ -108,8 +111,39 @@ layernorm_fwd_kernel(const void* __restrict__ z, const float* __restrict__ gamma
         if (lane + 32 * c < nchunks) load8_z<ZF32>(z, (size_t)row * H + (lane + 32 * c) * 8, r.v[c]);
     float mean, rstd;
     row_stats(r, nchunks, lane, H, mean, rstd);
-    ln_write(r, nchunks, lane, mean, rstd, gamma, beta, y + (size_t)row * H, 0, 0u, 1.f, 0);
+    ln_write(r, nchunks, lane, mean, rstd, gamma, beta, y + (size_t)row * H, y32 != nullptr ? y32 + (size_t)row * H : nullptr, 0, 0u, 1.f, 0);
     if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// LayerNorm of selected rows, fp32 in and out: the first-token / first-region hidden states the heads read
+// (vilbert.py:958,973,1599-1600) are taken from the LAST pre-LayerNorm sum (fp32) and never rounded to bf16 — the poolers and
+// the regressor are fp32, and with SmoothL1 / L1 losses their gradient scales with the regression error itself.
+__global__ void __launch_bounds__(ROW_THREADS)
+layernorm_rows_f32_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const int* __restrict__ row_index, long long row_step, float* __restrict__ out, int B, int H) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (ROW_THREADS / 32) + warp;
+    if (b >= B) return;
+    const size_t row = row_index != nullptr ? (size_t)__ldg(row_index + b) : (size_t)b * (size_t)row_step;
+    const int nchunks = H >> 3;
+    Row r;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+        if (lane + 32 * c < nchunks) load8_f32(z + row * H + (lane + 32 * c) * 8, r.v[c]);
+    float mean, rstd;
+    row_stats(r, nchunks, lane, H, mean, rstd);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunks) {
+            float g[8], bb[8], o[8];
+            load8_f32(gamma + ch * 8, g);
+            load8_f32(beta + ch * 8, bb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (r.v[c][j] - mean) * rstd * g[j] + bb[j];
+            store8_f32(out + (size_t)b * H + ch * 8, o);
+        }
+    }
 }
 
 // dz = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)), dxh = dy * gamma
@@ -483,7 +517,7 @@ struct TextEmbArgs {
     bf16* y; void* z; float* mean; float* rstd;
     int B, T, H;
     uint32_t thr; float scale; uint64_t seed; const unsigned long long* salt;
-    int z_f32; const int* src_row; const int* rows_dev;
+    int z_f32; const int* src_row; const int* rows_dev; float* y32;
 };
 
 __device__ __forceinline__ int first_qa_index(const long long* types_row, int T, int lane) {
@@ -555,7 +589,8 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_text_fwd_kernel(const TextE
     }
     float mean, rstd;
     row_stats(r, nchunks, lane, H, mean, rstd);
-    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)src * H, a.thr, a.scale, a.salt ? (a.seed ^ __ldg(a.salt)) : a.seed);
+    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, a.y32 != nullptr ? a.y32 + (size_t)row * H : nullptr,
+             (uint64_t)src * H, a.thr, a.scale, a.salt ? (a.seed ^ __ldg(a.salt)) : a.seed);
     if (lane == 0 && a.mean) { a.mean[row] = mean; a.rstd[row] = rstd; }
 }
 
@@ -642,7 +677,7 @@ struct VisEmbArgs {
     bf16* y; void* z; float* mean; float* rstd;
     int rows, H;
     uint32_t thr; float scale; uint64_t seed; const unsigned long long* salt;
-    int z_f32; const int* src_row; const int* rows_dev;
+    int z_f32; const int* src_row; const int* rows_dev; float* y32;
 };
 
 __global__ void __launch_bounds__(ROW_THREADS) embed_vis_fwd_kernel(const VisEmbArgs a) {
@@ -680,7 +715,8 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_vis_fwd_kernel(const VisEmb
     }
     float mean, rstd;
     row_stats(r, nchunks, lane, H, mean, rstd);
-    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, (uint64_t)src * H, a.thr, a.scale, a.salt ? (a.seed ^ __ldg(a.salt)) : a.seed);
+    ln_write(r, nchunks, lane, mean, rstd, a.gamma, a.beta, a.y + (size_t)row * H, a.y32 != nullptr ? a.y32 + (size_t)row * H : nullptr,
+             (uint64_t)src * H, a.thr, a.scale, a.salt ? (a.seed ^ __ldg(a.salt)) : a.seed);
     if (lane == 0 && a.mean) { a.mean[row] = mean; a.rstd[row] = rstd; }
 }
 
@@ -793,17 +829,27 @@ extern "C" CRCT_API int crct_additive_mask(const void* mask, int kind, float* ou
     return CRCT_OK;
 }
 
-extern "C" CRCT_API int crct_layernorm_fwd(const void* z, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+extern "C" CRCT_API int crct_layernorm_fwd(const void* z, const float* gamma, const float* beta, void* y, float* y32, float* mean, float* rstd,
                                   int rows, int H, int z_f32, const int32_t* rows_dev, crct_stream_t s) {
     if (!z || !gamma || !beta || !y || (mean == nullptr) != (rstd == nullptr)) CRCT_FAIL(CRCT_ERR_ARG, "crct_layernorm_fwd: bad pointer");
     if (int rc = check_row_width(H, "crct_layernorm_fwd")) return rc;
     if (rows <= 0) return CRCT_OK;
     if (z_f32)
         CRCT_CUDA(crct_launch_pdl(layernorm_fwd_kernel<true>, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, as_stream(s), z,
-                                  gamma, beta, reinterpret_cast<bf16*>(y), mean, rstd, rows, H, rows_dev));
+                                  gamma, beta, reinterpret_cast<bf16*>(y), y32, mean, rstd, rows, H, rows_dev));
     else
         CRCT_CUDA(crct_launch_pdl(layernorm_fwd_kernel<false>, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, as_stream(s), z,
-                                  gamma, beta, reinterpret_cast<bf16*>(y), mean, rstd, rows, H, rows_dev));
+                                  gamma, beta, reinterpret_cast<bf16*>(y), y32, mean, rstd, rows, H, rows_dev));
+    return CRCT_OK;
+}
+
+extern "C" CRCT_API int crct_layernorm_rows_f32(const float* z, const float* gamma, const float* beta, const int32_t* row_index,
+                                                long long row_step, float* out, int B, int H, crct_stream_t s) {
+    if (!z || !gamma || !beta || !out) CRCT_FAIL(CRCT_ERR_ARG, "crct_layernorm_rows_f32: null pointer");
+    if (int rc = check_row_width(H, "crct_layernorm_rows_f32")) return rc;
+    if (B <= 0) return CRCT_OK;
+    layernorm_rows_f32_kernel<<<row_grid(B), ROW_THREADS, 0, as_stream(s)>>>(z, gamma, beta, row_index, row_step, out, B, H);
+    CRCT_LAUNCH_CHECK();
     return CRCT_OK;
 }
 
@@ -925,7 +971,7 @@ extern "C" CRCT_API int crct_embed_text_fwd(const crct_embed_text_t* a, crct_str
     k.word = a->word; k.pos = a->pos; k.type = a->type; k.w_loc = a->w_loc; k.b_loc = a->b_loc; k.gamma = a->gamma; k.beta = a->beta;
     k.y = reinterpret_cast<bf16*>(a->y); k.z = a->z; k.mean = a->mean; k.rstd = a->rstd;
     k.B = a->B; k.T = a->T; k.H = a->H;
-    k.z_f32 = a->z_f32; k.src_row = a->src_row; k.rows_dev = a->rows_dev;
+    k.z_f32 = a->z_f32; k.src_row = a->src_row; k.rows_dev = a->rows_dev; k.y32 = a->y32;
     k.thr = crct_drop_threshold(a->dropout_p); k.scale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; k.seed = a->seed;
     k.salt = reinterpret_cast<const unsigned long long*>(a->salt);
     if (a->B * a->T <= 0) return CRCT_OK;
@@ -962,7 +1008,7 @@ extern "C" CRCT_API int crct_embed_vis_fwd(const crct_embed_vis_t* a, crct_strea
     k.w_loc = a->w_loc; k.b_loc = a->b_loc; k.color = a->color; k.gamma = a->gamma; k.beta = a->beta;
     k.y = reinterpret_cast<bf16*>(a->y); k.z = a->z; k.mean = a->mean; k.rstd = a->rstd;
     k.rows = a->rows; k.H = a->H;
-    k.z_f32 = a->z_f32; k.src_row = a->src_row; k.rows_dev = a->rows_dev;
+    k.z_f32 = a->z_f32; k.src_row = a->src_row; k.rows_dev = a->rows_dev; k.y32 = a->y32;
     k.thr = crct_drop_threshold(a->dropout_p); k.scale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; k.seed = a->seed;
     k.salt = reinterpret_cast<const unsigned long long*>(a->salt);
     if (a->rows <= 0) return CRCT_OK;

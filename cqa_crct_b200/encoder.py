@@ -225,6 +225,7 @@ class VisualDialogEncoder(nn.Module):
         self._side_stream = None
         self._wg_stream = None
         self._wg_hold = []
+        self._tail = {}                      # hidden width -> (last pre-LayerNorm sum, its LayerNorm): read by the heads
         self.train()                         # encoder_decorator.py:17
 
     # ------------------------------------------------------------------ parameters / devices
@@ -328,18 +329,21 @@ class VisualDialogEncoder(nn.Module):
         before the LayerNorm was the largest single contributor to the end-to-end error (tools/parity_sensitivity.py)."""
         N, K = W.shape
         z = torch.empty(M, N, dtype=torch.float32, device=x.device)
-        L.gemm(x, W, z, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES if self.fp32 else L.EPI_BIAS_RES_F32, aux=aux,
-               dropout_p=p, seed=seed, rows_dev=n, drop_rows=src)
+        L.gemm(x, W, z, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES if self.fp32 else L.EPI_BIAS_RES_F32,
+               aux=aux if self.fp32 else aux.res, dropout_p=p, seed=seed, rows_dev=n, drop_rows=src)
+        aux.res = None                     # consumed (same stream): the fp32 copy is not kept for the backward
         return z
 
     def _ln(self, z, pre, keep, n=None):
         rows, H = z.shape
         y = torch.empty(rows, H, dtype=self.act, device=z.device)
+        # the residual stream stays fp32: `y` (bf16) is the next GEMM's operand, `y.res` the copy the next residual add reads
+        y.res = None if self.fp32 else torch.empty(rows, H, dtype=torch.float32, device=z.device)
         mean = rstd = None
         if keep:
             mean = torch.empty(rows, dtype=torch.float32, device=z.device)
             rstd = torch.empty(rows, dtype=torch.float32, device=z.device)
-        L.layernorm_fwd(z, self._p(pre + '.weight'), self._p(pre + '.bias'), y, mean, rstd, rows_dev=n)
+        L.layernorm_fwd(z, self._p(pre + '.weight'), self._p(pre + '.bias'), y, mean, rstd, rows_dev=n, y32=y.res)
         return y, mean, rstd
 
     def _ffn_fwd(self, a, pre_i, pre_o, p_drop, seed, keep, rw=None):
@@ -351,6 +355,7 @@ class VisualDialogEncoder(nn.Module):
         h = self._linear(a, W1, self._p(pre_i + '.dense.bias'), M, L.EPI_BIAS_GELU, D2=dg, n=n)
         z = self._linear_res(h, W2, self._p(pre_o + '.dense.bias'), M, a, p_drop, seed, n, src)
         y, mean, rstd = self._ln(z, pre_o + '.LayerNorm', keep, n)
+        self._tail[z.shape[1]] = (z, pre_o + '.LayerNorm')       # the stream's latest pre-LayerNorm sum (fp32): what the heads read
         s = None
         if keep:
             s = _Saved()
@@ -600,12 +605,11 @@ class VisualDialogEncoder(nn.Module):
         H, Hv, Hb = cfg.hidden_size, cfg.v_hidden_size, cfg.bi_hidden_size
         hw0 = torch.empty(B, H, dtype=torch.float32, device=dev)
         hv0 = torch.empty(B, Hv, dtype=torch.float32, device=dev)
-        if rt.cu is not None:                  # packed rows: sample b's first token / region is row cu[b]
-            L.gather_rows_f32(t, rt.cu, hw0)
-            L.gather_rows_f32(v, rv.cu, hv0)
-        else:
-            L.gather_first(t, T * H, hw0)          # vilbert.py:958 / 1600
-            L.gather_first(v, R * Hv, hv0)         # vilbert.py:973 / 1599
+        # first token / region of every sample (vilbert.py:958,973 / 1599-1600), row cu[b] when packed: LayerNorm of the last
+        # pre-LayerNorm sum in fp32 — the heads never see the bf16 rounding of the sequence outputs t / v
+        (z_t, ln_t), (z_v, ln_v) = self._tail[H], self._tail[Hv]
+        L.layernorm_rows_f32(z_t, self._p(ln_t + '.weight'), self._p(ln_t + '.bias'), hw0, rt.cu, T)
+        L.layernorm_rows_f32(z_v, self._p(ln_v + '.weight'), self._p(ln_v + '.bias'), hv0, rv.cu, R)
         prefusion = torch.empty(B, 512, dtype=torch.float32, device=dev)          # cat((hv, hw), -1), regressor.py:40
         p_t, pt = self._fwd_problem(hw0, 'bert.t_pooler.dense', L.ACT_RELU)
         p_v, pv = self._fwd_problem(hv0, 'bert.v_pooler.dense', L.ACT_RELU)
@@ -752,6 +756,7 @@ class VisualDialogEncoder(nn.Module):
         lanes.v_wait_t()
         e = 'bert.embeddings'
         t = torch.empty(B * T, H, dtype=self.act, device=dev)
+        t.res = None if self.fp32 else torch.empty(B * T, H, dtype=torch.float32, device=dev)
         zt = torch.empty(B * T, H, dtype=torch.float32, device=dev) if keep else None      # pre-LayerNorm sums stay fp32
         mt = torch.empty(B * T, dtype=torch.float32, device=dev) if keep else None
         rt_ = torch.empty(B * T, dtype=torch.float32, device=dev) if keep else None
@@ -759,7 +764,7 @@ class VisualDialogEncoder(nn.Module):
         L.embed_text_fwd(ids, types, loc, self._p(e + '.word_embeddings.weight'), self._p(e + '.position_embeddings.weight'),
                          self._p(e + '.plotqa_type_embeddings.weight'), self._p(e + '.txt_location_embeddings.weight'),
                          self._p(e + '.txt_location_embeddings.bias'), self._p(e + '.LayerNorm.weight'), self._p(e + '.LayerNorm.bias'),
-                         t, zt, mt, rt_, dropout_p=p_et, seed=s_et, src_row=rt.src, rows_dev=rt.n)
+                         t, zt, mt, rt_, dropout_p=p_et, seed=s_et, src_row=rt.src, rows_dev=rt.n, y32=t.res)
         e = 'bert.v_embeddings'
         feat2 = feat.reshape(Bv * R, F)
         box2, cls2 = box.reshape(Bv * R, 4), cls.reshape(Bv * R)
@@ -770,22 +775,27 @@ class VisualDialogEncoder(nn.Module):
             gimg = self._linear(probs, self._w(e + '.new_image_embeddings.weight'), self._p(e + '.new_image_embeddings.bias'), Bv * R,
                                 n=rvq.n)
             v = torch.empty(Bv * R, Hv, dtype=self.act, device=dev)
+            v.res = None if self.fp32 else torch.empty(Bv * R, Hv, dtype=torch.float32, device=dev)
             zv = torch.empty(Bv * R, Hv, dtype=torch.float32, device=dev) if keep else None
             mv = torch.empty(Bv * R, dtype=torch.float32, device=dev) if keep else None
             rv_ = torch.empty(Bv * R, dtype=torch.float32, device=dev) if keep else None
             L.embed_vis_fwd(gimg, box2, cls2, self._p(e + '.new_loc_emb.weight'), self._p(e + '.new_loc_emb.bias'),
                             self._p(e + '.color_emb.weight'), self._p(e + '.LayerNorm.weight'), self._p(e + '.LayerNorm.bias'),
-                            v, zv, mv, rv_, dropout_p=p_ev, seed=s_ev, src_row=rvq.src, rows_dev=rvq.n)
+                            v, zv, mv, rv_, dropout_p=p_ev, seed=s_ev, src_row=rvq.src, rows_dev=rvq.n, y32=v.res)
             if group is not None:
                 # f3: the visual embedding depends on the image only — computed once per question above, fanned out to the
                 # question's candidate sequences here (the reference replicates the fp32 inputs on the host instead,
                 # fig_dataloader.py:690-693); from the first co-attention on the visual stream is per candidate
                 v_q = v
                 v = torch.empty(B * R, Hv, dtype=self.act, device=dev)
-                if self.varlen:
-                    L.gather_rows(v_q, rv.src, v, rows_dev=rv.n)
-                else:
-                    L.expand_blocks(v_q.view(Bv, R * Hv), group, v.view(B, R * Hv))
+                v.res = None if self.fp32 else torch.empty(B * R, Hv, dtype=torch.float32, device=dev)
+                for src_, dst_ in ((v_q, v), (v_q.res, v.res)):
+                    if src_ is None:
+                        continue
+                    if self.varlen:
+                        L.gather_rows(src_, rv.src, dst_, rows_dev=rv.n)
+                    else:
+                        L.expand_blocks(src_.view(Bv, R * Hv), group, dst_.view(B, R * Hv))
         # --- encoder (vilbert.py:852-939): text layers on the text lane, visual layers on the visual lane (v_layer[k-1]
         # and layer[5+k] are independent, vilbert.py:868-886; the 3520-row visual kernels fill the SMs the text kernels'
         # partial waves leave idle); the lanes meet inside every connection layer.
@@ -805,6 +815,7 @@ class VisualDialogEncoder(nn.Module):
         lanes.t_wait_v()
         self._x_hold = None
         logits, outs, scalars, s_heads = self._heads_fwd(t, v, rt, rv, labels, Rt, kind, keep)
+        self._tail = {}
         if keep:
             sv.B, sv.T, sv.R, sv.rows_t, sv.rows_v = B, T, R, rt, rv
             sv.ids, sv.types, sv.loc, sv.box2, sv.cls2, sv.probs = ids, types, loc, box2, cls2, probs

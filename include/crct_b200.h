@@ -57,7 +57,8 @@ typedef enum {
     CRCT_EPI_BIAS_RES = 2,  /* D = dropout(acc + bias) + aux                      vilbert.py:424-428,467-471,749-756 */
     CRCT_EPI_MUL = 3,       /* D = acc * aux   (aux = the D2 saved by BIAS_GELU)   backward of vilbert.py:456 */
     CRCT_EPI_F32 = 4,       /* D (fp32) = acc, or D += acc when accumulate != 0 (wgrad, split-K) */
-    CRCT_EPI_BIAS_RES_F32 = 5 /* CRCT_EPI_BIAS_RES with an fp32 D: the pre-LayerNorm sum z stays unrounded until the LayerNorm */
+    CRCT_EPI_BIAS_RES_F32 = 5 /* CRCT_EPI_BIAS_RES with fp32 D AND fp32 aux: the residual stream and the pre-LayerNorm sum z are
+                               * never rounded to bf16 (the reference's autocast keeps them fp32 too: its LayerNorm runs in fp32) */
 } crct_epilogue_t;
 
 typedef struct {
@@ -101,9 +102,15 @@ int crct_additive_mask(const void* mask, int kind, float* out, int n, crct_strea
  * `rows` then only sizes the grid.  This is how the var-len ("packed") layout runs inside a captured CUDA graph: the number
  * of valid token / region rows of a batch (crct_row_map) is never read by the host. */
 /* y = LayerNorm(z) with eps = 1e-12 inside the sqrt (vilbert.py:281-294).  z bf16 (z_f32 = 0) or fp32 (z_f32 = 1)
- * [rows,H], y bf16; mean/rstd fp32 [rows] or both NULL (inference). */
-int crct_layernorm_fwd(const void* z, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+ * [rows,H], y bf16 (the next GEMM's operand); y32 (or NULL): the same values in fp32 — the residual stream stays fp32 end to
+ * end, the next CRCT_EPI_BIAS_RES_F32 epilogue adds this copy; mean/rstd fp32 [rows] or both NULL (inference). */
+int crct_layernorm_fwd(const void* z, const float* gamma, const float* beta, void* y, float* y32, float* mean, float* rstd,
                        int rows, int H, int z_f32, const int32_t* rows_dev, crct_stream_t stream);
+/* out[b,:] (fp32) = LayerNorm(z[row,:]) for row = row_index[b] (row_index NULL: row = b * row_step), z fp32: the
+ * first-token / first-region states the heads read (vilbert.py:958,973,1599-1600) straight from the last pre-LayerNorm sum,
+ * without the bf16 rounding of the sequence output. */
+int crct_layernorm_rows_f32(const float* z, const float* gamma, const float* beta, const int32_t* row_index, long long row_step,
+                            float* out, int B, int H, crct_stream_t stream);
 /* LayerNorm backward.  dy may carry the dropout that FOLLOWED the LayerNorm in the forward (embeddings:
  * p_in, seed_in); dzm is dz with the dropout that PRECEDED the residual add re-applied (p_out, seed_out; element
  * counter row*H+col — the same stream the CRCT_EPI_BIAS_RES epilogue used), i.e. the gradient of the dense output. */
@@ -155,6 +162,7 @@ typedef struct {
     int32_t z_f32;            /* 1: z is written in fp32 */
     const int32_t* src_row;   /* packed layout: output row r is token src_row[r] = b*T + t (crct_row_map); NULL = all B*T rows */
     const int32_t* rows_dev;
+    float* y32;               /* optional fp32 copy of y (residual stream), as in crct_layernorm_fwd */
 } crct_embed_text_t;
 int crct_embed_text_fwd(const crct_embed_text_t* args, crct_stream_t stream);
 /* scatter of dz (after crct_layernorm_bwd) into the tables; all outputs += . */
@@ -181,6 +189,7 @@ typedef struct {
     int32_t z_f32;
     const int32_t* src_row;   /* packed layout: g / y / z row r belongs to region src_row[r] = b*R + i of box / cls */
     const int32_t* rows_dev;
+    float* y32;
 } crct_embed_vis_t;
 int crct_embed_vis_fwd(const crct_embed_vis_t* args, crct_stream_t stream);
 typedef struct {

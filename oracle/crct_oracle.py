@@ -73,7 +73,9 @@ def layer_schedule(cfg: Config) -> List[Tuple[str, int]]:
 # --------------------------------------------------------------------------------------
 # The reference arithmetic is the default (`_q` / `_qw` are identities).  Inside `bf16_emulation()` the
 # restatement additionally rounds to bf16 exactly where the CUDA path STORES bf16: tensor-core GEMM operands
-# (weights `_qw`, activations `_q`) and every activation / gradient tensor that goes through HBM.  All
+# (weights `_qw`, activations `_q`) and every activation / gradient tensor that goes through HBM in bf16.  The
+# residual stream does not: the CUDA path keeps the pre-LayerNorm sums `z` and the LayerNorm outputs in fp32 (plus a
+# bf16 copy of the latter as the next GEMM's A operand — the `_q(x)` inside `tlin`).  All
 # reductions, statistics, softmax, the heads and the losses stay fp32/fp64, as in the kernels.  Comparing the
 # CUDA path with this mode separates implementation error from the operand quantisation every bf16
 # tensor-core path has (tests/test_model_gpu.py states both tolerances).
@@ -168,12 +170,12 @@ def lin_bwd(dy, x, W):
 
 def tlin(x, W, b):
     """Linear on the tensor-core path (bf16 operands in emulation mode)."""
-    return x @ _qw(W).t() + b
+    return _q(x) @ _qw(W).t() + b          # the A operand is the bf16 copy of the (fp32) residual stream
 
 
 def tlin_bwd(dy, x, W):
     dy2, x2 = dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1])
-    return dy @ _qw(W), dy2.t() @ x2, dy2.sum(0)
+    return dy @ _qw(W), dy2.t() @ _q(x2), dy2.sum(0)
 
 
 class _Grads(dict):
@@ -206,9 +208,9 @@ def embed_text_fwd(w, ids, types, loc, pre='bert.embeddings.'):
     ty[ty == -1] = 0
     ty_on = (types != 0).unsqueeze(-1)
     te = w[pre + 'plotqa_type_embeddings.weight'][ty] * ty_on
-    z = _q(we + pe + te + le)
+    z = we + pe + te + le                                # pre-LayerNorm sums stay fp32 on the CUDA path
     y, mean, rstd = ln_fwd(z, w[pre + 'LayerNorm.weight'], w[pre + 'LayerNorm.bias'])
-    return _q(y), dict(z=z, mean=mean, rstd=rstd, pos=pos, qa=qa, loc_on=loc_on, ty=ty, ty_on=ty_on)
+    return y, dict(z=z, mean=mean, rstd=rstd, pos=pos, qa=qa, loc_on=loc_on, ty=ty, ty_on=ty_on)
 
 
 def embed_text_bwd(w, g, dy, c, ids, loc, pre='bert.embeddings.'):
@@ -235,11 +237,11 @@ def embed_text_bwd(w, g, dy, c, ids, loc, pre='bert.embeddings.'):
 def embed_vis_fwd(w, feat, box, cls, pre='bert.v_embeddings.'):
     """vilbert.py:1474-1496 (PlotQA branch: img + loc + color, no areas, mask_prob_img = 0)."""
     p = _q(torch.softmax(feat, dim=-1))
-    z = _q(_q(tlin(p, w[pre + 'new_image_embeddings.weight'], w[pre + 'new_image_embeddings.bias']))
-           + lin(box, w[pre + 'new_loc_emb.weight'], w[pre + 'new_loc_emb.bias'])
-           + w[pre + 'color_emb.weight'][cls])
+    z = (_q(tlin(p, w[pre + 'new_image_embeddings.weight'], w[pre + 'new_image_embeddings.bias']))
+         + lin(box, w[pre + 'new_loc_emb.weight'], w[pre + 'new_loc_emb.bias'])
+         + w[pre + 'color_emb.weight'][cls])
     y, mean, rstd = ln_fwd(z, w[pre + 'LayerNorm.weight'], w[pre + 'LayerNorm.bias'])
-    return _q(y), dict(p=p, z=z, mean=mean, rstd=rstd)
+    return y, dict(p=p, z=z, mean=mean, rstd=rstd)
 
 
 def embed_vis_bwd(w, g, dy, c, box, cls, pre='bert.v_embeddings.'):
@@ -268,9 +270,9 @@ def ffn_fwd(w, a, pre_i, pre_o):
     """intermediate (vilbert.py:454-457 / 585-588) + output (vilbert.py:467-471 / 598-602)."""
     u = tlin(a, w[pre_i + 'dense.weight'], w[pre_i + 'dense.bias'])
     h = _q(gelu(u))
-    z = _q(tlin(h, w[pre_o + 'dense.weight'], w[pre_o + 'dense.bias']) + a)
+    z = tlin(h, w[pre_o + 'dense.weight'], w[pre_o + 'dense.bias']) + a
     y, mean, rstd = ln_fwd(z, w[pre_o + 'LayerNorm.weight'], w[pre_o + 'LayerNorm.bias'])
-    return _q(y), dict(a=a, u=u, h=h, z=z, mean=mean, rstd=rstd)
+    return y, dict(a=a, u=u, h=h, z=z, mean=mean, rstd=rstd, y32=y)
 
 
 def ffn_bwd(w, g, dy, c, pre_i, pre_o):
@@ -296,9 +298,8 @@ def self_layer_fwd(w, x, add_mask, nh, pre):
     q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
     ctx, p, pd = attn_fwd(q, k, v, add_mask, nh)
     po = pre + 'attention.output.'
-    z1 = _q(tlin(ctx, w[po + 'dense.weight'], w[po + 'dense.bias']) + x)
+    z1 = tlin(ctx, w[po + 'dense.weight'], w[po + 'dense.bias']) + x
     a, mean1, rstd1 = ln_fwd(z1, w[po + 'LayerNorm.weight'], w[po + 'LayerNorm.bias'])
-    a = _q(a)
     y, cf = ffn_fwd(w, a, pre + 'intermediate.', pre + 'output.')
     return y, dict(x=x, q=q, k=k, v=v, p=p, pd=pd, ctx=ctx, z1=z1, mean1=mean1, rstd1=rstd1, ffn=cf, nh=nh)
 
@@ -339,11 +340,10 @@ def co_layer_fwd(w, v, t, v_mask, t_mask, nh, pre):
     ctx1, p1, pd1 = attn_fwd(q2, k1, v1, v_mask, nh)       # [B,T,Hb]
     ctx2, p2, pd2 = attn_fwd(q1, k2, v2, t_mask, nh)       # [B,R,Hb]
     po = pre + 'biOutput.'
-    zv = _q(tlin(ctx2, w[po + 'dense1.weight'], w[po + 'dense1.bias']) + v)
+    zv = tlin(ctx2, w[po + 'dense1.weight'], w[po + 'dense1.bias']) + v
     av, mv, rv = ln_fwd(zv, w[po + 'LayerNorm1.weight'], w[po + 'LayerNorm1.bias'])
-    zt = _q(tlin(ctx1, w[po + 'dense2.weight'], w[po + 'dense2.bias']) + t)
+    zt = tlin(ctx1, w[po + 'dense2.weight'], w[po + 'dense2.bias']) + t
     at, mt, rt = ln_fwd(zt, w[po + 'LayerNorm2.weight'], w[po + 'LayerNorm2.bias'])
-    av, at = _q(av), _q(at)
     yv, cfv = ffn_fwd(w, av, pre + 'v_intermediate.', pre + 'v_output.')
     yt, cft = ffn_fwd(w, at, pre + 't_intermediate.', pre + 't_output.')
     c = dict(v=v, t=t, q1=q1, k1=k1, v1=v1, q2=q2, k2=k2, v2=v2, p1=p1, pd1=pd1, p2=p2, pd2=pd2,
@@ -415,7 +415,8 @@ def mlp4_bwd(w, g, dy, c, pre):
 
 def heads_fwd(w, t, v):
     """Poolers (vilbert.py:955-976), classifier (vilbert.py:1052-1060), regressor (regressor.py:36-42)
-    evaluated densely on every row (rows without `needs_reg` are masked in the loss)."""
+    evaluated densely on every row (rows without `needs_reg` are masked in the loss).  `t`, `v`: the UNROUNDED last
+    LayerNorm outputs in emulation mode (the CUDA heads normalise the fp32 pre-LayerNorm rows themselves)."""
     hw0, hv0 = t[:, 0], v[:, 0]
     ut = lin(hw0, w['bert.t_pooler.dense.weight'], w['bert.t_pooler.dense.bias'])
     uv = lin(hv0, w['bert.v_pooler.dense.weight'], w['bert.v_pooler.dense.bias'])
@@ -527,12 +528,15 @@ def forward(w: Dict[str, torch.Tensor], cfg: Config, batch: dict, train: bool, l
     for kind, i in layer_schedule(cfg):
         if kind == 't':
             t, c = self_layer_fwd(w, t, t_mask, cfg.num_attention_heads, f'bert.encoder.layer.{i}.')
+            t32 = c['ffn']['y32']
         elif kind == 'v':
             v, c = self_layer_fwd(w, v, v_mask, cfg.v_num_attention_heads, f'bert.encoder.v_layer.{i}.')
+            v32 = c['ffn']['y32']
         else:
             v, t, c = co_layer_fwd(w, v, t, v_mask, t_mask, cfg.bi_num_attention_heads, f'bert.encoder.c_layer.{i}.')
+            v32, t32 = c['ffv']['y32'], c['fft']['y32']
         caches.append(c if keep_cache else None)
-    logits, reg, ch = heads_fwd(w, t, v)
+    logits, reg, ch = heads_fwd(w, t32, v32)            # unrounded last LayerNorm outputs (== t, v outside emulation mode)
     kind = 'L1_smooth' if train else 'L1'               # encoder_decorator.py:104,106
     L = losses_fwd(logits, reg, batch['next_sentence_labels'] if train else None, cast(batch['R']),
                    kind, l1, tol_margin)

@@ -276,8 +276,8 @@ def test_argument_validation_returns_status_and_message():
     a.B, a.nh, a.dh, a.Lq, a.Lk = 1, 2, 40, 8, 8
     a.ldq = a.ldk = a.ldv = a.ldo = 80
     assert lib.crct_attn_fwd(C.byref(a), None) == SHAPE and 'head dim 40' in msg()
-    assert lib.crct_layernorm_fwd(p, p, p, p, None, None, 4, 2048, 0, None, None) == SHAPE and 'row width 2048' in msg()
-    assert lib.crct_layernorm_fwd(p, p, p, p, p, None, 4, 768, 0, None, None) == ARG
+    assert lib.crct_layernorm_fwd(p, p, p, p, None, None, None, 4, 2048, 0, None, None) == SHAPE and 'row width 2048' in msg()
+    assert lib.crct_layernorm_fwd(p, p, p, p, None, p, None, 4, 768, 0, None, None) == ARG
     assert lib.crct_expand_blocks(p, p, p, 4, 6, None) == ARG
     assert lib.crct_select_answers(C.byref(L.SelectArgs()), None) == ARG and 'null pointer' in msg()
     lin = L.LinearArgs()

@@ -90,9 +90,11 @@ def test_gemm_device_row_count_forward_and_dgrad(M, N, K, rows):
         L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, epilogue=epi, aux=aux if epi == L.EPI_BIAS_RES else None, rows_dev=n)
         assert relmax(D[:rows].float(), want) < 6e-3
         assert bool((D[rows:] == 7.0).all())
-    Z = torch.full((M, N), 7.0, device=DEV)                                   # fp32 pre-LayerNorm sum
-    L.gemm(A, B, Z, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES_F32, aux=aux, rows_dev=n)
-    assert relmax(Z[:rows], ref + aux[:rows].float()) < 1e-5
+    Z = torch.full((M, N), 7.0, device=DEV)                                   # fp32 pre-LayerNorm sum, fp32 residual
+    aux32 = torch.randn(M, N, device=DEV)
+    aux32[rows:] = float('nan')
+    L.gemm(A, B, Z, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES_F32, aux=aux32, rows_dev=n)
+    assert relmax(Z[:rows], ref + aux32[:rows]) < 1e-5
     assert bool((Z[rows:] == 7.0).all())
     W = bf(torch.randn(K, N, device=DEV) * 0.5)                               # dgrad form
     D = torch.full((M, N), 7.0, device=DEV, dtype=torch.bfloat16)
@@ -107,11 +109,18 @@ def test_gemm_res_f32_matches_bf16_epilogue_and_dropout_stream():
     A, B = bf(torch.randn(M, K, device=DEV) * 0.5), bf(torch.randn(N, K, device=DEV) * 0.5)
     bias, aux = torch.randn(N, device=DEV), bf(torch.randn(M, N, device=DEV))
     for cg in (1, 2):
-        Z = torch.empty(M, N, device=DEV)
-        D = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-        L.gemm(A, B, Z, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES_F32, aux=aux, dropout_p=0.1, seed=9, cta_group=cg)
-        L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES, aux=aux, dropout_p=0.1, seed=9, cta_group=cg)
-        assert torch.equal(bf(Z), D)           # same accumulators, same dropout decisions: the bf16 form is the rounded fp32 form
+        for bn in (128, 256):
+            Z = torch.empty(M, N, device=DEV)
+            D = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+            L.gemm(A, B, Z, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES_F32, aux=aux.float(), dropout_p=0.1, seed=9, cta_group=cg, block_n=bn)
+            L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES, aux=aux, dropout_p=0.1, seed=9, cta_group=cg, block_n=bn)
+            assert torch.equal(bf(Z), D)       # same accumulators, same dropout decisions: the bf16 form is the rounded fp32 form
+    Mr, Nr = 200, 72                           # ragged: partial tile rows and a partial 16-column step
+    A2, B2 = bf(torch.randn(Mr, K, device=DEV) * 0.5), bf(torch.randn(Nr, K, device=DEV) * 0.5)
+    aux2 = torch.randn(Mr, Nr, device=DEV)
+    Z2 = torch.empty(Mr, Nr, device=DEV)
+    L.gemm(A2, B2, Z2, M=Mr, N=Nr, K=K, bias=bias[:Nr].contiguous(), epilogue=L.EPI_BIAS_RES_F32, aux=aux2)
+    assert relmax(Z2, A2.float() @ B2.float().t() + bias[:Nr] + aux2) < 1e-5
 
 
 @pytest.mark.parametrize('rows,No,Ki,valid', [(1000, 576, 192, 617), (9920, 768, 768, 6899), (9920, 3072, 768, 6848), (3520, 1024, 1024, 1903),
@@ -143,7 +152,9 @@ def test_layernorm_fp32_z_and_device_row_count(rows, H, valid):
     n = torch.tensor([valid], dtype=torch.int32, device=DEV)
     y = torch.full((rows, H), 7.0, device=DEV, dtype=torch.bfloat16)
     mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
-    L.layernorm_fwd(z, gamma, beta, y, mean, rstd, rows_dev=n)
+    y32 = torch.full((rows, H), 7.0, device=DEV)
+    L.layernorm_fwd(z, gamma, beta, y, mean, rstd, rows_dev=n, y32=y32)
+    assert torch.equal(bf(y32[:valid]), y[:valid]) and bool((y32[valid:] == 7.0).all())
     zz = z[:valid].double()
     mu, var = zz.mean(1, keepdim=True), zz.var(1, unbiased=False, keepdim=True)
     ref = (zz - mu) / torch.sqrt(var + 1e-12) * gamma.double() + beta.double()

@@ -26,8 +26,7 @@ def lines_with(*needles):
 
 GROUPS = {
     'weights': lines_with('_qw(W)'),
-    'z_preLN': lines_with('z = _q(', 'z1 = _q(', 'zv = _q(', 'zt = _q('),
-    'y_LN': lines_with('return _q(y)', 'a = _q(a)', 'av, at = _q'),
+    'a_operand': lines_with('return _q(x) @', '_q(x2)'),
     'qkv': lines_with('qkv = _q(', 'qkv1, qkv2 = _q'),
     'probs_ctx': lines_with('ctx = (_q(pd)', 'return _q(ctx)', 'dv = _q(pd)'),
     'h_gelu': lines_with('h = _q(gelu'),
@@ -36,7 +35,7 @@ GROUPS = {
     'bwd_res': lines_with('return _q(da + dz)', 'return _q(dx + dz1)', 'return _q(dv_in'),
     'bwd_attn': lines_with('ds = _q(', 'merge = lambda', 'dctx = _q(', 'dctx1, dctx2 = _q'),
 }
-FWD = ['weights', 'z_preLN', 'y_LN', 'qkv', 'probs_ctx', 'h_gelu']
+FWD = ['weights', 'a_operand', 'qkv', 'probs_ctx', 'h_gelu']
 BWD = ['bwd_dz', 'bwd_du_dgelu', 'bwd_res', 'bwd_attn']
 
 
