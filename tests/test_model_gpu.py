@@ -1,20 +1,28 @@
 """End-to-end parity on the B200: the CUDA path through the public `VisualDialogEncoder` / `glue_forward` API
 against (1) the oracle (fp64) on the same seeded inputs and weights and (2) the golden vectors the reference produced.
 
-Stated tolerances (bf16 operands and activation storage; fp32 accumulation, statistics, softmax, heads, losses),
-all relative to the scale (max |.|) of the compared tensor unless noted:
-  class logits            <= 6e-2   (measured 0.9e-2 .. 3.4e-2)
-  regression output       <= 2e-3   (measured 1e-4 .. 4e-4; the regressor and its inputs' first-token states are fp32)
-  per-row losses          <= 1e-3 absolute, total loss <= 2e-2 absolute
-  argmax of class logits  identical on every row whose reference margin exceeds twice the logit tolerance
-  gradients               global relative L2 error over all tensors <= 0.2 (measured 0.016 .. 0.127);
-                          per tensor ||got-ref|| <= 0.3 ||ref|| + 5e-3 max_t||ref_t||, cosine >= 0.95 for every tensor
-                          carrying more than 1 % of the largest gradient norm.
-Why not 1e-2 everywhere: the bf16 floor of THIS model at random weights is measured, not assumed — the oracle run
-twice with bf16 storage emulated at the CUDA path's rounding points (`oracle.bf16_emulation`), once accumulating in
-fp32 and once in fp64, disagrees with ITSELF by 1.6e-2 (logits) and 5e-2 (gradients) on `full_train_b4_mild`, and
-rounding only the GEMM weights to bf16 moves the fp32 reference's logits by 2.6e-2 on `full_eval_b8`
-(DESIGN.md "Numerical floor").  Kernel-level correctness is pinned separately and tightly in test_kernels_gpu.py."""
+The bars come from a YARDSTICK, not from this implementation: `tests/golden/yardstick_bf16.json` (oracle/make_yardstick.py)
+holds, per golden case, how far the UNMODIFIED reference moves from its own fp32 run when it is run under
+`torch.autocast(bfloat16)` — the reference's own mixed-precision recipe (CRCT/train.py:172 wraps the step in autocast).
+A bf16 tensor-core path cannot be asked to be closer to the fp32 reference than the reference's own bf16 run is; it is asked
+to be NO WORSE than 1.25x that, and additionally to meet the north star's absolute "about 1e-2" where the model is
+well-conditioned (tiny / reference-scale "mild" weights).  All errors relative to the scale (max |.|) of the compared tensor:
+  class logits       <= min(1e-2 [tiny, mild], 1.25 x yardstick)     measured 1.4e-3 .. 6.0e-3 (tiny / mild), 1.6e-2 / 2.8e-2 ("trained"
+                                                                      2x-wide weights; yardstick 2.6e-2 / 3.7e-2)
+  regression output  <= 1e-3                                          measured 1e-6 .. 4e-4 (yardstick 1e-4 .. 4e-3)
+  per-row losses     <= 1e-3 absolute, total loss <= 1e-2 absolute    measured <= 5.7e-3
+  argmax             identical on every row whose reference margin exceeds twice the logit bar
+  gradients          global relative L2 over all tensors <= 1.25 x yardstick     measured 0.004 / 0.010 / 0.017 (tiny; yardstick 0.0056 /
+                     0.0101 / 0.0171), 0.102 (mild; 0.0997), 0.114 (trained; 0.144);  per tensor ||got-ref|| <= 0.25 ||ref|| + 5e-3
+                     max_t||ref_t||, cosine >= 0.975 for every tensor carrying more than 1 % of the largest gradient norm (measured
+                     worst 0.19 / 0.982).
+Why the gradients of the full model sit at 0.10 and not 1e-2 (DESIGN.md "Numerical floor"): with the fp32 residual stream the
+forward agrees with the reference to 1.4e-3, yet ANY rounding of the saved activations moves the gradients of this 24-block
+post-LN network at random weights by 3e-2 .. 1.4e-1 — the reference's own autocast run by 0.0997, the oracle's emulation of
+this path's rounding points by 0.03 .. 0.09 depending on the seed (tools/parity_sensitivity.py).  Kernel-level correctness is
+pinned separately and tightly in test_kernels_gpu.py / test_varlen_gpu.py, the schedule and the backward derivation to 4e-6 in
+test_check_f32_gpu.py."""
+import json
 import os
 
 import pytest
@@ -43,11 +51,22 @@ def scale_err(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
-LOGIT_TOL, REG_TOL = 6e-2, 2e-3
+REG_TOL = 1e-3
+YARD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'yardstick_bf16.json')))
+
+
+def logit_bar(name):
+    bar = 1.25 * YARD[name]['logits_err']
+    return min(bar, 1e-2) if (name.startswith('tiny') or name.endswith('mild')) else bar
+
+
+def grad_bar(name):
+    return 1.25 * YARD[name]['grad_global_rel']
 
 
 def check_outputs(rec, scores, reg):
-    assert scale_err(scores, rec['logits']) < LOGIT_TOL
+    LOGIT_TOL = logit_bar(rec['name'])
+    assert scale_err(scores, rec['logits']) < LOGIT_TOL, (scale_err(scores, rec['logits']), LOGIT_TOL)
     assert scale_err(reg[0], rec['reg_pred']) < REG_TOL
     assert float((reg[1].cpu() - rec['reg_loss']).abs().max()) < 1e-3
     assert float((reg[2].cpu() - rec['reg_l1']).abs().max()) < 1e-3
@@ -66,7 +85,7 @@ def test_eval_forward_matches_reference_golden(name):
     assert loss is None and nsp is None
     check_outputs(rec, scores, reg)
     out, _ = O.forward(sd, O.Config(cfg.__dict__), batch, train=False, l1=rec['l1'], keep_cache=False)
-    assert scale_err(scores, out['logits']) < LOGIT_TOL
+    assert scale_err(scores, out['logits']) < logit_bar(name)
 
 
 @pytest.mark.parametrize('name', ['tiny_train_l1', 'tiny_train_smooth', 'tiny_ragged', 'full_train_b4', 'full_train_b4_mild'])
@@ -78,8 +97,8 @@ def test_train_forward_backward_matches_reference(name):
     loss.backward()
     torch.cuda.synchronize()
     check_outputs(rec, scores, reg)
-    assert abs(float(loss) - rec['loss']) < 2e-2
-    assert abs(float(nsp) - rec['nsp_loss']) < 2e-2
+    assert abs(float(loss) - rec['loss']) < 1e-2
+    assert abs(float(nsp) - rec['nsp_loss']) < 1e-2
     assert (int(reg[3][0]), int(reg[3][1])) == rec['reg_right']
     # full per-tensor gradients against the oracle (fp64), golden summaries against the reference itself
     out, cache = O.forward(sd, O.Config(cfg.__dict__), batch, train=True, l1=rec['l1'], dtype=torch.float64)
@@ -93,14 +112,14 @@ def test_train_forward_backward_matches_reference(name):
         got, ref = got.double().cpu(), ref.double()
         err, rn = float((got - ref).norm()), float(ref.norm())
         num, den = num + err * err, den + rn * rn
-        if err > 0.3 * rn + 5e-3 * gnorm:
+        if err > 0.25 * rn + 5e-3 * gnorm:
             bad.append((k, err / max(rn, 1e-30), rn / gnorm))
         if rn > 1e-2 * gnorm:
             cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
-            if cos < 0.95:
+            if cos < 0.975:
                 bad.append((k, 'cos', cos))
     assert not bad, bad[:10]
-    assert (num / den) ** 0.5 < 0.2
+    assert (num / den) ** 0.5 < grad_bar(name), ((num / den) ** 0.5, grad_bar(name))
     for k, s in rec['grads'].items():                   # the reference's own gradient norms (golden)
         if s['norm'] > 1e-2 * gnorm:
             got = named[k].grad.double().cpu().flatten()
@@ -223,3 +242,80 @@ def test_graphed_train_step_matches_eager_and_redraws_dropout(overlap_optimizer)
     g2 = GraphedTrainStep(m2, o2, params, gb, warmup_steps=1)
     losses = [float(g2.step(gb)) for _ in range(4)]
     assert len(set(round(x, 6) for x in losses)) > 1 and all(x == x for x in losses)
+
+
+def _full_model(style='mild', seed=1):
+    from cqa_crct_b200.spec import ModelConfig, synth_state_dict
+    cfg_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'cqa_crct_b200', 'config', 'vilbert.json')
+    cfg = ModelConfig(cfg_path)
+    params = default_params(cfg_path, device='cuda', max_seq_len=124, max_vis_features=44, L1=True)
+    m = VisualDialogEncoder(params)
+    sd = synth_state_dict(cfg, 228, seed, style)
+    m.load_state_dict({'bert_pretrained.' + k: v for k, v in sd.items()}, strict=True)
+    m.to('cuda').eval()
+    return m, params, cfg, sd
+
+
+def test_full_model_per_question_argmax_matches_the_oracle():
+    """The evaluation outcome itself (CRCT/evaluation.py:254-258,287-296) on the FULL model: 16 questions x 32 candidate
+    answers through `evaluate_batch` (question-level visual rows, packed tokens) against the fp32 oracle on the replicated
+    layout — the selected candidate is identical for every question whose best-vs-second probability margin in the oracle
+    exceeds 2e-3 (the logit bar of this operating point, 1e-2 of a ~0.2 logit scale, moves softmax(.)[0] by ~1e-3)."""
+    from cqa_crct_b200.evaluate import evaluate_batch, expand_question_batch
+    from cqa_crct_b200.synthetic import make_question_batch
+    from oracle.eval_oracle import select_and_score
+    m, params, cfg, sd = _full_model()
+    qb = make_question_batch(16, 124, 44, cfg.v_feature_size, seed=77, total=512)
+    out = evaluate_batch(m, qb, params, eval_batch_size=512)
+    full = expand_question_batch(qb)
+    with torch.no_grad():
+        o, _ = O.forward(sd, O.Config(cfg.__dict__), full, train=False, l1=True, keep_cache=False)
+    assert scale_err(out['logits'], o['logits']) < 1e-2
+    oref = select_and_score(o['logits'].float(), o['reg_pred'].float(), o['reg_dist'].float(), o['reg_l1'].float(), qb['num_ans'],
+                            qb['gt_id'], qb['needs_reg'], qb['tolerance_margin'])
+    p, off, sure = oref['prob'], 0, 0
+    for q, n in enumerate(qb['num_ans'].tolist()):
+        top = torch.sort(p[off:off + n], descending=True).values
+        if n == 1 or float(top[0] - top[1]) > 2e-3:
+            sure += 1
+            assert int(out['answers'][q]) == int(oref['answers'][q]), (q, float(top[0] - top[1]))
+        off += n
+    assert sure >= 8, sure                      # the margin rule must not make the test vacuous
+    assert float((out['prob'].cpu() - p).abs().max()) < 3e-3
+
+
+def test_full_size_b80_train_gradients_against_the_oracle():
+    """BASELINE configs[1] at its full size (B = 80, T = 124, R = 44, dropout off): loss, logits and the gradients of a spread of
+    tensors (embeddings, first / middle / last text, visual and co-attention blocks, poolers, classifier, regressor) against
+    the fp32 oracle run on the host cores."""
+    from cqa_crct_b200.synthetic import make_batch
+    m, params, cfg, sd = _full_model()
+    batch = make_batch(80, 124, 44, cfg.v_feature_size, seed=4242)
+    gb = {k: v.to('cuda') for k, v in batch.items()}
+    m.zero_grad()
+    loss, _, nsp, _, scores, reg, _ = glue_forward(m, gb, params)
+    loss.backward()
+    torch.cuda.synchronize()
+    out, cache = O.forward(sd, O.Config(cfg.__dict__), batch, train=True, l1=True)
+    g = O.backward(cache)
+    assert abs(float(loss) - float(out['loss'])) < 1e-2
+    assert scale_err(scores, out['logits']) < 1e-2
+    assert scale_err(reg[0], out['reg_pred']) < REG_TOL
+    named = dict(m.bert_pretrained.named_parameters())
+    picks = ['bert.embeddings.word_embeddings.weight', 'bert.embeddings.LayerNorm.weight', 'bert.v_embeddings.new_image_embeddings.weight',
+             'bert.encoder.layer.0.attention.self.query.weight', 'bert.encoder.layer.5.intermediate.dense.weight',
+             'bert.encoder.layer.11.output.dense.weight', 'bert.encoder.v_layer.0.attention.self.value.weight',
+             'bert.encoder.v_layer.5.output.dense.weight', 'bert.encoder.c_layer.0.biattention.key2.weight',
+             'bert.encoder.c_layer.3.biOutput.dense1.weight', 'bert.encoder.c_layer.5.t_output.dense.weight', 'bert.t_pooler.dense.weight',
+             'bert.v_pooler.dense.weight', 'cls.bi_seq_relationship.weight', 'regressor.fusion.0.weight', 'regressor.txt_pipe.0.weight']
+    gnorm = max(float(v.norm()) for v in g.values())
+    num = den = 0.0
+    for k, ref in g.items():
+        got = named[k].grad.double().cpu()
+        num, den = num + float((got - ref.double()).norm() ** 2), den + float(ref.double().norm() ** 2)
+    glob = (num / den) ** 0.5
+    assert glob < 1.25 * YARD['full_train_b4_mild']['grad_global_rel'], glob
+    for k in picks:
+        got, ref = named[k].grad.double().cpu(), g[k].double()
+        err, rn = float((got - ref).norm()), float(ref.norm())
+        assert err <= 0.25 * rn + 5e-3 * gnorm, (k, err / rn)
