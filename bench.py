@@ -8,11 +8,17 @@ all-reduce overlapped with backward for N > 1) + fused AdamW, dropout ON, B = 80
   value : whole-job samples/s with the batches already resident in HBM (CUDA events, max over ranks)
   e2e   : same metric through the reference-facing API (`glue_forward(model, batch, params)`) with HOST batches:
           pinned host -> device copies of every input and a device -> host read of the loss inside the timed region
-  roofline : the tcgen05 GEMM kernel (dominant: 97.7 % of the FLOPs): algorithmic FLOPs of all GEMM launches of one
-          step / their summed CUDA-event durations, against the measured bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline : the CPU restatement of the reference (oracle/, kind "port" — /root/reference does not exist on the
-          GPU box) timed on the host cores on a bounded sample of the same workload (rank 0, N = 1 only)
-`--impl reference` times that CPU path alone (all host threads) and prints the same JSON line with "impl": "reference".
+  roofline : the tcgen05 GEMM kernel (dominant: 97.7 % of the FLOPs): algorithmic FLOPs (valid rows only — the packed
+          layout does not run the padding) of all GEMM launches of one step / their summed durations, against the measured
+          bf16 peak in MEASURED_PEAKS.json.  Durations: CUDA events recorded INSIDE a captured single-stream replay of the
+          step (event-record graph nodes around every GEMM node: no host enqueue gaps), empty-pair overhead calibrated in
+          the same graph; the ncu launch list of the same step is committed under profiles/ and must agree within 5 %.
+  cpu_baseline : the reference's own PyTorch module (oracle/_ref, staged there by __graft_entry__.build(); kind "reference")
+          or, where that copy is absent, its CPU restatement (oracle/, kind "port"), timed on the host cores on a bounded
+          sample of the same workload (rank 0, N = 1 only)
+  workloads : (N = 1, --workload train) the other two BASELINE configs — eval B = 512 and the stress shape T = 248 / R = 88 —
+          measured in the same process with their own value / e2e / roofline
+`--impl reference` times the CPU path alone (all host threads) and prints the same JSON line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -92,91 +98,116 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_run(B, T, R, train, steps, warmup, budget_s=200.0):
-    """The reference algorithm on the host cores (oracle port, fp32, all threads).  Each step processes a bounded
-    sample of `Bs` sequences of the workload's shape; returns (samples/s, Bs, seconds per step, threads)."""
-    from oracle import crct_oracle as O
+REF_DIR = os.path.join(ROOT, 'oracle', '_ref')           # __graft_entry__.build() stages the reference's own files here (git-ignored)
+
+
+def _reference_arm_available():
+    return os.path.isfile(os.path.join(REF_DIR, 'CRCT', 'backbone', 'vilbert.py'))
+
+
+def cpu_reference_run(B, T, R, train, steps, warmup, budget_s=270.0):
+    """The reference on the host cores, fp32, all threads.  With oracle/_ref present: the UNMODIFIED reference module through
+    its own `encoder_decorator.forward`, dropout on, `loss.backward()`, the reference's `get_optimizer` AdamW + schedule
+    (CRCT/train.py:167-215 without autocast: CPU) on full B-sequence batches whenever `steps + warmup` of them fit the time
+    budget ("same_config"); otherwise (or without the copy) a bounded sample of `bs` sequences per step.
+    Returns (samples/s, bs, seconds per step, threads, kind, note)."""
     from cqa_crct_b200.spec import ModelConfig, synth_state_dict
-    from cqa_crct_b200.synthetic import make_batch
+    from cqa_crct_b200.synthetic import default_params, make_batch
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     cfg = ModelConfig(CFG)
-    ocfg = O.Config(cfg.__dict__)
     sd = synth_state_dict(cfg, 228, 0, 'mild')
-
-    def one(bs, seed):
-        batch = make_batch(bs, T, R, cfg.v_feature_size, seed=seed)
-        t0 = time.perf_counter()
+    if _reference_arm_available():
+        os.environ['CRCT_REFERENCE_ROOT'] = REF_DIR
+        from oracle import ref_shim
+        ref_shim.REFERENCE_ROOT = REF_DIR
+        params = default_params(CFG, max_seq_len=T, max_vis_features=R, L1=True)
+        params.update(lr=2e-5, image_lr=2e-5, wd=0.01)
+        enc = ref_shim.RefEncoder(CFG, params, seed=0)
+        m = enc.module
+        m.bert_pretrained.load_state_dict(sd, strict=True)
+        opt = sched = None
         if train:
-            out, cache = O.forward(sd, ocfg, batch, train=True, l1=True)
-            O.backward(cache)
+            m.train()
+            cwd = os.getcwd()
+            os.chdir(os.path.join(REF_DIR, 'CRCT'))          # utils.get_optimizer opens 'config/language_weights.json' relatively
+            try:
+                import utils as ref_utils
+                opt = ref_utils.get_optimizer(params, m)
+                sched = ref_utils.WarmupLinearScheduleNonZero(opt, warmup_steps=3000, t_total=200000, min_lr=1.3e-5)
+            finally:
+                os.chdir(cwd)
         else:
-            with torch.no_grad():
-                O.forward(sd, ocfg, batch, train=False, keep_cache=False)
-        return time.perf_counter() - t0
+            m.eval()
 
-    t_probe = one(2, 1)                                   # calibrate: seconds for 2 sequences (includes first-touch)
-    t_probe = min(t_probe, one(2, 2))
-    per_seq = t_probe / 2
+        def one(bs, seed):
+            batch = make_batch(bs, T, R, cfg.v_feature_size, seed=seed)
+            t0 = time.perf_counter()
+            if train:
+                loss = enc.glue_forward(m, batch, params)[0]
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+                sched.step()
+            else:
+                with torch.no_grad():
+                    enc.glue_forward(m, batch, params, evaluation=True)
+            return time.perf_counter() - t0
+        kind = 'reference'
+        note = 'UNMODIFIED reference module (oracle/_ref), encoder_decorator.forward' + (', dropout on, backward, get_optimizer AdamW + schedule' if train else ', eval')
+    else:
+        from oracle import crct_oracle as O
+        ocfg = O.Config(cfg.__dict__)
+
+        def one(bs, seed):
+            batch = make_batch(bs, T, R, cfg.v_feature_size, seed=seed)
+            t0 = time.perf_counter()
+            if train:
+                out, cache = O.forward(sd, ocfg, batch, train=True, l1=True)
+                O.backward(cache)
+            else:
+                with torch.no_grad():
+                    O.forward(sd, ocfg, batch, train=False, keep_cache=False)
+            return time.perf_counter() - t0
+        kind = 'port'
+        note = 'oracle port (no dropout, no optimizer step)'
+
+    nprobe = min(8, B)
+    t_probe = one(nprobe, 1)                              # calibrate: seconds for 8 sequences (includes first-touch)
+    t_probe = min(t_probe, one(nprobe, 2))
+    per_seq = t_probe / nprobe
     total_steps = steps + warmup
     bs = int(max(2, min(B, budget_s / max(1, total_steps) / per_seq)))
+    if bs >= 0.8 * B:
+        bs = B                                            # close enough: run the full batch (same_config)
     for i in range(warmup):
         one(bs, 10 + i)
     times = [one(bs, 100 + i) for i in range(steps)]
     sec = sum(times) / len(times)
-    return bs / sec, bs, sec, threads
+    return bs / sec, bs, sec, threads, kind, note
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='train', choices=list(WORKLOADS))
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--opt-overlap', action='store_true', help='run AdamW under the backward instead of after it (A/B; measured slower)')
-    ap.add_argument('--bucket-mb', type=float, default=25.0, help='gradient all-reduce bucket size (fp32 MB)')
-    ap.add_argument('--no-graph', action='store_true', help='enqueue every launch from Python instead of replaying the captured step')
-    args = ap.parse_args()
-    B, T, R, train = WORKLOADS[args.workload]
-    rank = int(os.environ.get('RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    metric = 'crct_train_samples_per_sec' if train else 'crct_eval_sequences_per_sec'
-    config = {'workload': f'CRCT {"train step (fwd+bwd+allreduce+AdamW, dropout on, L1 regression loss)" if train else "eval forward (hybrid head argmax + regression)"}'
-                          f', B={B}/GPU, T={T}, R={R}, full vilbert.json model (252.7M params), random-init weights',
-              'per_gpu_batch': B, 'global_batch': B * max(1, args.gpus), 'text_len': T, 'regions': R, 'parallelism': f'dp{max(1, args.gpus)}',
-              'l2': 'working set per step (0.5 GB bf16 weights + >4 GB activations) exceeds the 126 MB L2; inputs rotate over 4 batches'}
+def describe(name, B, T, R, train, gpus):
+    return {'workload': f'CRCT {"train step (fwd+bwd+allreduce+AdamW, dropout on, L1 regression loss)" if train else "eval forward (hybrid head argmax + regression)"}'
+                        f', B={B}/GPU, T={T}, R={R}, full vilbert.json model (252.7M params), random-init weights',
+            'per_gpu_batch': B, 'global_batch': B * max(1, gpus), 'text_len': T, 'regions': R, 'parallelism': f'dp{max(1, gpus)}',
+            'rows': 'var-len packed: only valid tokens / regions run (lengths U[48..T] / U[4..R] per sequence, device-side counts)',
+            'l2': 'working set per step (0.5 GB bf16 weights + >3 GB activations) exceeds the 126 MB L2; inputs rotate over 4 batches'}
 
-    if args.impl == 'reference':
-        if rank != 0:
-            return
-        v, bs, sec, threads = cpu_reference_run(B, T, R, train, max(1, args.steps), max(0, args.warmup))
-        line = {'impl': 'reference', 'metric': metric, 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-                                 'sample': f'{bs} sequences per step of the same shape (T={T}, R={R}), {"fwd+bwd" if train else "fwd"}, fp32, torch CPU ops'},
-                'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        emit(line)
-        return
 
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py --impl ours needs a B200; there is no CPU fallback')
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks=True):
+    """One BASELINE workload on this process's GPU: returns the fields of the JSON line (rank 0) or None."""
     from cqa_crct_b200 import _lib as L
     from cqa_crct_b200.encoder import VisualDialogEncoder, glue_forward
     from cqa_crct_b200.optim import FusedAdamW, WarmupLinearScheduleNonZero
     from cqa_crct_b200.parallel import DistributedDataParallel
     from cqa_crct_b200.synthetic import default_params, make_batch
-    L.device_check()
+    B, T, R, train = WORKLOADS[name]
+    config = describe(name, B, T, R, train, args.gpus)
     dev = torch.device('cuda', local_rank)
-    params = default_params(CFG, device=str(dev), max_seq_len=T, max_vis_features=R, L1=True, overlap_optimizer=args.opt_overlap)
+    params = default_params(CFG, device=str(dev), max_seq_len=T, max_vis_features=R, L1=True, overlap_optimizer=args.opt_overlap,
+                            varlen=not args.padded)
     torch.manual_seed(0)
     enc = VisualDialogEncoder(params).to(dev)
     model = DistributedDataParallel(enc, bucket_cap_mb=args.bucket_mb) if world > 1 else enc
@@ -251,28 +282,28 @@ def main():
     def timed(batches, read_loss):
         pipe = read_loss and gstep is not None
         if pipe:
-            pipelined(batches, args.warmup)
+            pipelined(batches, warmup)
         else:
-            for i in range(args.warmup):
+            for i in range(warmup):
                 step(batches[i % 4], read_loss)
         barrier()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        sampler = ClockSampler(local_rank) if (rank == 0 and with_clocks) else None
         if sampler:
             sampler.start()
         l0 = L.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if pipe:
-            pipelined(batches, args.steps)
+            pipelined(batches, steps)
         else:
-            for i in range(args.steps):
+            for i in range(steps):
                 # e2e (read_loss): the batch is HOST memory; glue_forward / the encoder copy every input to the device
                 # inside this region and the loss is read back every step
                 step(batches[i % 4], read_loss)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = (L.LAUNCHES - l0) if gstep is None else captured_launches * args.steps
+        launches = (L.LAUNCHES - l0) if gstep is None else captured_launches * steps
         clocks = sampler.stop() if sampler else None
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -281,100 +312,204 @@ def main():
         return ms, launches, clocks
 
     ms, launches, clocks = timed(resident, False)
-    ms_step = ms / args.steps
+    ms_step = ms / steps
     value = B * world / (ms_step / 1e3)
     e2e = None
     if not args.no_e2e:
         ms2, _, _ = timed(pinned, True)
-        e2e = {'value': B * world / (ms2 / args.steps / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
-               'ms_per_step': ms2 / args.steps}
+        e2e = {'value': B * world / (ms2 / steps / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
+               'ms_per_step': ms2 / steps}
 
-    # ---- roofline of the dominant kernel: every GEMM launch of ONE more step, timed with CUDA events on the launch stream
+    # ---- roofline of the dominant kernel: every GEMM launch of ONE more step
     roof = None
     if rank == 0:
         sustained, burst, hbm, src = load_peaks()
-        events, flops, gbytes = [], [], []
+        pairs, meta = [], []
         orig = L.gemm
+        in_graph = [False]
 
         def timed_gemm(A, Bm, D, **kw):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a = torch.cuda.Event(enable_timing=True, external=in_graph[0])
+            b = torch.cuda.Event(enable_timing=True, external=in_graph[0])
             a.record()
             orig(A, Bm, D, **kw)
             b.record()
-            events.append((a, b))
-            M_, K_ = kw['M'], kw['K']
-            if kw.get('rows_dev') is not None:        # packed rows: the kernel runs the device-side count, not the allocation
-                r = int(kw['rows_dev'])
-                if kw.get('a_major'):
-                    K_ = min(K_, r)
-                else:
-                    M_ = min(M_, r)
-            flops.append(2.0 * M_ * kw['N'] * K_)
-            mn = M_ * kw['N']                 # operands once + output (+ residual / multiplier read, + GELU' write)
-            gbytes.append(2.0 * (M_ * K_ + kw['N'] * K_) + mn * (4.0 if kw.get('epilogue') in (L.EPI_F32, L.EPI_BIAS_RES_F32) else 2.0)
-                          + (2.0 * mn if kw.get('aux') is not None else 0.0) + (2.0 * mn if kw.get('D2') is not None else 0.0))
+            pairs.append((a, b))
+            meta.append((kw['M'], kw['N'], kw['K'], kw.get('a_major', 0), kw.get('rows_dev'), kw.get('epilogue', L.EPI_BIAS),
+                         kw.get('aux') is not None, kw.get('D2') is not None))
 
-        L.gemm = timed_gemm
+        def null_pairs(n):
+            out = []
+            for _ in range(n):
+                a = torch.cuda.Event(enable_timing=True, external=in_graph[0])
+                b = torch.cuda.Event(enable_timing=True, external=in_graph[0])
+                a.record(); b.record()
+                out.append((a, b))
+            return out
+
         import cqa_crct_b200.encoder as E
-        E.L.gemm = timed_gemm
         require = getattr(model, 'require_sync', None)
         if require is not None:
             model.require_sync = False            # rank 0 alone runs this extra step: no collective
         lanes_were = enc.overlap_streams
         enc.overlap_streams = False               # one stream: a GEMM's event pair must not span kernels of the other lanes
+        hook_were, enc.grad_ready_hook = enc.grad_ready_hook, None
+        seg_were, enc.segment_ranges = enc.segment_ranges, False
+        timing = None
+        nulls, graph_keep = [], None
         try:
-            if train:
-                enc.zero_grad()
-                glue_forward(enc, resident[0], params)[0].backward()
-            else:
-                evaluate_batch(enc, resident[0], params, eval_batch_size=B)
-            torch.cuda.synchronize()
+            L.gemm = E.L.gemm = timed_gemm
+            if train and not args.no_graph_timing:
+                try:                              # events as graph nodes: no host in the loop
+                    in_graph[0] = True
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        g = torch.cuda.CUDAGraph()
+                        g.capture_begin()
+                        enc.zero_grad()
+                        for _ in enc.train_step_stages(resident[0], 1.0, 1.0):
+                            pass
+                        nulls = null_pairs(64)
+                        g.capture_end()
+                        for _ in range(3):
+                            g.replay()
+                    torch.cuda.synchronize()
+                    graph_keep = g
+                    _ = pairs[0][0].elapsed_time(pairs[0][1])
+                    timing = ('CUDA events recorded as graph nodes around every GEMM node of a captured single-stream replay of the step '
+                              '(no host enqueue gaps; the timed steps overlap the text lane, the visual lane and the weight gradients on three streams)')
+                except Exception as exc:          # external events unavailable: fall back to host-enqueued events
+                    sys.stderr.write(f'[bench] in-graph GEMM timing unavailable ({type(exc).__name__}: {exc}); using host-enqueued events\n')
+                    pairs.clear(); meta.clear(); nulls = []
+                    in_graph[0] = False
+                    torch.cuda.synchronize()
+            if timing is None:
+                in_graph[0] = False
+                if train:
+                    enc.zero_grad()
+                    glue_forward(enc, resident[0], params)[0].backward()
+                else:
+                    evaluate_batch(enc, resident[0], params, eval_batch_size=B)
+                nulls = null_pairs(200)
+                torch.cuda.synchronize()
+                timing = 'CUDA events around every GEMM launch of one extra step enqueued from Python on ONE stream'
         finally:
-            L.gemm = orig
-            E.L.gemm = orig
+            L.gemm = E.L.gemm = orig
             enc.overlap_streams = lanes_were
+            enc.grad_ready_hook, enc.segment_ranges = hook_were, seg_were
             if require is not None:
                 model.require_sync = True
-        # an empty event pair on the same stream is not 0: calibrate that record-to-record overhead and remove it
-        null = []
-        for _ in range(200):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); b.record()
-            null.append((a, b))
-        torch.cuda.synchronize()
-        overhead_ms = statistics.median(a.elapsed_time(b) for a, b in null)
-        raw_ms = sum(a.elapsed_time(b) for a, b in events)
-        gemm_ms = max(raw_ms - overhead_ms * len(events), 0.5 * raw_ms)
-        achieved = sum(flops) / (gemm_ms / 1e3) / 1e12
-        traffic = None                        # DRAM bytes per GEMM launch from the committed ncu capture of this workload
-        tp = os.path.join(ROOT, 'profiles', 'r01_gemm_dram_traffic.json')
-        if os.path.exists(tp):
-            td = json.load(open(tp))
-            if td.get('workload') == args.workload and td.get('gemm_launches_per_step') == len(events):
-                traffic = td['dram_bytes_per_launch']
+        overhead_ms = statistics.median(a.elapsed_time(b) for a, b in nulls)
+        raw_ms = sum(a.elapsed_time(b) for a, b in pairs)
+        gemm_ms = max(raw_ms - overhead_ms * len(pairs), 0.5 * raw_ms)
+        flops = gbytes = 0.0
+        for M_, N_, K_, a_major, rows_dev, epi, has_aux, has_d2 in meta:
+            if rows_dev is not None:              # packed rows: the kernel runs the device-side count, not the allocation
+                r = int(rows_dev)
+                if a_major:
+                    K_ = min(K_, r)
+                else:
+                    M_ = min(M_, r)
+            flops += 2.0 * M_ * N_ * K_
+            mn = M_ * N_                          # operands once + output (+ residual / multiplier read, + GELU' write)
+            res32 = epi == L.EPI_BIAS_RES_F32
+            gbytes += 2.0 * (M_ * K_ + N_ * K_) + mn * (4.0 if epi in (L.EPI_F32, L.EPI_BIAS_RES_F32) else 2.0) \
+                + ((4.0 if res32 else 2.0) * mn if has_aux else 0.0) + (2.0 * mn if has_d2 else 0.0)
+        del graph_keep
+        achieved = flops / (gemm_ms / 1e3) / 1e12
+        traffic, traffic_src = None, None         # DRAM bytes per GEMM launch from the committed ncu capture of this workload
+        for tp in ('r02_gemm_dram_traffic.json', 'r01_gemm_dram_traffic.json'):
+            tp = os.path.join(ROOT, 'profiles', tp)
+            if os.path.exists(tp):
+                td = json.load(open(tp))
+                if td.get('workload') == name and td.get('gemm_launches_per_step') == len(pairs):
+                    traffic, traffic_src = td['dram_bytes_per_launch'], os.path.basename(tp)
+                    break
+        padded_tflop = FWD_GFLOP_PER_SAMPLE.get((T, R), 40.396) * (3 if train else 1) * B / 1e3
         roof = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel', 'achieved': achieved, 'peak': sustained, 'unit': 'TFLOP/s',
-                'frac': achieved / sustained, 'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu, profiles/r01_gemm_dram_traffic.json)',
-                'algorithmic_bytes_per_launch': sum(gbytes) / max(1, len(gbytes)), 'peak_source': f'{src} (bf16_tflops_sustained; burst {burst})',
-                'launches_per_step': len(events), 'timing': 'CUDA events around every GEMM launch of one extra step run on ONE stream '
-                '(the timed steps overlap the text lane, the visual lane and the weight gradients on three streams)', 'gemm_ms_per_step': gemm_ms, 'gemm_ms_per_step_raw': raw_ms,
+                'frac': achieved / sustained, 'traffic': traffic, 'traffic_unit': f'DRAM bytes per launch (ncu, profiles/{traffic_src})',
+                'algorithmic_bytes_per_launch': gbytes / max(1, len(pairs)), 'peak_source': f'{src} (bf16_tflops_sustained; burst {burst})',
+                'launches_per_step': len(pairs), 'timing': timing, 'gemm_ms_per_step': gemm_ms, 'gemm_ms_per_step_raw': raw_ms,
                 'event_pair_overhead_us': overhead_ms * 1e3, 'gemm_share_of_step': gemm_ms / ms_step,
-                'algorithmic_tflop_per_step': sum(flops) / 1e12,
-                'model_tflops_whole_step': (FWD_GFLOP_PER_SAMPLE.get((T, R), 40.396) * (3 if train else 1) * B / 1e3) / (ms_step / 1e3)}
+                'algorithmic_tflop_per_step': flops / 1e12, 'padded_layout_tflop_per_step': padded_tflop,
+                'executed_tflops_whole_step': flops / 1e12 / (ms_step / 1e3),
+                'padded_equivalent_tflops_whole_step': padded_tflop / (ms_step / 1e3)}
     if world > 1:
         dist.barrier()
+    out = None
+    if rank == 0:
+        out = {'metric': 'crct_train_samples_per_sec' if train else 'crct_eval_sequences_per_sec', 'value': value, 'unit': 'samples/s',
+               'ms_per_step': ms_step, 'config': dict(config, launch='one CUDA graph per step (captured glue_forward + backward + AdamW)' if gstep is not None else 'per-kernel launches from Python'),
+               'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'gpu_launches_per_step': launches / steps, 'roofline': roof}
+    del gstep, model, enc, opt, resident, pinned
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='train', choices=list(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-sub', action='store_true', help='skip the eval / stress sub-results of the default train line')
+    ap.add_argument('--padded', action='store_true', help="run the reference's padded row layout instead of the packed one (A/B)")
+    ap.add_argument('--no-graph-timing', action='store_true', help='time the GEMMs with host-enqueued events (round-1 method)')
+    ap.add_argument('--opt-overlap', action='store_true', help='run AdamW under the backward instead of after it (A/B; measured slower)')
+    ap.add_argument('--bucket-mb', type=float, default=25.0, help='gradient all-reduce bucket size (fp32 MB)')
+    ap.add_argument('--no-graph', action='store_true', help='enqueue every launch from Python instead of replaying the captured step')
+    args = ap.parse_args()
+    B, T, R, train = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    metric = 'crct_train_samples_per_sec' if train else 'crct_eval_sequences_per_sec'
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        config = describe(args.workload, B, T, R, train, args.gpus)
+        v, bs, sec, threads, kind, note = cpu_reference_run(B, T, R, train, max(1, args.steps), max(0, args.warmup))
+        line = {'impl': 'reference', 'metric': metric, 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic', 'config': config, 'same_config': bool(bs == B and kind == 'reference'),
+                'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': kind,
+                                 'sample': f'{bs} sequences per step of the same shape (T={T}, R={R}), fp32 on the host cores: {note}'},
+                'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        emit(line)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a B200; there is no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from cqa_crct_b200 import _lib as L
+    L.device_check()
+    head = run_workload(args.workload, args, rank, world, local_rank, args.steps, args.warmup)
+    subs = None
+    if world == 1 and args.workload == 'train' and not args.no_sub:
+        # the two BASELINE configs that have no line of their own: same process, fewer steps, same measurement
+        subs = {name: run_workload(name, args, rank, world, local_rank, max(3, args.steps // 2), max(3, args.warmup // 2 + 1), with_clocks=False)
+                for name in ('eval', 'stress')}
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
-        v, bs, sec, threads = cpu_reference_run(B, T, R, train, 1, 0, budget_s=20.0)
-        cpu = {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-               'sample': f'1 step of {bs} sequences of the same shape, {"fwd+bwd" if train else "fwd"}, fp32 oracle port on torch CPU ops ({sec:.1f} s)'}
+        v, bs, sec, threads, kind, note = cpu_reference_run(B, T, R, train, 1, 0, budget_s=25.0)
+        cpu = {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': kind,
+               'sample': f'1 step of {bs} sequences of the same shape, fp32 on the host cores ({sec:.1f} s): {note}'}
 
     if rank == 0:
-        line = {'metric': metric, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-                'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
-                'data': 'synthetic', 'config': dict(config, launch='one CUDA graph per step (captured glue_forward + backward + AdamW)' if gstep is not None else 'per-kernel launches from Python'),
-                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
-                'gpu_launches_per_step': launches / args.steps, 'roofline': roof, 'cpu_baseline': cpu}
+        line = {'metric': head['metric'], 'value': head['value'], 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+                'data': 'synthetic', 'config': head['config'], 'clocks': head['clocks'], 'e2e': head['e2e'], 'gpu_launches': head['gpu_launches'],
+                'gpu_launches_per_step': head['gpu_launches_per_step'], 'roofline': head['roofline'], 'cpu_baseline': cpu}
+        if subs is not None:
+            line['workloads'] = subs
         emit(line)
     if world > 1:
         dist.destroy_process_group()

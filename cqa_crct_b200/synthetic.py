@@ -20,7 +20,7 @@ IMG_CLASS = 228          # `<IMG>` whole-figure box, CRCT/fig_dataloader.py:338
 
 
 def make_batch(B: int, T: int = 124, R: int = 44, feat_dim: int = 1024, seed: int = 1234,
-               vocab_size: int = 30522, categories: int = 228) -> Dict[str, torch.Tensor]:
+               vocab_size: int = 30522, categories: int = 228, min_answer: int = 1) -> Dict[str, torch.Tensor]:
     """One batch in the layout `encoder_decorator.forward` consumes
     (reference: CRCT/backbone/encoder_decorator.py:81-116).
 
@@ -44,7 +44,7 @@ def make_batch(B: int, T: int = 124, R: int = 44, feat_dim: int = 1024, seed: in
         lt = int(randint(lo_len, T))
         lq_hi = max(1, min(40, lt - 6))
         lq = int(randint(min(8, lq_hi), lq_hi))
-        la = int(randint(1, 4))
+        la = int(randint(min_answer, 4))                 # answer tokens incl. the closing [SEP]
         n_chart = max(0, lt - 1 - lq - la - 2)          # [CLS] chart.. [SEP] question [SEP] answer.. (last = [SEP])
         lt = 1 + n_chart + 1 + lq + la                   # exact valid length
         ids = randint(1000, vocab_size - 1, (lt,))
@@ -119,12 +119,15 @@ def default_params(model_config: str, device: str = 'cpu', **over) -> dict:
 
 
 def make_question_batch(Q: int, T: int = 124, R: int = 44, feat_dim: int = 1024, seed: int = 1234, vocab_size: int = 30522,
-                        min_ans: int = 2, max_ans: int = 48, total: int = None) -> Dict[str, torch.Tensor]:
+                        min_ans: int = 2, max_ans: int = 48, total: int = None, distinct: bool = False) -> Dict[str, torch.Tensor]:
     """One EVALUATION batch in the de-duplicated layout of `cqa_crct_b200.evaluate` (f3): Q questions, question q with
     `num_ans[q]` candidate answers (reference: one dataset item per question with all its candidates,
     CRCT/fig_dataloader.py:584-587,648,690-693; up to EVAL_PADDED_SIZE = 120 candidates, fixed vocabulary alone = 35).
     Text tensors hold one row per candidate (N = sum(num_ans)), visual tensors and R one row per question.
-    `total` forces N (the last question absorbs the difference)."""
+    `total` forces N (the last question absorbs the difference).  `distinct`: the candidates of a question are independent random
+    sequences instead of sharing everything but the answer span — at random-init weights candidates that differ in 1-3 answer
+    tokens are separated by 1e-5 .. 1e-3 in probability (no usable argmax margin); independent sequences are separated like
+    trained candidates are."""
     g = torch.Generator().manual_seed(seed ^ 0x5EED)
     num_ans = torch.randint(min_ans, max_ans + 1, (Q,), generator=g)
     if total is not None:
@@ -133,13 +136,16 @@ def make_question_batch(Q: int, T: int = 124, R: int = 44, feat_dim: int = 1024,
         num_ans[-1] = total - base * (Q - 1)
         assert int(num_ans[-1]) >= 1
     N = int(num_ans.sum())
-    txt = make_batch(N, T, R=1, feat_dim=8, seed=seed + 1, vocab_size=vocab_size)
+    txt = make_batch(N, T, R=1, feat_dim=8, seed=seed + 1, vocab_size=vocab_size, min_answer=2)     # candidates differ in >= 1 token
     vis = make_batch(Q, T=8, R=R, feat_dim=feat_dim, seed=seed + 2, vocab_size=vocab_size)
     # candidates of one question share everything but the answer tokens: copy the first candidate's row, then re-draw the
     # answer span (type 1) of the others
     off = 0
     for q in range(Q):
         n = int(num_ans[q])
+        if distinct:
+            off += n
+            continue
         for k in ('tokens', 'loc', 'segments', 'sep_indices', 'hist_len'):
             txt[k][off + 1:off + n] = txt[k][off]
         ans = (txt['segments'][off] == 1).nonzero().view(-1)

@@ -7,9 +7,9 @@
                                            all tensors together <= 2e-5 relative L2 (measured 2.5e-7 .. 4.2e-6)
     (fp32 storage and arithmetic; the oracle runs in fp64, the goldens come from the reference in fp32);
 (2) the bf16 production path vs check mode ON THE DEVICE, dropout ON (both draw the same counter-based masks), at a size
-    the CPU oracle does not reach in seconds: logits <= 6e-2 of scale (measured 1.5e-2), loss <= 2e-2 (2e-4), regression <= 5e-3 (2.2e-3),
-    gradients global relative L2 <= 0.2 (7.2e-2) —
-    the bf16 floor documented in test_model_gpu.py / DESIGN.md;
+    the CPU oracle does not reach in seconds: logits <= 1e-2 of scale (measured 6.8e-3 .. 7.6e-3), loss <= 1e-3 (6e-5 .. 9e-5),
+    regression <= 1e-3 (2.6e-4), gradients global relative L2 <= 7.5e-2 (5.8e-2; 2.7e-2 at the stress shape, bar 4e-2) — bars =
+    measured x 1.3, see test_model_gpu.py / DESIGN.md for the floor they sit on;
 (3) the check-mode GEMM and attention kernels on their own against torch (ragged shapes, every operand major / epilogue)."""
 import math
 import os
@@ -112,7 +112,7 @@ def test_bf16_path_against_check_mode_with_dropout_on_full_model():
     (l32, s32, r32, g32), (l16, s16, r16, g16) = res['fp32'], res['bf16']
     e_logit, e_grad = scale_err(s16, s32), float((g16 - g32).norm() / g32.norm())
     print(f'bf16 vs fp32 check, dropout on: loss {l16:.5f} / {l32:.5f}, logits {e_logit:.2e}, reg {scale_err(r16, r32):.2e}, gradients {e_grad:.2e}')
-    assert abs(l16 - l32) < 2e-2 and e_logit < 6e-2 and scale_err(r16, r32) < 5e-3 and e_grad < 0.2
+    assert abs(l16 - l32) < 1e-3 and e_logit < 1e-2 and scale_err(r16, r32) < 1e-3 and e_grad < 7.5e-2
     # a different mask stream would not be a rounding-sized difference: same model, other salt
     torch.manual_seed(6)
     params = default_params(cfg_path, device='cuda', L1=True)
@@ -214,7 +214,7 @@ def test_edge_case_batches(precision):
     m = VisualDialogEncoder(params, precision=precision)
     m.load_state_dict({'bert_pretrained.' + k: v for k, v in sd.items()}, strict=True)
     m.to(DEV).eval()
-    tol_logit, tol_loss, tol_grad = (2e-5, 1e-5, 2e-5) if precision == 'fp32' else (6e-2, 2e-2, 0.2)
+    tol_logit, tol_loss, tol_grad = (2e-5, 1e-5, 2e-5) if precision == 'fp32' else (2e-2, 5e-3, 0.1)
     for name, batch in _edge_batches(cfg).items():
         gb = {k: v.to(DEV) for k, v in batch.items()}
         m.zero_grad()
@@ -229,6 +229,8 @@ def test_edge_case_batches(precision):
         named = dict(m.bert_pretrained.named_parameters())
         num = sum(float((named[k].grad.double().cpu() - v).norm() ** 2) for k, v in g.items())
         den = sum(float(v.norm() ** 2) for v in g.values())
+        print(f'edge case {name} [{precision}]: logits {scale_err(scores, out["logits"]):.2e}, loss {abs(float(loss) - float(out["loss"])):.1e}, '
+              f'gradients {(num / den) ** 0.5:.2e}')
         assert (num / den) ** 0.5 < tol_grad, (name, (num / den) ** 0.5)
         assert torch.isfinite(m.arena.g32).all(), name
 
@@ -275,7 +277,7 @@ def test_full_size_b80_properties():
     (l16, s16, g16), (l32, s32, g32) = res['bf16'], res['fp32']
     e_logit, e_grad = scale_err(s16, s32), float((g16 - g32).norm() / g32.norm())
     print(f'B=80 train, dropout on, bf16 vs fp32 check: loss {l16:.5f} / {l32:.5f}, logits {e_logit:.2e}, gradients {e_grad:.2e}')
-    assert abs(l16 - l32) < 2e-2 and e_logit < 6e-2 and e_grad < 0.2
+    assert abs(l16 - l32) < 1e-3 and e_logit < 1e-2 and e_grad < 7.5e-2
 
 
 def test_stress_shape_bf16_vs_check_mode():
@@ -303,7 +305,7 @@ def test_stress_shape_bf16_vs_check_mode():
     (l32, s32, g32), (l16, s16, g16) = res['fp32'], res['bf16']
     e_logit, e_grad = scale_err(s16, s32), float((g16 - g32).norm() / g32.norm())
     print(f'stress shape, bf16 vs fp32 check: loss {l16:.5f} / {l32:.5f}, logits {e_logit:.2e}, gradients {e_grad:.2e}')
-    assert abs(l16 - l32) < 2e-2 and e_logit < 6e-2 and e_grad < 0.2
+    assert abs(l16 - l32) < 1e-3 and e_logit < 1e-2 and e_grad < 4e-2
 
 
 def test_question_batch_full_model_bit_identical_to_replicated_layout():

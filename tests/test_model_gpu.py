@@ -258,30 +258,34 @@ def _full_model(style='mild', seed=1):
 
 def test_full_model_per_question_argmax_matches_the_oracle():
     """The evaluation outcome itself (CRCT/evaluation.py:254-258,287-296) on the FULL model: 16 questions x 32 candidate
-    answers through `evaluate_batch` (question-level visual rows, packed tokens) against the fp32 oracle on the replicated
-    layout — the selected candidate is identical for every question whose best-vs-second probability margin in the oracle
-    exceeds 2e-3 (the logit bar of this operating point, 1e-2 of a ~0.2 logit scale, moves softmax(.)[0] by ~1e-3)."""
+    sequences through `evaluate_batch` (question-level visual rows, packed tokens) against the fp32 oracle on the replicated
+    layout.  Stated in probabilities p = softmax(nsp)[:,0] (what the argmax runs over):
+      * every candidate's p within 1.5e-3 of the oracle's (logits <= 1e-2 of their scale);
+      * REGRET: the oracle probability of the candidate the CUDA path selects is within 1e-3 of the oracle's best, for every question;
+      * IDENTITY: the selected candidate is the oracle's wherever the oracle's best-vs-second margin exceeds 2e-3, and that
+        covers at least half of the questions (independent candidate sequences: `distinct=True`)."""
     from cqa_crct_b200.evaluate import evaluate_batch, expand_question_batch
     from cqa_crct_b200.synthetic import make_question_batch
-    from oracle.eval_oracle import select_and_score
     m, params, cfg, sd = _full_model()
-    qb = make_question_batch(16, 124, 44, cfg.v_feature_size, seed=77, total=512)
+    qb = make_question_batch(16, 124, 44, cfg.v_feature_size, seed=77, total=512, distinct=True)
     out = evaluate_batch(m, qb, params, eval_batch_size=512)
     full = expand_question_batch(qb)
     with torch.no_grad():
         o, _ = O.forward(sd, O.Config(cfg.__dict__), full, train=False, l1=True, keep_cache=False)
     assert scale_err(out['logits'], o['logits']) < 1e-2
-    oref = select_and_score(o['logits'].float(), o['reg_pred'].float(), o['reg_dist'].float(), o['reg_l1'].float(), qb['num_ans'],
-                            qb['gt_id'], qb['needs_reg'], qb['tolerance_margin'])
-    p, off, sure = oref['prob'], 0, 0
+    p = torch.softmax(o['logits'], 1)[:, 0]
+    pc = out['prob'].cpu()
+    assert float((pc - p).abs().max()) < 1.5e-3
+    off, sure = 0, 0
     for q, n in enumerate(qb['num_ans'].tolist()):
-        top = torch.sort(p[off:off + n], descending=True).values
-        if n == 1 or float(top[0] - top[1]) > 2e-3:
+        top = torch.sort(p[off:off + n], descending=True)
+        chosen = int(out['answers'][q])
+        assert float(top.values[0] - p[off + chosen]) <= 1e-3, (q, float(top.values[0] - p[off + chosen]))
+        if n == 1 or float(top.values[0] - top.values[1]) > 2e-3:
             sure += 1
-            assert int(out['answers'][q]) == int(oref['answers'][q]), (q, float(top[0] - top[1]))
+            assert chosen == int(top.indices[0]), (q, float(top.values[0] - top.values[1]))
         off += n
     assert sure >= 8, sure                      # the margin rule must not make the test vacuous
-    assert float((out['prob'].cpu() - p).abs().max()) < 3e-3
 
 
 def test_full_size_b80_train_gradients_against_the_oracle():
