@@ -416,6 +416,13 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
             res32 = epi == L.EPI_BIAS_RES_F32
             gbytes += 2.0 * (M_ * K_ + N_ * K_) + mn * (4.0 if epi in (L.EPI_F32, L.EPI_BIAS_RES_F32) else 2.0) \
                 + ((4.0 if res32 else 2.0) * mn if has_aux else 0.0) + (2.0 * mn if has_d2 else 0.0)
+        dump = os.environ.get('CRCT_BENCH_DUMP_GEMMS')       # per-launch table for tools/gemm_table.py
+        if dump:
+            rows_ = []
+            for (a, b), (M_, N_, K_, a_major, rows_dev, epi, has_aux, has_d2) in zip(pairs, meta):
+                r = int(rows_dev) if rows_dev is not None else None
+                rows_.append({'M': M_, 'N': N_, 'K': K_, 'a_major': a_major, 'rows': r, 'epi': epi, 'us': (a.elapsed_time(b) - overhead_ms) * 1e3})
+            json.dump({'workload': name, 'overhead_us': overhead_ms * 1e3, 'launches': rows_}, open(f'{dump}.{name}.json', 'w'))
         del graph_keep
         achieved = flops / (gemm_ms / 1e3) / 1e12
         traffic, traffic_src = None, None         # DRAM bytes per GEMM launch from the committed ncu capture of this workload

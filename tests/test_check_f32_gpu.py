@@ -214,7 +214,7 @@ def test_edge_case_batches(precision):
     m = VisualDialogEncoder(params, precision=precision)
     m.load_state_dict({'bert_pretrained.' + k: v for k, v in sd.items()}, strict=True)
     m.to(DEV).eval()
-    tol_logit, tol_loss, tol_grad = (2e-5, 1e-5, 2e-5) if precision == 'fp32' else (2e-2, 5e-3, 0.1)
+    tol_logit, tol_loss, tol_grad = (2e-5, 1e-5, 2e-5) if precision == 'fp32' else (1e-2, 1e-3, 5e-2)      # bf16 measured: logits <= 4.2e-3, loss <= 1e-4, gradients <= 3.1e-2
     for name, batch in _edge_batches(cfg).items():
         gb = {k: v.to(DEV) for k, v in batch.items()}
         m.zero_grad()

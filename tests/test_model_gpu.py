@@ -260,10 +260,12 @@ def test_full_model_per_question_argmax_matches_the_oracle():
     """The evaluation outcome itself (CRCT/evaluation.py:254-258,287-296) on the FULL model: 16 questions x 32 candidate
     sequences through `evaluate_batch` (question-level visual rows, packed tokens) against the fp32 oracle on the replicated
     layout.  Stated in probabilities p = softmax(nsp)[:,0] (what the argmax runs over):
-      * every candidate's p within 1.5e-3 of the oracle's (logits <= 1e-2 of their scale);
-      * REGRET: the oracle probability of the candidate the CUDA path selects is within 1e-3 of the oracle's best, for every question;
-      * IDENTITY: the selected candidate is the oracle's wherever the oracle's best-vs-second margin exceeds 2e-3, and that
-        covers at least half of the questions (independent candidate sequences: `distinct=True`)."""
+      * every candidate's p within 1e-3 of the oracle's (measured 5.7e-4; logits <= 1e-2 of their scale, measured 6.6e-3);
+      * REGRET: the oracle probability of the candidate the CUDA path selects is within 6e-4 of the oracle's best, for every
+        question (measured 1.2e-4 on the one question — margin 1.25e-4 — where the selection differs);
+      * IDENTITY: the selected candidate is the oracle's wherever the oracle's best-vs-second margin exceeds 1.2e-3 (twice the
+        largest within-question differential error measured, 5.5e-4), which covers at least half of the questions
+        (independent candidate sequences, `distinct=True`: margins 6e-5 .. 9e-3 at random-init weights)."""
     from cqa_crct_b200.evaluate import evaluate_batch, expand_question_batch
     from cqa_crct_b200.synthetic import make_question_batch
     m, params, cfg, sd = _full_model()
@@ -275,13 +277,13 @@ def test_full_model_per_question_argmax_matches_the_oracle():
     assert scale_err(out['logits'], o['logits']) < 1e-2
     p = torch.softmax(o['logits'], 1)[:, 0]
     pc = out['prob'].cpu()
-    assert float((pc - p).abs().max()) < 1.5e-3
+    assert float((pc - p).abs().max()) < 1e-3
     off, sure = 0, 0
     for q, n in enumerate(qb['num_ans'].tolist()):
         top = torch.sort(p[off:off + n], descending=True)
         chosen = int(out['answers'][q])
-        assert float(top.values[0] - p[off + chosen]) <= 1e-3, (q, float(top.values[0] - p[off + chosen]))
-        if n == 1 or float(top.values[0] - top.values[1]) > 2e-3:
+        assert float(top.values[0] - p[off + chosen]) <= 6e-4, (q, float(top.values[0] - p[off + chosen]))
+        if n == 1 or float(top.values[0] - top.values[1]) > 1.2e-3:
             sure += 1
             assert chosen == int(top.indices[0]), (q, float(top.values[0] - top.values[1]))
         off += n
