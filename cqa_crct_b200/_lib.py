@@ -28,7 +28,7 @@ class GemmArgs(C.Structure):
                 ('M', i32), ('N', i32), ('K', i32), ('lda', i32), ('ldb', i32), ('ldd', i32), ('ldaux', i32),
                 ('a_major', i32), ('b_major', i32), ('epilogue', i32), ('accumulate', i32), ('split_k', i32),
                 ('block_n', i32), ('dropout_p', f32), ('seed', u64), ('max_ctas', i32), ('cta_group', i32), ('dbg', i32 * 7), ('salt', vp),
-                ('a_rows_dev', vp), ('drop_rows', vp)]
+                ('a_rows_dev', vp), ('rows_hint', i32), ('drop_rows', vp)]
 
 
 class LnBwdArgs(C.Structure):
@@ -225,6 +225,7 @@ def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None
     a.dropout_p, a.seed, a.max_ctas, a.cta_group = dropout_p, seed, max_ctas, cta_group
     a.salt = ptr(SALT)
     a.a_rows_dev, a.drop_rows = ptr(rows_dev), ptr(drop_rows)
+    a.rows_hint = int(getattr(rows_dev, 'hint', 0) or 0)      # expected row count (tile-shape choice only)
     if f32 and rows_dev is not None:
         raise CrctError('the fp32 check mode runs the padded layout (no device-side row counts)')
     if dbg is not None:

@@ -28,11 +28,11 @@ constexpr int EPI_COLS = 16;            // accumulator columns per epilogue step
 
 template <int BN>
 struct Cfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = BN * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int TMEM_COLS = (BN == 128) ? 256 : 512;      // two accumulator stages of BN columns; allocations are powers of two
     static constexpr int BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
     static constexpr int BIAS_BYTES = 2 * 256 * 4;              // per accumulator stage: the tile's bias slice
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
@@ -867,17 +867,24 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
     int bn = a->block_n;
     if (bn == 0) {
-        auto cost = [&](int b) {
-            long tiles = (long)((a->M + tile_m - 1) / tile_m) * ((a->N + b - 1) / b);
+        // rows the kernel is EXPECTED to run (packed layout: the host never reads *a_rows_dev; the caller's estimate of it only
+        // picks the tile shape): a 1.09-wave problem on 128x256 tiles (6900 x 768 -> 162 tiles on 148 SMs) costs two full waves
+        const int m_eff = (a->a_rows_dev && !a->a_major && a->rows_hint > 0 && a->rows_hint < a->M) ? a->rows_hint : a->M;
+        auto cost = [&](int b, int penalty_pct) {
+            long tiles = (long)((m_eff + tile_m - 1) / tile_m) * ((a->N + b - 1) / b);
             const long slots = pair ? sms / 2 : sms;
-            return ((tiles + slots - 1) / slots) * (long)b;
+            return ((tiles + slots - 1) / slots) * (long)b * penalty_pct;
         };
         // 128x256 tiles move 1.33x fewer operand bytes per FLOP through L2/smem than 128x128 (measured faster on every
-        // CRCT shape, wgrad included: profiles/r01_wgrad_shapes.log); 128-wide only when it removes a mostly-empty tile column
-        bn = (a->N <= 128 || cost(128) * 5 < cost(256) * 4) ? 128 : 256;
+        // CRCT shape, wgrad included: profiles/r01_wgrad_shapes.log): a narrower tile must win by its penalty to be chosen
+        bn = 256;
+        long best = cost(256, 100);
+        if (!pair && a->N > 128 && cost(192, 106) < best) { bn = 192; best = cost(192, 106); }
+        if (a->N <= 128 || cost(128, 125) < best) bn = 128;
         if (f32 && a->accumulate && a->N >= 256) bn = 256;       // split-K refills the SMs: wave count is not the issue (measured)
     }
-    if (bn != 128 && bn != 256) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: block_n must be 0, 128 or 256");
+    if (bn != 128 && bn != 192 && bn != 256) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: block_n must be 0, 128, 192 or 256");
+    if (bn == 192 && pair) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_bf16: block_n 192 is a single-CTA tile (cta_group 1)");
     const int num_m_tiles = (a->M + tile_m - 1) / tile_m;
     const int num_n_tiles = (a->N + bn - 1) / bn;
     const int slots = pair ? sms / 2 : sms;          // concurrently resident tiles
@@ -947,5 +954,6 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     }
     const int grid = p.num_tiles < sms ? p.num_tiles : sms;
     if (bn == 256) return dispatch<256>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
+    if (bn == 192) return dispatch<192>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
     return dispatch<128>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
 }

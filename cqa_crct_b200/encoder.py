@@ -155,9 +155,12 @@ class _Rows:
     [cu[b], cu[b+1]); `n` = the device word cu[B] every kernel reads its row count from (buffers are still allocated for B*L
     rows — the host never learns the count, so one captured CUDA graph serves every batch), `src[r]` = padded position of row r."""
 
-    def __init__(self, B, L, cu=None, src=None, mask_add=None):
+    def __init__(self, B, L, cu=None, src=None, mask_add=None, fill=None):
         self.B, self.L, self.cu, self.src, self.mask_add = B, L, cu, src, mask_add
         self.n = cu[B:B + 1] if cu is not None else None
+        if self.n is not None:
+            # the caller's estimate of the valid fraction -> expected row count, read by the GEMM's tile-shape choice only
+            self.n.hint = int(fill * B * L) if fill else 0
 
 
 class _CrctFunction(torch.autograd.Function):
@@ -193,6 +196,9 @@ class VisualDialogEncoder(nn.Module):
         # var-len ("packed") rows: only the tokens / regions whose mask is 1 go through the encoder (csrc/varlen.cu); exact —
         # masked keys have probability 0 in the reference.  The fp32 check mode runs the reference's padded layout.
         self.varlen = bool(params.get('varlen', True)) and not self.fp32
+        # (text, visual) expected fraction of valid rows — an ESTIMATE (e.g. of the previous / an example batch) that only steers
+        # the GEMM tile shapes; set by graph.GraphedTrainStep / evaluate.evaluate_batch from host-side batch data, or by the user
+        self.row_fill_hint = params.get('row_fill_hint', None)
         config_path = params['model_config']
         assert os.path.exists(config_path), "model_config file not found"      # encoder_decorator.py:13
         self.params = params
@@ -732,13 +738,14 @@ class VisualDialogEncoder(nn.Module):
         i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
         if self.varlen:
             # packed rows (csrc/varlen.cu): compact the valid tokens / regions once; no additive masks from here on
-            rt = _Rows(B, T, i32(B + 1), i32(B * T))
+            ft, fv = self.row_fill_hint if self.row_fill_hint else (None, None)
+            rt = _Rows(B, T, i32(B + 1), i32(B * T), fill=ft)
             L.row_map(amask, rt.cu, rt.src)
-            rvq = _Rows(Bv, R, i32(Bv + 1), i32(Bv * R))           # per question (f3) == per sequence without `group`
+            rvq = _Rows(Bv, R, i32(Bv + 1), i32(Bv * R), fill=fv)  # per question (f3) == per sequence without `group`
             L.row_map(imask, rvq.cu, rvq.src)
             rv = rvq
             if group is not None:          # candidate n shares the packed region rows of question group[n]
-                rv = _Rows(B, R, i32(B + 1), i32(B * R))
+                rv = _Rows(B, R, i32(B + 1), i32(B * R), fill=fv)
                 L.group_map(rvq.cu, group, rv.cu, rv.src)
         else:
             t_mask = torch.empty(B, T, dtype=torch.float32, device=dev)

@@ -77,6 +77,12 @@ def to_device(qb: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
     off = torch.zeros(qb['num_ans'].numel() + 1, dtype=torch.int64)
     off[1:] = torch.cumsum(qb['num_ans'].view(-1).cpu(), 0)
     out['_offsets'] = off.to(device, non_blocking=True)
+    # expected fraction of valid rows (host-side data, no device read-back): steers the GEMM tile shapes only
+    seq_len = torch.gather(qb['sep_indices'].cpu(), 1, qb['hist_len'].cpu().view(-1, 1)).squeeze(1) + 1
+    T = qb['tokens'].shape[1]
+    fv_q = (qb['image_mask'].cpu() != 0).float().mean(1)                    # per question; candidates inherit their question's rows
+    out['_fill'] = (max(float(seq_len.clamp(max=T).sum()) / float(seq_len.numel() * T), 1e-3),
+                    max(float((fv_q * qb['num_ans'].cpu().view(-1).float()).sum() / qb['num_ans'].sum()), 1e-3))
     return out
 
 
@@ -97,6 +103,8 @@ def evaluate_batch(model, qb: Dict[str, torch.Tensor], params: dict, eval_batch_
     if '_group' not in qb:
         qb = to_device(qb, dev)
     grp_host = qb['_group_host']
+    if enc.varlen and params.get('row_fill_hint') is None and '_fill' in qb:
+        enc.row_fill_hint = qb['_fill']
     N, Q = qb['tokens'].shape[0], qb['num_ans'].numel()
     if N != grp_host.numel():
         raise ValueError(f'{N} candidate sequences but sum(num_ans) = {grp_host.numel()}')

@@ -30,6 +30,16 @@ import torch
 import torch.distributed as dist
 
 
+def fill_fractions(batch) -> tuple:
+    """(text, visual) fraction of valid rows of a batch (encoder_decorator.py:118-120 lengths; image_mask), computed with torch ops
+    on whatever device the batch lives on — one read-back, done once before capture."""
+    seq_len = torch.gather(batch['sep_indices'], 1, batch['hist_len'].view(-1, 1)).squeeze(1) + 1
+    T = batch['tokens'].shape[1]
+    ft = float(seq_len.clamp(max=T).sum()) / float(seq_len.numel() * T)
+    fv = float((batch['image_mask'] != 0).sum()) / float(batch['image_mask'].numel())
+    return max(ft, 1e-3), max(fv, 1e-3)
+
+
 class GraphedTrainStep:
     def __init__(self, model, optimizer, params: dict, example_batch: Dict[str, torch.Tensor], scheduler=None,
                  warmup_steps: int = 2):
@@ -41,6 +51,8 @@ class GraphedTrainStep:
         self.static = {k: v.to(dev).clone() for k, v in example_batch.items() if k != 'needs_reg'}
         self.nsp_coeff, self.reg_coeff = float(params.get('nsp_loss_coeff', 1.0)), float(params.get('reg_loss_coeff', 1.0))
         optimizer.enable_device_scalars()
+        if enc.row_fill_hint is None and enc.varlen:
+            enc.row_fill_hint = fill_fractions(example_batch)       # tile shapes are frozen at capture: chosen for this fill
         enc.segment_ranges = self.world > 1      # per-bucket ranges only when the step is cut for the exchange
         self.segments = []                # [(graph, (lo, hi) bucket finished by this segment or None)]
         self._copy_stream = torch.cuda.Stream(device=dev)

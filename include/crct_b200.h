@@ -74,7 +74,7 @@ typedef struct {
     int32_t epilogue;   /* crct_epilogue_t */
     int32_t accumulate; /* CRCT_EPI_F32: 1 = atomically add into D */
     int32_t split_k;    /* >= 1; > 1 requires CRCT_EPI_F32 with accumulate */
-    int32_t block_n;    /* 0 = choose; else 128 or 256 */
+    int32_t block_n;    /* 0 = choose; else 128, 192 (single-CTA tiles only) or 256 */
     float dropout_p;    /* CRCT_EPI_BIAS_RES: 0 = off */
     uint64_t seed;      /* dropout stream; element counter = m * N + n */
     int32_t max_ctas;   /* 0 = one persistent CTA per SM; else cap (tests) */
@@ -85,6 +85,8 @@ typedef struct {
                                 * — M for a_major = 0 (tiles past it are skipped, rows past it are not written), GEMM-K for the
                                 * wgrad form a_major = b_major = 1 (rows past it contribute nothing).  The M / K fields are then
                                 * the upper bounds the buffers were allocated for.  Not with cta_group = 2. */
+    int32_t rows_hint;         /* with a_rows_dev: the caller's ESTIMATE of *a_rows_dev (0 = unknown).  Only steers the tile-shape
+                                * choice (waves on 148 SMs); never read for correctness. */
     const int32_t* drop_rows;  /* optional DEVICE int32 [M]: the dropout element counter of output row m is drop_rows[m] * N + n
                                 * instead of m * N + n (packed rows draw the masks of their padded positions: crct_row_map's src_row) */
 } crct_gemm_t;

@@ -307,3 +307,34 @@ def test_packed_training_step_with_dropout_draws_the_padded_masks(name):
         grads.append(m.arena.g32[:m.arena.live_end].double().clone())
     assert abs(losses[0] - losses[1]) < 1e-6, losses
     assert float((grads[0] - grads[1]).norm() / grads[1].norm()) < 2e-4
+
+
+@pytest.mark.parametrize('M,N,K', [(200, 192, 192), (1000, 768, 3072), (6899, 768, 768), (1903, 1024, 1024), (9920, 2304, 768), (1000, 200, 128)])
+def test_gemm_192_wide_tiles_all_forms(M, N, K):
+    """block_n = 192 (single-CTA tile; the tile shape the policy picks for ~1.1-wave problems on 256-wide tiles)."""
+    torch.manual_seed(M + N)
+    A, B = bf(torch.randn(M, K, device=DEV) * 0.5), bf(torch.randn(N, K, device=DEV) * 0.5)
+    bias, aux = torch.randn(N, device=DEV), bf(torch.randn(M, N, device=DEV))
+    ref = A.float() @ B.float().t() + bias
+    D, D2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16), torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, block_n=192)
+    assert relmax(D.float(), ref) < 6e-3
+    L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_GELU, D2=D2, block_n=192)
+    assert relmax(D.float(), torch.nn.functional.gelu(ref)) < 6e-3
+    L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES, aux=aux, block_n=192, dropout_p=0.1, seed=3)
+    L.gemm(A, B, D2, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES, aux=aux, block_n=256, dropout_p=0.1, seed=3)
+    assert torch.equal(D, D2)                     # same accumulation order per element, same dropout counters: tile shape is invisible
+    Z = torch.empty(M, N, device=DEV)
+    L.gemm(A, B, Z, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_RES_F32, aux=aux.float(), block_n=192)
+    assert relmax(Z, ref + aux.float()) < 1e-5
+    W = bf(torch.randn(K, N, device=DEV) * 0.5)   # dgrad form (MN-major B)
+    L.gemm(A, W, D, M=M, N=N, K=K, b_major=1, epilogue=L.EPI_MUL, aux=aux, block_n=192)
+    assert relmax(D.float(), (A.float() @ W.float()) * aux.float()) < 6e-3
+    dW = torch.zeros(K, N, device=DEV)            # wgrad form: dW[K,N] += A^T aux  (both MN-major), GEMM-K = M rows
+    L.gemm(A, aux, dW, M=K, N=N, K=M, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, block_n=192)
+    assert relmax(dW, A.float().t() @ aux.float()) < 1e-4
+    n = torch.tensor([max(1, M // 2)], dtype=torch.int32, device=DEV)          # hint-driven policy with a device-side count
+    n.hint = int(n)
+    D.fill_(7.0)
+    L.gemm(A, B, D, M=M, N=N, K=K, bias=bias, rows_dev=n)
+    assert relmax(D[:int(n)].float(), ref[:int(n)]) < 6e-3 and bool((D[int(n):] == 7.0).all())
