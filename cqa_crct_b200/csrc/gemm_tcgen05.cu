@@ -863,7 +863,7 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     const int sms = a->max_ctas > 0 ? a->max_ctas : crct_num_sms();
     if (sms <= 0) return CRCT_ERR_CUDA;
 
-    const bool pair = a->cta_group == 2 || (a->cta_group == 0 && !a->a_rows_dev && crct_gemm_auto_pair(a));
+    const bool pair = a->cta_group == 2 || (a->cta_group == 0 && !a->a_rows_dev && a->block_n != 192 && crct_gemm_auto_pair(a));
     const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
     int bn = a->block_n;
     if (bn == 0) {
