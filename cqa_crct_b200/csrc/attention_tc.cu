@@ -1,0 +1,521 @@
+// K2/K3 on the 5th-generation tensor cores — fused attention forward / backward with tcgen05.mma, TMEM accumulators and
+// TMA operand loads, for every CRCT attention whose sequences fit ONE 128-row tile (text self 16 x 48 at T <= 124, visual
+// self 16 x 64 at R <= 44, both co-attention directions 32 x 32): one CTA per (sample, head).
+//
+//   forward    S = Q K^T  -> TMEM        (tcgen05.mma  M = 128 queries, N = key tile, K = dh; Q, K by TMA, 128B swizzle)
+//              P = dropout(softmax(S / sqrt(dh) [+ mask]))   one thread per query row: tcgen05.ld, exp2, bf16 P -> smem
+//              O = P V    -> TMEM        (A = P from shared memory K-major, B = V as loaded: MN-major)
+//   backward   S = Q K^T, dP = dO V^T -> TMEM;  P, dS (bf16) -> smem;
+//              dV = P^T dO, dK = dS^T Q (A = the same P / dS tiles read MN-major), dQ = dS K (A = dS read K-major)
+//
+// reference: CRCT/backbone/vilbert.py:397-412 (text), :527-543 (visual), :684-723 (co-attention, both directions).
+// Q / K / V / dO tiles are [rows x 64 columns] boxes of the packed projections (head h = columns [h*dh, h*dh + 64): the
+// columns past dh belong to the next head and are never multiplied — the MMAs run K = dh).  Rows past a sample's length
+// (packed layout: the next sample's rows; padded layout: masked rows) are excluded by INDEX (probability exactly 0, operand
+// rows cleared in shared memory where a 0 x garbage product could otherwise produce NaN).  Dropout counters, log-sum-exp
+// and masks are laid out exactly as in the mma.sync kernels of attention.cu, which remain the path for longer sequences
+// (stress shape T = 248) and the A/B reference (CRCT_ATTN_LEGACY=1).
+#include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+int crct_make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer);
+
+namespace {
+
+constexpr int TC_THREADS = 128;
+constexpr int QT = 128;                       // query tile = TMEM lanes
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (see gemm_tcgen05.cu)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, majors, N >> 3, M >> 4
+__device__ __forceinline__ constexpr uint32_t idesc(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+// K-major operand tile [rows][64 bf16] (one 128-byte swizzle atom wide): descriptor of the 16-element k-step `ks`
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int ks) { return smem_desc(tile + (uint32_t)ks * 32u, 16u, 1024u); }
+// MN-major operand: tile [k rows][64 (M or N) elements]; 64-wide atoms `atom_bytes` apart; k-step = 16 rows
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int ks, uint32_t atom_bytes) {
+    return smem_desc(tile + (uint32_t)ks * 2048u, atom_bytes, 1024u);
+}
+// byte offset of the 16-byte chunk holding columns [8*chunk, 8*chunk + 8) of row r in a [rows][64] 128B-swizzled tile
+__device__ __forceinline__ uint32_t swz(int r, int chunk) { return (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4); }
+
+struct TcParams {
+    const float* mask_add;
+    const bf16* out;  int ldo;                // forward: written; backward: read (D = sum dO * O)
+    bf16* out_w;
+    const bf16* dout; int lddo;
+    float* lse;
+    bf16* dq; bf16* dk; bf16* dv;
+    int lddq, lddk, lddv;
+    int B, nh, Lq, Lk;
+    float scale;
+    uint32_t thr; float dscale; uint64_t seed; const unsigned long long* salt;
+    const int* cu_q; const int* cu_k;
+};
+
+// ------------------------------------------------------------------------------------------------ forward
+// shared memory (1024-byte aligned): Q [128][128 B] | K [LKT][128 B] | V [LKT][128 B] | barriers | mask [LKT] f32
+// P [128][LKT] bf16 (K-major, 64-key atoms of 16 KB) aliases Q (+ K): both are dead once S is in TMEM.
+template <int DH, int LKT>
+__global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                                 const __grid_constant__ CUtensorMap tmV, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* g = smem_raw + (base - raw);
+    constexpr uint32_t Q_BYTES = QT * 128, KV_BYTES = LKT * 128;
+    const uint32_t sQ = base, sK = base + Q_BYTES, sV = sK + KV_BYTES, sBar = sV + KV_BYTES;
+    const uint32_t bar_tma = sBar, bar_mma = sBar + 8, tmem_slot = sBar + 16;
+    float* mask_s = reinterpret_cast<float*>(g + Q_BYTES + 2 * KV_BYTES + 32);
+    uint8_t* gP = g;                                                  // P tile (generic pointer), aliases Q / K
+    uint8_t* gV = g + Q_BYTES + KV_BYTES;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    pdl_launch_dependents();
+    if (tid == 0) {
+        ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV);
+        ptx::mbar_init(bar_tma, 1);
+        ptx::mbar_init(bar_mma, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 0) {
+        ptx::tmem_alloc(tmem_slot, LKT);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(g + Q_BYTES + 2 * KV_BYTES + 16);
+    pdl_wait();
+
+    const int b = blockIdx.x / p.nh, h = blockIdx.x % p.nh;
+    int qrow0 = b * p.Lq, krow0 = b * p.Lk, Lq = p.Lq, Lk = p.Lk;
+    if (p.cu_q != nullptr) { qrow0 = __ldg(p.cu_q + b); Lq = min(p.Lq, __ldg(p.cu_q + b + 1) - qrow0); }
+    if (p.cu_k != nullptr) { krow0 = __ldg(p.cu_k + b); Lk = min(p.Lk, __ldg(p.cu_k + b + 1) - krow0); }
+    const int Lk16 = (Lk + 15) & ~15;
+
+    if (tid == 0) {
+        ptx::mbar_arrive_expect_tx(bar_tma, Q_BYTES + 2 * KV_BYTES);
+        ptx::tma_load_2d(sQ, &tmQ, bar_tma, h * DH, qrow0);
+        ptx::tma_load_2d(sK, &tmK, bar_tma, h * DH, krow0);
+        ptx::tma_load_2d(sV, &tmV, bar_tma, h * DH, krow0);
+    }
+    if (tid < LKT) mask_s[tid] = (p.mask_add != nullptr && tid < Lk) ? p.mask_add[(size_t)b * p.Lk + tid] * LOG2E : 0.f;
+    ptx::mbar_wait(bar_tma, 0);
+    if (tid == 0) {                                                   // S = Q K^T : DH / 16 instructions, 128 x LKT x 16 each
+        ptx::tc_fence_after();
+        constexpr uint32_t id = idesc(QT, LKT, false, false);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) ptx::tc_mma_bf16(tmem, desc_kmajor(sQ, ks), desc_kmajor(sK, ks), id, ks > 0 ? 1u : 0u);
+        ptx::tc_commit(bar_mma);
+    }
+    // V rows in [Lk, Lk16) meet P columns that are written as 0: clear them, so that no stale NaN pattern is multiplied
+    if (tid >= Lk && tid < Lk16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(gV + (size_t)tid * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();                                                  // mask_s visible
+    ptx::mbar_wait(bar_mma, 0);
+    __syncwarp();
+    ptx::tc_fence_after();
+
+    // ---- softmax of row `tid` (TMEM lane tid), scores in the log2 domain: s2 = s * scale * log2(e) + mask * log2(e)
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const float scale2 = p.scale * LOG2E;
+    const bool live = tid < Lq;
+    float m = -INFINITY;
+    for (int c0 = 0; c0 < Lk; c0 += 32) {
+        uint32_t v[32];
+        ptx::tc_ld_32x32(trow + (uint32_t)c0, v);
+        ptx::tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (c0 + j < Lk) m = fmaxf(m, fmaf(__uint_as_float(v[j]), scale2, mask_s[c0 + j]));
+    }
+    const CrctDrop32 drop = crct_drop32((p.thr != 0u && p.salt) ? (p.seed ^ __ldg(p.salt)) : p.seed, p.thr);
+    const uint32_t ctr0 = ((uint32_t)blockIdx.x * (uint32_t)p.Lq + (uint32_t)tid) * (uint32_t)p.Lk;
+    float l = 0.f;
+    for (int c0 = 0; c0 < Lk16; c0 += 32) {
+        uint32_t v[32];
+        ptx::tc_ld_32x32(trow + (uint32_t)c0, v);
+        ptx::tc_wait_ld();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {                              // 8 columns = one 16-byte chunk of the P tile
+            const int c = c0 + ch * 8;
+            if (c >= Lk16) break;
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                float p0 = 0.f, p1 = 0.f;
+                if (live && c + j < Lk) p0 = fast_exp2(fmaf(__uint_as_float(v[ch * 8 + j]), scale2, mask_s[c + j]) - m);
+                if (live && c + j + 1 < Lk) p1 = fast_exp2(fmaf(__uint_as_float(v[ch * 8 + j + 1]), scale2, mask_s[c + j + 1]) - m);
+                l += p0 + p1;
+                if (p.thr != 0u) {
+                    bool k0, k1;
+                    crct_keep2_32(drop, ctr0 + (uint32_t)(c + j), k0, k1);
+                    p0 = k0 ? p0 * p.dscale : 0.f;
+                    p1 = k1 ? p1 * p.dscale : 0.f;
+                }
+                pk[j >> 1] = pack_bf16x2(p0, p1);
+            }
+            *reinterpret_cast<uint4*>(gP + (size_t)(c >> 6) * (QT * 128) + swz(tid, (c & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+    if (live && p.lse != nullptr) p.lse[(size_t)blockIdx.x * p.Lq + tid] = (m + __log2f(l)) * LN2;
+    ptx::fence_proxy_async();                                         // P / cleared V rows (generic stores) -> tensor-core reads
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {                                                   // O = P V : Lk16 / 16 instructions, 128 x DH x 16 each
+        ptx::tc_fence_after();
+        constexpr uint32_t id = idesc(QT, DH, false, true);
+        for (int ks = 0; ks < Lk16 / 16; ++ks)
+            ptx::tc_mma_bf16(tmem, desc_kmajor(sQ + (uint32_t)(ks >> 2) * (QT * 128), ks & 3), desc_mnmajor(sV, ks, LKT * 128), id, ks > 0 ? 1u : 0u);
+        ptx::tc_commit(bar_mma);
+    }
+    ptx::mbar_wait(bar_mma, 1);
+    __syncwarp();
+    ptx::tc_fence_after();
+    if (live) {
+        const float inv = 1.f / l;
+        bf16* dst = p.out_w + (size_t)(qrow0 + tid) * p.ldo + h * DH;
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 16) {
+            uint32_t v[16];
+            ptx::tc_ld_32x16(trow + (uint32_t)c0, v);
+            ptx::tc_wait_ld();
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);   o0.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+            o0.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);   o0.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+            o1.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);   o1.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+            o1.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv); o1.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+            *reinterpret_cast<uint4*>(dst + c0) = o0;
+            *reinterpret_cast<uint4*>(dst + c0 + 8) = o1;
+        }
+    } else {                                                          // warp-collective tcgen05.ld: every lane of the warp executes it
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 16) {
+            uint32_t v[16];
+            ptx::tc_ld_32x16(trow + (uint32_t)c0, v);
+            ptx::tc_wait_ld();
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc(tmem, LKT);
+}
+
+template <int DH, int LKT>
+int launch_fwd_tc(const crct_attn_fwd_t* a, const TcParams& p, cudaStream_t st) {
+    CUtensorMap tmQ, tmK, tmV;
+    const uint64_t W = (uint64_t)a->nh * a->dh;
+    if (int rc = crct_make_tmap_bf16_2d(&tmQ, a->q, W, (uint64_t)a->B * a->Lq, a->ldq, 64, QT)) return rc;
+    if (int rc = crct_make_tmap_bf16_2d(&tmK, a->k, W, (uint64_t)a->B * a->Lk, a->ldk, 64, LKT)) return rc;
+    if (int rc = crct_make_tmap_bf16_2d(&tmV, a->v, W, (uint64_t)a->B * a->Lk, a->ldv, 64, LKT)) return rc;
+    constexpr int SMEM = QT * 128 + 2 * LKT * 128 + 32 + LKT * 4 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        CRCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, LKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    CRCT_CUDA(crct_launch_pdl(attn_fwd_tc_kernel<DH, LKT>, dim3(a->B * a->nh), dim3(TC_THREADS), SMEM, st, tmQ, tmK, tmV, p));
+    return CRCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// shared memory: Q [128][128 B] | dO [128][128 B] | K [LKT][128 B] | V [LKT][128 B] | X [128 q][128 keys] bf16 = two 64-key atoms of
+// 16 KB | barriers | mask.  X holds dS first (dK = dS^T Q and dQ = dS K read it MN-major / K-major), then — once those MMAs have
+// retired — P (dV = P^T dO), which the threads keep packed in registers meanwhile: one pass over the scores, one 32 KB tile,
+// 80 KB per CTA = two CTAs per SM.  TMEM (256 columns): S [0,128) and dP [128,256) first, then dK [0,64), dQ [64,128),
+// dV [128,192).
+template <int DH, int LKT, int QBOX>
+__global__ void __launch_bounds__(TC_THREADS) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                                                                 const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                                                                 const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* g = smem_raw + (base - raw);
+    constexpr uint32_t Q_BYTES = QT * 128, KV_BYTES = LKT * 128, X_BYTES = 2 * QT * 128;
+    constexpr uint32_t OFF_DO = Q_BYTES, OFF_K = 2 * Q_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_X = OFF_V + KV_BYTES, OFF_BAR = OFF_X + X_BYTES;
+    const uint32_t sQ = base, sdO = base + OFF_DO, sK = base + OFF_K, sV = base + OFF_V, sX = base + OFF_X;
+    const uint32_t bar_tma = base + OFF_BAR, bar_mma = bar_tma + 8, tmem_slot = bar_tma + 16;
+    float* mask_s = reinterpret_cast<float*>(g + OFF_BAR + 32);
+    uint8_t* gX = g + OFF_X;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    pdl_launch_dependents();
+    if (tid == 0) {
+        ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmdO); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV);
+        ptx::mbar_init(bar_tma, 1);
+        ptx::mbar_init(bar_mma, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 0) {
+        ptx::tmem_alloc(tmem_slot, 256);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(g + OFF_BAR + 16);
+    pdl_wait();
+
+    const int b = blockIdx.x / p.nh, h = blockIdx.x % p.nh;
+    int qrow0 = b * p.Lq, krow0 = b * p.Lk, Lq = p.Lq, Lk = p.Lk;
+    if (p.cu_q != nullptr) { qrow0 = __ldg(p.cu_q + b); Lq = min(p.Lq, __ldg(p.cu_q + b + 1) - qrow0); }
+    if (p.cu_k != nullptr) { krow0 = __ldg(p.cu_k + b); Lk = min(p.Lk, __ldg(p.cu_k + b + 1) - krow0); }
+    const int Lk16 = (Lk + 15) & ~15, Lq16 = (Lq + 15) & ~15;
+
+    if (tid == 0) {
+        ptx::mbar_arrive_expect_tx(bar_tma, 2 * QBOX * 128 + 2 * KV_BYTES);
+        ptx::tma_load_2d(sQ, &tmQ, bar_tma, h * DH, qrow0);
+        ptx::tma_load_2d(sdO, &tmdO, bar_tma, h * DH, qrow0);
+        ptx::tma_load_2d(sK, &tmK, bar_tma, h * DH, krow0);
+        ptx::tma_load_2d(sV, &tmV, bar_tma, h * DH, krow0);
+    }
+    mask_s[tid] = (p.mask_add != nullptr && tid < Lk) ? p.mask_add[(size_t)b * p.Lk + tid] * LOG2E : 0.f;
+    // this thread's query row: log-sum-exp (log2 domain) and D = sum_d dO * O
+    const bool live = tid < Lq;
+    float lse2 = 0.f, Dr = 0.f;
+    if (live) {
+        lse2 = p.lse[(size_t)blockIdx.x * p.Lq + tid] * LOG2E;
+        const bf16* o = p.out + (size_t)(qrow0 + tid) * p.ldo + h * DH;
+        const bf16* dd = p.dout + (size_t)(qrow0 + tid) * p.lddo + h * DH;
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+            float fo[8], fd[8];
+            load8_bf16(o + c * 8, fo);
+            load8_bf16(dd + c * 8, fd);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Dr = fmaf(fo[j], fd[j], Dr);
+        }
+    }
+    // the key half [64,128) of X is read by the M = 128 MMAs even when every key lives in the first atom: keep it finite
+    if (Lk16 <= 64) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(gX + QT * 128 + (size_t)tid * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    ptx::mbar_wait(bar_tma, 0);
+    if (tid == 0) {                                   // S = Q K^T -> [0,LKT) ; dP = dO V^T -> [128,128+LKT)
+        ptx::tc_fence_after();
+        constexpr uint32_t id = idesc(QT, LKT, false, false);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) ptx::tc_mma_bf16(tmem, desc_kmajor(sQ, ks), desc_kmajor(sK, ks), id, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) ptx::tc_mma_bf16(tmem + 128u, desc_kmajor(sdO, ks), desc_kmajor(sV, ks), id, ks > 0 ? 1u : 0u);
+        ptx::tc_commit(bar_mma);
+    }
+    __syncthreads();                                  // mask_s visible
+    ptx::mbar_wait(bar_mma, 0);
+    __syncwarp();
+    ptx::tc_fence_after();
+    // operand rows that meet zero rows / columns of P and dS must be finite: clear Q, dO rows [Lq, Lq16) and K rows [Lk, Lk16)
+    // (S and dP, which read them, are complete)
+    if (tid >= Lq && tid < Lq16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            *reinterpret_cast<uint4*>(g + (size_t)tid * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(g + OFF_DO + (size_t)tid * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    if (tid >= Lk && tid < Lk16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(g + OFF_K + (size_t)tid * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const float scale2 = p.scale * LOG2E;
+    const CrctDrop32 drop = crct_drop32((p.thr != 0u && p.salt) ? (p.seed ^ __ldg(p.salt)) : p.seed, p.thr);
+    const uint32_t ctr0 = ((uint32_t)blockIdx.x * (uint32_t)p.Lq + (uint32_t)tid) * (uint32_t)p.Lk;
+    uint32_t preg[LKT / 2];                           // this row's (dropped) probabilities, packed bf16, until X is free again
+#pragma unroll
+    for (int c0 = 0; c0 < LKT; c0 += 16) {
+        if (c0 < Lk16) {                              // warp-uniform
+            uint32_t vs[16], vd[16];
+            ptx::tc_ld_32x16(trow + (uint32_t)c0, vs);
+            ptx::tc_ld_32x16(trow + 128u + (uint32_t)c0, vd);
+            ptx::tc_wait_ld();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int c = c0 + ch * 8;
+                uint32_t ds[4];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    float pr0 = 0.f, pr1 = 0.f;
+                    if (live && c + j < Lk) pr0 = fast_exp2(fmaf(__uint_as_float(vs[ch * 8 + j]), scale2, mask_s[c + j]) - lse2);
+                    if (live && c + j + 1 < Lk) pr1 = fast_exp2(fmaf(__uint_as_float(vs[ch * 8 + j + 1]), scale2, mask_s[c + j + 1]) - lse2);
+                    float f0 = 1.f, f1 = 1.f;
+                    if (p.thr != 0u) {
+                        bool k0, k1;
+                        crct_keep2_32(drop, ctr0 + (uint32_t)(c + j), k0, k1);
+                        f0 = k0 ? p.dscale : 0.f;
+                        f1 = k1 ? p.dscale : 0.f;
+                    }
+                    // dS = P (dP * keep - D) * scale ; zero probability => zero (also where dP holds garbage: select, not multiply)
+                    const float d0 = pr0 != 0.f ? pr0 * (__uint_as_float(vd[ch * 8 + j]) * f0 - Dr) * p.scale : 0.f;
+                    const float d1 = pr1 != 0.f ? pr1 * (__uint_as_float(vd[ch * 8 + j + 1]) * f1 - Dr) * p.scale : 0.f;
+                    preg[(c + j) >> 1] = pack_bf16x2(pr0 * f0, pr1 * f1);
+                    ds[j >> 1] = pack_bf16x2(d0, d1);
+                }
+                *reinterpret_cast<uint4*>(gX + (size_t)(c >> 6) * (QT * 128) + swz(tid, (c & 63) >> 3)) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+            }
+        }
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        ptx::tc_fence_after();
+        // dK [keys x DH] = dS^T Q : A = X read MN-major (M = keys, two 64-key atoms), B = Q as loaded (MN-major), K = queries
+        constexpr uint32_t id_t = idesc(QT, DH, true, true);
+        for (int ks = 0; ks < Lq16 / 16; ++ks)
+            ptx::tc_mma_bf16(tmem, desc_mnmajor(sX, ks, QT * 128), desc_mnmajor(sQ, ks, QT * 128), id_t, ks > 0 ? 1u : 0u);
+        // dQ [queries x DH] = dS K : A = X read K-major, B = K as loaded (MN-major), K = keys
+        constexpr uint32_t id_q = idesc(QT, DH, false, true);
+        for (int ks = 0; ks < Lk16 / 16; ++ks)
+            ptx::tc_mma_bf16(tmem + 64u, desc_kmajor(sX + (uint32_t)(ks >> 2) * (QT * 128), ks & 3), desc_mnmajor(sK, ks, LKT * 128), id_q, ks > 0 ? 1u : 0u);
+        ptx::tc_commit(bar_mma);
+    }
+    ptx::mbar_wait(bar_mma, 1);                       // dK, dQ retired: X may be overwritten with P
+    __syncwarp();
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < LKT; c += 8) {
+        if (c < Lk16)
+            *reinterpret_cast<uint4*>(gX + (size_t)(c >> 6) * (QT * 128) + swz(tid, (c & 63) >> 3)) =
+                make_uint4(preg[c / 2], preg[c / 2 + 1], preg[c / 2 + 2], preg[c / 2 + 3]);
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {                                   // dV [keys x DH] = P^T dO
+        ptx::tc_fence_after();
+        constexpr uint32_t id_t = idesc(QT, DH, true, true);
+        for (int ks = 0; ks < Lq16 / 16; ++ks)
+            ptx::tc_mma_bf16(tmem + 128u, desc_mnmajor(sX, ks, QT * 128), desc_mnmajor(sdO, ks, QT * 128), id_t, ks > 0 ? 1u : 0u);
+        ptx::tc_commit(bar_mma);
+    }
+    // meanwhile: dK (lanes = keys) and dQ (lanes = queries) leave TMEM
+    const int col = h * DH;
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 16) {
+        uint32_t vk[16], vq[16];
+        ptx::tc_ld_32x16(trow + (uint32_t)c0, vk);
+        ptx::tc_ld_32x16(trow + 64u + (uint32_t)c0, vq);
+        ptx::tc_wait_ld();
+        if (tid < Lk) {
+            bf16* d = p.dk + (size_t)(krow0 + tid) * p.lddk + col + c0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) *reinterpret_cast<uint32_t*>(d + j) = pack_bf16x2(__uint_as_float(vk[j]), __uint_as_float(vk[j + 1]));
+        }
+        if (live) {
+            bf16* d = p.dq + (size_t)(qrow0 + tid) * p.lddq + col + c0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) *reinterpret_cast<uint32_t*>(d + j) = pack_bf16x2(__uint_as_float(vq[j]), __uint_as_float(vq[j + 1]));
+        }
+    }
+    ptx::mbar_wait(bar_mma, 0);                       // third completion of the barrier: parity 0 again
+    __syncwarp();
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 16) {
+        uint32_t vv[16];
+        ptx::tc_ld_32x16(trow + 128u + (uint32_t)c0, vv);
+        ptx::tc_wait_ld();
+        if (tid < Lk) {
+            bf16* d = p.dv + (size_t)(krow0 + tid) * p.lddv + col + c0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) *reinterpret_cast<uint32_t*>(d + j) = pack_bf16x2(__uint_as_float(vv[j]), __uint_as_float(vv[j + 1]));
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
+template <int DH, int LKT, int QBOX>
+int launch_bwd_tc(const crct_attn_bwd_t* a, const TcParams& p, cudaStream_t st) {
+    CUtensorMap tmQ, tmdO, tmK, tmV;
+    const uint64_t W = (uint64_t)a->nh * a->dh;
+    if (int rc = crct_make_tmap_bf16_2d(&tmQ, a->q, W, (uint64_t)a->B * a->Lq, a->ldq, 64, QBOX)) return rc;
+    if (int rc = crct_make_tmap_bf16_2d(&tmdO, a->dout, W, (uint64_t)a->B * a->Lq, a->lddo, 64, QBOX)) return rc;
+    if (int rc = crct_make_tmap_bf16_2d(&tmK, a->k, W, (uint64_t)a->B * a->Lk, a->ldk, 64, LKT)) return rc;
+    if (int rc = crct_make_tmap_bf16_2d(&tmV, a->v, W, (uint64_t)a->B * a->Lk, a->ldv, 64, LKT)) return rc;
+    constexpr int SMEM = 2 * QT * 128 + 2 * LKT * 128 + 2 * QT * 128 + 32 + 128 * 4 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        CRCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<DH, LKT, QBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    CRCT_CUDA(crct_launch_pdl(attn_bwd_tc_kernel<DH, LKT, QBOX>, dim3(a->B * a->nh), dim3(TC_THREADS), SMEM, st, tmQ, tmdO, tmK, tmV, p));
+    return CRCT_OK;
+}
+
+template <int DH>
+int dispatch_bwd_tc(const crct_attn_bwd_t* a, const TcParams& p, cudaStream_t st) {
+    const bool wk = a->Lk > 64, wq = a->Lq > 64;
+    if (wk) return wq ? launch_bwd_tc<DH, 128, 128>(a, p, st) : launch_bwd_tc<DH, 128, 64>(a, p, st);
+    return wq ? launch_bwd_tc<DH, 64, 128>(a, p, st) : launch_bwd_tc<DH, 64, 64>(a, p, st);
+}
+
+}  // namespace
+
+bool crct_attn_tc_eligible(int dh, int Lq, int Lk, const void* q, const void* k, const void* v, int ldq, int ldk, int ldv) {
+    static const bool legacy = getenv("CRCT_ATTN_LEGACY") != nullptr;
+    if (legacy || getenv("CRCT_ATTN_LEGACY_NOW") != nullptr) return false;      // A/B switch (the second form is read per call: tests)
+    if (dh != 32 && dh != 48 && dh != 64) return false;
+    if (Lq > 128 || Lk > 128) return false;
+    return ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+           (ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0;
+}
+
+int crct_attn_fwd_tc(const crct_attn_fwd_t* a, crct_stream_t s) {
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.mask_add = a->mask_add;
+    p.out_w = reinterpret_cast<bf16*>(a->out); p.ldo = a->ldo; p.lse = a->lse;
+    p.B = a->B; p.nh = a->nh; p.Lq = a->Lq; p.Lk = a->Lk;
+    p.scale = 1.0f / sqrtf((float)a->dh);
+    p.thr = crct_drop_threshold(a->dropout_p); p.dscale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; p.seed = a->seed;
+    p.salt = reinterpret_cast<const unsigned long long*>(a->salt);
+    p.cu_q = a->cu_q; p.cu_k = a->cu_k;
+    cudaStream_t st = as_stream(s);
+    const bool wide = a->Lk > 64;
+    switch (a->dh) {
+        case 32: return wide ? launch_fwd_tc<32, 128>(a, p, st) : launch_fwd_tc<32, 64>(a, p, st);
+        case 48: return wide ? launch_fwd_tc<48, 128>(a, p, st) : launch_fwd_tc<48, 64>(a, p, st);
+        case 64: return wide ? launch_fwd_tc<64, 128>(a, p, st) : launch_fwd_tc<64, 64>(a, p, st);
+    }
+    CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_fwd: head dim %d not in {32,48,64}", a->dh);
+}
+
+int crct_attn_bwd_tc(const crct_attn_bwd_t* a, crct_stream_t s) {
+    if ((reinterpret_cast<uintptr_t>(a->dout) & 15) || (a->lddo % 8)) CRCT_FAIL(CRCT_ERR_ARG, "crct_attn_bwd: dout must be 16-byte aligned, lddo a multiple of 8");
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.mask_add = a->mask_add;
+    p.out = reinterpret_cast<const bf16*>(a->out); p.ldo = a->ldo;
+    p.dout = reinterpret_cast<const bf16*>(a->dout); p.lddo = a->lddo;
+    p.lse = const_cast<float*>(a->lse);
+    p.dq = reinterpret_cast<bf16*>(a->dq); p.dk = reinterpret_cast<bf16*>(a->dk); p.dv = reinterpret_cast<bf16*>(a->dv);
+    p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+    p.B = a->B; p.nh = a->nh; p.Lq = a->Lq; p.Lk = a->Lk;
+    p.scale = 1.0f / sqrtf((float)a->dh);
+    p.thr = crct_drop_threshold(a->dropout_p); p.dscale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f; p.seed = a->seed;
+    p.salt = reinterpret_cast<const unsigned long long*>(a->salt);
+    p.cu_q = a->cu_q; p.cu_k = a->cu_k;
+    cudaStream_t st = as_stream(s);
+    switch (a->dh) {
+        case 32: return dispatch_bwd_tc<32>(a, p, st);
+        case 48: return dispatch_bwd_tc<48>(a, p, st);
+        case 64: return dispatch_bwd_tc<64>(a, p, st);
+    }
+    CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_bwd: head dim %d not in {32,48,64}", a->dh);
+}

@@ -27,6 +27,10 @@ void crct_set_error(const char* fmt, ...);
 
 static inline cudaStream_t as_stream(crct_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 int crct_num_sms();
+// tcgen05 / TMEM / TMA attention (attention_tc.cu): single-tile sequences (Lq, Lk <= 128); attention.cu dispatches to it
+bool crct_attn_tc_eligible(int dh, int Lq, int Lk, const void* q, const void* k, const void* v, int ldq, int ldk, int ldv);
+int crct_attn_fwd_tc(const crct_attn_fwd_t* a, crct_stream_t s);
+int crct_attn_bwd_tc(const crct_attn_bwd_t* a, crct_stream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  A kernel launched through crct_launch_pdl may have its CTAs scheduled — and run

@@ -831,6 +831,11 @@ int dispatch(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensor
 
 }  // namespace
 
+// 2-D bf16 tensor map with 128-byte swizzle for the other TMA users of the library (attention_tc.cu)
+int crct_make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+    return make_tmap(tm, ptr, inner, outer, ld, box_inner, box_outer);
+}
+
 // auto policy for cta_group == 0
 static bool crct_gemm_auto_pair(const crct_gemm_t* a) {
     // measured on B200 (profiles/r01_gemm_shapes.log): the CTA pair wins ~4 % once there are >= 8 tile columns to
