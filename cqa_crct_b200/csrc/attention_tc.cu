@@ -79,13 +79,14 @@ __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_co
 
     const int tid = threadIdx.x, warp = tid >> 5;
     pdl_launch_dependents();
-    if (tid == 0) {
+    if (tid == 32) {                                   // warp 1: descriptors + barriers; warp 0 (converged) allocates tensor memory
         ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV);
         ptx::mbar_init(bar_tma, 1);
         ptx::mbar_init(bar_mma, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 0) {
+        __syncwarp();
         ptx::tmem_alloc(tmem_slot, LKT);
         ptx::tmem_relinquish();
     }
@@ -182,33 +183,29 @@ __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_co
     ptx::mbar_wait(bar_mma, 1);
     __syncwarp();
     ptx::tc_fence_after();
-    if (live) {
-        const float inv = 1.f / l;
+    {
+        // tcgen05.ld is warp-collective (.sync.aligned): every lane executes the same loads, only the stores are predicated
+        const float inv = live ? 1.f / l : 0.f;
         bf16* dst = p.out_w + (size_t)(qrow0 + tid) * p.ldo + h * DH;
 #pragma unroll
         for (int c0 = 0; c0 < DH; c0 += 16) {
             uint32_t v[16];
             ptx::tc_ld_32x16(trow + (uint32_t)c0, v);
             ptx::tc_wait_ld();
-            uint4 o0, o1;
-            o0.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);   o0.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-            o0.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);   o0.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-            o1.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);   o1.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
-            o1.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv); o1.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
-            *reinterpret_cast<uint4*>(dst + c0) = o0;
-            *reinterpret_cast<uint4*>(dst + c0 + 8) = o1;
-        }
-    } else {                                                          // warp-collective tcgen05.ld: every lane of the warp executes it
-#pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 16) {
-            uint32_t v[16];
-            ptx::tc_ld_32x16(trow + (uint32_t)c0, v);
-            ptx::tc_wait_ld();
+            if (live) {
+                uint4 o0, o1;
+                o0.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);   o0.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+                o0.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);   o0.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+                o1.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);   o1.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+                o1.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv); o1.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+                *reinterpret_cast<uint4*>(dst + c0) = o0;
+                *reinterpret_cast<uint4*>(dst + c0 + 8) = o1;
+            }
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 0) ptx::tmem_dealloc(tmem, LKT);
+    if (warp == 0) { __syncwarp(); ptx::tmem_dealloc(tmem, LKT); }
 }
 
 template <int DH, int LKT>
@@ -251,13 +248,14 @@ __global__ void __launch_bounds__(TC_THREADS) attn_bwd_tc_kernel(const __grid_co
 
     const int tid = threadIdx.x, warp = tid >> 5;
     pdl_launch_dependents();
-    if (tid == 0) {
+    if (tid == 32) {
         ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmdO); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV);
         ptx::mbar_init(bar_tma, 1);
         ptx::mbar_init(bar_mma, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 0) {
+        __syncwarp();
         ptx::tmem_alloc(tmem_slot, 256);
         ptx::tmem_relinquish();
     }
@@ -437,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS) attn_bwd_tc_kernel(const __grid_co
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+    if (warp == 0) { __syncwarp(); ptx::tmem_dealloc(tmem, 256); }
 }
 
 template <int DH, int LKT, int QBOX>
