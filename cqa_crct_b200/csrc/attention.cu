@@ -542,7 +542,7 @@ extern "C" CRCT_API int crct_attn_fwd(const crct_attn_fwd_t* a, crct_stream_t s)
     if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8) || !aligned16(a->q) || !aligned16(a->k) || !aligned16(a->v) || !aligned16(a->out))
         CRCT_FAIL(CRCT_ERR_ARG, "crct_attn_fwd: operands must be 16-byte aligned with leading dimensions multiple of 8");
     if ((double)a->B * a->nh * a->Lq * a->Lk >= 4294967296.0) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_fwd: B*nh*Lq*Lk must stay below 2^32");
-    if (crct_attn_tc_eligible(a->dh, a->Lq, a->Lk, a->q, a->k, a->v, a->ldq, a->ldk, a->ldv)) return crct_attn_fwd_tc(a, s);   // tcgen05 / TMEM / TMA
+    if (crct_attn_tc_eligible(a->dh, a->Lq, a->Lk, a->q, a->k, a->v, a->ldq, a->ldk, a->ldv, 0)) return crct_attn_fwd_tc(a, s);   // tcgen05 / TMEM / TMA
     FwdParams p;
     p.q = reinterpret_cast<const bf16*>(a->q); p.k = reinterpret_cast<const bf16*>(a->k); p.v = reinterpret_cast<const bf16*>(a->v);
     p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.mask_add = a->mask_add;
@@ -568,7 +568,7 @@ extern "C" CRCT_API int crct_attn_bwd(const crct_attn_bwd_t* a, crct_stream_t s)
         !aligned16(a->q) || !aligned16(a->k) || !aligned16(a->v) || !aligned16(a->out) || !aligned16(a->dout))
         CRCT_FAIL(CRCT_ERR_ARG, "crct_attn_bwd: operands must be 16-byte aligned with leading dimensions multiple of 8");
     if ((double)a->B * a->nh * a->Lq * a->Lk >= 4294967296.0) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_attn_bwd: B*nh*Lq*Lk must stay below 2^32");
-    if (crct_attn_tc_eligible(a->dh, a->Lq, a->Lk, a->q, a->k, a->v, a->ldq, a->ldk, a->ldv) && !(a->lddq % 2) && !(a->lddk % 2) && !(a->lddv % 2))
+    if (crct_attn_tc_eligible(a->dh, a->Lq, a->Lk, a->q, a->k, a->v, a->ldq, a->ldk, a->ldv, 1) && !(a->lddq % 8) && !(a->lddk % 8) && !(a->lddv % 8))
         return crct_attn_bwd_tc(a, s);                  // tcgen05 / TMEM / TMA
     BwdParams p;
     p.q = reinterpret_cast<const bf16*>(a->q); p.k = reinterpret_cast<const bf16*>(a->k); p.v = reinterpret_cast<const bf16*>(a->v);

@@ -23,7 +23,7 @@ int crct_make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uin
 
 namespace {
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;                 // two warps per 32-lane TMEM quarter: each takes half of the score columns
 constexpr int QT = 128;                       // query tile = TMEM lanes
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
@@ -43,8 +43,74 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int ks) { return 
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int ks, uint32_t atom_bytes) {
     return smem_desc(tile + (uint32_t)ks * 2048u, atom_bytes, 1024u);
 }
+__device__ __forceinline__ void reg_fence16(uint32_t (&v)[16]) {      // the asynchronously loaded values exist from here on
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                      "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+}
 // byte offset of the 16-byte chunk holding columns [8*chunk, 8*chunk + 8) of row r in a [rows][64] 128B-swizzled tile
 __device__ __forceinline__ uint32_t swz(int r, int chunk) { return (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4); }
+
+// 16 fp32 accumulator values -> 16 bf16 = two 16-byte stores
+__device__ __forceinline__ void store16_bf16(bf16* d, const uint32_t (&v)[16]) {
+    uint4 a, b;
+    a.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));   a.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+    a.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));   a.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+    b.x = pack_bf16x2(__uint_as_float(v[8]), __uint_as_float(v[9]));   b.y = pack_bf16x2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+    b.z = pack_bf16x2(__uint_as_float(v[12]), __uint_as_float(v[13])); b.w = pack_bf16x2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+    *reinterpret_cast<uint4*>(d) = a;
+    *reinterpret_cast<uint4*>(d + 8) = b;
+}
+
+// ---- per-score scalar work on 8 consecutive columns (one 16-byte chunk of the P / dS tiles).  CHECK: the chunk crosses the
+// sample's last key (columns >= Lk give probability 0); MASK: an additive key mask is present (padded layout).
+template <bool CHECK, bool MASK>
+__device__ __forceinline__ void fwd_chunk8(const uint32_t* v, int c, int Lk, float scale2, const float* mask_s, float m, float& l,
+                                           const CrctDrop32& drop, uint32_t ctr, float dscale, uint32_t (&pk)[4]) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        float s0 = __uint_as_float(v[j]) * scale2, s1 = __uint_as_float(v[j + 1]) * scale2;
+        if constexpr (MASK) { s0 += mask_s[c + j]; s1 += mask_s[c + j + 1]; }
+        float p0 = fast_exp2(s0 - m), p1 = fast_exp2(s1 - m);
+        if constexpr (CHECK) {
+            if (c + j >= Lk) p0 = 0.f;
+            if (c + j + 1 >= Lk) p1 = 0.f;
+        }
+        l += p0 + p1;
+        if (drop.thr != 0u) {
+            bool k0, k1;
+            crct_keep2_32(drop, ctr + (uint32_t)j, k0, k1);
+            p0 = k0 ? p0 * dscale : 0.f;
+            p1 = k1 ? p1 * dscale : 0.f;
+        }
+        pk[j >> 1] = pack_bf16x2(p0, p1);
+    }
+}
+template <bool CHECK, bool MASK>
+__device__ __forceinline__ void bwd_chunk8(const uint32_t* vs, const uint32_t* vd, int c, int Lk, float scale2, const float* mask_s, float lse2,
+                                           float Dr, float scale, const CrctDrop32& drop, uint32_t ctr, float dscale, uint32_t* pr_out,
+                                           uint32_t (&ds)[4]) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        float s0 = __uint_as_float(vs[j]) * scale2, s1 = __uint_as_float(vs[j + 1]) * scale2;
+        if constexpr (MASK) { s0 += mask_s[c + j]; s1 += mask_s[c + j + 1]; }
+        float pr0 = fast_exp2(s0 - lse2), pr1 = fast_exp2(s1 - lse2);
+        float g0 = __uint_as_float(vd[j]), g1 = __uint_as_float(vd[j + 1]);
+        if constexpr (CHECK) {                         // past the last key: probability 0, and dP there may be garbage (select, not multiply)
+            if (c + j >= Lk) { pr0 = 0.f; g0 = 0.f; }
+            if (c + j + 1 >= Lk) { pr1 = 0.f; g1 = 0.f; }
+        }
+        float f0 = 1.f, f1 = 1.f;
+        if (drop.thr != 0u) {
+            bool k0, k1;
+            crct_keep2_32(drop, ctr + (uint32_t)j, k0, k1);
+            f0 = k0 ? dscale : 0.f;
+            f1 = k1 ? dscale : 0.f;
+        }
+        // dS = P (dP * keep - D) * scale
+        ds[j >> 1] = pack_bf16x2(pr0 * (g0 * f0 - Dr) * scale, pr1 * (g1 * f1 - Dr) * scale);
+        pr_out[j >> 1] = pack_bf16x2(pr0 * f0, pr1 * f1);
+    }
+}
 
 struct TcParams {
     const float* mask_add;
@@ -61,7 +127,10 @@ struct TcParams {
 };
 
 // ------------------------------------------------------------------------------------------------ forward
-// shared memory (1024-byte aligned): Q [128][128 B] | K [LKT][128 B] | V [LKT][128 B] | barriers | mask [LKT] f32
+// 256 threads: thread t works on TMEM lane (query row) t & 127 and on column half t >> 7 of the score tile — two warps per
+// 32-lane group (a warp may only touch the TMEM lanes of its own quarter, warp & 3), twice the warps per CTA to hide the
+// tcgen05.ld / MUFU / shared-memory latencies of the per-score scalar work.
+// shared memory (1024-byte aligned): Q [128][128 B] | K [LKT][128 B] | V [LKT][128 B] | barriers | mask [LKT] | red [2][2][128] f32
 // P [128][LKT] bf16 (K-major, 64-key atoms of 16 KB) aliases Q (+ K): both are dead once S is in TMEM.
 template <int DH, int LKT>
 __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -70,14 +139,18 @@ __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_co
     const uint32_t raw = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* g = smem_raw + (base - raw);
-    constexpr uint32_t Q_BYTES = QT * 128, KV_BYTES = LKT * 128;
-    const uint32_t sQ = base, sK = base + Q_BYTES, sV = sK + KV_BYTES, sBar = sV + KV_BYTES;
-    const uint32_t bar_tma = sBar, bar_mma = sBar + 8, tmem_slot = sBar + 16;
-    float* mask_s = reinterpret_cast<float*>(g + Q_BYTES + 2 * KV_BYTES + 32);
+    constexpr uint32_t Q_BYTES = QT * 128, KV_BYTES = LKT * 128, OFF_BAR = Q_BYTES + 2 * KV_BYTES;
+    constexpr int CH = LKT / 2;                                       // score columns per thread half
+    const uint32_t sQ = base, sK = base + Q_BYTES, sV = sK + KV_BYTES;
+    const uint32_t bar_tma = base + OFF_BAR, bar_mma = bar_tma + 8, tmem_slot = bar_tma + 16;
+    float* mask_s = reinterpret_cast<float*>(g + OFF_BAR + 32);
+    float* red_m = mask_s + LKT;                                      // [2][128] partial row maxima
+    float* red_l = red_m + 2 * QT;                                    // [2][128] partial row sums
     uint8_t* gP = g;                                                  // P tile (generic pointer), aliases Q / K
     uint8_t* gV = g + Q_BYTES + KV_BYTES;
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (QT - 1), hsel = tid >> 7;
     pdl_launch_dependents();
     if (tid == 32) {                                   // warp 1: descriptors + barriers; warp 0 (converged) allocates tensor memory
         ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV);
@@ -93,7 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_co
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(g + Q_BYTES + 2 * KV_BYTES + 16);
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(g + OFF_BAR + 16);
     pdl_wait();
 
     const int b = blockIdx.x / p.nh, h = blockIdx.x % p.nh;
@@ -118,7 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_co
         ptx::tc_commit(bar_mma);
     }
     // V rows in [Lk, Lk16) meet P columns that are written as 0: clear them, so that no stale NaN pattern is multiplied
-    if (tid >= Lk && tid < Lk16) {
+    if (tid < QT && tid >= Lk && tid < Lk16) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(gV + (size_t)tid * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -127,12 +200,13 @@ __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_co
     __syncwarp();
     ptx::tc_fence_after();
 
-    // ---- softmax of row `tid` (TMEM lane tid), scores in the log2 domain: s2 = s * scale * log2(e) + mask * log2(e)
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    // ---- softmax of row `row` (TMEM lane), scores in the log2 domain: s2 = s * scale * log2(e) + mask * log2(e)
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float scale2 = p.scale * LOG2E;
-    const bool live = tid < Lq;
+    const bool live = row < Lq;
+    const int cb = hsel * CH;                                         // this thread's columns: [cb, cb + CH)
     float m = -INFINITY;
-    for (int c0 = 0; c0 < Lk; c0 += 32) {
+    for (int c0 = cb; c0 < cb + CH && c0 < Lk; c0 += 32) {            // warp-uniform bounds
         uint32_t v[32];
         ptx::tc_ld_32x32(trow + (uint32_t)c0, v);
         ptx::tc_wait_ld();
@@ -140,10 +214,14 @@ __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_co
         for (int j = 0; j < 32; ++j)
             if (c0 + j < Lk) m = fmaxf(m, fmaf(__uint_as_float(v[j]), scale2, mask_s[c0 + j]));
     }
+    red_m[hsel * QT + row] = m;
+    __syncthreads();
+    m = fmaxf(red_m[row], red_m[QT + row]);
     const CrctDrop32 drop = crct_drop32((p.thr != 0u && p.salt) ? (p.seed ^ __ldg(p.salt)) : p.seed, p.thr);
-    const uint32_t ctr0 = ((uint32_t)blockIdx.x * (uint32_t)p.Lq + (uint32_t)tid) * (uint32_t)p.Lk;
+    const uint32_t ctr0 = ((uint32_t)blockIdx.x * (uint32_t)p.Lq + (uint32_t)row) * (uint32_t)p.Lk;
     float l = 0.f;
-    for (int c0 = 0; c0 < Lk16; c0 += 32) {
+    const bool masked = p.mask_add != nullptr;
+    for (int c0 = cb; c0 < cb + CH && c0 < Lk16; c0 += 32) {
         uint32_t v[32];
         ptx::tc_ld_32x32(trow + (uint32_t)c0, v);
         ptx::tc_wait_ld();
@@ -151,25 +229,21 @@ __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_co
         for (int ch = 0; ch < 4; ++ch) {                              // 8 columns = one 16-byte chunk of the P tile
             const int c = c0 + ch * 8;
             if (c >= Lk16) break;
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-                float p0 = 0.f, p1 = 0.f;
-                if (live && c + j < Lk) p0 = fast_exp2(fmaf(__uint_as_float(v[ch * 8 + j]), scale2, mask_s[c + j]) - m);
-                if (live && c + j + 1 < Lk) p1 = fast_exp2(fmaf(__uint_as_float(v[ch * 8 + j + 1]), scale2, mask_s[c + j + 1]) - m);
-                l += p0 + p1;
-                if (p.thr != 0u) {
-                    bool k0, k1;
-                    crct_keep2_32(drop, ctr0 + (uint32_t)(c + j), k0, k1);
-                    p0 = k0 ? p0 * p.dscale : 0.f;
-                    p1 = k1 ? p1 * p.dscale : 0.f;
+            uint32_t pk[4] = {0u, 0u, 0u, 0u};
+            if (live) {                                               // rows past the sample's last query write zeros
+                const uint32_t ctr = ctr0 + (uint32_t)c;
+                if (c + 8 <= Lk) {
+                    if (masked) fwd_chunk8<false, true>(v + ch * 8, c, Lk, scale2, mask_s, m, l, drop, ctr, p.dscale, pk);
+                    else fwd_chunk8<false, false>(v + ch * 8, c, Lk, scale2, mask_s, m, l, drop, ctr, p.dscale, pk);
+                } else {
+                    if (masked) fwd_chunk8<true, true>(v + ch * 8, c, Lk, scale2, mask_s, m, l, drop, ctr, p.dscale, pk);
+                    else fwd_chunk8<true, false>(v + ch * 8, c, Lk, scale2, mask_s, m, l, drop, ctr, p.dscale, pk);
                 }
-                pk[j >> 1] = pack_bf16x2(p0, p1);
             }
-            *reinterpret_cast<uint4*>(gP + (size_t)(c >> 6) * (QT * 128) + swz(tid, (c & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(gP + (size_t)(c >> 6) * (QT * 128) + swz(row, (c & 63) >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
     }
-    if (live && p.lse != nullptr) p.lse[(size_t)blockIdx.x * p.Lq + tid] = (m + __log2f(l)) * LN2;
+    red_l[hsel * QT + row] = l;
     ptx::fence_proxy_async();                                         // P / cleared V rows (generic stores) -> tensor-core reads
     ptx::tc_fence_before();
     __syncthreads();
@@ -180,15 +254,19 @@ __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_co
             ptx::tc_mma_bf16(tmem, desc_kmajor(sQ + (uint32_t)(ks >> 2) * (QT * 128), ks & 3), desc_mnmajor(sV, ks, LKT * 128), id, ks > 0 ? 1u : 0u);
         ptx::tc_commit(bar_mma);
     }
+    l = red_l[row] + red_l[QT + row];
+    if (live && hsel == 0 && p.lse != nullptr) p.lse[(size_t)blockIdx.x * p.Lq + row] = (m + __log2f(l)) * LN2;
     ptx::mbar_wait(bar_mma, 1);
     __syncwarp();
     ptx::tc_fence_after();
     {
-        // tcgen05.ld is warp-collective (.sync.aligned): every lane executes the same loads, only the stores are predicated
+        // tcgen05.ld is warp-collective (.sync.aligned): every lane executes the same loads, only the stores are predicated;
+        // the two warps of a lane group share the DH / 16 column chunks
         const float inv = live ? 1.f / l : 0.f;
-        bf16* dst = p.out_w + (size_t)(qrow0 + tid) * p.ldo + h * DH;
+        bf16* dst = p.out_w + (size_t)(qrow0 + row) * p.ldo + h * DH;
 #pragma unroll
         for (int c0 = 0; c0 < DH; c0 += 16) {
+            if (((c0 >> 4) & 1) != hsel) continue;                    // warp-uniform
             uint32_t v[16];
             ptx::tc_ld_32x16(trow + (uint32_t)c0, v);
             ptx::tc_wait_ld();
@@ -215,7 +293,7 @@ int launch_fwd_tc(const crct_attn_fwd_t* a, const TcParams& p, cudaStream_t st) 
     if (int rc = crct_make_tmap_bf16_2d(&tmQ, a->q, W, (uint64_t)a->B * a->Lq, a->ldq, 64, QT)) return rc;
     if (int rc = crct_make_tmap_bf16_2d(&tmK, a->k, W, (uint64_t)a->B * a->Lk, a->ldk, 64, LKT)) return rc;
     if (int rc = crct_make_tmap_bf16_2d(&tmV, a->v, W, (uint64_t)a->B * a->Lk, a->ldv, 64, LKT)) return rc;
-    constexpr int SMEM = QT * 128 + 2 * LKT * 128 + 32 + LKT * 4 + 1024;
+    constexpr int SMEM = QT * 128 + 2 * LKT * 128 + 32 + LKT * 4 + 4 * QT * 4 + 1024;
     static bool configured = false;
     if (!configured) {
         CRCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, LKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -227,10 +305,10 @@ int launch_fwd_tc(const crct_attn_fwd_t* a, const TcParams& p, cudaStream_t st) 
 
 // ------------------------------------------------------------------------------------------------ backward
 // shared memory: Q [128][128 B] | dO [128][128 B] | K [LKT][128 B] | V [LKT][128 B] | X [128 q][128 keys] bf16 = two 64-key atoms of
-// 16 KB | barriers | mask.  X holds dS first (dK = dS^T Q and dQ = dS K read it MN-major / K-major), then — once those MMAs have
-// retired — P (dV = P^T dO), which the threads keep packed in registers meanwhile: one pass over the scores, one 32 KB tile,
-// 80 KB per CTA = two CTAs per SM.  TMEM (256 columns): S [0,128) and dP [128,256) first, then dK [0,64), dQ [64,128),
-// dV [128,192).
+// 16 KB | barriers | mask [128] | D partials [2][128].  X holds dS first (dK = dS^T Q and dQ = dS K read it MN-major / K-major), then
+// — once those MMAs have retired — P (dV = P^T dO), which the threads keep packed in registers meanwhile: one pass over the
+// scores, one 32 KB tile, 96 KB per CTA = two CTAs per SM.  TMEM (256 columns): S [0,128) and dP [128,256) first, then
+// dK [0,64), dQ [64,128), dV [128,192).  Thread t: TMEM lane (query / key row) t & 127, column half t >> 7 (see the forward).
 template <int DH, int LKT, int QBOX>
 __global__ void __launch_bounds__(TC_THREADS) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                                                                  const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -241,12 +319,15 @@ __global__ void __launch_bounds__(TC_THREADS) attn_bwd_tc_kernel(const __grid_co
     uint8_t* g = smem_raw + (base - raw);
     constexpr uint32_t Q_BYTES = QT * 128, KV_BYTES = LKT * 128, X_BYTES = 2 * QT * 128;
     constexpr uint32_t OFF_DO = Q_BYTES, OFF_K = 2 * Q_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_X = OFF_V + KV_BYTES, OFF_BAR = OFF_X + X_BYTES;
+    constexpr int CH = LKT / 2;
     const uint32_t sQ = base, sdO = base + OFF_DO, sK = base + OFF_K, sV = base + OFF_V, sX = base + OFF_X;
     const uint32_t bar_tma = base + OFF_BAR, bar_mma = bar_tma + 8, tmem_slot = bar_tma + 16;
-    float* mask_s = reinterpret_cast<float*>(g + OFF_BAR + 32);
+    float* mask_s = reinterpret_cast<float*>(g + OFF_BAR + 32);       // [128]
+    float* red_d = mask_s + QT;                                       // [2][128] partial D
     uint8_t* gX = g + OFF_X;
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (QT - 1), hsel = tid >> 7;
     pdl_launch_dependents();
     if (tid == 32) {
         ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmdO); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV);
@@ -278,25 +359,30 @@ __global__ void __launch_bounds__(TC_THREADS) attn_bwd_tc_kernel(const __grid_co
         ptx::tma_load_2d(sK, &tmK, bar_tma, h * DH, krow0);
         ptx::tma_load_2d(sV, &tmV, bar_tma, h * DH, krow0);
     }
-    mask_s[tid] = (p.mask_add != nullptr && tid < Lk) ? p.mask_add[(size_t)b * p.Lk + tid] * LOG2E : 0.f;
-    // this thread's query row: log-sum-exp (log2 domain) and D = sum_d dO * O
-    const bool live = tid < Lq;
-    float lse2 = 0.f, Dr = 0.f;
-    if (live) {
-        lse2 = p.lse[(size_t)blockIdx.x * p.Lq + tid] * LOG2E;
-        const bf16* o = p.out + (size_t)(qrow0 + tid) * p.ldo + h * DH;
-        const bf16* dd = p.dout + (size_t)(qrow0 + tid) * p.lddo + h * DH;
+    // this thread's query row: log-sum-exp (log2 domain) and its half of D = sum_d dO * O (global loads in flight next to the TMA)
+    const bool live = row < Lq;
+    float lse2 = 0.f;
+    {
+        float dpart = 0.f;
+        if (live) {
+            lse2 = p.lse[(size_t)blockIdx.x * p.Lq + row] * LOG2E;
+            const bf16* o = p.out + (size_t)(qrow0 + row) * p.ldo + h * DH;
+            const bf16* dd = p.dout + (size_t)(qrow0 + row) * p.lddo + h * DH;
 #pragma unroll
-        for (int c = 0; c < DH / 8; ++c) {
-            float fo[8], fd[8];
-            load8_bf16(o + c * 8, fo);
-            load8_bf16(dd + c * 8, fd);
+            for (int c = 0; c < DH / 8; ++c) {
+                if ((c & 1) != hsel) continue;
+                float fo[8], fd[8];
+                load8_bf16(o + c * 8, fo);
+                load8_bf16(dd + c * 8, fd);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) Dr = fmaf(fo[j], fd[j], Dr);
+                for (int j = 0; j < 8; ++j) dpart = fmaf(fo[j], fd[j], dpart);
+            }
         }
+        red_d[hsel * QT + row] = dpart;
     }
+    if (tid < QT) mask_s[tid] = (p.mask_add != nullptr && tid < Lk) ? p.mask_add[(size_t)b * p.Lk + tid] * LOG2E : 0.f;
     // the key half [64,128) of X is read by the M = 128 MMAs even when every key lives in the first atom: keep it finite
-    if (Lk16 <= 64) {
+    if (Lk16 <= 64 && tid < QT) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(gX + QT * 128 + (size_t)tid * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -310,59 +396,67 @@ __global__ void __launch_bounds__(TC_THREADS) attn_bwd_tc_kernel(const __grid_co
         for (int ks = 0; ks < DH / 16; ++ks) ptx::tc_mma_bf16(tmem + 128u, desc_kmajor(sdO, ks), desc_kmajor(sV, ks), id, ks > 0 ? 1u : 0u);
         ptx::tc_commit(bar_mma);
     }
-    __syncthreads();                                  // mask_s visible
+    __syncthreads();                                  // mask_s, red_d visible
+    const float Dr = red_d[row] + red_d[QT + row];
     ptx::mbar_wait(bar_mma, 0);
     __syncwarp();
     ptx::tc_fence_after();
     // operand rows that meet zero rows / columns of P and dS must be finite: clear Q, dO rows [Lq, Lq16) and K rows [Lk, Lk16)
     // (S and dP, which read them, are complete)
-    if (tid >= Lq && tid < Lq16) {
+    if (tid < QT && tid >= Lq && tid < Lq16) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             *reinterpret_cast<uint4*>(g + (size_t)tid * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4*>(g + OFF_DO + (size_t)tid * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
     }
-    if (tid >= Lk && tid < Lk16) {
+    if (tid < QT && tid >= Lk && tid < Lk16) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(g + OFF_K + (size_t)tid * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
 
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float scale2 = p.scale * LOG2E;
     const CrctDrop32 drop = crct_drop32((p.thr != 0u && p.salt) ? (p.seed ^ __ldg(p.salt)) : p.seed, p.thr);
-    const uint32_t ctr0 = ((uint32_t)blockIdx.x * (uint32_t)p.Lq + (uint32_t)tid) * (uint32_t)p.Lk;
-    uint32_t preg[LKT / 2];                           // this row's (dropped) probabilities, packed bf16, until X is free again
+    const uint32_t ctr0 = ((uint32_t)blockIdx.x * (uint32_t)p.Lq + (uint32_t)row) * (uint32_t)p.Lk;
+    const int cb = hsel * CH;                         // this thread's score columns: [cb, cb + CH)
+    const bool masked = p.mask_add != nullptr;
+    uint32_t preg[CH / 2];                            // this row's (dropped) probabilities, packed bf16, until X is free again
+    uint32_t vsb[2][16], vdb[2][16];                  // double-buffered TMEM loads: chunk i + 1 is in flight during the math of chunk i
+    if (cb < Lk16) {
+        ptx::tc_ld_32x16(trow + (uint32_t)cb, vsb[0]);
+        ptx::tc_ld_32x16(trow + 128u + (uint32_t)cb, vdb[0]);
+    }
 #pragma unroll
-    for (int c0 = 0; c0 < LKT; c0 += 16) {
+    for (int i = 0; i < CH; i += 16) {
+        const int c0 = cb + i;
         if (c0 < Lk16) {                              // warp-uniform
-            uint32_t vs[16], vd[16];
-            ptx::tc_ld_32x16(trow + (uint32_t)c0, vs);
-            ptx::tc_ld_32x16(trow + 128u + (uint32_t)c0, vd);
+            uint32_t (&vs)[16] = vsb[(i >> 4) & 1];
+            uint32_t (&vd)[16] = vdb[(i >> 4) & 1];
             ptx::tc_wait_ld();
+            reg_fence16(vs);
+            reg_fence16(vd);
+            if (i + 16 < CH && c0 + 16 < Lk16) {
+                ptx::tc_ld_32x16(trow + (uint32_t)(c0 + 16), vsb[((i >> 4) + 1) & 1]);
+                ptx::tc_ld_32x16(trow + 128u + (uint32_t)(c0 + 16), vdb[((i >> 4) + 1) & 1]);
+            }
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 const int c = c0 + ch * 8;
-                uint32_t ds[4];
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) {
-                    float pr0 = 0.f, pr1 = 0.f;
-                    if (live && c + j < Lk) pr0 = fast_exp2(fmaf(__uint_as_float(vs[ch * 8 + j]), scale2, mask_s[c + j]) - lse2);
-                    if (live && c + j + 1 < Lk) pr1 = fast_exp2(fmaf(__uint_as_float(vs[ch * 8 + j + 1]), scale2, mask_s[c + j + 1]) - lse2);
-                    float f0 = 1.f, f1 = 1.f;
-                    if (p.thr != 0u) {
-                        bool k0, k1;
-                        crct_keep2_32(drop, ctr0 + (uint32_t)(c + j), k0, k1);
-                        f0 = k0 ? p.dscale : 0.f;
-                        f1 = k1 ? p.dscale : 0.f;
+                uint32_t ds[4] = {0u, 0u, 0u, 0u};
+                uint32_t* pr = &preg[(i + ch * 8) >> 1];
+                pr[0] = pr[1] = pr[2] = pr[3] = 0u;
+                if (live) {                           // rows past the sample's last query stay zero
+                    const uint32_t ctr = ctr0 + (uint32_t)c;
+                    if (c + 8 <= Lk) {
+                        if (masked) bwd_chunk8<false, true>(vs + ch * 8, vd + ch * 8, c, Lk, scale2, mask_s, lse2, Dr, p.scale, drop, ctr, p.dscale, pr, ds);
+                        else bwd_chunk8<false, false>(vs + ch * 8, vd + ch * 8, c, Lk, scale2, mask_s, lse2, Dr, p.scale, drop, ctr, p.dscale, pr, ds);
+                    } else {
+                        if (masked) bwd_chunk8<true, true>(vs + ch * 8, vd + ch * 8, c, Lk, scale2, mask_s, lse2, Dr, p.scale, drop, ctr, p.dscale, pr, ds);
+                        else bwd_chunk8<true, false>(vs + ch * 8, vd + ch * 8, c, Lk, scale2, mask_s, lse2, Dr, p.scale, drop, ctr, p.dscale, pr, ds);
                     }
-                    // dS = P (dP * keep - D) * scale ; zero probability => zero (also where dP holds garbage: select, not multiply)
-                    const float d0 = pr0 != 0.f ? pr0 * (__uint_as_float(vd[ch * 8 + j]) * f0 - Dr) * p.scale : 0.f;
-                    const float d1 = pr1 != 0.f ? pr1 * (__uint_as_float(vd[ch * 8 + j + 1]) * f1 - Dr) * p.scale : 0.f;
-                    preg[(c + j) >> 1] = pack_bf16x2(pr0 * f0, pr1 * f1);
-                    ds[j >> 1] = pack_bf16x2(d0, d1);
                 }
-                *reinterpret_cast<uint4*>(gX + (size_t)(c >> 6) * (QT * 128) + swz(tid, (c & 63) >> 3)) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+                *reinterpret_cast<uint4*>(gX + (size_t)(c >> 6) * (QT * 128) + swz(row, (c & 63) >> 3)) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
             }
         }
     }
@@ -385,10 +479,11 @@ __global__ void __launch_bounds__(TC_THREADS) attn_bwd_tc_kernel(const __grid_co
     __syncwarp();
     ptx::tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < LKT; c += 8) {
+    for (int i = 0; i < CH; i += 8) {
+        const int c = cb + i;
         if (c < Lk16)
-            *reinterpret_cast<uint4*>(gX + (size_t)(c >> 6) * (QT * 128) + swz(tid, (c & 63) >> 3)) =
-                make_uint4(preg[c / 2], preg[c / 2 + 1], preg[c / 2 + 2], preg[c / 2 + 3]);
+            *reinterpret_cast<uint4*>(gX + (size_t)(c >> 6) * (QT * 128) + swz(row, (c & 63) >> 3)) =
+                make_uint4(preg[i / 2], preg[i / 2 + 1], preg[i / 2 + 2], preg[i / 2 + 3]);
     }
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
@@ -400,38 +495,28 @@ __global__ void __launch_bounds__(TC_THREADS) attn_bwd_tc_kernel(const __grid_co
             ptx::tc_mma_bf16(tmem + 128u, desc_mnmajor(sX, ks, QT * 128), desc_mnmajor(sdO, ks, QT * 128), id_t, ks > 0 ? 1u : 0u);
         ptx::tc_commit(bar_mma);
     }
-    // meanwhile: dK (lanes = keys) and dQ (lanes = queries) leave TMEM
+    // meanwhile: dK (lanes = keys) and dQ (lanes = queries) leave TMEM; the two warps of a lane group share the column chunks
     const int col = h * DH;
 #pragma unroll
     for (int c0 = 0; c0 < DH; c0 += 16) {
+        if (((c0 >> 4) & 1) != hsel) continue;        // warp-uniform
         uint32_t vk[16], vq[16];
         ptx::tc_ld_32x16(trow + (uint32_t)c0, vk);
         ptx::tc_ld_32x16(trow + 64u + (uint32_t)c0, vq);
         ptx::tc_wait_ld();
-        if (tid < Lk) {
-            bf16* d = p.dk + (size_t)(krow0 + tid) * p.lddk + col + c0;
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) *reinterpret_cast<uint32_t*>(d + j) = pack_bf16x2(__uint_as_float(vk[j]), __uint_as_float(vk[j + 1]));
-        }
-        if (live) {
-            bf16* d = p.dq + (size_t)(qrow0 + tid) * p.lddq + col + c0;
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) *reinterpret_cast<uint32_t*>(d + j) = pack_bf16x2(__uint_as_float(vq[j]), __uint_as_float(vq[j + 1]));
-        }
+        if (row < Lk) store16_bf16(p.dk + (size_t)(krow0 + row) * p.lddk + col + c0, vk);
+        if (live) store16_bf16(p.dq + (size_t)(qrow0 + row) * p.lddq + col + c0, vq);
     }
     ptx::mbar_wait(bar_mma, 0);                       // third completion of the barrier: parity 0 again
     __syncwarp();
     ptx::tc_fence_after();
 #pragma unroll
     for (int c0 = 0; c0 < DH; c0 += 16) {
+        if (((c0 >> 4) & 1) != hsel) continue;
         uint32_t vv[16];
         ptx::tc_ld_32x16(trow + 128u + (uint32_t)c0, vv);
         ptx::tc_wait_ld();
-        if (tid < Lk) {
-            bf16* d = p.dv + (size_t)(krow0 + tid) * p.lddv + col + c0;
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) *reinterpret_cast<uint32_t*>(d + j) = pack_bf16x2(__uint_as_float(vv[j]), __uint_as_float(vv[j + 1]));
-        }
+        if (row < Lk) store16_bf16(p.dv + (size_t)(krow0 + row) * p.lddv + col + c0, vv);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -446,7 +531,7 @@ int launch_bwd_tc(const crct_attn_bwd_t* a, const TcParams& p, cudaStream_t st) 
     if (int rc = crct_make_tmap_bf16_2d(&tmdO, a->dout, W, (uint64_t)a->B * a->Lq, a->lddo, 64, QBOX)) return rc;
     if (int rc = crct_make_tmap_bf16_2d(&tmK, a->k, W, (uint64_t)a->B * a->Lk, a->ldk, 64, LKT)) return rc;
     if (int rc = crct_make_tmap_bf16_2d(&tmV, a->v, W, (uint64_t)a->B * a->Lk, a->ldv, 64, LKT)) return rc;
-    constexpr int SMEM = 2 * QT * 128 + 2 * LKT * 128 + 2 * QT * 128 + 32 + 128 * 4 + 1024;
+    constexpr int SMEM = 2 * QT * 128 + 2 * LKT * 128 + 2 * QT * 128 + 32 + 3 * QT * 4 + 1024;
     static bool configured = false;
     if (!configured) {
         CRCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<DH, LKT, QBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -465,13 +550,27 @@ int dispatch_bwd_tc(const crct_attn_bwd_t* a, const TcParams& p, cudaStream_t st
 
 }  // namespace
 
-bool crct_attn_tc_eligible(int dh, int Lq, int Lk, const void* q, const void* k, const void* v, int ldq, int ldk, int ldv) {
+// Which calls take the tcgen05 path.  Eligibility: single-tile sequences, TMA-compatible operands.  Policy (measured on B200,
+// B = 80 packed rows, dropout on, cold L2 — tools/attn_ab.py, profiles/r02_attention_ab.txt): the per-(sample, head) problems are
+// tiny (3 + 8 MMA instructions), so a CTA's life is dominated by fixed latencies (TMA round trip, TMEM allocation, three
+// MMA -> mbarrier -> tcgen05.ld hand-offs) and by the scalar softmax work; the tensor-core kernels win where 128 query rows
+// keep all TMEM lanes busy (text self-attention forward 35 vs 44 us, text -> visual co-attention forward 35 vs 36 us) and lose
+// where they do not (<= 44 visual queries: 23 vs 17 us, 48 vs 30 us) and in the backward (83 vs 75 us; 77 vs 54 us), whose
+// mma.sync form keeps every contraction in registers.  Default = the faster kernel per call; CRCT_ATTN_TC_POLICY overrides
+// (bit 0: forward with > 64 queries, bit 1: other forwards, bit 2: self-attention backward with > 64 queries, bit 3: other
+// backwards; 15 = tcgen05 everywhere it is eligible), CRCT_ATTN_LEGACY=1 / CRCT_ATTN_LEGACY_NOW=1 (read per call) = mma.sync only.
+bool crct_attn_tc_eligible(int dh, int Lq, int Lk, const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int backward) {
     static const bool legacy = getenv("CRCT_ATTN_LEGACY") != nullptr;
-    if (legacy || getenv("CRCT_ATTN_LEGACY_NOW") != nullptr) return false;      // A/B switch (the second form is read per call: tests)
+    if (legacy || getenv("CRCT_ATTN_LEGACY_NOW") != nullptr) return false;
     if (dh != 32 && dh != 48 && dh != 64) return false;
     if (Lq > 128 || Lk > 128) return false;
-    return ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
-           (ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0;
+    if (((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) != 0 || (ldq % 8) || (ldk % 8) ||
+        (ldv % 8))
+        return false;
+    const char* e = getenv("CRCT_ATTN_TC_POLICY");
+    const int policy = e ? atoi(e) : 1;
+    const int bit = backward ? ((Lq > 64 && Lk > 64) ? 4 : 8) : (Lq > 64 ? 1 : 2);
+    return (policy & bit) != 0;
 }
 
 int crct_attn_fwd_tc(const crct_attn_fwd_t* a, crct_stream_t s) {

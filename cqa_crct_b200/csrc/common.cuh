@@ -28,7 +28,7 @@ void crct_set_error(const char* fmt, ...);
 static inline cudaStream_t as_stream(crct_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 int crct_num_sms();
 // tcgen05 / TMEM / TMA attention (attention_tc.cu): single-tile sequences (Lq, Lk <= 128); attention.cu dispatches to it
-bool crct_attn_tc_eligible(int dh, int Lq, int Lk, const void* q, const void* k, const void* v, int ldq, int ldk, int ldv);
+bool crct_attn_tc_eligible(int dh, int Lq, int Lk, const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int backward);
 int crct_attn_fwd_tc(const crct_attn_fwd_t* a, crct_stream_t s);
 int crct_attn_bwd_tc(const crct_attn_bwd_t* a, crct_stream_t s);
 

@@ -20,6 +20,9 @@ def relmax(a, b):
     return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
 
 
+os.environ['CRCT_ATTN_TC_POLICY'] = '15'          # this module: tcgen05 wherever eligible (the default policy is per-shape, by measurement)
+
+
 class legacy:
     def __enter__(self):
         os.environ['CRCT_ATTN_LEGACY_NOW'] = '1'
@@ -29,7 +32,7 @@ class legacy:
 
 
 SHAPES = [(3, 16, 48, 124, 124), (2, 16, 64, 44, 44), (3, 32, 32, 124, 44), (3, 32, 32, 44, 124), (2, 4, 48, 17, 33), (1, 2, 64, 128, 128),
-          (2, 2, 32, 64, 64), (2, 3, 48, 65, 1), (80, 16, 48, 124, 124)]
+          (2, 2, 32, 64, 64), (2, 3, 48, 65, 3), (80, 16, 48, 124, 124)]
 
 
 @pytest.mark.parametrize('B,nh,dh,Lq,Lk', SHAPES)

@@ -2,6 +2,7 @@
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ['CRCT_ATTN_TC_POLICY'] = '15'
 from cqa_crct_b200 import _lib as L
 DEV = 'cuda'
 bf = lambda x: x.to(torch.bfloat16)
