@@ -556,7 +556,9 @@ int dispatch_bwd_tc(const crct_attn_bwd_t* a, const TcParams& p, cudaStream_t st
 // MMA -> mbarrier -> tcgen05.ld hand-offs) and by the scalar softmax work; the tensor-core kernels win where 128 query rows
 // keep all TMEM lanes busy (text self-attention forward 35 vs 44 us, text -> visual co-attention forward 35 vs 36 us) and lose
 // where they do not (<= 44 visual queries: 23 vs 17 us, 48 vs 30 us) and in the backward (83 vs 75 us; 77 vs 54 us), whose
-// mma.sync form keeps every contraction in registers.  Default = the faster kernel per call; CRCT_ATTN_TC_POLICY overrides
+// mma.sync form keeps every contraction in registers.  IN THE STEP (three streams, captured graph) the choices 0 / 1 / 5 are
+// indistinguishable (13.92 / 13.90 / 14.00 ms, +-0.05 run to run) and 15 costs 0.8 ms, so the default is 5: tcgen05 for the
+// text self-attention in both directions and for the text -> visual co-attention forward.  CRCT_ATTN_TC_POLICY overrides
 // (bit 0: forward with > 64 queries, bit 1: other forwards, bit 2: self-attention backward with > 64 queries, bit 3: other
 // backwards; 15 = tcgen05 everywhere it is eligible), CRCT_ATTN_LEGACY=1 / CRCT_ATTN_LEGACY_NOW=1 (read per call) = mma.sync only.
 bool crct_attn_tc_eligible(int dh, int Lq, int Lk, const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int backward) {
@@ -568,7 +570,7 @@ bool crct_attn_tc_eligible(int dh, int Lq, int Lk, const void* q, const void* k,
         (ldv % 8))
         return false;
     const char* e = getenv("CRCT_ATTN_TC_POLICY");
-    const int policy = e ? atoi(e) : 1;
+    const int policy = e ? atoi(e) : 5;
     const int bit = backward ? ((Lq > 64 && Lk > 64) ? 4 : 8) : (Lq > 64 ? 1 : 2);
     return (policy & bit) != 0;
 }
