@@ -68,9 +68,11 @@ __device__ __forceinline__ void fwd_chunk8(const uint32_t* v, int c, int Lk, flo
                                            const CrctDrop32& drop, uint32_t ctr, float dscale, uint32_t (&pk)[4]) {
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-        float s0 = __uint_as_float(v[j]) * scale2, s1 = __uint_as_float(v[j + 1]) * scale2;
-        if constexpr (MASK) { s0 += mask_s[c + j]; s1 += mask_s[c + j + 1]; }
-        float p0 = fast_exp2(s0 - m), p1 = fast_exp2(s1 - m);
+        // explicit roundings (no fused contraction): the masked and the mask-free form give the same bits where the mask is 0,
+        // so the packed layout reproduces the padded one exactly
+        float s0 = __fmul_rn(__uint_as_float(v[j]), scale2), s1 = __fmul_rn(__uint_as_float(v[j + 1]), scale2);
+        if constexpr (MASK) { s0 = __fadd_rn(s0, mask_s[c + j]); s1 = __fadd_rn(s1, mask_s[c + j + 1]); }
+        float p0 = fast_exp2(__fsub_rn(s0, m)), p1 = fast_exp2(__fsub_rn(s1, m));
         if constexpr (CHECK) {
             if (c + j >= Lk) p0 = 0.f;
             if (c + j + 1 >= Lk) p1 = 0.f;
@@ -91,9 +93,9 @@ __device__ __forceinline__ void bwd_chunk8(const uint32_t* vs, const uint32_t* v
                                            uint32_t (&ds)[4]) {
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-        float s0 = __uint_as_float(vs[j]) * scale2, s1 = __uint_as_float(vs[j + 1]) * scale2;
-        if constexpr (MASK) { s0 += mask_s[c + j]; s1 += mask_s[c + j + 1]; }
-        float pr0 = fast_exp2(s0 - lse2), pr1 = fast_exp2(s1 - lse2);
+        float s0 = __fmul_rn(__uint_as_float(vs[j]), scale2), s1 = __fmul_rn(__uint_as_float(vs[j + 1]), scale2);
+        if constexpr (MASK) { s0 = __fadd_rn(s0, mask_s[c + j]); s1 = __fadd_rn(s1, mask_s[c + j + 1]); }
+        float pr0 = fast_exp2(__fsub_rn(s0, lse2)), pr1 = fast_exp2(__fsub_rn(s1, lse2));
         float g0 = __uint_as_float(vd[j]), g1 = __uint_as_float(vd[j + 1]);
         if constexpr (CHECK) {                         // past the last key: probability 0, and dP there may be garbage (select, not multiply)
             if (c + j >= Lk) { pr0 = 0.f; g0 = 0.f; }
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS) attn_fwd_tc_kernel(const __grid_co
         ptx::tc_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-            if (c0 + j < Lk) m = fmaxf(m, fmaf(__uint_as_float(v[j]), scale2, mask_s[c0 + j]));
+            if (c0 + j < Lk) m = fmaxf(m, __fadd_rn(__fmul_rn(__uint_as_float(v[j]), scale2), mask_s[c0 + j]));
     }
     red_m[hsel * QT + row] = m;
     __syncthreads();
