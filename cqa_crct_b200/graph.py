@@ -67,6 +67,12 @@ class GraphedTrainStep:
         # update takes bandwidth and SM slots from cold-operand GEMMs that are themselves latency-sensitive — so it is off by
         # default; stream priorities (chain above fillers) measured neutral to slightly negative and were removed.
         self.overlap_optimizer = self.world == 1 and bool(params.get('overlap_optimizer', False))
+        # data parallel: AdamW bucket by bucket, each launch waiting only for ITS bucket's all-reduce — the update of the early
+        # buckets (heads, top blocks) runs under the exchange of the late ones (embeddings: 94 MB that become final only at the
+        # very end of the backward), so what stays exposed after the backward is the last bucket's exchange + its update
+        # instead of every exchange still in flight + the whole 1.3 ms optimizer pass.
+        self.pipeline_optimizer = self.world > 1 and bool(params.get('pipeline_optimizer', True))
+        self._scratch = torch.zeros(4, dtype=torch.float32, device=dev)
         self._opt_stream = torch.cuda.Stream(device=dev) if self.overlap_optimizer else None
         self._opt_pending = None
         self.opt_chunk = int(params.get('optimizer_chunk', 24 << 20))      # elements per optimizer launch (~0.13 ms of HBM time)
@@ -118,7 +124,10 @@ class GraphedTrainStep:
         self.enc.arena.mark_bf16_fresh()
 
     def _optimizer_tail(self):
-        if not self.overlap_optimizer:
+        if self.pipeline_optimizer:
+            from . import _lib as L
+            L.fill_zero(self._scratch)            # the last segment only anchors the per-bucket updates `step()` enqueues: keep it non-empty
+        elif not self.overlap_optimizer:
             self.opt.step_captured()
 
     def _eager_step(self):
@@ -126,9 +135,13 @@ class GraphedTrainStep:
         works = []
         for lo, hi in self._buckets(self._stages()):
             if self.world > 1:
-                works.append(dist.all_reduce(self.enc.arena.g32[lo:hi], op=dist.ReduceOp.AVG, group=self.ddp.pg, async_op=True))
-        for w in works:
+                works.append((dist.all_reduce(self.enc.arena.g32[lo:hi], op=dist.ReduceOp.AVG, group=self.ddp.pg, async_op=True), lo, hi))
+        for w, lo, hi in works:
             w.wait()
+            if self.pipeline_optimizer:
+                self.opt.step_range_captured(lo, hi)
+        if self.pipeline_optimizer:
+            self.enc.arena.mark_bf16_fresh()
         self._optimizer_tail()
 
     def _buckets(self, stages):
@@ -209,12 +222,16 @@ class GraphedTrainStep:
         works = []
         for g, bucket in self.segments:
             if bucket is None:
-                for w in works:
-                    w.wait()                     # compute stream waits for the exchanges before the optimizer segment
+                for w, lo, hi in works:
+                    w.wait()                     # compute stream waits for this bucket's exchange ...
+                    if self.pipeline_optimizer:
+                        self.opt.step_range_captured(lo, hi)      # ... and updates it while the later buckets are still on the wire
+                if self.pipeline_optimizer:
+                    self.enc.arena.mark_bf16_fresh()
             g.replay()
             if bucket is not None:
-                works.append(dist.all_reduce(self.enc.arena.g32[bucket[0]:bucket[1]], op=dist.ReduceOp.AVG,
-                                             group=self.ddp.pg, async_op=True))
+                works.append((dist.all_reduce(self.enc.arena.g32[bucket[0]:bucket[1]], op=dist.ReduceOp.AVG,
+                                              group=self.ddp.pg, async_op=True), bucket[0], bucket[1]))
         if self.sched is not None:
             self.sched.step()
         return self.loss

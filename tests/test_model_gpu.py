@@ -325,3 +325,56 @@ def test_full_size_b80_train_gradients_against_the_oracle():
         got, ref = named[k].grad.double().cpu(), g[k].double()
         err, rn = float((got - ref).norm()), float(ref.norm())
         assert err <= 0.25 * rn + 5e-3 * gnorm, (k, err / rn)
+
+
+def test_weights_changed_after_the_first_forward_are_picked_up():
+    """after `.to('cuda')` the nn.Parameters no longer share the arena's version counter; load_state_dict /
+    optimizers / manual copy_ into a parameter must still refresh the bf16 operand copy (several checkpoints evaluated with
+    one model object)."""
+    from cqa_crct_b200.spec import synth_state_dict
+    rec = load_golden('tiny_eval')
+    m, params, cfg, sd, batch, gb = build(rec)
+    with torch.no_grad():
+        s1 = glue_forward(m, gb, params, evaluation=True)[4].clone()
+    sd2 = synth_state_dict(cfg, 228, 7, 'mild')
+    m.load_state_dict({'bert_pretrained.' + k: v for k, v in sd2.items()}, strict=True)
+    with torch.no_grad():
+        s2 = glue_forward(m, gb, params, evaluation=True)[4].clone()
+    fresh = VisualDialogEncoder(params)
+    fresh.load_state_dict({'bert_pretrained.' + k: v for k, v in sd2.items()}, strict=True)
+    fresh.to('cuda').eval()
+    with torch.no_grad():
+        s3 = glue_forward(fresh, gb, params, evaluation=True)[4]
+    assert not torch.equal(s1, s2) and torch.equal(s2, s3)
+    with torch.no_grad():                                   # an in-place edit of one parameter
+        m.bert_pretrained.cls.bi_seq_relationship.bias.add_(1.0)
+        s4 = glue_forward(m, gb, params, evaluation=True)[4]
+    assert float((s4 - s2 - 1.0).abs().max()) < 1e-5
+
+
+def test_two_forwards_before_the_first_backward_keep_their_own_dropout_masks():
+    """l1 = model(a); l2 = model(b); (l1 + l2).backward() — each pass recomputes the masks of ITS forward (per-pass
+    salt snapshot), so the summed gradient equals the sum of the two separately back-propagated passes with the same salts."""
+    rec = load_golden('tiny_train_l1')
+    m, params, cfg, sd, batch, gb = build(rec)
+    m.train()
+    gb2 = {k: v.clone() for k, v in gb.items()}
+    gb2['tokens'] = gb['tokens'].roll(1, 0)
+
+    def salt_reset():
+        m._salt = None                                       # re-seed the live counter: same sequence of per-pass salts
+    salt_reset()
+    m.zero_grad()
+    l1 = glue_forward(m, gb, params)[0]
+    l2 = glue_forward(m, gb2, params)[0]
+    (l1 + l2).backward()
+    both = m.arena.g32.clone()
+    salt_reset()
+    m.zero_grad()
+    l1b = glue_forward(m, gb, params)[0]
+    l1b.backward()
+    l2b = glue_forward(m, gb2, params)[0]
+    l2b.backward()
+    torch.cuda.synchronize()
+    assert float(l1) == float(l1b) and float(l2) == float(l2b)
+    assert rel_err(both, m.arena.g32) < 1e-4
