@@ -72,7 +72,8 @@ class GraphedTrainStep:
         # very end of the backward), so what stays exposed after the backward is the last bucket's exchange + its update
         # instead of every exchange still in flight + the whole 1.3 ms optimizer pass.
         self.pipeline_optimizer = self.world > 1 and bool(params.get('pipeline_optimizer', True))
-        self._scratch = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._scratch = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._scratch16 = torch.zeros(8, dtype=torch.bfloat16, device=dev)
         self._opt_stream = torch.cuda.Stream(device=dev) if self.overlap_optimizer else None
         self._opt_pending = None
         self.opt_chunk = int(params.get('optimizer_chunk', 24 << 20))      # elements per optimizer launch (~0.13 ms of HBM time)
@@ -126,7 +127,7 @@ class GraphedTrainStep:
     def _optimizer_tail(self):
         if self.pipeline_optimizer:
             from . import _lib as L
-            L.fill_zero(self._scratch)            # the last segment only anchors the per-bucket updates `step()` enqueues: keep it non-empty
+            L.cast_f32_to_bf16(self._scratch, self._scratch16)      # the last segment only anchors the per-bucket updates `step()` enqueues: keep it non-empty
         elif not self.overlap_optimizer:
             self.opt.step_captured()
 

@@ -75,12 +75,13 @@ def _run(rank, world, port, out_path, config='tiny.json', T=32, R=12, B=8):
     torch.cuda.synchronize()
     n_live = enc.arena.live_end
     upd = float((enc.arena.w32[:n_live] - enc2.arena.w32[:n_live]).norm() / enc2.arena.w32[:n_live].norm())
+    mom = max(float((opt.m - opt2.m).norm() / opt2.m.norm()), float((opt.v - opt2.v).norm() / opt2.v.norm()))
     w = enc.arena.w32[:enc.arena.live_end].clone()
     ws = [torch.zeros_like(w) for _ in range(world)]
     dist.all_gather(ws, w)
     graph_same = all(torch.equal(ws[0], x) for x in ws)
     if rank == 0:
-        torch.save({'rel': rel, 'same': same, 'buckets': nb, 'graph_same': graph_same, 'segments': len(gs.segments), 'graph_vs_eager': upd,
+        torch.save({'rel': rel, 'same': same, 'buckets': nb, 'graph_same': graph_same, 'segments': len(gs.segments), 'graph_vs_eager': upd, 'moments': mom,
                     'pipelined': gs.pipeline_optimizer}, out_path)
     dist.destroy_process_group()
 
@@ -94,7 +95,10 @@ def test_two_gpu_gradients_equal_single_gpu_full_batch(tmp_path):
     assert r['buckets'] >= 2               # the exchange really was bucketed
     assert r['rel'] < 2e-3, r              # = full-batch gradients: per-sample arithmetic is batch-independent, only fp32 summation order differs
     assert r['graph_same'] and r['segments'] >= 3, r     # graphed data-parallel steps keep the replicas identical
-    assert r['pipelined'] and r['graph_vs_eager'] < 1e-5, r      # per-bucket AdamW behind each bucket's all-reduce == exchange, then whole-arena AdamW
+    # per-bucket AdamW behind each bucket's all-reduce == exchange, then whole-arena AdamW: the Adam moments (linear in the
+    # gradients) agree to fp32 summation noise; the weights to 2e-4 (Adam turns gradients that are pure rounding noise — key biases,
+    # whose true gradient is 0 — into +-lr updates; a bucket updated twice or not at all would show at >= 7e-4)
+    assert r['pipelined'] and r['moments'] < 1e-4 and r['graph_vs_eager'] < 2e-4, r
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
@@ -104,4 +108,4 @@ def test_two_gpu_full_model(tmp_path):
     mp.spawn(_run, args=(2, _free_port(), out, 'vilbert.json', 124, 44, 8), nprocs=2, join=True)
     r = torch.load(out)
     assert r['same'] and r['buckets'] >= 10 and r['rel'] < 2e-3, r
-    assert r['graph_same'] and r['pipelined'] and r['graph_vs_eager'] < 1e-5, r
+    assert r['graph_same'] and r['pipelined'] and r['moments'] < 1e-4 and r['graph_vs_eager'] < 2e-4, r
