@@ -58,24 +58,28 @@ def _run(rank, world, port, out_path, config='tiny.json', T=32, R=12, B=8):
     from cqa_crct_b200.optim import FusedAdamW
     ddp.require_sync = True
     opt = FusedAdamW(ddp, lr=2e-5, image_lr=2e-5)
-    gs = GraphedTrainStep(ddp, opt, params, half, warmup_steps=1)
-    for _ in range(2):
-        gs.step(half)
-    torch.cuda.synchronize()
-    # the pipelined per-bucket optimizer of the graphed step == the same three steps with exchange -> whole-arena AdamW
+    gs = GraphedTrainStep(ddp, opt, params, half, warmup_steps=1)          # runs ONE eager step (per-bucket AdamW behind each all-reduce)
+    # the pipelined per-bucket optimizer == exchange, then whole-arena AdamW: after one step the Adam moments (linear / quadratic in
+    # the gradients) agree to fp32 summation noise
     enc2 = VisualDialogEncoder(params)
     enc2.load_state_dict({'bert_pretrained.' + k: v for k, v in synth_state_dict(cfg, 228, 7, 'mild').items()})
     enc2.to(f'cuda:{rank}').eval()
     ddp2 = DistributedDataParallel(enc2, bucket_cap_mb=1.0 if config == 'tiny.json' else 25.0)
     opt2 = FusedAdamW(ddp2, lr=2e-5, image_lr=2e-5)
-    for _ in range(3):
+
+    def eager_step():
         opt2.zero_grad()
         glue_forward(ddp2, half, params)[0].backward()
         opt2.step()
+    eager_step()
+    torch.cuda.synchronize()
+    mom = max(float((opt.m - opt2.m).norm() / opt2.m.norm()), float((opt.v - opt2.v).norm() / opt2.v.norm()))
+    for _ in range(2):
+        gs.step(half)
+        eager_step()
     torch.cuda.synchronize()
     n_live = enc.arena.live_end
     upd = float((enc.arena.w32[:n_live] - enc2.arena.w32[:n_live]).norm() / enc2.arena.w32[:n_live].norm())
-    mom = max(float((opt.m - opt2.m).norm() / opt2.m.norm()), float((opt.v - opt2.v).norm() / opt2.v.norm()))
     w = enc.arena.w32[:enc.arena.live_end].clone()
     ws = [torch.zeros_like(w) for _ in range(world)]
     dist.all_gather(ws, w)
@@ -98,7 +102,7 @@ def test_two_gpu_gradients_equal_single_gpu_full_batch(tmp_path):
     # per-bucket AdamW behind each bucket's all-reduce == exchange, then whole-arena AdamW: the Adam moments (linear in the
     # gradients) agree to fp32 summation noise; the weights to 2e-4 (Adam turns gradients that are pure rounding noise — key biases,
     # whose true gradient is 0 — into +-lr updates; a bucket updated twice or not at all would show at >= 7e-4)
-    assert r['pipelined'] and r['moments'] < 1e-4 and r['graph_vs_eager'] < 2e-4, r
+    assert r['pipelined'] and r['moments'] < 1e-5 and r['graph_vs_eager'] < 2e-4, r
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
@@ -108,4 +112,4 @@ def test_two_gpu_full_model(tmp_path):
     mp.spawn(_run, args=(2, _free_port(), out, 'vilbert.json', 124, 44, 8), nprocs=2, join=True)
     r = torch.load(out)
     assert r['same'] and r['buckets'] >= 10 and r['rel'] < 2e-3, r
-    assert r['graph_same'] and r['pipelined'] and r['moments'] < 1e-4 and r['graph_vs_eager'] < 2e-4, r
+    assert r['graph_same'] and r['pipelined'] and r['moments'] < 1e-5 and r['graph_vs_eager'] < 2e-4, r
