@@ -207,7 +207,7 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
     config = describe(name, B, T, R, train, args.gpus)
     dev = torch.device('cuda', local_rank)
     params = default_params(CFG, device=str(dev), max_seq_len=T, max_vis_features=R, L1=True, overlap_optimizer=args.opt_overlap,
-                            varlen=not args.padded)
+                            varlen=not args.padded, pipeline_optimizer=not args.no_opt_pipeline)
     torch.manual_seed(0)
     enc = VisualDialogEncoder(params).to(dev)
     model = DistributedDataParallel(enc, bucket_cap_mb=args.bucket_mb) if world > 1 else enc
@@ -313,6 +313,13 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
 
     ms, launches, clocks = timed(resident, False)
     ms_step = ms / steps
+    if args.trace and gstep is not None and world > 1:            # per-bucket timeline of one step (rank 0 writes it)
+        barrier()
+        tr = gstep.trace_step(resident[0])
+        barrier()
+        if rank == 0:
+            os.makedirs(os.path.dirname(os.path.abspath(args.trace)), exist_ok=True)
+            json.dump(dict(tr, n_gpus=world, ms_per_step_timed=ms_step), open(args.trace, 'w'), indent=1)
     value = B * world / (ms_step / 1e3)
     e2e = None
     if not args.no_e2e:
@@ -468,6 +475,8 @@ def main():
     ap.add_argument('--no-graph-timing', action='store_true', help='time the GEMMs with host-enqueued events (round-1 method)')
     ap.add_argument('--opt-overlap', action='store_true', help='run AdamW under the backward instead of after it (A/B; measured slower)')
     ap.add_argument('--bucket-mb', type=float, default=25.0, help='gradient all-reduce bucket size (fp32 MB)')
+    ap.add_argument('--trace', default=None, help='N > 1: write the per-bucket timeline of one step (JSON) to this path')
+    ap.add_argument('--no-opt-pipeline', action='store_true', help='N > 1: whole-arena AdamW after the last all-reduce (A/B)')
     ap.add_argument('--no-graph', action='store_true', help='enqueue every launch from Python instead of replaying the captured step')
     args = ap.parse_args()
     B, T, R, train = WORKLOADS[args.workload]

@@ -205,6 +205,44 @@ class GraphedTrainStep:
         ev.record()
         return _PendingLoss(self._loss_host, slot, ev)
 
+    def trace_step(self, batch: Optional[Dict[str, torch.Tensor]] = None) -> dict:
+        """One `step()` with CUDA events on the compute stream: when each graph segment has finished (= the bucket it completes is
+        handed to NCCL) and when the compute stream gets past each bucket's all-reduce (then runs that bucket's AdamW).  Times in ms
+        from the start of the step; `exposed_ms` = end of step - end of the last backward segment = exchange + update time that
+        nothing hides.  Synchronises; for timelines (profiles/), not for throughput numbers."""
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        t0 = ev(); t0.record()
+        if batch is not None:
+            for k, dst in self.static.items():
+                dst.copy_(batch[k], non_blocking=True)
+        self.opt.push_device_scalars()
+        works, seg_end, ready = [], [], []
+        for g, bucket in self.segments:
+            if bucket is None:
+                for w, lo, hi in works:
+                    w.wait()
+                    if self.pipeline_optimizer:
+                        self.opt.step_range_captured(lo, hi)
+                    e = ev(); e.record(); ready.append((e, lo, hi))
+                if self.pipeline_optimizer:
+                    self.enc.arena.mark_bf16_fresh()
+            g.replay()
+            if bucket is not None:
+                e = ev(); e.record(); seg_end.append(e)
+                works.append((dist.all_reduce(self.enc.arena.g32[bucket[0]:bucket[1]], op=dist.ReduceOp.AVG, group=self.ddp.pg, async_op=True),
+                              bucket[0], bucket[1]))
+        t1 = ev(); t1.record()
+        torch.cuda.synchronize()
+        if self.sched is not None:
+            self.sched.step()
+        out = {'step_ms': t0.elapsed_time(t1), 'segment_end_ms': [t0.elapsed_time(e) for e in seg_end],
+               'bucket_done_ms': [t0.elapsed_time(e) for e, _, _ in ready], 'bucket_mb': [(hi - lo) * 4 / 2 ** 20 for _, lo, hi in ready],
+               'optimizer': 'per bucket, behind its all-reduce' if self.pipeline_optimizer else 'whole arena after the last all-reduce'}
+        if seg_end:
+            out['backward_end_ms'] = out['segment_end_ms'][-1]
+            out['exposed_ms'] = out['step_ms'] - out['backward_end_ms']
+        return out
+
     def step(self, batch: Optional[Dict[str, torch.Tensor]] = None):
         """Copy `batch` (or the prefetched batch) into the static inputs, replay the captured step, return the (static)
         loss tensor."""
