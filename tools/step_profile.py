@@ -17,11 +17,14 @@ from cqa_crct_b200.synthetic import default_params, make_batch  # noqa: E402
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 80
 cfg = os.path.join(ROOT, 'cqa_crct_b200', 'config', 'vilbert.json')
-params = default_params(cfg, device='cuda', L1=True)
+from cqa_crct_b200.graph import fill_fractions  # noqa: E402
+hb = make_batch(B, 124, 44, 1024, seed=5)
+params = default_params(cfg, device='cuda', L1=True, row_fill_hint=fill_fractions(hb))      # tile shapes as in the captured bench step
 torch.manual_seed(0)
 m = VisualDialogEncoder(params).to('cuda').train()
+m.overlap_streams = os.environ.get('CRCT_PROFILE_LANES', '0') == '1'       # one stream: ncu serialises the launches anyway
 opt = FusedAdamW(m)
-gb = {k: v.to('cuda') for k, v in make_batch(B, 124, 44, 1024, seed=5).items()}
+gb = {k: v.to('cuda') for k, v in hb.items()}
 for i in range(steps):
     torch.cuda.synchronize()
     l0, t0 = L.LAUNCHES, time.perf_counter()
