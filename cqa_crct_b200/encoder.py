@@ -272,7 +272,10 @@ class VisualDialogEncoder(nn.Module):
     def zero_grad(self, set_to_none: bool = False):
         """Gradients live in the arena: zeroing is one memset; `set_to_none` is ignored on purpose."""
         if self.arena.g32 is not None:
-            self.arena.g32[:self.arena.live_end].zero_()
+            if self.arena.g32.is_cuda:
+                L.fill_zero(self.arena.g32[:self.arena.live_end])       # one memset node on the stream (no ATen fill kernels in the step)
+            else:
+                self.arena.g32[:self.arena.live_end].zero_()
 
     def flat_parameters(self):
         return self.arena.w32, self.arena.g32, self.arena.w16
