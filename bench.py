@@ -456,6 +456,10 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
         out = {'metric': 'crct_train_samples_per_sec' if train else 'crct_eval_sequences_per_sec', 'value': value, 'unit': 'samples/s',
                'ms_per_step': ms_step, 'config': dict(config, launch='one CUDA graph per step (captured glue_forward + backward + AdamW)' if gstep is not None else 'per-kernel launches from Python'),
                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'gpu_launches_per_step': launches / steps, 'roofline': roof}
+        if not train:                         # BASELINE's "eval Q/s": questions (with all their candidate answers) per second
+            out['questions_per_sec'] = value * config['questions_per_batch'] / B
+            if e2e is not None:
+                e2e['questions_per_sec'] = e2e['value'] * config['questions_per_batch'] / B
     del gstep, model, enc, opt, resident, pinned
     torch.cuda.empty_cache()
     return out
