@@ -836,6 +836,8 @@ int crct_make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uin
     return make_tmap(tm, ptr, inner, outer, ld, box_inner, box_outer);
 }
 
+static inline bool max_ctas_unset(const crct_gemm_t* a) { return a->max_ctas <= 0; }
+
 // auto policy for cta_group == 0
 static bool crct_gemm_auto_pair(const crct_gemm_t* a) {
     // measured on B200 (profiles/r01_gemm_shapes.log): the CTA pair wins ~4 % once there are >= 8 tile columns to
@@ -957,7 +959,21 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
         if (bn == 256) return dispatch2<256>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid2, st);
         return dispatch2<128>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid2, st);
     }
-    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    {
+        // balanced persistent grid: a 1.46-wave problem (216 tiles) takes two tile-times on 148 CTAs and on 108 CTAs alike — with
+        // 108, the other 40 SMs are free for the kernels of the other streams (visual lane, weight gradients) for the whole
+        // duration instead of only after the first wave.  Expected tile count (packed rows: from the caller's row estimate).
+        static const bool balance = getenv("CRCT_GEMM_NO_BALANCE") == nullptr;
+        const int m_eff = (a->a_rows_dev && !a->a_major && a->rows_hint > 0 && a->rows_hint < a->M) ? a->rows_hint : a->M;
+        const long tiles_eff = (long)((m_eff + tile_m - 1) / tile_m) * num_n_tiles * split_k;
+        if (balance && tiles_eff > sms && max_ctas_unset(a)) {
+            const long waves = (tiles_eff + sms - 1) / sms;
+            int g = (int)((tiles_eff + waves - 1) / waves);
+            g += g / 16;                       // slack for batches with more valid rows than estimated
+            if (g < grid) grid = g;
+        }
+    }
     if (bn == 256) return dispatch<256>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
     if (bn == 192) return dispatch<192>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
     return dispatch<128>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
