@@ -345,6 +345,25 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
             meta.append((kw['M'], kw['N'], kw['K'], kw.get('a_major', 0), kw.get('rows_dev'), kw.get('epilogue', L.EPI_BIAS),
                          kw.get('aux') is not None, kw.get('D2') is not None))
 
+        orig_grouped = L.gemm_wgrad_grouped
+
+        def timed_grouped(problems):
+            a = torch.cuda.Event(enable_timing=True, external=in_graph[0])
+            b = torch.cuda.Event(enable_timing=True, external=in_graph[0])
+            a.record()
+            orig_grouped(problems)
+            b.record()
+            pairs.append((a, b))
+            meta.append([(q.M, q.N, q.K, 1, wg_rows.get(q.a_rows_dev), L.EPI_F32, False, False) for q in problems])
+
+        wg_rows = {}                              # device pointer of a row count -> its tensor (grouped problems carry raw pointers)
+        orig_args = L.gemm_args
+
+        def tracking_args(A, Bm, D, **kw):
+            if kw.get('rows_dev') is not None:
+                wg_rows[kw['rows_dev'].data_ptr()] = kw['rows_dev']
+            return orig_args(A, Bm, D, **kw)
+
         def null_pairs(n):
             out = []
             for _ in range(n):
@@ -366,6 +385,7 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
         nulls, graph_keep = [], None
         try:
             L.gemm = E.L.gemm = timed_gemm
+            L.gemm_wgrad_grouped, L.gemm_args = timed_grouped, tracking_args
             if train and not args.no_graph_timing:
                 try:                              # events as graph nodes: no host in the loop
                     in_graph[0] = True
@@ -403,6 +423,7 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
                 timing = 'CUDA events around every GEMM launch of one extra step enqueued from Python on ONE stream'
         finally:
             L.gemm = E.L.gemm = orig
+            L.gemm_wgrad_grouped, L.gemm_args = orig_grouped, orig_args
             enc.overlap_streams = lanes_were
             enc.grad_ready_hook, enc.segment_ranges = hook_were, seg_were
             if require is not None:
@@ -411,7 +432,9 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
         raw_ms = sum(a.elapsed_time(b) for a, b in pairs)
         gemm_ms = max(raw_ms - overhead_ms * len(pairs), 0.5 * raw_ms)
         flops = gbytes = 0.0
-        for M_, N_, K_, a_major, rows_dev, epi, has_aux, has_d2 in meta:
+        n_problems = sum(len(m_) if isinstance(m_, list) else 1 for m_ in meta)
+        flat = [q for m_ in meta for q in (m_ if isinstance(m_, list) else [m_])]
+        for M_, N_, K_, a_major, rows_dev, epi, has_aux, has_d2 in flat:
             if rows_dev is not None:              # packed rows: the kernel runs the device-side count, not the allocation
                 r = int(rows_dev)
                 if a_major:
@@ -426,9 +449,14 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
         dump = os.environ.get('CRCT_BENCH_DUMP_GEMMS')       # per-launch table for tools/gemm_table.py
         if dump:
             rows_ = []
-            for (a, b), (M_, N_, K_, a_major, rows_dev, epi, has_aux, has_d2) in zip(pairs, meta):
-                r = int(rows_dev) if rows_dev is not None else None
-                rows_.append({'M': M_, 'N': N_, 'K': K_, 'a_major': a_major, 'rows': r, 'epi': epi, 'us': (a.elapsed_time(b) - overhead_ms) * 1e3})
+            for (a, b), m_ in zip(pairs, meta):
+                grp = m_ if isinstance(m_, list) else [m_]
+                us = (a.elapsed_time(b) - overhead_ms) * 1e3
+                tot_f = sum(2.0 * q[0] * q[1] * q[2] for q in grp)
+                for (M_, N_, K_, a_major, rows_dev, epi, has_aux, has_d2) in grp:      # a grouped launch's time is split by nominal FLOPs
+                    r = int(rows_dev) if rows_dev is not None else None
+                    rows_.append({'M': M_, 'N': N_, 'K': K_, 'a_major': a_major, 'rows': r, 'epi': epi, 'us': us * (2.0 * M_ * N_ * K_) / tot_f,
+                                  'grouped': len(grp)})
             json.dump({'workload': name, 'overhead_us': overhead_ms * 1e3, 'launches': rows_}, open(f'{dump}.{name}.json', 'w'))
         del graph_keep
         achieved = flops / (gemm_ms / 1e3) / 1e12
@@ -444,7 +472,7 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
         roof = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel', 'achieved': achieved, 'peak': sustained, 'unit': 'TFLOP/s',
                 'frac': achieved / sustained, 'traffic': traffic, 'traffic_unit': f'DRAM bytes per launch (ncu, profiles/{traffic_src})',
                 'algorithmic_bytes_per_launch': gbytes / max(1, len(pairs)), 'peak_source': f'{src} (bf16_tflops_sustained; burst {burst})',
-                'launches_per_step': len(pairs), 'timing': timing, 'gemm_ms_per_step': gemm_ms, 'gemm_ms_per_step_raw': raw_ms,
+                'launches_per_step': len(pairs), 'gemm_problems_per_step': n_problems, 'timing': timing, 'gemm_ms_per_step': gemm_ms, 'gemm_ms_per_step_raw': raw_ms,
                 'event_pair_overhead_us': overhead_ms * 1e3, 'gemm_share_of_step': gemm_ms / ms_step,
                 'algorithmic_tflop_per_step': flops / 1e12, 'padded_layout_tflop_per_step': padded_tflop,
                 'executed_tflops_whole_step': flops / 1e12 / (ms_step / 1e3),

@@ -102,7 +102,7 @@ class ScoreArgs(C.Structure):
 
 
 # every symbol include/crct_b200.h declares (tests check the .so exports exactly these)
-EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf16', 'crct_cast_f32_to_bf16',
+EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf16', 'crct_gemm_wgrad_grouped', 'crct_cast_f32_to_bf16',
            'crct_additive_mask', 'crct_layernorm_fwd', 'crct_layernorm_bwd', 'crct_layernorm_bwd_params', 'crct_colsum_bf16', 'crct_softmax_rows',
            'crct_embed_text_fwd', 'crct_embed_text_bwd', 'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd',
            'crct_attn_bwd', 'crct_linear_f32', 'crct_linear_f32_batched', 'crct_gather_first', 'crct_scatter_first', 'crct_colsum_f32',
@@ -149,6 +149,7 @@ def lib():
         _lib.crct_f32_gather_first.argtypes = [vp, C.c_longlong, vp, C.c_int, C.c_int, vp]
         _lib.crct_f32_scatter_first.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, vp]
         _lib.crct_linear_f32_batched.argtypes = [vp, C.c_int, vp]
+        _lib.crct_gemm_wgrad_grouped.argtypes = [vp, C.c_int, vp]
         _lib.crct_scale_rows.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp]
         _lib.crct_pool_mul_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
         _lib.crct_pool_mul_bwd.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
@@ -198,10 +199,10 @@ def _f32(t, what):
         raise CrctError(f'{what} must be float32, got {t.dtype}')
 
 
-def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None, aux=None, D2=None,
-         lda=None, ldb=None, ldd=None, ldaux=None, accumulate=0, split_k=0, block_n=0, dropout_p=0.0, seed=0,
-         max_ctas=0, dbg=None, cta_group=0, rows_dev=None, drop_rows=None):
-    """D[M,N] = epilogue(A·Bᵀ) — see include/crct_b200.h for operand majors.  fp32 operands select the check-mode kernel."""
+def gemm_args(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None, aux=None, D2=None,
+              lda=None, ldb=None, ldd=None, ldaux=None, accumulate=0, split_k=0, block_n=0, dropout_p=0.0, seed=0,
+              max_ctas=0, dbg=None, cta_group=0, rows_dev=None, drop_rows=None):
+    """crct_gemm_t for D[M,N] = epilogue(A·Bᵀ) — see include/crct_b200.h for operand majors (dtype checks included)."""
     f32 = _is32(A)
     if f32:
         for t, w in ((B, 'B'), (aux, 'aux'), (D2, 'D2'), (bias, 'bias'), (D, 'D')):
@@ -231,7 +232,19 @@ def gemm(A, B, D, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BIAS, bias=None
     if dbg is not None:
         for i, v in enumerate(dbg):
             a.dbg[i] = v
-    check((lib().crct_f32_gemm if f32 else lib().crct_gemm_bf16)(C.byref(a), stream_ptr()))
+    return a
+
+
+def gemm(A, B, D, **kw):
+    """D[M,N] = epilogue(A·Bᵀ).  fp32 operands select the check-mode kernel."""
+    a = gemm_args(A, B, D, **kw)
+    check((lib().crct_f32_gemm if _is32(A) else lib().crct_gemm_bf16)(C.byref(a), stream_ptr()))
+
+
+def gemm_wgrad_grouped(problems):
+    """Up to 8 weight-gradient problems (gemm_args(..., a_major=1, b_major=1, epilogue=EPI_F32, accumulate=1)) in one launch."""
+    arr = (GemmArgs * len(problems))(*problems)
+    check(lib().crct_gemm_wgrad_grouped(arr, len(problems), stream_ptr()))
 
 
 def cast_f32_to_bf16(src, dst):

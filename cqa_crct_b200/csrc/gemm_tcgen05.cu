@@ -555,6 +555,178 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// Grouped weight-gradient launch: up to MAXG independent problems dW_g[out,in] += dy_g^T x_g (both operands MN-major, fp32
+// split-K accumulation) through ONE persistent tile list.  A training step has 121 such GEMMs — four per text / visual layer
+// (QKV, attention output, FFN in, FFN out), none of them on the backward's critical path; launched one by one each pays its
+// own pipeline fill and tail (~5 us of a 14-33 us kernel) and its own wave quantisation (the 1900-row visual problems fill a
+// fraction of the SMs).  The host defers a layer's weight gradients and issues them together: same tile kernel, same
+// per-problem device-side K (`a_rows_dev`) and k-tail clearing, per-problem tensor maps indexed out of the kernel parameters.
+// ---------------------------------------------------------------------------------------------
+constexpr int MAXG = 8;
+struct GroupParams {
+    int count;
+    int tile_start[MAXG + 1];            // prefix sums of tiles per problem
+    KParams p[MAXG];
+};
+struct GroupMaps {
+    CUtensorMap a[MAXG];
+    CUtensorMap b[MAXG];
+};
+
+struct GroupTile {
+    int g, m0, n0, kb0, kb1, kb_total, k_tail;
+};
+// tile index -> problem, tile origin and k-block range (device-side K resolved here: every role derives the same values)
+template <int BN>
+__device__ __forceinline__ GroupTile group_tile(const GroupParams& gp, int tile) {
+    GroupTile t;
+    int g = 0;
+    while (g + 1 < gp.count && tile >= gp.tile_start[g + 1]) ++g;
+    const KParams& P = gp.p[g];
+    const int local = tile - gp.tile_start[g];
+    int K = P.K;
+    if (P.a_rows_dev != nullptr) K = max(1, min(__ldg(P.a_rows_dev), P.K));
+    t.g = g;
+    t.kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+    t.k_tail = P.a_rows_dev != nullptr ? K % BLOCK_K : 0;
+    const int kbps = (t.kb_total + P.split_k - 1) / P.split_k;
+    const int ks = local % P.split_k, mn = local / P.split_k;
+    t.m0 = (mn / P.num_n_tiles) * BLOCK_M;
+    t.n0 = (mn % P.num_n_tiles) * BN;
+    t.kb0 = ks * kbps;
+    t.kb1 = min(t.kb_total, t.kb0 + kbps);
+    return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_wgrad_grouped_kernel(const __grid_constant__ GroupMaps tm, const __grid_constant__ GroupParams gp) {
+    using C = Cfg<BN>;
+    constexpr int EPI = CRCT_EPI_F32;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - raw_addr);
+    const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
+    auto smem_a = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
+    auto smem_b = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES + C::A_BYTES; };
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * C::STAGES + i); };
+    auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * C::STAGES + 2 + i); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(tfull_bar(i), 1);
+            ptx::mbar_init(tempty_bar(i), NUM_EPI_WARPS);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
+    const int total = gp.tile_start[gp.count];
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const GroupTile t = group_tile<BN>(gp, tile);
+                for (int kb = t.kb0; kb < t.kb1; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    const int k0 = kb * BLOCK_K;
+#pragma unroll
+                    for (int j = 0; j < BLOCK_M / 64; ++j)
+                        ptx::tma_load_2d(smem_a(stage) + j * (BLOCK_K * 128), &tm.a[t.g], full_bar(stage), t.m0 + j * 64, k0);
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        ptx::tma_load_2d(smem_b(stage) + j * (BLOCK_K * 128), &tm.b[t.g], full_bar(stage), t.n0 + j * 64, k0);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp walks the loop: any problem may have a partial last k-block) =====================
+        constexpr uint32_t idesc = make_idesc<BN, true, true>();
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const GroupTile t = group_tile<BN>(gp, tile);
+            if (t.kb0 >= t.kb1) continue;
+            const KParams& P = gp.p[t.g];
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            ++it;
+            ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = t.kb0; kb < t.kb1; ++kb) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::tc_fence_after();
+                if (t.k_tail != 0 && kb == t.kb_total - 1) {
+                    zero_k_tail(gbase + (size_t)stage * C::STAGE_BYTES, BLOCK_M / 64, t.k_tail, lane);
+                    zero_k_tail(gbase + (size_t)stage * C::STAGE_BYTES + C::A_BYTES, BN / 64, t.k_tail, lane);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t adesc = make_smem_desc(smem_a(stage) + k * P.a_kstep, P.a_lbo, P.a_sbo);
+                        const uint64_t bdesc = make_smem_desc(smem_b(stage) + k * P.b_kstep, P.b_lbo, P.b_sbo);
+                        ptx::tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+                    }
+                    ptx::tc_commit(empty_bar(stage));
+                }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            }
+            if (lane == 0) ptx::tc_commit(tfull_bar(acc));
+            __syncwarp();
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue (fp32 red.add into the gradient arena) =====================
+        int it = 0;
+        AuxTile<BN, EPI> aux;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const GroupTile t = group_tile<BN>(gp, tile);
+            if (t.kb0 >= t.kb1) continue;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            ++it;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            epilogue_tile<BN, EPI>(gp.p[t.g], tmem_base + (uint32_t)(acc * BN), t.m0, t.n0, warp, lane, nullptr, aux, false, 0, 0);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.  Each CTA stages its own
 // 128 rows of A and only HALF of the B tile (BN/2 rows); one tcgen05.mma.cta_group::2 (M = 256) issued by the leader
 // CTA drives both SMs' tensor cores and reads B from both shared memories.  Per SM and per k-block that is 32 KB of TMA
@@ -977,4 +1149,72 @@ extern "C" CRCT_API int crct_gemm_bf16(const crct_gemm_t* a, crct_stream_t strea
     if (bn == 256) return dispatch<256>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
     if (bn == 192) return dispatch<192>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
     return dispatch<128>(a->a_major, a->b_major, a->epilogue, tmA, tmB, p, grid, st);
+}
+
+// Grouped weight gradients (see gemm_wgrad_grouped_kernel): `count` problems in the wgrad form of crct_gemm_bf16
+// (a_major = b_major = 1, CRCT_EPI_F32, accumulate = 1), one launch.
+extern "C" CRCT_API int crct_gemm_wgrad_grouped(const crct_gemm_t* probs, int count, crct_stream_t stream) {
+    if (!probs || count <= 0 || count > MAXG) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_wgrad_grouped: 1 .. %d problems", MAXG);
+    const int sms = crct_num_sms();
+    if (sms <= 0) return CRCT_ERR_CUDA;
+    constexpr int BN = 256;
+    long work = 0;
+    int kb_eff[MAXG], mn[MAXG];
+    for (int g = 0; g < count; ++g) {
+        const crct_gemm_t* a = &probs[g];
+        if (!a->A || !a->B || !a->D) CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_wgrad_grouped: null pointer in problem %d", g);
+        if (!a->a_major || !a->b_major || a->epilogue != CRCT_EPI_F32 || !a->accumulate)
+            CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_wgrad_grouped: problem %d is not in the weight-gradient form (a_major = b_major = 1, CRCT_EPI_F32, accumulate)", g);
+        if (a->M <= 0 || a->N <= 0 || a->K <= 0 || (a->N % 8)) CRCT_FAIL(CRCT_ERR_SHAPE, "crct_gemm_wgrad_grouped: bad shape in problem %d", g);
+        if ((a->lda % 8) || (a->ldb % 8) || (a->ldd % 4) || (((uintptr_t)a->A | (uintptr_t)a->B | (uintptr_t)a->D) & 15))
+            CRCT_FAIL(CRCT_ERR_ARG, "crct_gemm_wgrad_grouped: alignment of problem %d", g);
+        const int k_eff = (a->a_rows_dev && a->rows_hint > 0 && a->rows_hint < a->K) ? a->rows_hint : a->K;
+        kb_eff[g] = (k_eff + BLOCK_K - 1) / BLOCK_K;
+        mn[g] = ((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + BN - 1) / BN);
+        work += (long)mn[g] * kb_eff[g];
+    }
+    // k-blocks per tile such that the whole group is about two waves of equal-cost tiles (>= 4 k-blocks: pipeline depth)
+    long kb_target = (work + 2L * sms - 1) / (2L * sms);
+    if (kb_target < 4) kb_target = 4;
+    GroupParams gp;
+    GroupMaps tm;
+    memset(&gp, 0, sizeof(gp));
+    gp.count = count;
+    for (int g = 0; g < count; ++g) {
+        const crct_gemm_t* a = &probs[g];
+        const int kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
+        int split = a->split_k > 0 ? a->split_k : (int)((kb_eff[g] + kb_target / 2) / kb_target);
+        if (split < 1) split = 1;
+        if (split > kb_total) split = kb_total;
+        KParams& p = gp.p[g];
+        p.M = a->M; p.N = a->N; p.K = a->K;
+        p.num_n_tiles = (a->N + BN - 1) / BN;
+        p.split_k = split;
+        p.num_tiles = mn[g] * split;
+        p.kb_total = kb_total;
+        p.kb_per_split = (kb_total + split - 1) / split;
+        p.D = a->D; p.ldd = a->ldd; p.accumulate = 1;
+        p.a_lbo = BLOCK_K * 128; p.a_sbo = 1024; p.a_kstep = UMMA_K * 128;
+        p.b_lbo = BLOCK_K * 128; p.b_sbo = 1024; p.b_kstep = UMMA_K * 128;
+        p.a_rows_dev = a->a_rows_dev;
+        p.tile_m = BLOCK_M;
+        gp.tile_start[g + 1] = gp.tile_start[g] + p.num_tiles;
+        if (int rc = make_tmap(&tm.a[g], a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BLOCK_K)) return rc;
+        if (int rc = make_tmap(&tm.b[g], a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K)) return rc;
+    }
+    for (int g = count; g < MAXG; ++g) { tm.a[g] = tm.a[0]; tm.b[g] = tm.b[0]; gp.tile_start[g + 1] = gp.tile_start[count]; }
+    const int total = gp.tile_start[count];
+    int grid = total < sms ? total : sms;
+    if (total > sms) {
+        const int waves = (total + sms - 1) / sms;
+        grid = (total + waves - 1) / waves;
+    }
+    auto kern = gemm_wgrad_grouped_kernel<BN>;
+    static bool configured = false;
+    if (!configured) {
+        CRCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+        configured = true;
+    }
+    CRCT_CUDA(crct_launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), Cfg<BN>::SMEM_BYTES, as_stream(stream), tm, gp));
+    return CRCT_OK;
 }

@@ -231,6 +231,8 @@ class VisualDialogEncoder(nn.Module):
         self._side_stream = None
         self._wg_stream = None
         self._wg_hold = []
+        self._wg_pending = []                # deferred weight-gradient problems [(crct_gemm_t, operands, producer stream)]
+        self.group_wgrads = bool(params.get('group_wgrads', True))
         self._tail = {}                      # hidden width -> (last pre-LayerNorm sum, its LayerNorm): read by the heads
         self.train()                         # encoder_decorator.py:17
 
@@ -408,13 +410,44 @@ class VisualDialogEncoder(nn.Module):
         """gW[out,in] += dy^T x  (fp32 accumulate, split-K) and, when `gb` is given, gb += colsum(dy); `n`: device row count."""
         rows, No = dy.shape
         Ki = x.shape[1]
+        kw = dict(M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, lda=dy.stride(0), ldb=x.stride(0), ldd=Ki,
+                  rows_dev=n)
+        if self.group_wgrads and not self.fp32:
+            # deferred: a layer's weight gradients go out together as ONE grouped launch (crct_gemm_wgrad_grouped)
+            if gb is not None:
+                with self._wg(dy):
+                    L.colsum_bf16(dy, gb, rows_dev=n)
+            self._wg_pending.append((L.gemm_args(dy, x, gW, **kw), (dy, x), torch.cuda.current_stream(dy.device)))
+            if len(self._wg_pending) >= 8:
+                self._wgrad_flush()
+            return
         with self._wg(dy, x):
             if gb is not None:
                 L.colsum_bf16(dy, gb, rows_dev=n)
-            L.gemm(dy, x, gW, M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, lda=dy.stride(0),
-                   ldb=x.stride(0), ldd=Ki, rows_dev=n)
+            L.gemm(dy, x, gW, **kw)
+
+    def _wgrad_flush(self):
+        """Issue the deferred weight gradients as one grouped launch on the weight-gradient stream, ordered after everything their
+        producer streams have enqueued so far."""
+        if not self._wg_pending:
+            return
+        pend, self._wg_pending = self._wg_pending, []
+        args = [a for a, _, _ in pend]
+        if not self.overlap_streams:
+            L.gemm_wgrad_grouped(args)
+            return
+        dev = pend[0][1][0].device
+        if self._wg_stream is None or self._wg_stream.device != dev:
+            self._wg_stream = torch.cuda.Stream(device=dev)
+        for cur in {id(c): c for _, _, c in pend}.values():
+            self._wg_stream.wait_stream(cur)
+        with torch.cuda.stream(self._wg_stream):
+            L.gemm_wgrad_grouped(args)
+        for _, tensors, cur in pend:
+            self._wg_hold.append((tensors, cur))       # operands stay referenced until the chain has joined the stream
 
     def _wgrad_join(self):
+        self._wgrad_flush()
         if self._wg_hold:
             for cur in {id(c): c for _, c in self._wg_hold}.values():
                 cur.wait_stream(self._wg_stream)
@@ -494,6 +527,7 @@ class VisualDialogEncoder(nn.Module):
         Wqkv = self.arena.fused(self._wflat(), mods, '.weight')
         dx = torch.empty_like(dy)
         L.gemm(dqkv, Wqkv, dx, M=M, N=H, K=3 * H, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dz1, rows_dev=rw.n)
+        self._wgrad_flush()                # this layer's four weight gradients: one launch
         return dx
 
     def _co_layer_fwd(self, v, t, rv, rt, pre, layer, keep, lanes):
@@ -580,6 +614,7 @@ class VisualDialogEncoder(nn.Module):
         dt = torch.empty_like(dyt)
         L.gemm(dqkv2, self.arena.fused(self._wflat(), m2, '.weight'), dt, M=Mt, N=H, K=ld, b_major=1, epilogue=L.EPI_BIAS_RES, aux=dzt,
                rows_dev=rt.n)
+        self._wgrad_flush()                # the block's eight weight gradients (both streams): one launch
         return dv, dt
 
     # ------------------------------------------------------------------ heads (fp32, CUDA cores)

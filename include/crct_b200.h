@@ -92,6 +92,12 @@ typedef struct {
 } crct_gemm_t;
 
 int crct_gemm_bf16(const crct_gemm_t* args, crct_stream_t stream);
+/* Up to 8 independent weight-gradient problems (the wgrad form above: a_major = b_major = 1, CRCT_EPI_F32, accumulate = 1) in ONE
+ * launch: one persistent tile list over all problems, per-problem split-K chosen so that the group is about two waves of
+ * equal-cost tiles.  A layer's weight gradients (QKV, attention output, FFN in / out — backward of vilbert.py:388-390,420,446,463)
+ * are not on the backward's critical path; issued together they share one pipeline fill / tail and fill the SMs that the small
+ * (visual-stream) problems leave idle.  `split_k` of a problem > 0 overrides the choice; `a_rows_dev` / `rows_hint` as above. */
+int crct_gemm_wgrad_grouped(const crct_gemm_t* problems, int count, crct_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4  row kernels (HBM-bound, one warp per row, fp32 statistics).  Row width H: multiple of 8, <= 1024.

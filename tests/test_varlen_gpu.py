@@ -143,6 +143,54 @@ def test_gemm_device_row_count_wgrad(rows, No, Ki, valid, split):
     assert relmax(gb, dy[:valid].float().sum(0)) < 1e-4
 
 
+GROUPS = {
+    'text_layer': [(9920, 2304, 768, 6899), (9920, 768, 768, 6899), (9920, 3072, 768, 6899), (9920, 768, 3072, 6899)],
+    'visual_layer': [(3520, 3072, 1024, 1903), (3520, 1024, 1024, 1903), (3520, 1024, 1024, None), (3520, 1024, 1024, 1903)],
+    'co_block': [(9920, 1024, 768, 6848), (3520, 2048, 1024, 1903), (9920, 768, 1024, 6848), (3520, 1024, 1024, 1903),
+                 (9920, 3072, 768, 6848), (9920, 768, 3072, 6848), (3520, 1024, 1024, 1903), (3520, 1024, 1024, 1903)],
+    'ragged': [(992, 256, 128, 3), (1000, 576, 192, 617), (128, 128, 64, None), (37, 64, 72, 1)],
+    'single': [(992, 768, 3072, 64)],
+}
+
+
+@pytest.mark.parametrize('name', sorted(GROUPS))
+@pytest.mark.parametrize('split', [0, 3])
+def test_gemm_wgrad_grouped_matches_separate_launches(name, split):
+    """crct_gemm_wgrad_grouped: up to 8 weight-gradient problems of different shapes / device-side row counts in ONE launch give what
+    the same problems give one by one (fp32 accumulation on top of existing contents, NaN rows past the count contribute nothing)."""
+    torch.manual_seed(len(name))
+    probs, keep = [], []
+    for i, (rows, No, Ki, valid) in enumerate(GROUPS[name]):
+        dy, x = bf(torch.randn(rows, No, device=DEV) * 0.5), bf(torch.randn(rows, Ki, device=DEV) * 0.5)
+        n = None
+        if valid is not None:
+            dy[valid:] = float('nan')
+            x[valid:] = float('nan')
+            n = torch.tensor([valid], dtype=torch.int32, device=DEV)
+            n.hint = valid
+        v = rows if valid is None else valid
+        ref = dy[:v].float().t() @ x[:v].float()
+        dW = torch.full((No, Ki), float(i + 1), device=DEV)
+        probs.append(L.gemm_args(dy, x, dW, M=No, N=Ki, K=rows, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, split_k=split,
+                                 lda=No, ldb=Ki, ldd=Ki, rows_dev=n))
+        keep.append((dy, x, n, dW, ref, i + 1))
+    L.gemm_wgrad_grouped(probs)
+    for dy, x, n, dW, ref, base in keep:
+        assert bool(torch.isfinite(dW).all())
+        assert relmax(dW - base, ref) < 1e-4
+
+
+def test_gemm_wgrad_grouped_rejects_other_forms():
+    dy, x = bf(torch.randn(256, 128, device=DEV)), bf(torch.randn(256, 64, device=DEV))
+    dW = torch.zeros(128, 64, device=DEV)
+    ok = L.gemm_args(dy, x, dW, M=128, N=64, K=256, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=1, lda=128, ldb=64, ldd=64)
+    with pytest.raises(L.CrctError):
+        L.gemm_wgrad_grouped([ok] * 9)
+    bad = L.gemm_args(dy, x, dW, M=128, N=64, K=256, a_major=1, b_major=1, epilogue=L.EPI_F32, accumulate=0, lda=128, ldb=64, ldd=64)
+    with pytest.raises(L.CrctError):
+        L.gemm_wgrad_grouped([bad])
+
+
 @pytest.mark.parametrize('rows,H,valid', [(9920, 768, 6899), (3520, 1024, 1903), (37, 192, 5)])
 def test_layernorm_fp32_z_and_device_row_count(rows, H, valid):
     torch.manual_seed(rows)
