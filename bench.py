@@ -207,7 +207,7 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
     config = describe(name, B, T, R, train, args.gpus)
     dev = torch.device('cuda', local_rank)
     params = default_params(CFG, device=str(dev), max_seq_len=T, max_vis_features=R, L1=True, overlap_optimizer=args.opt_overlap,
-                            varlen=not args.padded, pipeline_optimizer=not args.no_opt_pipeline)
+                            varlen=not args.padded, pipeline_optimizer=not args.no_opt_pipeline, shard_optimizer=not args.no_shard_optimizer)
     torch.manual_seed(0)
     enc = VisualDialogEncoder(params).to(dev)
     model = DistributedDataParallel(enc, bucket_cap_mb=args.bucket_mb) if world > 1 else enc
@@ -243,6 +243,10 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
         from cqa_crct_b200.graph import GraphedTrainStep
         gstep = GraphedTrainStep(model, opt, params, resident[0], scheduler=sched, warmup_steps=2)
         captured_launches = gstep.launches_per_step
+        if world > 1:
+            config['exchange'] = ('per bucket: reduce-scatter (fp32 avg) -> AdamW on the 1/N shard -> all-gather of the fp32 masters -> bf16 re-cast, on a side stream'
+                                  if gstep.shard_optimizer else 'per bucket: all-reduce (fp32 avg) -> replicated AdamW' if gstep.pipeline_optimizer
+                                  else 'per bucket: all-reduce (fp32 avg); whole-arena AdamW after the last one')
 
     def step(batch, read_loss=False):
         if gstep is not None:                                # captured step: copy inputs into the static buffers, replay
@@ -303,7 +307,7 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = (L.LAUNCHES - l0) if gstep is None else captured_launches * steps
+        launches = (L.LAUNCHES - l0) + (0 if gstep is None else captured_launches * steps)      # replayed graph launches + what ran outside the graphs
         clocks = sampler.stop() if sampler else None
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -508,6 +512,7 @@ def main():
     ap.add_argument('--opt-overlap', action='store_true', help='run AdamW under the backward instead of after it (A/B; measured slower)')
     ap.add_argument('--bucket-mb', type=float, default=25.0, help='gradient all-reduce bucket size (fp32 MB)')
     ap.add_argument('--trace', default=None, help='N > 1: write the per-bucket timeline of one step (JSON) to this path')
+    ap.add_argument('--no-shard-optimizer', action='store_true', help='N > 1: all-reduce + replicated AdamW instead of reduce-scatter / sharded AdamW / all-gather (A/B)')
     ap.add_argument('--no-opt-pipeline', action='store_true', help='N > 1: whole-arena AdamW after the last all-reduce (A/B)')
     ap.add_argument('--no-graph', action='store_true', help='enqueue every launch from Python instead of replaying the captured step')
     args = ap.parse_args()

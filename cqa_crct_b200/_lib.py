@@ -88,7 +88,7 @@ class LossArgs(C.Structure):
 class AdamWArgs(C.Structure):
     _fields_ = [('w', vp), ('g', vp), ('m', vp), ('v', vp), ('w_bf16', vp), ('group_of_block64', vp), ('n', C.c_size_t),
                 ('lr', f32 * 4), ('weight_decay', f32 * 4), ('beta1', f32), ('beta2', f32), ('eps', f32), ('step', i32),
-                ('grad_scale', f32), ('dyn', vp)]
+                ('grad_scale', f32), ('dyn', vp), ('group_offset', C.c_size_t)]
 
 
 class SelectArgs(C.Structure):
@@ -453,8 +453,9 @@ def bump_salt(salt, snapshot=None):
     check(lib().crct_bump_salt_to(ptr(salt), ptr(snapshot), stream_ptr()))
 
 
-def adamw(w, g, m, v, w_bf16, group, n, lr4, wd4, beta1, beta2, eps, step, grad_scale=1.0, dyn=None):
+def adamw(w, g, m, v, w_bf16, group, n, lr4, wd4, beta1, beta2, eps, step, grad_scale=1.0, dyn=None, group_offset=0):
     a = AdamWArgs()
+    a.group_offset = group_offset
     a.w, a.g, a.m, a.v, a.w_bf16, a.group_of_block64, a.n = ptr(w), ptr(g), ptr(m), ptr(v), ptr(w_bf16), ptr(group), n
     for i in range(4):
         a.lr[i], a.weight_decay[i] = lr4[i], wd4[i]

@@ -253,10 +253,11 @@ struct AdamParams {
     float lr[4], wd[4];
     float beta1, beta2, eps, bc1, bc2_sqrt, gscale;
     const float* dyn;          // device {lr[4], bc1, bc2_sqrt} overriding the by-value fields (graph replay)
+    size_t group_offset;
 };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams p) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (size_t)gridDim.x * blockDim.x) {
-        const int grp = p.group ? (p.group[i >> 6] & 3) : 0;
+        const int grp = p.group ? (p.group[(i + p.group_offset) >> 6] & 3) : 0;
         const float lr = p.dyn ? __ldg(p.dyn + grp) : p.lr[grp], wd = p.wd[grp];
         const float bc1 = p.dyn ? __ldg(p.dyn + 4) : p.bc1, bc2_sqrt = p.dyn ? __ldg(p.dyn + 5) : p.bc2_sqrt;
         const float gr = p.g[i] * p.gscale;
@@ -393,6 +394,7 @@ extern "C" CRCT_API int crct_adamw(const crct_adamw_t* a, crct_stream_t s) {
     p.bc2_sqrt = sqrtf(1.f - powf(a->beta2, (float)a->step));
     p.gscale = a->grad_scale;
     p.dyn = a->dyn;
+    p.group_offset = a->group_offset;
     size_t blocks = (a->n + 255) / 256;
     const size_t cap = (size_t)crct_num_sms() * 8;
     if (blocks > cap) blocks = cap;

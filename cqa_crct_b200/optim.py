@@ -110,16 +110,19 @@ class FusedAdamW:
                 self.betas[0], self.betas[1], self.eps, 1, grad_scale, dyn=self.dyn)
         arena.mark_bf16_fresh()
 
-    def step_range_captured(self, lo: int, hi: int, grad_scale: float = 1.0):
-        """The same update restricted to arena elements [lo, hi) (multiples of 64), scalars from `self.dyn`: lets the step
-        run the optimizer for the part of the arena whose gradients are final while the backward is still producing the
-        rest (AdamW is HBM-bound, the backward's GEMMs are tensor-bound)."""
+    def step_range_captured(self, lo: int, hi: int, grad_scale: float = 1.0, refresh_bf16: bool = True):
+        """The same update restricted to arena elements [lo, hi), scalars from `self.dyn`: lets the step run the optimizer for the
+        part of the arena whose gradients are final while the backward is still producing the rest, and lets a data-parallel rank
+        update only ITS SHARD of a bucket (graph.py).  `lo` need not be a multiple of 64: the (lr, weight decay) table is indexed
+        through `group_offset`."""
         arena = self.enc.arena
         hi = min(hi, self.n)
-        if lo % 64 or hi % 64 or hi <= lo:
-            raise ValueError(f'optimizer range [{lo}, {hi}) must be a non-empty multiple of 64 elements')
-        L.adamw(arena.w32[lo:hi], arena.g32[lo:hi], self.m[lo:hi], self.v[lo:hi], arena.w16[lo:hi], self.group[lo // 64:hi // 64], hi - lo,
-                self.base_lr, self.wd, self.betas[0], self.betas[1], self.eps, 1, grad_scale, dyn=self.dyn)
+        if lo < 0 or hi <= lo:
+            raise ValueError(f'optimizer range [{lo}, {hi}) is empty')
+        b0 = lo // 64
+        L.adamw(arena.w32[lo:hi], arena.g32[lo:hi], self.m[lo:hi], self.v[lo:hi], arena.w16[lo:hi] if refresh_bf16 else None,
+                self.group[b0:(hi + 63) // 64], hi - lo, self.base_lr, self.wd, self.betas[0], self.betas[1], self.eps, 1, grad_scale,
+                dyn=self.dyn, group_offset=lo - b0 * 64)
 
     # ---- checkpoint layout (f4): what `torch.optim.AdamW(...).state_dict()` gives for `get_optimizer`'s grouping
     def _named(self):

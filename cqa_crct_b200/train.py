@@ -219,6 +219,8 @@ def train(gpu: int, params: dict) -> dict:
                 start_t = time.time()
         # ---- end of epoch: checkpoint (train.py:282-291), then evaluation on the (synthetic) validation questions
         step_iter_id = start_iter_id + num_step_iterations
+        if gstep is not None and params['save_path']:
+            gstep.consolidate_optimizer_state()        # sharded optimizer: the Adam moments live on their owner ranks (collective)
         if params['rank'] == 0 and params['save_path']:
             path = ckpt.save_checkpoint(params['save_path'], cont_epoch + epoch_id, step_iter_id, crct_model, optimizer, scheduler)
             written.append(path)

@@ -349,6 +349,8 @@ typedef struct {
     int32_t step;                       /* 1-based */
     float grad_scale;                   /* e.g. 1/world_size after a sum all-reduce */
     const float* dyn;                   /* optional DEVICE array {lr[0..3], 1-beta1^t, sqrt(1-beta2^t)} overriding lr/step (CUDA-graph replay) */
+    size_t group_offset;                /* element i belongs to block (i + group_offset) / 64 of group_of_block64: lets a data-parallel
+                                           rank update ITS SHARD of a gradient bucket (a range that starts inside a 64-element block) */
 } crct_adamw_t;
 int crct_adamw(const crct_adamw_t* args, crct_stream_t stream);
 
