@@ -242,8 +242,9 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, int row, int co
 
 // ---- CRCT_EPI_BIAS_RES_F32: z (fp32) = dropout(acc + bias) + aux (fp32).  The residual stream stays fp32 end to end: the
 // LayerNorm writes its output twice (bf16 = the next GEMM's operand, fp32 = the next residual), and this epilogue adds the
-// fp32 copy.  16 fp32 columns per lane and step = 64 bytes: held one STEP ahead inside a tile and — step 0 only — one TILE
-// ahead (the tile-ahead scheme of the bf16 aux would need 64 registers per lane at BN = 256).
+// fp32 copy.  16 fp32 columns per lane and step = 64 bytes.  Like the bf16 aux it is fetched ONE TILE AHEAD (BN/4 registers per
+// lane: 48 at BN = 192): with the first version's one-STEP-ahead loads every step waited a DRAM round trip (ncu: 27 us for the
+// K = 768 out-projection against 15 us with the bias epilogue — three exposed ~1.5 us latencies per tile).
 __device__ __forceinline__ void aux32_load(const KParams& p, int row, int col, float (&f)[EPI_COLS]) {
 #pragma unroll
     for (int i = 0; i < EPI_COLS; ++i) f[i] = 0.f;
@@ -303,7 +304,11 @@ struct AuxTile {
 };
 template <int BN>
 struct AuxTile<BN, CRCT_EPI_BIAS_RES_F32> {
-    float f[EPI_COLS];
+    // BN <= 192: the lane's whole row slice of the tile (BN/4 fp32 columns = 48 registers), fetched a tile ahead.
+    // BN = 256 (64 registers: spills under the 96-register cap of a 640-thread CTA): step 0 a tile ahead, the rest a step ahead.
+    static constexpr bool TILE_AHEAD = BN <= 192;
+    static constexpr int HELD = TILE_AHEAD ? EpiGeom<BN>::STEPS : 1;
+    float f[HELD][EPI_COLS];
 };
 
 // aux (residual / multiplier) is fetched ONE TILE AHEAD: a lane keeps its row's BN/4 columns of the current tile in
@@ -314,7 +319,8 @@ __device__ __forceinline__ void aux_load_tile(const KParams& p, int m0, int n0, 
     const int row = m0 + (warp & 3) * 32 + lane;
     const int cbase = n0 + ((warp - EPI_WARP0) >> 2) * (BN / 4);
     if constexpr (EPI == CRCT_EPI_BIAS_RES_F32) {
-        aux32_load(p, row, cbase, aux.f);
+#pragma unroll
+        for (int c = 0; c < AuxTile<BN, EPI>::HELD; ++c) aux32_load(p, row, cbase + c * EPI_COLS, aux.f[c]);
     } else {
 #pragma unroll
         for (int c = 0; c < EpiGeom<BN>::STEPS; ++c) prefetch_aux<EPI>(p, row, cbase + c * EPI_COLS, aux.r[c]);
@@ -357,19 +363,31 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
     uint32_t v[2][EPI_COLS];
     ptx::tc_ld_32x16(taddr, v[0]);
     if constexpr (EPI == CRCT_EPI_BIAS_RES_F32) {
-        float ax[2][EPI_COLS];
+        if constexpr (AuxTile<BN, EPI>::TILE_AHEAD) {
 #pragma unroll
-        for (int i = 0; i < EPI_COLS; ++i) ax[0][i] = aux.f[i];
+            for (int c = 0; c < STEPS; ++c) {
+                const int cc = cbase + c * EPI_COLS;
+                ptx::tc_wait_ld();
+                reg_fence16(v[c & 1]);
+                if (c + 1 < STEPS) ptx::tc_ld_32x16(taddr + (uint32_t)((c + 1) * EPI_COLS), v[(c + 1) & 1]);
+                if (n0 + cc < p.N) epilogue_chunk_res32(p, row, n0 + cc, v[c & 1], bias_s + cc, aux.f[c], seed, drow);
+                if (has_next) aux32_load(p, rown, n0n + cc, aux.f[c]);                         // the same registers: next tile's step c
+            }
+        } else {
+            float ax[2][EPI_COLS];
 #pragma unroll
-        for (int c = 0; c < STEPS; ++c) {
-            const int cc = cbase + c * EPI_COLS;
-            if (c + 1 < STEPS) aux32_load(p, row, n0 + cc + EPI_COLS, ax[(c + 1) & 1]);        // one step ahead
-            ptx::tc_wait_ld();
-            reg_fence16(v[c & 1]);
-            if (c + 1 < STEPS) ptx::tc_ld_32x16(taddr + (uint32_t)((c + 1) * EPI_COLS), v[(c + 1) & 1]);
-            if (n0 + cc < p.N) epilogue_chunk_res32(p, row, n0 + cc, v[c & 1], bias_s + cc, ax[c & 1], seed, drow);
+            for (int i = 0; i < EPI_COLS; ++i) ax[0][i] = aux.f[0][i];
+#pragma unroll
+            for (int c = 0; c < STEPS; ++c) {
+                const int cc = cbase + c * EPI_COLS;
+                if (c + 1 < STEPS) aux32_load(p, row, n0 + cc + EPI_COLS, ax[(c + 1) & 1]);    // one step ahead
+                ptx::tc_wait_ld();
+                reg_fence16(v[c & 1]);
+                if (c + 1 < STEPS) ptx::tc_ld_32x16(taddr + (uint32_t)((c + 1) * EPI_COLS), v[(c + 1) & 1]);
+                if (n0 + cc < p.N) epilogue_chunk_res32(p, row, n0 + cc, v[c & 1], bias_s + cc, ax[c & 1], seed, drow);
+            }
+            if (has_next) aux32_load(p, rown, n0n + cbase, aux.f[0]);                          // step 0 of the next tile
         }
-        if (has_next) aux32_load(p, rown, n0n + cbase, aux.f);                                 // step 0 of the next tile
     } else {
 #pragma unroll
         for (int c = 0; c < STEPS; ++c) {
