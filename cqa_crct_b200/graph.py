@@ -86,6 +86,8 @@ class GraphedTrainStep:
         self._scratch = torch.zeros(8, dtype=torch.float32, device=dev)
         self._scratch16 = torch.zeros(8, dtype=torch.bfloat16, device=dev)
         self._opt_stream = torch.cuda.Stream(device=dev) if (self.overlap_optimizer or self.shard_optimizer) else None
+        self._cast_stream = torch.cuda.Stream(device=dev) if self.shard_optimizer else None
+        self.shard_chunk = int(params.get('shard_chunk_mb', 48.0) * (1 << 20) / 4)       # elements per reduce-scatter / all-gather
         self._opt_pending = None
         self.opt_chunk = int(params.get('optimizer_chunk', 24 << 20))      # elements per optimizer launch (~0.13 ms of HBM time)
         side = torch.cuda.Stream(device=dev)
@@ -154,37 +156,63 @@ class GraphedTrainStep:
         slo, shi = self.shard_bounds(lo, hi)
         return dist.reduce_scatter_tensor(g[slo:shi], g[lo:hi], op=dist.ReduceOp.AVG, group=self.ddp.pg, async_op=True), lo, hi
 
+    def _chunks(self, lo, hi):
+        """A bucket as exchange units of <= `shard_chunk` elements (multiples of 64 * world): the last bucket of the backward is the
+        94 MB word-embedding gradient — in one piece its reduce-scatter, update, all-gather and re-cast would run strictly one
+        after the other behind the backward; in pieces they pipeline."""
+        unit = 64 * self.world
+        step = max(unit, self.shard_chunk // unit * unit)
+        n = max(1, -(-(hi - lo) // step))
+        per = -(-(hi - lo) // n)
+        per = -(-per // unit) * unit
+        out, a = [], lo
+        while a < hi:
+            b = min(hi, a + per)
+            if hi - b < unit:
+                b = hi
+            out.append((a, b))
+            a = b
+        return out
+
     def _update_shard(self, work, lo, hi, ev=None):
-        """On the optimizer stream: wait for the bucket's reduce-scatter, AdamW on the own shard, all-gather the masters, re-cast."""
+        """Optimizer stream: wait for the piece's reduce-scatter, AdamW on the own shard, start the all-gather of the masters.
+        Cast stream: wait for that all-gather, re-cast the piece's bf16 operand copy — so the next piece's AdamW does not queue behind
+        this piece's gather."""
         from . import _lib as L
         arena = self.enc.arena
         slo, shi = self.shard_bounds(lo, hi)
         with torch.cuda.stream(self._opt_stream):
             work.wait()
             self.opt.step_range_captured(slo, shi, refresh_bf16=False)
-            dist.all_gather_into_tensor(arena.w32[lo:hi], arena.w32[slo:shi], group=self.ddp.pg, async_op=True).wait()
+            gather = dist.all_gather_into_tensor(arena.w32[lo:hi], arena.w32[slo:shi], group=self.ddp.pg, async_op=True)
+        with torch.cuda.stream(self._cast_stream):
+            gather.wait()
             L.cast_f32_to_bf16(arena.w32[lo:hi], arena.w16[lo:hi])
             if ev is not None:
                 ev.record()
 
     def _run_sharded(self, units, on_segment=None, on_bucket=None):
-        """`units` yields a bucket (lo, hi) right after the work that finishes it has been enqueued on the compute stream.  A bucket's
-        update chain is enqueued one bucket late, so that the NEXT bucket's reduce-scatter sits ahead of this one's all-gather on
+        """`units` yields a bucket (lo, hi) right after the work that finishes it has been enqueued on the compute stream.  A piece's
+        update chain is enqueued one piece late, so that the NEXT piece's reduce-scatter sits ahead of this one's all-gather on
         NCCL's (in-order) stream: the gradient exchange never waits behind a parameter gather."""
         cur = torch.cuda.current_stream()
         self._opt_stream.wait_stream(cur)
+        self._cast_stream.wait_stream(cur)
         pend = []
         for bucket in units:
             if bucket is None:
                 continue
             if on_segment:
                 on_segment()
-            pend.append(self._scatter_bucket(*bucket))
-            while len(pend) > 1:
-                self._update_shard(*pend.pop(0), ev=on_bucket() if on_bucket else None)
+            for lo, hi in reversed(self._chunks(*bucket)):       # tail first, like the backward
+                pend.append(self._scatter_bucket(lo, hi))
+                while len(pend) > 1:
+                    self._update_shard(*pend.pop(0), ev=on_bucket(*pend[0][1:]) if on_bucket else None)
         while pend:
-            self._update_shard(*pend.pop(0), ev=on_bucket() if on_bucket else None)
+            item = pend.pop(0)
+            self._update_shard(*item, ev=on_bucket(*item[1:]) if on_bucket else None)
         cur.wait_stream(self._opt_stream)
+        cur.wait_stream(self._cast_stream)
         self.enc.arena.mark_bf16_fresh()
 
     def _replay_units(self):
@@ -197,10 +225,11 @@ class GraphedTrainStep:
         `FusedAdamW.state_dict()` saves — CRCT/train.py:283-288 writes the optimizer state on rank 0).  Collective: call on every rank."""
         if not self.shard_optimizer:
             return
-        for lo, hi in [b for _, b in self.segments if b is not None]:
-            slo, shi = self.shard_bounds(lo, hi)
-            for t in (self.opt.m, self.opt.v):
-                dist.all_gather_into_tensor(t[lo:hi], t[slo:shi], group=self.ddp.pg)
+        for bucket in [b for _, b in self.segments if b is not None]:
+            for lo, hi in self._chunks(*bucket):
+                slo, shi = self.shard_bounds(lo, hi)
+                for t in (self.opt.m, self.opt.v):
+                    dist.all_gather_into_tensor(t[lo:hi], t[slo:shi], group=self.ddp.pg)
 
     def _eager_step(self):
         self.opt.zero_grad()
@@ -296,8 +325,10 @@ class GraphedTrainStep:
             def seg():
                 e = ev(); e.record(); seg_end.append(e)
 
-            def bucket_ev():
-                e = ev(); ready.append(e)
+            sizes = []
+
+            def bucket_ev(lo, hi):
+                e = ev(); ready.append(e); sizes.append((hi - lo) * 4 / 2 ** 20)
                 return e
             self._run_sharded(self._replay_units(), on_segment=seg, on_bucket=bucket_ev)
             t1 = ev(); t1.record()
@@ -306,7 +337,7 @@ class GraphedTrainStep:
                 self.sched.step()
             bk = [b for _, b in self.segments if b is not None]
             out = {'step_ms': t0.elapsed_time(t1), 'segment_end_ms': [t0.elapsed_time(e) for e in seg_end],
-                   'bucket_done_ms': [t0.elapsed_time(e) for e in ready], 'bucket_mb': [(hi - lo) * 4 / 2 ** 20 for lo, hi in bk],
+                   'bucket_done_ms': [t0.elapsed_time(e) for e in ready], 'bucket_mb': sizes,
                    'optimizer': 'sharded: reduce-scatter -> AdamW on 1/N -> all-gather -> bf16 cast, per bucket on a side stream'}
             out['backward_end_ms'] = out['segment_end_ms'][-1]
             out['exposed_ms'] = out['step_ms'] - out['backward_end_ms']

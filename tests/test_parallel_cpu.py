@@ -105,3 +105,23 @@ def test_block_ranges_tile_the_live_arena():
         for (lo, hi), (lo2, hi2) in zip(ranges, ranges[1:]):
             assert hi2 == lo, (lo, hi, lo2, hi2)
         assert ranges[-1][0] == 0 and ranges[0][1] == a.live_end
+
+
+def test_sharded_optimizer_pieces_and_shards_tile_every_bucket():
+    """Host arithmetic of the sharded optimizer (graph.GraphedTrainStep._chunks / shard_bounds): the exchange pieces of a bucket are
+    contiguous, cover it exactly, each splits evenly over the ranks, and the ranks' shards of a piece tile the piece."""
+    import types
+    from cqa_crct_b200.graph import GraphedTrainStep as G
+    for world in (2, 4, 8):
+        for chunk_mb in (1.0, 32.0):
+            for lo, hi in [(0, 64), (0, 64 * world), (128, 128 + 25140480), (320, 320 + 64 * world * 3 + 64), (0, 23440896 + 76800),
+                           (6400, 6400 + 20478976)]:
+                ranks = [types.SimpleNamespace(world=world, rank=r, shard_chunk=int(chunk_mb * (1 << 20) / 4)) for r in range(world)]
+                pieces = G._chunks(ranks[0], lo, hi)
+                assert pieces[0][0] == lo and pieces[-1][1] == hi and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+                assert all((b - a) % world == 0 and b > a for a, b in pieces)
+                assert all(b - a <= max(64 * world, ranks[0].shard_chunk) + 64 * world for a, b in pieces)
+                for a, b in pieces:
+                    shards = [G.shard_bounds(o, a, b) for o in ranks]
+                    assert shards[0][0] == a and shards[-1][1] == b and all(x[1] == y[0] for x, y in zip(shards, shards[1:]))
+                    assert len({s1 - s0 for s0, s1 in shards}) == 1
