@@ -87,7 +87,10 @@ class GraphedTrainStep:
         self._scratch16 = torch.zeros(8, dtype=torch.bfloat16, device=dev)
         self._opt_stream = torch.cuda.Stream(device=dev) if (self.overlap_optimizer or self.shard_optimizer) else None
         self._cast_stream = torch.cuda.Stream(device=dev) if self.shard_optimizer else None
-        self.shard_chunk = int(params.get('shard_chunk_mb', 48.0) * (1 << 20) / 4)       # elements per reduce-scatter / all-gather
+        # optional: exchange a bucket in pieces of <= shard_chunk_mb.  Off by default — measured at 8 GPUs (profiles/r02_ab_8gpu_exchange.txt):
+        # every extra collective costs ~0.1-0.2 ms of latency on NCCL's in-order stream, and behind the backward those latencies are
+        # exposed (26 pieces: 1.47 ms after the backward; 19 whole buckets: 1.07 ms)
+        self.shard_chunk = int(params.get('shard_chunk_mb', 0.0) * (1 << 20) / 4) or (1 << 62)
         self._opt_pending = None
         self.opt_chunk = int(params.get('optimizer_chunk', 24 << 20))      # elements per optimizer launch (~0.13 ms of HBM time)
         side = torch.cuda.Stream(device=dev)
@@ -157,9 +160,8 @@ class GraphedTrainStep:
         return dist.reduce_scatter_tensor(g[slo:shi], g[lo:hi], op=dist.ReduceOp.AVG, group=self.ddp.pg, async_op=True), lo, hi
 
     def _chunks(self, lo, hi):
-        """A bucket as exchange units of <= `shard_chunk` elements (multiples of 64 * world): the last bucket of the backward is the
-        94 MB word-embedding gradient — in one piece its reduce-scatter, update, all-gather and re-cast would run strictly one
-        after the other behind the backward; in pieces they pipeline."""
+        """A bucket as exchange units of <= `shard_chunk` elements (multiples of 64 * world); one unit unless params['shard_chunk_mb']
+        is set (see __init__ for the measurement)."""
         unit = 64 * self.world
         step = max(unit, self.shard_chunk // unit * unit)
         n = max(1, -(-(hi - lo) // step))
