@@ -62,12 +62,12 @@ def main():
     if len(sys.argv) > 2:
         open(sys.argv[2], 'w').write(text)
     if len(sys.argv) > 3:
-        g = [d for d in step if 'gemm_tcgen05' in d['name']]
+        g = [d for d in step if 'gemm_tcgen05' in d['name'] or 'gemm_wgrad_grouped' in d['name']]
         json.dump({'workload': 'train', 'gemm_launches_per_step': len(g),
                    'dram_bytes_per_launch': sum(d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0) for d in g) / max(1, len(g)),
                    'dram_bytes_read_per_step': sum(d.get('dram__bytes_read.sum', 0) for d in g), 'dram_bytes_written_per_step': sum(d.get('dram__bytes_write.sum', 0) for d in g),
                    'gemm_us_per_step_ncu': sum(d.get('gpu__time_duration.sum', 0) for d in g),
-                   'how': 'ncu launch list of one eager train step (tools/step_profile.py), dram__bytes_read.sum + dram__bytes_write.sum per gemm_tcgen05 launch'}, open(sys.argv[3], 'w'), indent=1)
+                   'how': 'ncu launch list of one eager train step (tools/step_profile.py), dram__bytes_read.sum + dram__bytes_write.sum per gemm_tcgen05 / gemm_wgrad_grouped launch'}, open(sys.argv[3], 'w'), indent=1)
 
 
 if __name__ == '__main__':
