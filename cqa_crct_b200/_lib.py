@@ -101,6 +101,27 @@ class ScoreArgs(C.Structure):
                 ('total', vp), ('Q', i32)]
 
 
+MAX_CONNECTIONS = 16
+
+
+class ConfigArgs(C.Structure):      # crct_config_t
+    _fields_ = [('hidden_size', i32), ('num_hidden_layers', i32), ('num_attention_heads', i32), ('intermediate_size', i32),
+                ('v_hidden_size', i32), ('v_num_hidden_layers', i32), ('v_num_attention_heads', i32), ('v_intermediate_size', i32),
+                ('v_feature_size', i32), ('bi_hidden_size', i32), ('bi_num_attention_heads', i32), ('max_position_embeddings', i32),
+                ('num_connections', i32), ('v_biattention_id', i32 * MAX_CONNECTIONS), ('t_biattention_id', i32 * MAX_CONNECTIONS),
+                ('l1', i32), ('tol_margin', f32)]
+
+
+class BatchArgs(C.Structure):       # crct_batch_t
+    _fields_ = [('tokens', vp), ('segments', vp), ('loc', vp), ('attention_mask', vp), ('image_feat', vp), ('image_loc', vp),
+                ('image_target', vp), ('image_mask', vp), ('R4', vp), ('group', vp), ('B', i32), ('Bq', i32), ('T', i32), ('R', i32),
+                ('attention_mask_kind', i32), ('image_mask_kind', i32), ('text_fill', f32), ('region_fill', f32)]
+
+
+class OutArgs(C.Structure):         # crct_out_t
+    _fields_ = [('logits', vp), ('reg_pred', vp), ('reg_loss', vp), ('reg_l1', vp), ('reg_dist', vp), ('scalars', vp)]
+
+
 # every symbol include/crct_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf16', 'crct_gemm_wgrad_grouped', 'crct_cast_f32_to_bf16',
            'crct_additive_mask', 'crct_layernorm_fwd', 'crct_layernorm_bwd', 'crct_layernorm_bwd_params', 'crct_colsum_bf16', 'crct_softmax_rows',
@@ -111,7 +132,8 @@ EXPORTS = ['crct_last_error', 'crct_version', 'crct_device_check', 'crct_gemm_bf
            'crct_layernorm_rows_f32', 'crct_row_map', 'crct_group_map', 'crct_gather_rows', 'crct_gather_rows_f32', 'crct_scatter_rows_f32', 'crct_fill_zero',
            'crct_f32_gemm', 'crct_f32_layernorm_fwd', 'crct_f32_layernorm_bwd', 'crct_f32_layernorm_bwd_params', 'crct_f32_attn_fwd',
            'crct_f32_attn_bwd', 'crct_f32_embed_text_fwd', 'crct_f32_embed_text_bwd', 'crct_f32_embed_vis_fwd', 'crct_f32_embed_vis_bwd',
-           'crct_f32_softmax_rows', 'crct_f32_gather_first', 'crct_f32_scatter_first']
+           'crct_f32_softmax_rows', 'crct_f32_gather_first', 'crct_f32_scatter_first',
+           'crct_create', 'crct_destroy', 'crct_bind_params', 'crct_workspace_bytes', 'crct_forward']
 
 _lib = None
 SALT = None         # device int64[1] tensor XOR-ed into every dropout seed on the device (set by the encoder); None = off
@@ -155,6 +177,12 @@ def lib():
         _lib.crct_pool_mul_bwd.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_uint64, vp, vp]
         _lib.crct_bump_salt.argtypes = [vp, vp]
         _lib.crct_bump_salt_to.argtypes = [vp, vp, vp]
+        _lib.crct_create.argtypes = [vp, vp]
+        _lib.crct_destroy.argtypes = [vp]
+        _lib.crct_bind_params.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+        _lib.crct_workspace_bytes.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.crct_workspace_bytes.restype = C.c_size_t
+        _lib.crct_forward.argtypes = [vp, vp, vp, vp, C.c_size_t, vp]
         for name in ('crct_gemm_bf16', 'crct_layernorm_bwd', 'crct_layernorm_bwd_params', 'crct_embed_text_fwd', 'crct_embed_text_bwd',
                      'crct_embed_vis_fwd', 'crct_embed_vis_bwd', 'crct_attn_fwd', 'crct_attn_bwd', 'crct_linear_f32',
                      'crct_hybrid_loss', 'crct_adamw', 'crct_select_answers', 'crct_score_answers', 'crct_f32_gemm', 'crct_f32_layernorm_bwd',

@@ -233,7 +233,7 @@ class VisualDialogEncoder(nn.Module):
         self._wg_hold = []
         self._wg_pending = []                # deferred weight-gradient problems [(crct_gemm_t, operands, producer stream)]
         self.group_wgrads = bool(params.get('group_wgrads', True))
-        self._tail = {}                      # hidden width -> (last pre-LayerNorm sum, its LayerNorm): read by the heads
+        self._tail = {}                      # id(row layout of the stream) -> (last pre-LayerNorm sum, its LayerNorm): read by the heads
         self.train()                         # encoder_decorator.py:17
 
     # ------------------------------------------------------------------ parameters / devices
@@ -366,7 +366,8 @@ class VisualDialogEncoder(nn.Module):
         h = self._linear(a, W1, self._p(pre_i + '.dense.bias'), M, L.EPI_BIAS_GELU, D2=dg, n=n)
         z = self._linear_res(h, W2, self._p(pre_o + '.dense.bias'), M, a, p_drop, seed, n, src)
         y, mean, rstd = self._ln(z, pre_o + '.LayerNorm', keep, n)
-        self._tail[z.shape[1]] = (z, pre_o + '.LayerNorm')       # the stream's latest pre-LayerNorm sum (fp32): what the heads read
+        self._tail[id(rw)] = (z, pre_o + '.LayerNorm')           # the stream's latest pre-LayerNorm sum (fp32): what the heads read
+        # (keyed by the stream's row layout, not by width: hidden_size may equal v_hidden_size)
         s = None
         if keep:
             s = _Saved()
@@ -651,7 +652,7 @@ class VisualDialogEncoder(nn.Module):
         hv0 = torch.empty(B, Hv, dtype=torch.float32, device=dev)
         # first token / region of every sample (vilbert.py:958,973 / 1599-1600), row cu[b] when packed: LayerNorm of the last
         # pre-LayerNorm sum in fp32 — the heads never see the bf16 rounding of the sequence outputs t / v
-        (z_t, ln_t), (z_v, ln_v) = self._tail[H], self._tail[Hv]
+        (z_t, ln_t), (z_v, ln_v) = self._tail[id(rt)], self._tail[id(rv)]
         L.layernorm_rows_f32(z_t, self._p(ln_t + '.weight'), self._p(ln_t + '.bias'), hw0, rt.cu, T)
         L.layernorm_rows_f32(z_v, self._p(ln_v + '.weight'), self._p(ln_v + '.bias'), hv0, rv.cu, R)
         prefusion = torch.empty(B, 512, dtype=torch.float32, device=dev)          # cat((hv, hw), -1), regressor.py:40

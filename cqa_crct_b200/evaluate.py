@@ -47,6 +47,23 @@ def expand_question_batch(qb: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor
     return out
 
 
+C_FORWARD_MAX = 256        # candidate sequences per chunk up to which the C-scheduled forward is used (above: GPU-bound either way)
+
+
+def _use_c_forward(enc, params, n):
+    return (bool(params.get('c_forward', True)) and n <= C_FORWARD_MAX and enc.varlen and not enc.fp32 and not enc.training
+            and enc.cfg.max_position_embeddings >= 1)
+
+
+def _c_model(enc):
+    cm = enc.__dict__.get('_c_model')
+    if cm is None:
+        from .capi import CModel
+        cm = CModel(enc)
+        enc.__dict__['_c_model'] = cm           # plain attribute (not a submodule / parameter)
+    return cm
+
+
 def _chunk_forward(model, qb_dev, params, c0, c1, grp):
     """One chunk of candidate sequences [c0, c1) through the model (the body of encoder_decorator.forward:73-158 in its
     evaluation branch, with the visual tensors taken once per question)."""
@@ -59,6 +76,15 @@ def _chunk_forward(model, qb_dev, params, c0, c1, grp):
     Rq = qb_dev['R'][q0:q1].contiguous()
     Rc = torch.empty(c1 - c0, 4, dtype=torch.float32, device=tokens.device)
     L.expand_blocks(Rq, group, Rc)
+    if _use_c_forward(model, params, c1 - c0):
+        # small chunks (one question with its candidates, interactive use): the Python schedule is host-bound at ~8 ms per forward
+        # whatever the batch; the library-scheduled forward (crct_forward, csrc/model.cu) enqueues the same kernels in the same
+        # order from C++ — bit-identical outputs, 2.3 ms at B = 1, 3.0 ms at B = 32, 6.5 ms at B = 128 (tools/capi_latency.py)
+        out = _c_model(model).forward(
+            {'tokens': tokens, 'segments': qb_dev['segments'][sl], 'loc': qb_dev['loc'][sl], 'attention_mask': attention_mask,
+             'image_feat': qb_dev['image_feat'][q0:q1], 'image_loc': qb_dev['image_loc'][q0:q1], 'image_target': qb_dev['image_target'][q0:q1],
+             'image_mask': qb_dev['image_mask'][q0:q1], 'R': Rc}, group=group, fill=model.row_fill_hint or (0.0, 0.0))
+        return out['logits'], [out['reg_pred'], out['reg_loss'], out['reg_l1'], (out['scalars'][3], out['scalars'][4]), out['reg_dist']]
     _, _, _, scores, reg, _ = model(
         tokens, qb_dev['loc'][sl], qb_dev['image_feat'][q0:q1], qb_dev['image_loc'][q0:q1], sep_indices=sep_indices,
         sep_len=hist_len + 1, token_type_ids=qb_dev['segments'][sl], masked_lm_labels=qb_dev['mask'][sl],

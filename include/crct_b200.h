@@ -391,6 +391,66 @@ typedef struct {
 int crct_score_answers(const crct_score_t* args, crct_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Whole-model entry points: the INFERENCE forward of the model behind
+ * `encoder_decorator.py:73 forward(..., evaluation=True)` — embeddings, the 12 + 6 + 6 layer schedule of
+ * vilbert.py:822-946, poolers, classifier, regressor and the loss / metric vectors of vilbert.py:1586-1657 — scheduled by the
+ * library itself (csrc/model.cu) on top of the operator entry points above, for hosts without Python (or that want one call
+ * per batch: ~300 kernel launches enqueued from C++).  Same kernels in the same order as `VisualDialogEncoder.forward` in
+ * evaluation mode: the outputs agree BIT FOR BIT (tests/test_model_capi_gpu.py).  The training forward / backward schedule stays in
+ * the reference's host language (cqa_crct_b200/encoder.py), where autograd, DDP and the optimizers hook in.
+ *   - the handle owns only host-side tables (configuration, parameter pointers); parameters, inputs, outputs and the
+ *     workspace are DEVICE memory owned by the caller; nothing is allocated, freed or synchronised;
+ *   - parameters are bound BY NAME (the reference's state_dict keys without the `bert_pretrained.` prefix): the fp32 master
+ *     tensor and its bf16 operand copy; q|k|v (and query1|key1|value1, query2|key2|value2) must be adjacent in memory in that
+ *     order, weights and biases separately (the fused projections read them as one [3H, H] matrix) — checked at bind time;
+ *   - rows are packed (var-len) as in the Python host: masks select the valid tokens / regions.
+ * -------------------------------------------------------------------------------------------- */
+#define CRCT_MAX_CONNECTIONS 16
+typedef struct {
+    int32_t hidden_size, num_hidden_layers, num_attention_heads, intermediate_size;              /* text stream (config/vilbert.json) */
+    int32_t v_hidden_size, v_num_hidden_layers, v_num_attention_heads, v_intermediate_size, v_feature_size;
+    int32_t bi_hidden_size, bi_num_attention_heads;
+    int32_t max_position_embeddings;
+    int32_t num_connections;                                                                       /* len(v_biattention_id) */
+    int32_t v_biattention_id[CRCT_MAX_CONNECTIONS], t_biattention_id[CRCT_MAX_CONNECTIONS];
+    int32_t l1;                     /* params['L1']: 1 = L1Loss, 0 = SmoothL1Loss(beta = 0.5)   vilbert.py:1525-1528 */
+    float tol_margin;               /* params['tol_margin'] */
+} crct_config_t;
+typedef struct crct_model_s* crct_handle_t;
+int crct_create(const crct_config_t* config, crct_handle_t* out);
+int crct_destroy(crct_handle_t h);
+/* names[i]: parameter name; w32[i]: fp32 master (device); w16[i]: bf16 copy (device; may be NULL for biases, LayerNorm,
+ * embedding tables and the fp32 heads); numel[i]: elements.  May be called again after the caller moved its buffers. */
+int crct_bind_params(crct_handle_t h, const char* const* names, const float* const* w32, const void* const* w16, const size_t* numel, int n);
+/* B candidate sequences of T tokens; Bq visual rows of R regions (Bq == B, or the number of QUESTIONS with `group`). */
+size_t crct_workspace_bytes(crct_handle_t h, int B, int Bq, int T, int R);
+typedef struct {
+    const int64_t* tokens;       /* [B,T]            batch['tokens'] */
+    const int64_t* segments;     /* [B,T]            token_type_ids in {-1,0..11} */
+    const float* loc;            /* [B,T,4]          txt_loc */
+    const void* attention_mask;  /* [B,T]            valid tokens; kind below */
+    const float* image_feat;     /* [Bq,R,F] */
+    const float* image_loc;      /* [Bq,R,4] */
+    const int64_t* image_target; /* [Bq,R]           class ids -> color_emb */
+    const void* image_mask;      /* [Bq,R]           valid regions */
+    const float* R4;             /* [B,4]            gt_reg[0] = (value, needs_reg, tolerance, scale) */
+    const int64_t* group;        /* [B] question index of every candidate (f3), or NULL when Bq == B */
+    int32_t B, Bq, T, R;
+    int32_t attention_mask_kind, image_mask_kind;   /* 0 = bool / uint8, 1 = int64, 2 = fp32 (as crct_additive_mask) */
+    float text_fill, region_fill;                   /* expected fraction of valid rows (0 = unknown): tile-shape choice only */
+} crct_batch_t;
+typedef struct {
+    float* logits;      /* [B,2]  seq_relationship_score */
+    float* reg_pred;    /* [B]    reg[0] */
+    float* reg_loss;    /* [B]    reg[1] */
+    float* reg_l1;      /* [B]    reg[2] */
+    float* reg_dist;    /* [B]    reg[4] */
+    float* scalars;     /* [5]    {loss, nsp (0 at inference), mean reg loss, #(+-5 %), #(<= tol_margin)} = reg[3] counts in [3], [4] */
+} crct_out_t;
+int crct_forward(crct_handle_t h, const crct_batch_t* batch, const crct_out_t* out, void* workspace, size_t workspace_bytes,
+                 crct_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * fp32 CHECK MODE (csrc/check_f32.cu): the operators above with fp32 activation storage and plain fp32 CUDA-core
  * arithmetic (exact erf, IEEE division, no tensor cores).  Same argument structs and the same dropout streams as the
  * production entry points; every pointer documented as bf16 above is fp32 here.  `VisualDialogEncoder(params,

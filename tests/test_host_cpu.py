@@ -178,7 +178,8 @@ def test_ctypes_structures_match_the_header_layout(tmp_path):
     pairs = {'crct_gemm_t': L.GemmArgs, 'crct_ln_bwd_t': L.LnBwdArgs, 'crct_embed_text_t': L.EmbedTextArgs,
              'crct_embed_text_bwd_t': L.EmbedTextBwdArgs, 'crct_embed_vis_t': L.EmbedVisArgs, 'crct_embed_vis_bwd_t': L.EmbedVisBwdArgs,
              'crct_attn_fwd_t': L.AttnFwdArgs, 'crct_attn_bwd_t': L.AttnBwdArgs, 'crct_linear_t': L.LinearArgs, 'crct_loss_t': L.LossArgs,
-             'crct_adamw_t': L.AdamWArgs, 'crct_select_t': L.SelectArgs, 'crct_score_t': L.ScoreArgs}
+             'crct_adamw_t': L.AdamWArgs, 'crct_select_t': L.SelectArgs, 'crct_score_t': L.ScoreArgs, 'crct_config_t': L.ConfigArgs,
+             'crct_batch_t': L.BatchArgs, 'crct_out_t': L.OutArgs}
     hdr_path = os.path.join(ROOT, 'include', 'crct_b200.h')
     text = re.sub(r'/\*.*?\*/', '', open(hdr_path).read(), flags=re.S)
     structs = dict((name, body) for body, name in re.findall(r'typedef struct \{(.*?)\}\s*(\w+);', text, flags=re.S))
@@ -221,12 +222,23 @@ def test_library_is_callable_from_plain_c(tmp_path):
                    '  crct_gemm_t g = {0};\n'
                    '  int rc2 = crct_gemm_bf16(&g, 0);\n'
                    '  printf("%d|%d|%d|%s\\n", v, rc, rc2, crct_last_error());\n'
+                   '  crct_config_t c = {0};\n'          # whole-model entry points from plain C: create / size / destroy (tiny.json numbers)
+                   '  c.hidden_size = 192; c.num_hidden_layers = 3; c.num_attention_heads = 4; c.intermediate_size = 256;\n'
+                   '  c.v_hidden_size = 128; c.v_num_hidden_layers = 2; c.v_num_attention_heads = 2; c.v_intermediate_size = 128; c.v_feature_size = 128;\n'
+                   '  c.bi_hidden_size = 128; c.bi_num_attention_heads = 4; c.max_position_embeddings = 64; c.num_connections = 2;\n'
+                   '  c.v_biattention_id[1] = 1; c.t_biattention_id[0] = 1; c.t_biattention_id[1] = 2; c.l1 = 1; c.tol_margin = 0.01f;\n'
+                   '  crct_handle_t h = 0;\n'
+                   '  int rc3 = crct_create(&c, &h);\n'
+                   '  size_t ws = crct_workspace_bytes(h, 6, 6, 32, 12);\n'
+                   '  printf("%d|%zu|%d\\n", rc3, ws, crct_destroy(h));\n'
                    '  return 0;\n}\n')
     exe = tmp_path / 'use'
     libdir = os.path.dirname(L.LIB_PATH)
     subprocess.run(['gcc', '-std=c11', '-I', os.path.join(ROOT, 'include'), '-o', str(exe), str(src), '-L', libdir, '-l:libcrct_b200.so',
                     f'-Wl,-rpath,{libdir}'], check=True)
-    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip()
+    out, out2 = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    rc3, ws, rc4 = out2.split('|')
+    assert int(rc3) == 0 and int(ws) > 0 and int(rc4) == 0
     v, rc, rc2, msg = out.split('|', 3)
     assert int(v) >= 100
     assert int(rc2) != 0 and msg                      # null operands are rejected with a message, never dereferenced
@@ -288,3 +300,42 @@ def test_argument_validation_returns_status_and_message():
     assert lib.crct_linear_f32_batched(C.byref(lin), 13, None) == ARG
     f = L.GemmArgs()
     assert lib.crct_f32_gemm(C.byref(f), None) == ARG and 'crct_f32_gemm' in msg()
+
+
+def test_whole_model_entry_points_validate_on_the_host(tmp_path):
+    """crct_create / crct_bind_params / crct_workspace_bytes / crct_forward without a GPU: configuration and binding
+    errors come back as status codes with messages; the forward refuses to run without an sm_100 device (no fallback)."""
+    import ctypes as C
+    from cqa_crct_b200.capi import config_args
+    lib = L.lib()
+    cfg = ModelConfig(os.path.join(CONFIG_DIR, 'tiny.json'))
+    params = default_params(os.path.join(CONFIG_DIR, 'tiny.json'))
+    h = C.c_void_p()
+    bad = config_args(cfg, params)
+    bad.num_attention_heads = 5                                   # 192 % 5 != 0   (vilbert.py:364-368)
+    assert lib.crct_create(C.byref(bad), C.byref(h)) == -4 and b'heads' in lib.crct_last_error()
+    bad = config_args(cfg, params)
+    bad.t_biattention_id[1] = 7                                   # beyond the layer count (vilbert.py:193-194)
+    assert lib.crct_create(C.byref(bad), C.byref(h)) == -1 and b'biattention' in lib.crct_last_error()
+    assert lib.crct_create(C.byref(config_args(cfg, params)), C.byref(h)) == 0 and h.value
+    assert lib.crct_workspace_bytes(h, 6, 6, 32, 12) > 0 and lib.crct_workspace_bytes(h, 0, 6, 32, 12) == 0
+    assert lib.crct_workspace_bytes(h, 12, 6, 32, 12) > lib.crct_workspace_bytes(h, 6, 6, 32, 12)
+    # binding: host arithmetic only (pointers are not dereferenced) — adjacency of the fused projections is checked
+    spec = [p for p in arena_order(cfg, param_spec(cfg)) if p.live]
+    off, _, _ = arena_offsets(arena_order(cfg, param_spec(cfg)))
+    base32, base16 = 0x10000000, 0x40000000
+    n = len(spec)
+    names = (C.c_char_p * n)(*[p.name.encode() for p in spec])
+    numel = (C.c_size_t * n)(*[p.numel for p in spec])
+    w32 = (C.c_void_p * n)(*[base32 + 4 * off[p.name] for p in spec])
+    w16 = (C.c_void_p * n)(*[base16 + 2 * off[p.name] for p in spec])
+    assert lib.crct_bind_params(h, names, w32, w16, numel, n) == 0, lib.crct_last_error()
+    k = [p.name for p in spec].index('bert.encoder.layer.1.attention.self.key.weight')
+    w16b = (C.c_void_p * n)(*[base16 + 2 * off[p.name] + (64 if i == k else 0) for i, p in enumerate(spec)])
+    assert lib.crct_bind_params(h, names, w32, w16b, numel, n) == -1 and b'adjacent' in lib.crct_last_error()
+    assert lib.crct_bind_params(h, names, w32, w16, numel, n - 1) == -1 and b'missing' in lib.crct_last_error()     # last tensor dropped
+    if not torch.cuda.is_available():
+        ba, o = L.BatchArgs(), L.OutArgs()
+        assert lib.crct_forward(h, C.byref(ba), C.byref(o), C.c_void_p(16), 16, None) in (-2, -3)       # no device: status, not a crash
+        assert lib.crct_last_error()
+    assert lib.crct_destroy(h) == 0
