@@ -264,6 +264,11 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
             return out['answers'].cpu(), out['reg_output'].cpu()
         return None
 
+    eval_pipe = None
+    if not train and not args.no_eval_pipeline:
+        from cqa_crct_b200.evaluate import EvalPipeline
+        eval_pipe = EvalPipeline(model, params, eval_batch_size=B)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -272,8 +277,16 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
     def pipelined(batches, n):
         """e2e loop of the captured step: the next batch's host->device copies are staged while the current step runs,
         every step's loss is read on the host one step late (so the queue never drains); the last loss is read before
-        the region closes."""
+        the region closes.  Evaluation: the same overlap through `evaluate.EvalPipeline` (H2D of batch i+1 under the kernels
+        of batch i, answers + regression values of batch i read after batch i+1 has been enqueued)."""
         prev = None
+        if not train:
+            for i in range(n):
+                h = eval_pipe.submit(batches[i % 4])
+                if prev is not None:
+                    prev.result()
+                prev = h
+            return prev.result()
         gstep.prefetch(batches[0])
         for i in range(n):
             h = gstep.step_async()
@@ -284,7 +297,7 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, with_clocks
         return prev.item()
 
     def timed(batches, read_loss):
-        pipe = read_loss and gstep is not None
+        pipe = read_loss and (gstep is not None or eval_pipe is not None)
         if pipe:
             pipelined(batches, warmup)
         else:
@@ -512,6 +525,7 @@ def main():
     ap.add_argument('--opt-overlap', action='store_true', help='run AdamW under the backward instead of after it (A/B; measured slower)')
     ap.add_argument('--bucket-mb', type=float, default=25.0, help='gradient all-reduce bucket size (fp32 MB)')
     ap.add_argument('--trace', default=None, help='N > 1: write the per-bucket timeline of one step (JSON) to this path')
+    ap.add_argument('--no-eval-pipeline', action='store_true', help='eval e2e: synchronous evaluate_batch per batch instead of evaluate.EvalPipeline (A/B)')
     ap.add_argument('--no-shard-optimizer', action='store_true', help='N > 1: all-reduce + replicated AdamW instead of reduce-scatter / sharded AdamW / all-gather (A/B)')
     ap.add_argument('--no-opt-pipeline', action='store_true', help='N > 1: whole-arena AdamW after the last all-reduce (A/B)')
     ap.add_argument('--no-graph', action='store_true', help='enqueue every launch from Python instead of replaying the captured step')

@@ -163,3 +163,64 @@ def evaluate_batch(model, qb: Dict[str, torch.Tensor], params: dict, eval_batch_
     total_correct += batch_total
     return {'answers': answers, 'prob': prob, 'reg_output': sel[0], 'reg_loss': sel[1], 'reg_t_loss': sel[2], 'flags': flags,
             'total_correct': total_correct, 'logits': logits}
+
+
+class EvalPipeline:
+    """Overlapped evaluation loop (the reference's loop is synchronous per batch: copy, forward, `.item()`s — CRCT/evaluation.py:231-317).
+
+        pipe = EvalPipeline(model, params, eval_batch_size)
+        pending = None
+        for host_batch in loader:                      # pinned host tensors (question batches)
+            h = pipe.submit(host_batch)                # H2D on a copy stream, forward + selection enqueued behind it, results -> pinned host
+            if pending is not None:
+                answers, reg_output = pending.result() # waits only for THAT batch
+            pending = h
+
+    The host->device copies of batch i+1 run under the kernels of batch i, and the host reads batch i's answers after batch i+1 has
+    been enqueued, so the GPU never idles between batches.  Same arithmetic as `evaluate_batch` (it is what runs); `total_correct`
+    accumulates on the device across submits."""
+
+    def __init__(self, model, params: dict, eval_batch_size: int = 512, depth: int = 3):
+        self.model, self.params, self.ebs = model, params, eval_batch_size
+        enc = getattr(model, 'module', model)
+        self.dev = enc.arena.w32.device
+        self._copy = torch.cuda.Stream(device=self.dev)
+        self.total_correct = torch.zeros(6, 2, dtype=torch.float64, device=self.dev)
+        self._slots = [None] * depth            # pinned result buffers, reused round-robin
+        self._i = 0
+
+    def submit(self, qb: Dict[str, torch.Tensor], force_gt: bool = False):
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self._copy):
+            dev_qb = to_device(qb, self.dev)
+            ready = torch.cuda.Event()
+            ready.record(self._copy)
+        cur.wait_event(ready)
+        for v in dev_qb.values():
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(cur)            # allocated on the copy stream, consumed on the compute stream
+        out = evaluate_batch(self.model, dev_qb, self.params, self.ebs, total_correct=self.total_correct, force_gt=force_gt, reduce=False)
+        Q = out['answers'].numel()
+        slot = self._i % len(self._slots)
+        self._i += 1
+        buf = self._slots[slot]
+        if buf is None or buf[0].numel() < Q:
+            buf = (torch.empty(Q, dtype=torch.int64).pin_memory(), torch.empty(Q, dtype=torch.float32).pin_memory(), None)
+        if buf[2] is not None:
+            buf[2].synchronize()                # the result that used this slot `depth` submits ago has been read
+        buf[0][:Q].copy_(out['answers'], non_blocking=True)
+        buf[1][:Q].copy_(out['reg_output'], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._slots[slot] = (buf[0], buf[1], done)
+        return _PendingAnswers(buf[0], buf[1], Q, done, out)
+
+
+class _PendingAnswers:
+    def __init__(self, answers, reg, Q, event, out):
+        self._a, self._r, self._q, self._e, self.device_out = answers, reg, Q, event, out
+
+    def result(self):
+        """(answers [Q] int64, reg_output [Q] fp32) on the host; blocks until this batch (not the queue behind it) has finished."""
+        self._e.synchronize()
+        return self._a[:self._q].clone(), self._r[:self._q].clone()

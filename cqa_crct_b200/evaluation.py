@@ -20,7 +20,7 @@ import torch.distributed as dist
 
 from . import checkpoint as ckpt
 from .encoder import VisualDialogEncoder
-from .evaluate import evaluate_batch
+from .evaluate import EvalPipeline, evaluate_batch
 from .parallel import DistributedDataParallel
 from .synthetic import make_question_batch
 
@@ -47,12 +47,14 @@ def plotqa_evaluate(batches: Iterable[dict], params: dict, eval_batch_size: int,
     total = torch.zeros(6, 2, dtype=torch.float64, device=dev)          # :211
     outs = []
     force = '_REGS' in params.get('qa_file', '')                         # :288-289
+    pipe = EvalPipeline(dialog_encoder, params, eval_batch_size)         # next batch's copies under this batch's kernels; no host read-back
+    pipe.total_correct = total
     for qb in batches:
         if qb['id'].shape[0] == 0:                                       # :233-234
             continue
-        out = evaluate_batch(dialog_encoder, qb, params, eval_batch_size, total_correct=total, force_gt=force, reduce=False)
+        h = pipe.submit(qb, force_gt=force)
         if collect:
-            outs.append(out)
+            outs.append(h.device_out)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(total, op=dist.ReduceOp.SUM)                     # :519-521, once for the whole run (the sum is associative)
     return total, outs

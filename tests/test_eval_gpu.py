@@ -111,3 +111,30 @@ def test_training_rejects_shared_visual_rows():
     gb = {k: v.cuda() for k, v in qb.items()}
     with pytest.raises(ValueError):
         glue_forward(m, gb, params)                              # 3 visual rows for sum(num_ans) text rows, no image_group
+
+
+def test_eval_pipeline_equals_batch_by_batch_evaluation():
+    """evaluate.EvalPipeline (H2D of the next batch under the current batch's kernels, results read one batch late) returns what
+    `evaluate_batch` returns batch by batch, and accumulates the same accuracy table."""
+    from cqa_crct_b200.evaluate import EvalPipeline
+    m, params, cfg, sd = _tiny_model()
+    batches = [make_question_batch(5 + i, 32, 12, cfg.v_feature_size, seed=40 + i, vocab_size=cfg.vocab_size, max_ans=7) for i in range(5)]
+    pinned = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()} for b in batches]
+    total = None
+    want = []
+    for b in batches:
+        out = evaluate_batch(m, b, params, eval_batch_size=16, total_correct=total)
+        total = out['total_correct']
+        want.append((out['answers'].cpu(), out['reg_output'].cpu()))
+    pipe = EvalPipeline(m, params, eval_batch_size=16, depth=2)
+    got, pending = [], None
+    for b in pinned:
+        h = pipe.submit(b)
+        if pending is not None:
+            got.append(pending.result())
+        pending = h
+    got.append(pending.result())
+    assert len(got) == len(want)
+    for (a, r), (a2, r2) in zip(got, want):
+        assert torch.equal(a, a2) and torch.equal(r, r2)
+    assert torch.equal(pipe.total_correct.cpu(), total.cpu())
