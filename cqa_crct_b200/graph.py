@@ -216,6 +216,7 @@ class GraphedTrainStep:
         cur.wait_stream(self._opt_stream)
         cur.wait_stream(self._cast_stream)
         self.enc.arena.mark_bf16_fresh()
+        self.opt.moments_partial = True          # until consolidate_optimizer_state(): optimizer.state_dict() refuses to run
 
     def _replay_units(self):
         for g, bucket in self.segments:
@@ -232,6 +233,7 @@ class GraphedTrainStep:
                 slo, shi = self.shard_bounds(lo, hi)
                 for t in (self.opt.m, self.opt.v):
                     dist.all_gather_into_tensor(t[lo:hi], t[slo:shi], group=self.ddp.pg)
+        self.opt.moments_partial = False
 
     def _eager_step(self):
         self.opt.zero_grad()

@@ -52,6 +52,7 @@ class FusedAdamW:
         self.step_count = 0
         self.lr_factor = 1.0
         self.min_lr = 0.0
+        self.moments_partial = False    # set by graph.GraphedTrainStep (sharded optimizer): m / v are only current on their owner rank
         self.dyn = None            # device {lr[4], 1-beta1^t, sqrt(1-beta2^t)} for CUDA-graph replay (see graph.py)
         self._dyn_host = None
 
@@ -140,6 +141,7 @@ class FusedAdamW:
         a gradient.  The reference's 36 never-used tensors have no state entry there either (their .grad stays None
         under `find_unused_parameters=True`, CRCT/train.py:141).  The moment tensors are VIEWS of the flat arenas —
         `torch.save` writes them without a copy through Python."""
+        self._require_complete_moments()
         arena = self.enc.arena
         lrs = self.current_lrs()
         groups, state = [], {}
@@ -195,7 +197,13 @@ class FusedAdamW:
                 base[self.group_of(p)] = float(g.get('initial_lr', g['lr']))
         self.base_lr = [b if b is not None else old for b, old in zip(base, self.base_lr)]
 
+    def _require_complete_moments(self):
+        if self.moments_partial:
+            raise RuntimeError('the Adam moments are sharded over the data-parallel ranks (graph.GraphedTrainStep, sharded optimizer): call '
+                               'GraphedTrainStep.consolidate_optimizer_state() on EVERY rank before reading the optimizer state')
+
     def flat_state_dict(self):
+        self._require_complete_moments()
         return {'step': self.step_count, 'exp_avg': self.m, 'exp_avg_sq': self.v, 'lr_factor': self.lr_factor, 'min_lr': self.min_lr}
 
 

@@ -159,6 +159,7 @@ def train(gpu: int, params: dict) -> dict:
         gstep = GraphedTrainStep(model, optimizer, params, example, scheduler=scheduler, warmup_steps=2)
         # the capture warm-up ran real steps on the example batch: restore the pre-capture state
         enc.arena.w32.copy_(snapshot[0]); optimizer.m.copy_(snapshot[1]); optimizer.v.copy_(snapshot[2])
+        optimizer.moments_partial = False              # restored in full on every rank
         optimizer.step_count, scheduler.last_epoch = snapshot[3], snapshot[4]
         optimizer.lr_factor = scheduler.factor(scheduler.last_epoch)
         enc.arena.refresh_bf16()

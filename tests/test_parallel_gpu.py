@@ -60,6 +60,13 @@ def _run(rank, world, port, out_path, config='tiny.json', T=32, R=12, B=8, shard
     ddp.require_sync = True
     opt = FusedAdamW(ddp, lr=2e-5, image_lr=2e-5)
     gs = GraphedTrainStep(ddp, opt, params, half, warmup_steps=1)          # runs ONE eager step (sharded / per-bucket AdamW)
+    guarded = True
+    if gs.shard_optimizer:                                                 # reading sharded moments without gathering them must fail loudly
+        try:
+            opt.state_dict()
+            guarded = False
+        except RuntimeError:
+            pass
     gs.consolidate_optimizer_state()                                       # sharded: every rank now holds the complete moments
     # the pipelined per-bucket optimizer == exchange, then whole-arena AdamW: after one step the Adam moments (linear / quadratic in
     # the gradients) agree to fp32 summation noise
@@ -92,7 +99,7 @@ def _run(rank, world, port, out_path, config='tiny.json', T=32, R=12, B=8, shard
     graph_same = all(torch.equal(ws[0], x) for x in ws)
     if rank == 0:
         torch.save({'rel': rel, 'same': same, 'buckets': nb, 'graph_same': graph_same, 'segments': len(gs.segments), 'graph_vs_eager': upd, 'moments': mom,
-                    'moments3': mom3, 'cast_ok': cast_ok, 'pipelined': gs.pipeline_optimizer, 'sharded': gs.shard_optimizer}, out_path)
+                    'moments3': mom3, 'cast_ok': cast_ok, 'pipelined': gs.pipeline_optimizer, 'sharded': gs.shard_optimizer, 'guarded': guarded}, out_path)
     dist.destroy_process_group()
 
 
@@ -112,6 +119,7 @@ def test_two_gpu_gradients_equal_single_gpu_full_batch(tmp_path):
     # gathered from their owners before the comparison.  After three steps the two paths' gradients have drifted apart with their
     # weights (2e-4; this post-LN network turns that into percents of gradient change): `moments3` only guards against
     # a shard whose moments never arrived (zeros: error ~1)
+    assert r['guarded']
     assert r['sharded'] and not r['pipelined'] and r['moments'] < 1e-5 and r['moments3'] < 0.2 and r['graph_vs_eager'] < 2e-4 and r['cast_ok'], r
 
 
