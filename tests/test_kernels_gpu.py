@@ -416,3 +416,39 @@ def test_heads_linear_loss_adamw():
     dpo = torch.randn_like(pt); dut, duv = torch.empty_like(pt), torch.empty_like(pt)
     L.pool_mul_bwd(dpo, pt, pv, dut, duv, 0.0, 0)
     assert relmax(dut, dpo * pv * (pt > 0)) < 1e-6 and relmax(duv, dpo * pt * (pv > 0)) < 1e-6
+
+
+def test_adamw_vector_form_equals_scalar_form_and_shard_offsets():
+    """The 128-bit AdamW kernel (4 consecutive elements per thread) gives the bits of the scalar kernel; a range that starts inside a
+    64-element block (`group_offset`, a data-parallel rank's shard) picks up the right (lr, weight decay) group in both forms."""
+    torch.manual_seed(5)
+    n = 64 * 40
+    w0, g0 = torch.randn(n + 8, device=DEV), torch.randn(n + 8, device=DEV)
+    m0, v0 = torch.rand(n + 8, device=DEV) * 0.1, torch.rand(n + 8, device=DEV) * 0.01
+    group = (torch.arange(n // 64 + 1, device=DEV) % 4).to(torch.uint8)
+    lr4, wd4 = [2e-3, 1e-3, 5e-4, 3e-3], [0.01, 0.0, 0.02, 0.0]
+
+    def run(lo, hi, shift):
+        """update elements [lo, hi) of a copy whose storage is shifted by `shift` elements (shift = 1: misaligned -> scalar kernel)"""
+        w, g, m, v = (torch.empty(n + 8, device=DEV) for _ in range(4))
+        w16 = torch.zeros(n + 8, device=DEV, dtype=torch.bfloat16)
+        for dst, src in ((w, w0), (g, g0), (m, m0), (v, v0)):
+            dst[shift:shift + n].copy_(src[:n])
+        s = slice(shift + lo, shift + hi)
+        L.adamw(w[s], g[s], m[s], v[s], w16[s] if shift == 0 else None, group[lo // 64:], hi - lo, lr4, wd4, 0.9, 0.999, 1e-8, 3, group_offset=lo % 64)
+        return w[shift:shift + n].clone(), m[shift:shift + n].clone(), v[shift:shift + n].clone(), w16[:n].clone()
+
+    for lo, hi in ((0, n), (64 * 3 + 8, 64 * 17 + 24), (64 * 5 + 60, 64 * 5 + 64)):
+        wa, ma, va, w16a = run(lo, hi, 0)          # aligned: vector kernel
+        wb, mb, vb, _ = run(lo, hi, 1)             # storage shifted by one float: scalar kernel
+        assert torch.equal(wa, wb) and torch.equal(ma, mb) and torch.equal(va, vb)
+        assert torch.equal(wa[:lo], w0[:lo]) and torch.equal(wa[hi:], w0[hi:n])       # nothing outside the range is touched
+        assert not torch.equal(wa[lo:hi], w0[lo:hi])
+        assert torch.equal(w16a[lo:hi], wa[lo:hi].to(torch.bfloat16))
+        # reference arithmetic (torch.optim.AdamW semantics) with the per-block groups
+        gi = group[(torch.arange(lo, hi, device=DEV) // 64)].long() % 4
+        lr, wd = torch.tensor(lr4, device=DEV)[gi], torch.tensor(wd4, device=DEV)[gi]
+        g, m, v, w = g0[lo:hi], m0[lo:hi], v0[lo:hi], w0[lo:hi]
+        m1, v1 = 0.9 * m + 0.1 * g, 0.999 * v + 0.001 * g * g
+        ref = w * (1 - lr * wd) - lr / (1 - 0.9 ** 3) * m1 / (v1.sqrt() / (1 - 0.999 ** 3) ** 0.5 + 1e-8)
+        assert relmax(wa[lo:hi], ref) < 1e-5
