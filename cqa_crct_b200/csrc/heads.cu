@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinBatch 
         }
         __syncthreads();
         if (k0 + BK < k_hi) fetch(k0 + BK);
+        // M = batch size (80) is 1.25 tiles: in the second m tile only the warps whose rows exist do the arithmetic
+        // (a warp owns rows [m0 + 8 * warp, + 8)); the others only take part in the loads and barriers
+        if (m0 + (threadIdx.x >> 5) * 8 < p.M) {
 #pragma unroll 8
         for (int kk = 0; kk < BK; ++kk) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_f32_kernel(const LinBatch 
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
         }
         __syncthreads();
     }

@@ -51,7 +51,10 @@ torch.cuda.synchronize()
 names = {'gemm': 'GEMM (fwd / dgrad)', 'gemm_wgrad_grouped': 'grouped weight gradients', 'attn_fwd': 'attention fwd', 'attn_bwd': 'attention bwd',
          'layernorm_fwd': 'LayerNorm fwd', 'layernorm_bwd': 'LayerNorm bwd (dz)', 'layernorm_bwd_params': 'LayerNorm bwd (column sums)',
          'colsum_bf16': 'bias-gradient column sums', 'embed_text_fwd': 'embeddings', 'embed_vis_fwd': 'embeddings', 'embed_text_bwd': 'embeddings',
-         'embed_vis_bwd': 'embeddings', 'softmax_rows': 'embeddings', 'adamw': 'AdamW', 'row_map': 'row maps'}
+         'embed_vis_bwd': 'embeddings', 'softmax_rows': 'embeddings', 'adamw': 'AdamW', 'row_map': 'row maps',
+         'linear_f32_batched': 'heads: batched fp32 linear launches', 'layernorm_rows_f32': 'heads: other', 'pool_mul_fwd': 'heads: other',
+         'pool_mul_bwd': 'heads: other', 'hybrid_loss': 'heads: other', 'scale_rows': 'heads: other', 'scatter_rows_f32': 'heads: other',
+         'fill_zero': 'memsets'}
 saved = {n: getattr(L, n) for n in names}
 hf, hb_ = enc._heads_fwd, enc._heads_bwd
 try:
@@ -94,4 +97,6 @@ for ms, sec, n in sorted(rows, reverse=True):
     print(f'{ms:8.3f} ms  {n:4d} calls  {sec}')
     if not sec.startswith('heads'):
         acc += ms
+    if os.environ.get('SECTION_DETAIL') and sec.startswith(os.environ['SECTION_DETAIL']):
+        print('           per call (us):', ' '.join(f'{(a.elapsed_time(b) - ovh) * 1e3:.1f}' for a, b in pairs[sec]))
 print(f'{acc:8.3f} ms  sum of the kernel families (heads sections contain their own launches only; GEMM etc. do not run inside them)')
