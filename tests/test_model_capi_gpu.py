@@ -54,6 +54,13 @@ def test_c_forward_equals_python_forward_bit_for_bit(config, B, T, R):
     _same(out, scores, reg)
     out2 = cm.forward(_c_inputs(gb), fill=(0.7, 0.5))             # the fill hints steer tile shapes only
     _same(out2, scores, reg)
+    if B <= 8:                                                    # crct_forward is capturable: replayed from a CUDA graph, other batch, same shapes
+        gb2 = {k: v.cuda() for k, v in make_batch(B, T, R, cfg.v_feature_size, seed=18, vocab_size=cfg.vocab_size).items()}
+        cm.forward_graphed(_c_inputs(gb))
+        out3 = cm.forward_graphed(_c_inputs(gb2))
+        with torch.no_grad():
+            _, _, _, _, scores2, reg2 = glue_forward(m, gb2, params, evaluation=True)
+        _same(out3, scores2, reg2)
 
 
 @pytest.mark.parametrize('config,Q,T,R', [('tiny.json', 9, 32, 12), ('vilbert.json', 4, 124, 44)])

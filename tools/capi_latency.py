@@ -29,7 +29,10 @@ for B in [int(x) for x in sys.argv[1:]] or [1, 32, 128, 512]:
     def c():
         return cm.forward(inp, fill=fill)['logits']
     assert torch.equal(py(), c())
-    for name, fn in (('python schedule', py), ('crct_forward  ', c)):
+    def cg():
+        return cm.forward_graphed(inp, fill=fill)['logits']
+    assert torch.equal(py(), cg())
+    for name, fn in (('python schedule', py), ('crct_forward  ', c), ('crct_forward in a CUDA graph', cg)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
