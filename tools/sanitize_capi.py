@@ -1,11 +1,12 @@
+"""compute-sanitizer --tool memcheck python tools/sanitize_*.py : tiny-model runs of the library-scheduled forward / one training step (grouped weight gradients, 128-bit AdamW) for out-of-bounds and misaligned accesses."""
 import os, sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cqa_crct_b200.capi import CModel
 from cqa_crct_b200.encoder import VisualDialogEncoder
 from cqa_crct_b200.evaluate import candidate_groups, expand_question_batch
 from cqa_crct_b200.spec import ModelConfig, synth_state_dict
 from cqa_crct_b200.synthetic import default_params, make_batch, make_question_batch
-cfgp = '/root/repo/cqa_crct_b200/config/tiny.json'
+cfgp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'cqa_crct_b200', 'config', 'tiny.json')
 cfg = ModelConfig(cfgp)
 params = default_params(cfgp, device='cuda', max_seq_len=32, max_vis_features=12, L1=True)
 m = VisualDialogEncoder(params)
