@@ -1191,9 +1191,34 @@ extern "C" CRCT_API int crct_gemm_wgrad_grouped(const crct_gemm_t* probs, int co
         mn[g] = ((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + BN - 1) / BN);
         work += (long)mn[g] * kb_eff[g];
     }
-    // k-blocks per tile such that the whole group is about two waves of equal-cost tiles (>= 4 k-blocks: pipeline depth)
-    long kb_target = (work + 2L * sms - 1) / (2L * sms);
-    if (kb_target < 4) kb_target = 4;
+    // Split-K per problem: tiles of (about) equal k-depth `kb_target`.  The depth is chosen by cost over a few candidates — waves on
+    // the SMs x (deepest tile + the fixed cost of a tile: fill, fp32 red.add epilogue): a text layer's four problems are
+    // 216 tiles of 108 k-blocks, i.e. 1.46 waves un-split (two tile-times on 108 CTAs: ncu showed 74 % tensor-pipe when active but
+    // 51 % of elapsed, 40 SMs idle); split in two they are 432 tiles = 2.92 waves of half the depth (-20 %).
+    constexpr long TILE_FIXED_KB = 16;           // flat between 8 and 24 (tools/section_times.py: 2.02-2.03 ms per step; 2.25 ms before)
+    auto split_for = [&](int g, long target) {
+        if (probs[g].split_k > 0) return (long)probs[g].split_k;
+        long sp = (kb_eff[g] + target / 2) / target;
+        const long kb_total = (probs[g].K + BLOCK_K - 1) / BLOCK_K;
+        if (sp < 1) sp = 1;
+        if (sp > kb_total) sp = kb_total;
+        return sp;
+    };
+    long kb_target = 0, best_cost = -1;
+    for (int w = 1; w <= 6; ++w) {
+        long target = (work + (long)w * sms - 1) / ((long)w * sms);
+        if (target < 4) target = 4;                  // pipeline depth
+        long tiles = 0, deepest = 0;
+        for (int g = 0; g < count; ++g) {
+            const long sp = split_for(g, target);
+            tiles += (long)mn[g] * sp;
+            const long depth = (kb_eff[g] + sp - 1) / sp;
+            if (depth > deepest) deepest = depth;
+        }
+        const long waves = (tiles + sms - 1) / sms;
+        const long cost = waves * (deepest + TILE_FIXED_KB);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; kb_target = target; }
+    }
     GroupParams gp;
     GroupMaps tm;
     memset(&gp, 0, sizeof(gp));
@@ -1201,9 +1226,7 @@ extern "C" CRCT_API int crct_gemm_wgrad_grouped(const crct_gemm_t* probs, int co
     for (int g = 0; g < count; ++g) {
         const crct_gemm_t* a = &probs[g];
         const int kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
-        int split = a->split_k > 0 ? a->split_k : (int)((kb_eff[g] + kb_target / 2) / kb_target);
-        if (split < 1) split = 1;
-        if (split > kb_total) split = kb_total;
+        int split = (int)split_for(g, kb_target);
         KParams& p = gp.p[g];
         p.M = a->M; p.N = a->N; p.K = a->K;
         p.num_n_tiles = (a->N + BN - 1) / BN;
