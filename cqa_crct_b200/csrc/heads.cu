@@ -7,6 +7,7 @@
 // reference: CRCT/backbone/vilbert.py:955-976 (poolers), :1052-1060 (classifier), CRCT/backbone/regressor.py:36-42,
 //            vilbert.py:1586-1657 (losses, metrics), CRCT/backbone/encoder_decorator.py:144-153 (loss combine).
 #include "common.cuh"
+#include <stdlib.h>
 #include <cooperative_groups.h>
 
 namespace {
@@ -320,9 +321,12 @@ extern "C" CRCT_API int crct_linear_f32_batched(const crct_linear_t* problems, i
     LinBatch b;
     memset(&b, 0, sizeof(b));
     int gy = 0, n = 0, S = 1;
-    auto ksplit = [](int K) {                            // at most two 64-deep slabs per CTA, up to 8 CTAs
+    // one 64-deep slab per CTA where the cluster size allows (K <= 512): the per-launch time of these latency chains fell from
+    // 15-17 us to 11 us with one slab instead of two (tools/section_times.py, heads 0.60 -> 0.53 ms per step)
+    constexpr int KSPLIT_SLABS = 1;
+    auto ksplit = [](int K) {                            // at most KSPLIT_SLABS 64-deep slabs per CTA, up to 8 CTAs
         int sp = 1;
-        while (sp < 8 && sp * 2 * BK < K) sp *= 2;
+        while (sp < 8 && sp * KSPLIT_SLABS * BK < K) sp *= 2;
         return sp;
     };
     for (int i = 0; i < count; ++i) {
