@@ -209,7 +209,8 @@ class GraphedTrainStep:
             for lo, hi in reversed(self._chunks(*bucket)):       # tail first, like the backward
                 pend.append(self._scatter_bucket(lo, hi))
                 while len(pend) > 1:
-                    self._update_shard(*pend.pop(0), ev=on_bucket(*pend[0][1:]) if on_bucket else None)
+                    item = pend.pop(0)
+                    self._update_shard(*item, ev=on_bucket(*item[1:]) if on_bucket else None)
         while pend:
             item = pend.pop(0)
             self._update_shard(*item, ev=on_bucket(*item[1:]) if on_bucket else None)
